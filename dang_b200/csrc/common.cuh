@@ -1,0 +1,210 @@
+// common.cuh -- shared device helpers for the dang Gibbs hot path (sm_100a).
+//
+// Everything here is fp64: the reference's arithmetic is real(dp) throughout and the parity
+// contract is 1e-10 relative.  The per-pixel normal-equation blocks are 2x2..4x4, so there is
+// no tensor-core work anywhere; the kernels are HBM-streaming with warp-shuffle + block
+// reductions (BASELINE.json north_star).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DG_MAX_BANDS 32
+#define DG_MAX_COMPS 8
+#define DG_MAX_CG 4      // diffuse components per CG group
+#define DG_MAXIND 2
+#define DG_THREADS 256
+
+// src/dang_util_mod.f90:12-13 (pi from healpix_types)
+#define DG_PI 3.141592653589793238462643383279502884197
+#define DG_KB 1.3806503e-23
+#define DG_H (1.0545726691251021e-34 * 2.0 * DG_PI)
+
+struct BandView {
+  double nu_c;  // Hz
+  int n;        // 0 <=> delta band
+  int off;      // offset into bp_nu0 / bp_tau0
+};
+
+struct CompView {
+  int type;     // DANG_COMP_*
+  int nind;
+  double nu_ref;
+  double *amp;             // [nmaps][Ppad]
+  double *idx[DG_MAXIND];  // each [nmaps][Ppad]
+};
+
+// Model description handed to kernels by value (lives in the constant bank: every thread reads
+// the same entries, which is exactly what the LDC path is for).
+struct ModelView {
+  int nbands, ncomp, nmaps;
+  int64_t P;     // pixels owned by this handle
+  int64_t Ppad;  // plane stride (multiple of 64 doubles so every plane is 512 B aligned)
+  int64_t pix_lo, npix;  // global offset / full-sky size (RNG slots are global)
+  BandView band[DG_MAX_BANDS];
+  CompView comp[DG_MAX_COMPS];
+  const double *bp_nu0, *bp_tau0;
+  const double *sig, *rms;   // [nbands][nmaps][Ppad]
+  const unsigned char *mask; // [Ppad], 1 = use pixel (mask /= 0 and /= missval)
+  double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
+};
+
+__device__ __forceinline__ size_t plane_off(const ModelView &mv, int band, int k) {
+  return ((size_t)band * mv.nmaps + (size_t)k) * (size_t)mv.Ppad;
+}
+
+// streaming loads: read-only path, do not pollute L1
+__device__ __forceinline__ double ldg_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldg_stream2(const double *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y)
+               : "l"(p));
+  return v;
+}
+
+// ---------------------------------------------------------------- SEDs
+// eval_sed, src/dang_component_mod.f90:778-813; evaluate_powerlaw :886-918; evaluate_mbb :920-958.
+// The arithmetic keeps the reference's form (pow / exp()-1, same operation order) so that the
+// only difference to glibc is the last-ulp behaviour of CUDA's pow/exp.
+__device__ __forceinline__ double sed_powerlaw(const ModelView &mv, const BandView &b,
+                                               double nu_ref, double beta) {
+  if (b.n == 0) return pow(b.nu_c / nu_ref, beta);
+  double spectrum = 0.0;
+  for (int i = 0; i < b.n; i++) {
+    const double nu0 = mv.bp_nu0[b.off + i];
+    if (nu0 == 0.0) continue;
+    spectrum = spectrum + mv.bp_tau0[b.off + i] * pow(nu0 / nu_ref, beta);
+  }
+  return spectrum;
+}
+
+__device__ __forceinline__ double sed_mbb(const ModelView &mv, const BandView &b, double nu_ref,
+                                          double beta, double td) {
+  const double z = DG_H / (DG_KB * td);
+  const double eref = exp(z * nu_ref) - 1.0;
+  if (b.n == 0) return eref / (exp(z * b.nu_c) - 1.0) * pow(b.nu_c / nu_ref, beta + 1.0);
+  double spectrum = 0.0;
+  for (int i = 0; i < b.n; i++) {
+    const double nu0 = mv.bp_nu0[b.off + i];
+    if (nu0 == 0.0) continue;
+    spectrum = spectrum +
+               mv.bp_tau0[b.off + i] * eref / (exp(z * nu0) - 1.0) * pow(nu0 / nu_ref, beta + 1.0);
+  }
+  return spectrum;
+}
+
+__device__ __forceinline__ double sed_eval(const ModelView &mv, int ic, int band, double t0,
+                                           double t1) {
+  const CompView &c = mv.comp[ic];
+  if (c.type == 1) return sed_powerlaw(mv, mv.band[band], c.nu_ref, t0);
+  return sed_mbb(mv, mv.band[band], c.nu_ref, t0, t1);
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Stream definition shared with the test oracle (DESIGN.md "RNG"):
+// counter = {slot_lo, slot_hi, stream, 'DANG'}, key = {seed_lo, seed_hi}.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__host__ __device__ __forceinline__ void philox_uniform2(uint64_t seed, uint32_t stream,
+                                                         uint64_t slot, double &u1, double &u2) {
+  uint32_t c[4] = {(uint32_t)slot, (uint32_t)(slot >> 32), stream, 0x44414e47u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint64_t a = ((uint64_t)c[0] << 32) | c[1];
+  const uint64_t b = ((uint64_t)c[2] << 32) | c[3];
+  u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// rand_normal(0,1), src/dang_util_mod.f90:100-110: Box-Muller, sine branch
+__host__ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t stream,
+                                                         uint64_t slot) {
+  double u1, u2;
+  philox_uniform2(seed, stream, slot, u1, u2);
+  const double r = sqrt(-2.0 * log(u1));
+  return r * sin(2.0 * DG_PI * u2);
+}
+
+enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3 };
+
+// ---------------------------------------------------------------- deterministic reductions
+// Two-stage tree: per-thread serial partial -> warp shuffle -> shared-memory tree over warps
+// -> one partial per block in global memory -> fixed-order final sum by the block that
+// finishes last.  The result depends only on (grid, block) sizes, never on scheduling.
+template <int NV>
+__device__ __forceinline__ void warp_reduce(double (&v)[NV]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+}
+
+// Reduces v over the block; valid in warp 0 afterwards (all lanes).
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *smem /* NV*32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  warp_reduce<NV>(v);
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; i++) smem[i * 32 + warp] = v[i];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = (lane < nwarp) ? smem[i * 32 + lane] : 0.0;
+    warp_reduce<NV>(v);
+  }
+}
+
+// Block partial -> global; the last block to arrive sums all partials in block order and
+// writes `out[NV]`.  `ticket` must be zero on entry and is reset to zero on exit.
+// Returns true in the threads of warp 0 of the last block (so a caller can append work).
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *smem, double *partials,
+                                            unsigned int *ticket, double *out) {
+  __shared__ bool is_last;
+  block_reduce<NV>(v, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) partials[(size_t)i * gridDim.x + blockIdx.x] = v[i];
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    double a = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      a += __ldcg(&partials[(size_t)i * gridDim.x + b]);
+    acc[i] = a;
+  }
+  __syncthreads();  // smem reuse
+  block_reduce<NV>(acc, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) out[i] = acc[i];
+    *ticket = 0;
+    __threadfence();
+  }
+  return threadIdx.x < 32;
+}

@@ -1,0 +1,1230 @@
+// dang_gpu.cu -- C ABI (include/dang_gpu.h) of the B200-native dang Gibbs hot path.
+//
+// One handle owns one GPU and one contiguous RING pixel range.  All work is enqueued on the
+// handle's stream; cross-rank traffic is an NCCL all-gather of a few doubles followed by a
+// rank-ordered sum on every rank (deterministic, identical bits everywhere).
+// There is deliberately no CPU fallback: every error surfaces as a nonzero return code.
+#include "../../include/dang_gpu.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_cg.cuh"
+#include "kernels_data.cuh"
+#include "kernels_mh.cuh"
+
+// ---------------------------------------------------------------- errors
+namespace {
+
+struct DgError : std::runtime_error {
+  int code;
+  DgError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+std::string vfmt(const char *f, va_list ap) {
+  char buf[1024];
+  vsnprintf(buf, sizeof buf, f, ap);
+  return buf;
+}
+[[noreturn]] void fail(int code, const char *f, ...) {
+  va_list ap;
+  va_start(ap, f);
+  std::string m = vfmt(f, ap);
+  va_end(ap);
+  throw DgError(code, m);
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      fail(DANG_GPU_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,               \
+           cudaGetErrorString(e_));                                                           \
+  } while (0)
+
+thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------- NCCL (loaded lazily)
+// Only multi-rank runs touch NCCL; it is dlopen'ed so a single-GPU Fortran host needs no NCCL.
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void *nccl_comm_t;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+  int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+void nccl_load() {
+  if (g_nccl.lib) return;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) fail(DANG_GPU_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                          \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                            \
+  if (!g_nccl.field) fail(DANG_GPU_ENCCL, "libnccl lacks symbol %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllGather, "ncclAllGather");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+}
+#define NCK(call)                                                                       \
+  do {                                                                                  \
+    int r_ = (call);                                                                    \
+    if (r_ != 0) fail(DANG_GPU_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+const int NCCL_DOUBLE = 8;  // ncclFloat64
+
+// ---------------------------------------------------------------- host-side objects
+struct BandHost {
+  bool set = false;
+  double nu_c = 0;
+  int n = 0;
+  std::vector<double> nu0, tau0;
+};
+
+struct IndexHost {
+  int sample_index = 0, index_mode = DANG_INDEX_PERPIXEL, lnl_type = 0, prior_type = 0;
+  double gauss[2] = {0, 1}, uni[2] = {-1e300, 1e300}, step = 0;
+  int sample_nside = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
+};
+
+struct CompHost {
+  bool set = false;
+  int type = 0, cg_group = 0, sample_amplitude = 0, nind = 0;
+  std::string label;
+  double nu_ref = 0;
+  double *amp = nullptr;               // [nmaps][Ppad]
+  double *idx[DG_MAXIND] = {nullptr, nullptr};
+  IndexHost index[DG_MAXIND];
+};
+
+struct CgGroupHost {
+  bool set = false;
+  int cg_group = 0, i_max = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
+  double converge = 0;
+  double *x[3] = {nullptr, nullptr, nullptr};  // Q10: persists across Gibbs iterations
+  size_t x_len[3] = {0, 0, 0};
+};
+
+struct KStat {
+  int64_t launches = 0;
+  double ms = 0, bytes = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+const int GATHER_MAX = 128;  // doubles per rank in one scalar exchange
+
+}  // namespace
+
+struct dang_gpu {
+  int device = 0, nside = 0, nmaps = 0, nbands = 0, ncomp = 0, num_sms = 0;
+  int64_t npix = 0, lo = 0, hi = 0, P = 0, Ppad = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // options
+  int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0;
+
+  // ddata
+  bool maps_set = false;
+  double *sig = nullptr, *rms = nullptr;
+  unsigned char *mask = nullptr;
+  double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
+
+  BandHost band[DG_MAX_BANDS];
+  double *bp_nu0 = nullptr, *bp_tau0 = nullptr;
+  bool bp_dirty = true;
+  CompHost comp[DG_MAX_COMPS];
+  std::vector<CgGroupHost> cg;
+
+  // scratch
+  double *M = nullptr, *r = nullptr, *d = nullptr, *eta = nullptr;
+  size_t M_len = 0, v_len = 0, eta_len = 0;
+  int cg_layout = -1;
+  double *D = nullptr;  size_t D_len = 0;       // streaming full-sky data
+  double *zbuf = nullptr, *ubuf = nullptr; size_t zu_len = 0;
+  unsigned char *decisions = nullptr; double *lnl_trace = nullptr; size_t dec_len = 0;
+  int dec_mode = 0, dec_nsample = 0;            // 1 full-sky, 2 per-pixel
+  double *stage = nullptr; size_t stage_len = 0; // device staging for strided host copies
+  double *partials = nullptr; unsigned int *tickets = nullptr;
+  int grid_cap = 0;
+  double *sums_local = nullptr, *gathered = nullptr;
+  CgScalars *cg_scalars = nullptr;
+  MhScalars *mh_scalars = nullptr;
+  void *pinned = nullptr;  // small pinned buffer for scalar read-back
+  std::vector<double> last_trace;
+
+  // comm
+  int nranks = 1, rank = 0;
+  nccl_comm_t comm = nullptr;
+
+  // instrumentation
+  int64_t launches = 0;
+  KStat kstat[DANG_K_COUNT];
+  cudaEvent_t ev[16] = {};
+};
+
+namespace {
+
+// ---------------------------------------------------------------- helpers
+void set_device(dang_gpu *h) { CK(cudaSetDevice(h->device)); }
+
+template <typename T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void ensure(double *&buf, size_t &len, size_t need) {
+  if (len >= need) return;
+  if (buf) CK(cudaFree(buf));
+  buf = nullptr;
+  CK(cudaMalloc(&buf, need * sizeof(double)));
+  len = need;
+}
+
+int grid_for(dang_gpu *h, int64_t work, int threads, int blocks_per_sm) {
+  int64_t need = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)h->num_sms * blocks_per_sm;
+  if (cap > h->grid_cap) cap = h->grid_cap;
+  int64_t g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+struct KTimer {
+  dang_gpu *h;
+  int kid;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KTimer(dang_gpu *h_, int kid_, double bytes) : h(h_), kid(kid_) {
+    h->launches++;
+    h->kstat[kid].launches++;
+    h->kstat[kid].bytes += bytes;
+    if (h->profile) {
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&b));
+      CK(cudaEventRecord(a, h->stream));
+    }
+  }
+  void done() {
+    CK(cudaGetLastError());
+    if (h->profile) {
+      CK(cudaEventRecord(b, h->stream));
+      h->kstat[kid].pending.emplace_back(a, b);
+    }
+  }
+};
+
+void resolve_stats(dang_gpu *h) {
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < DANG_K_COUNT; k++) {
+    for (auto &pr : h->kstat[k].pending) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+      h->kstat[k].ms += ms;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    h->kstat[k].pending.clear();
+  }
+}
+
+// host (npix-strided, full sky) <-> device (Ppad-strided slice) plane copies
+void h2d_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
+  CK(cudaMemcpy2DAsync(dst, h->Ppad * sizeof(double), src + h->lo, h->npix * sizeof(double),
+                       h->P * sizeof(double), nplanes, cudaMemcpyHostToDevice, h->stream));
+}
+void d2h_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
+  CK(cudaMemcpy2DAsync(dst + h->lo, h->npix * sizeof(double), src, h->Ppad * sizeof(double),
+                       h->P * sizeof(double), nplanes, cudaMemcpyDeviceToHost, h->stream));
+}
+
+void upload_bandpasses(dang_gpu *h) {
+  if (!h->bp_dirty) return;
+  std::vector<double> nu0, tau0;
+  for (int j = 0; j < h->nbands; j++) {
+    nu0.insert(nu0.end(), h->band[j].nu0.begin(), h->band[j].nu0.end());
+    tau0.insert(tau0.end(), h->band[j].tau0.begin(), h->band[j].tau0.end());
+  }
+  dfree(h->bp_nu0);
+  dfree(h->bp_tau0);
+  if (!nu0.empty()) {
+    CK(cudaMalloc(&h->bp_nu0, nu0.size() * sizeof(double)));
+    CK(cudaMalloc(&h->bp_tau0, tau0.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(h->bp_nu0, nu0.data(), nu0.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bp_tau0, tau0.data(), tau0.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->bp_dirty = false;
+}
+
+ModelView model_view(dang_gpu *h) {
+  if (!h->maps_set) fail(DANG_GPU_ESTATE, "dang_gpu_upload_maps has not been called");
+  upload_bandpasses(h);
+  ModelView mv;
+  memset(&mv, 0, sizeof mv);
+  mv.nbands = h->nbands;
+  mv.ncomp = h->ncomp;
+  mv.nmaps = h->nmaps;
+  mv.P = h->P;
+  mv.Ppad = h->Ppad;
+  mv.pix_lo = h->lo;
+  mv.npix = h->npix;
+  int off = 0;
+  for (int j = 0; j < h->nbands; j++) {
+    if (!h->band[j].set) fail(DANG_GPU_ESTATE, "band %d has not been set", j);
+    mv.band[j].nu_c = h->band[j].nu_c;
+    mv.band[j].n = h->band[j].n;
+    mv.band[j].off = off;
+    off += h->band[j].n;
+    mv.gain[j] = h->gain[j];
+    mv.offset[j] = h->offset[j];
+  }
+  for (int c = 0; c < h->ncomp; c++) {
+    if (!h->comp[c].set) fail(DANG_GPU_ESTATE, "component %d has not been set", c);
+    mv.comp[c].type = h->comp[c].type;
+    mv.comp[c].nind = h->comp[c].nind;
+    mv.comp[c].nu_ref = h->comp[c].nu_ref;
+    mv.comp[c].amp = h->comp[c].amp;
+    for (int l = 0; l < DG_MAXIND; l++) mv.comp[c].idx[l] = h->comp[c].idx[l];
+  }
+  mv.bp_nu0 = h->bp_nu0;
+  mv.bp_tau0 = h->bp_tau0;
+  mv.sig = h->sig;
+  mv.rms = h->rms;
+  mv.mask = h->mask;
+  return mv;
+}
+
+// exchange `cnt` doubles of sums_local between ranks; result in h->gathered as [rank][cnt]
+void gather(dang_gpu *h, int cnt) {
+  if (cnt > GATHER_MAX) fail(DANG_GPU_EINVAL, "gather of %d doubles exceeds %d", cnt, GATHER_MAX);
+  if (h->nranks == 1) {
+    CK(cudaMemcpyAsync(h->gathered, h->sums_local, cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    NCK(g_nccl.AllGather(h->sums_local, h->gathered, cnt, NCCL_DOUBLE, h->comm, h->stream));
+  }
+}
+
+int flag_planes(int flag, int plane[2]) {  // 0-based planes; returns S
+  if (flag & 8) {
+    plane[0] = 1;
+    plane[1] = 2;
+    return 2;
+  }
+  int k = 0;
+  if (flag & 1) k = 0;
+  else if (flag & 2) k = 1;
+  else if (flag & 4) k = 2;
+  else fail(DANG_GPU_EUNSUPPORTED, "pol flag %d (T+Q+U) is dead code in the reference (SURVEY Q2)", flag);
+  plane[0] = plane[1] = k;
+  return 1;
+}
+
+double bytes_w(double n) { return n * 8.0; }
+
+// ---------------------------------------------------------------- amplitude draw
+template <int C>
+void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const double *eta,
+                   uint64_t seed, const int *comps, const int *og, int nog, int *n_iter,
+                   double *delta_final) {
+  constexpr int T = C * (C + 1) / 2;
+  ModelView mv = model_view(h);
+  CgView<C> cv;
+  memset(&cv, 0, sizeof cv);
+  cv.S = flag_planes(g.pol_flag[flag_n], cv.plane);
+  for (int c = 0; c < C; c++) cv.comp[c] = comps[c];
+  cv.nog = nog;
+  for (int o = 0; o < nog; o++) cv.og[o] = og[o];
+  const int S = cv.S;
+  for (int s = 0; s < S; s++)
+    if (cv.plane[s] >= h->nmaps) fail(DANG_GPU_EINVAL, "pol flag needs plane %d, nmaps = %d", cv.plane[s] + 1, h->nmaps);
+  const size_t vs = (size_t)S * h->Ppad;  // doubles per component
+  const int64_t n2 = (int64_t)(vs / 2);
+
+  // self%x: allocate + seed from c%amplitude on first use only (cg_search :227-239, Q10)
+  if (!g.x[flag_n] || g.x_len[flag_n] != C * vs) {
+    if (g.x[flag_n]) CK(cudaFree(g.x[flag_n]));
+    CK(cudaMalloc(&g.x[flag_n], C * vs * sizeof(double)));
+    g.x_len[flag_n] = C * vs;
+    CK(cudaMemsetAsync(g.x[flag_n], 0, C * vs * sizeof(double), h->stream));
+    for (int c = 0; c < C; c++)
+      for (int s = 0; s < S; s++)  // initialize_x :1216-1224
+        CK(cudaMemcpyAsync(g.x[flag_n] + c * vs + (size_t)s * h->Ppad,
+                           h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
+                           h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (h->M_len < T * vs) {
+    ensure(h->M, h->M_len, T * vs);
+    h->cg_layout = -1;
+  }
+  if (h->v_len < C * vs) {
+    size_t l1 = h->v_len, l2 = h->v_len;
+    ensure(h->r, l1, C * vs);
+    ensure(h->d, l2, C * vs);
+    h->v_len = C * vs;
+    h->cg_layout = -1;
+  }
+  // padding lanes must hold zeros (they are swept by the vectorised passes and nothing ever
+  // writes a nonzero there), so clear only when the plane layout of the scratch changes
+  if (h->cg_layout != C * 16 + S) {
+    CK(cudaMemsetAsync(h->M, 0, T * vs * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->r, 0, C * vs * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d, 0, C * vs * sizeof(double), h->stream));
+    h->cg_layout = C * 16 + S;
+  }
+  cv.M = h->M;
+  cv.r = h->r;
+  cv.d = h->d;
+  cv.x = g.x[flag_n];
+  cv.seed = seed;
+  cv.fluct = 0;
+  cv.eta = nullptr;
+  if (ml_mode == DANG_ML_SAMPLE) {  // :254-264
+    cv.fluct = h->fix_q1 ? 2 : 1;
+    if (eta) {
+      ensure(h->eta, h->eta_len, vs);
+      h2d_planes(h, h->eta, eta, S);  // host eta is [stokes][npix]
+      cv.eta = h->eta;
+    }
+  }
+
+  CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+  {
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    const double n_el = (double)S * h->P;
+    KTimer kt(h, DANG_K_RHS_BLOCKS,
+              bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + 2.0 * C)) + bytes_w((double)h->P * 3));
+    rhs_blocks_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    kt.done();
+  }
+  gather(h, 4);
+  {
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    cg_init_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks, g.i_max, g.converge);
+    kt.done();
+  }
+
+  struct Snap { double delta_new; int iter, done; };
+  auto read_state = [&]() -> Snap {
+    CgScalars *hs = (CgScalars *)h->pinned;
+    CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, trace), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return Snap{hs->delta_new, hs->iter, hs->done};
+  };
+
+  const int grid = grid_for(h, n2, DG_THREADS, 4);
+  const double el = (double)vs;
+  int enq = 0;  // passes enqueued
+  Snap sn = read_state();
+  while (!sn.done && enq < g.i_max - 1) {
+    int chunk = h->cg_chunk;
+    if (chunk > g.i_max - 1 - enq) chunk = g.i_max - 1 - enq;
+    for (int it = 0; it < chunk; it++) {
+      if (!h->cg_two_pass) {
+        {
+          KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * (T + 6.0 * C)));
+          cg_fused_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+              h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local);
+          kt.done();
+        }
+        gather(h, 4);
+        KTimer ks(h, DANG_K_SCALAR, 0);
+        cg_fused_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+        ks.done();
+      } else {
+        {
+          KTimer kt(h, DANG_K_CG_DQ, bytes_w(el * (T + 3.0 * C)));
+          cg_dq_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, h->M, h->r, h->d, n2,
+                                                                    h->partials, h->tickets, h->sums_local);
+          kt.done();
+        }
+        gather(h, 4);
+        {
+          KTimer ks(h, DANG_K_SCALAR, 0);
+          cg_dq_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+          ks.done();
+        }
+        {
+          KTimer kt(h, DANG_K_CG_UPDATE, bytes_w(el * (T + 5.0 * C)));
+          cg_update_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+              h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local);
+          kt.done();
+        }
+        gather(h, 4);
+        KTimer ks(h, DANG_K_SCALAR, 0);
+        cg_rr_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+        ks.done();
+      }
+    }
+    enq += chunk;
+    sn = read_state();
+  }
+
+  // unpack_amplitudes :1327-1335: x -> c%amplitude planes
+  for (int c = 0; c < C; c++)
+    for (int s = 0; s < S; s++)
+      CK(cudaMemcpyAsync(h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
+                         g.x[flag_n] + c * vs + (size_t)s * h->Ppad, h->P * sizeof(double),
+                         cudaMemcpyDeviceToDevice, h->stream));
+  {
+    CgScalars *hs = (CgScalars *)h->pinned;
+    CK(cudaMemcpyAsync(hs, h->cg_scalars, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int n = hs->iter < 256 ? hs->iter : 256;
+    h->last_trace.assign(hs->trace, hs->trace + n);
+    if (n_iter) *n_iter = hs->iter;
+    if (delta_final) *delta_final = hs->delta_new;
+  }
+}
+
+void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *eta, uint64_t seed,
+              int *n_iter, double *delta_final) {
+  CgGroupHost *g = nullptr;
+  for (auto &gg : h->cg)
+    if (gg.set && gg.cg_group == cg_group) g = &gg;
+  if (!g) fail(DANG_GPU_ESTATE, "CG group %d has not been set", cg_group);
+  if (flag_n < 0 || flag_n >= g->nflag) fail(DANG_GPU_EINVAL, "flag_n %d out of range", flag_n);
+  int comps[DG_MAX_COMPS], og[DG_MAX_COMPS], C = 0, nog = 0;
+  for (int c = 0; c < h->ncomp; c++) {
+    const CompHost &cc = h->comp[c];
+    if (!cc.set) fail(DANG_GPU_ESTATE, "component %d has not been set", c);
+    if (cc.cg_group == cg_group && cc.sample_amplitude) comps[C++] = c;
+    else og[nog++] = c;  // :430
+  }
+  if (C == 0) fail(DANG_GPU_EINVAL, "Woah there, number of CG components = 0 for CG group %d", cg_group);
+  if (C > DG_MAX_CG) fail(DANG_GPU_EUNSUPPORTED, "%d diffuse components in one CG group (max %d)", C, DG_MAX_CG);
+  switch (C) {
+    case 1: cg_solve_impl<1>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+    case 2: cg_solve_impl<2>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+    case 3: cg_solve_impl<3>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+    default: cg_solve_impl<4>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+  }
+}
+
+// ---------------------------------------------------------------- chi-square
+template <int NC>
+void launch_chisq(dang_gpu *h, const ModelView &mv, const ChisqView &cv, int grid) {
+  chisq_kernel<NC><<<grid, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+}
+
+void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, double *chi_map,
+               double out4[4]) {
+  if (pol_lo < 1 || pol_hi > h->nmaps || pol_lo > pol_hi) fail(DANG_GPU_EINVAL, "bad pol_type range %d..%d", pol_lo, pol_hi);
+  ModelView mv = model_view(h);
+  ChisqView cv;
+  cv.k_lo = pol_lo - 1;
+  cv.k_hi = pol_hi - 1;
+  cv.sky = sky;
+  cv.res = res;
+  cv.chi_map = chi_map;
+  const int grid = grid_for(h, h->P, DG_THREADS, 4);
+  const bool maps = sky || res;
+  const double nk = maps ? h->nmaps : (pol_hi - pol_lo + 1);
+  double bytes = bytes_w((double)h->P * nk * (2.0 * h->nbands + h->ncomp * 2.0));
+  if (maps) bytes += bytes_w((double)h->P * h->nmaps * h->nbands * ((sky ? 1 : 0) + (res ? 1 : 0)));
+  KTimer kt(h, maps ? DANG_K_SKYMODEL : DANG_K_CHISQ, bytes);
+  if (h->ncomp <= 1) launch_chisq<1>(h, mv, cv, grid);
+  else if (h->ncomp == 2) launch_chisq<2>(h, mv, cv, grid);
+  else if (h->ncomp == 3) launch_chisq<3>(h, mv, cv, grid);
+  else if (h->ncomp == 4) launch_chisq<4>(h, mv, cv, grid);
+  else launch_chisq<DG_MAX_COMPS>(h, mv, cv, grid);
+  kt.done();
+  gather(h, 4);
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 4; i++) {
+    out4[i] = 0.0;
+    for (int g = 0; g < h->nranks; g++) out4[i] += hp[g * 4 + i];
+  }
+}
+
+// ---------------------------------------------------------------- spectral-parameter draw
+void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode, MhView &mh) {
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  const CompHost &c = h->comp[ic];
+  if (nind < 0 || nind >= c.nind) fail(DANG_GPU_EINVAL, "component %d has no index %d", ic, nind);
+  const IndexHost &ix = c.index[nind];
+  if (ix.sample_nside != h->nside)
+    fail(DANG_GPU_EUNSUPPORTED, "sample_nside %d /= nside %d needs HEALPix udgrade_ring (DESIGN.md, out of scope)",
+         ix.sample_nside, h->nside);
+  memset(&mh, 0, sizeof mh);
+  mh.ic = ic;
+  mh.nind = nind;
+  if (map_n == -1) {  // :157-163
+    mh.S = 2;
+    mh.plane[0] = 1;
+    mh.plane[1] = 2;
+  } else if (map_n >= 1 && map_n <= 3) {
+    mh.S = 1;
+    mh.plane[0] = mh.plane[1] = map_n - 1;
+  } else {
+    fail(DANG_GPU_EUNSUPPORTED, "map_n = %d (T+Q+U) is unreachable in the reference (SURVEY Q2)", map_n);
+  }
+  for (int s = 0; s < mh.S; s++)
+    if (mh.plane[s] >= h->nmaps) fail(DANG_GPU_EINVAL, "map_n %d needs plane %d, nmaps = %d", map_n, mh.plane[s] + 1, h->nmaps);
+  mh.nsample = nsample;
+  mh.ml_mode = ml_mode;
+  mh.lnl_type = ix.lnl_type;
+  mh.prior_type = ix.prior_type;
+  mh.is_synch = c.label == "synch";
+  mh.gauss[0] = ix.gauss[0];
+  mh.gauss[1] = ix.gauss[1];
+  mh.uni[0] = ix.uni[0];
+  mh.uni[1] = ix.uni[1];
+  mh.step = ix.step;
+}
+
+void ensure_zu(dang_gpu *h, size_t n) {
+  if (h->zu_len >= n) return;
+  dfree(h->zbuf);
+  dfree(h->ubuf);
+  CK(cudaMalloc(&h->zbuf, n * sizeof(double)));
+  CK(cudaMalloc(&h->ubuf, n * sizeof(double)));
+  h->zu_len = n;
+}
+
+void ensure_decisions(dang_gpu *h, size_t n) {
+  if (h->dec_len >= n) return;
+  dfree(h->decisions);
+  dfree(h->lnl_trace);
+  CK(cudaMalloc(&h->decisions, n));
+  CK(cudaMalloc(&h->lnl_trace, n * sizeof(double)));
+  h->dec_len = n;
+}
+
+void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
+                     double *accept) {
+  ModelView mv = model_view(h);
+  const size_t n = (size_t)mh.nsample * h->P;
+  mh.seed = seed;
+  if (z) {
+    ensure_zu(h, n > 0 ? n : 1);
+    // host [l][npix] -> device [l][P]
+    CK(cudaMemcpy2DAsync(h->zbuf, h->P * sizeof(double), z + h->lo, h->npix * sizeof(double),
+                         h->P * sizeof(double), mh.nsample, cudaMemcpyHostToDevice, h->stream));
+    mh.z = h->zbuf;
+    if (u) {
+      CK(cudaMemcpy2DAsync(h->ubuf, h->P * sizeof(double), u + h->lo, h->npix * sizeof(double),
+                           h->P * sizeof(double), mh.nsample, cudaMemcpyHostToDevice, h->stream));
+      mh.u = h->ubuf;
+    } else if (mh.ml_mode == DANG_ML_SAMPLE) {
+      fail(DANG_GPU_EINVAL, "z injected without u");
+    }
+  }
+  h->dec_mode = 0;
+  if (h->record) {
+    ensure_decisions(h, n > 0 ? n : 1);
+    CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
+    CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));  // NaN pattern
+    mh.decisions = h->decisions;
+    mh.lnl_trace = h->lnl_trace;
+    h->dec_mode = 2;
+    h->dec_nsample = mh.nsample;
+  }
+  const size_t smem = (size_t)(2 * h->nbands * mh.S + h->nbands) * DG_MH_THREADS * sizeof(double);
+  if (smem > 200 * 1024) fail(DANG_GPU_EUNSUPPORTED, "per-pixel chain needs %zu B of shared memory", smem);
+  CK(cudaFuncSetAttribute(mh_perpixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = grid_for(h, h->P, DG_MH_THREADS, 8);
+  const double n_el = (double)mh.S * h->P;
+  KTimer kt(h, DANG_K_MH_PERPIXEL, bytes_w(n_el * (2.0 * h->nbands + h->ncomp + 1) + (double)h->P * 4));
+  mh_perpixel_kernel<<<grid, DG_MH_THREADS, smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local);
+  kt.done();
+  gather(h, 1);
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double a = 0;
+  for (int g = 0; g < h->nranks; g++) a += hp[g];
+  if (accept) *accept = a;
+}
+
+void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
+                    double *accept) {
+  if (mh.lnl_type != DANG_LNL_CHISQ)
+    fail(DANG_GPU_EUNSUPPORTED, "full-sky sampling supports lnl_type 'chisq' only (DESIGN.md)");
+  if (mh.prior_type == DANG_PRIOR_JEFFREYS)
+    fail(DANG_GPU_EUNSUPPORTED, "full-sky Jeffreys prior is not built (DESIGN.md)");
+  ModelView mv = model_view(h);
+  mh.seed = seed;
+  const size_t n = (size_t)mh.nsample;
+  if (z) {
+    ensure_zu(h, n > 0 ? n : 1);
+    CK(cudaMemcpyAsync(h->zbuf, z, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    mh.z = h->zbuf;
+    if (u) {
+      CK(cudaMemcpyAsync(h->ubuf, u, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      mh.u = h->ubuf;
+    } else if (mh.ml_mode == DANG_ML_SAMPLE) {
+      fail(DANG_GPU_EINVAL, "z injected without u");
+    }
+  }
+  ensure_decisions(h, n > 0 ? n : 1);
+  CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
+  CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));
+  mh.decisions = h->decisions;
+  mh.lnl_trace = h->lnl_trace;
+  h->dec_mode = 1;
+  h->dec_nsample = mh.nsample;
+
+  CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+  {
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    mh_first_pixel_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->sums_local);
+    kt.done();
+  }
+  gather(h, 2);
+  {
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    mh_fullsky_init_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, 2);
+    kt.done();
+  }
+  const double n_el = (double)mh.S * h->P;
+  if (h->fullsky_stream) {
+    const size_t dl = (size_t)h->nbands * mh.S * h->Ppad;
+    ensure(h->D, h->D_len, dl);
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    {
+      KTimer kt(h, DANG_K_MH_DATA, bytes_w(n_el * (2.0 * h->nbands + h->ncomp * 2.0)));
+      mh_data_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->D);
+      kt.done();
+    }
+    for (int l = 0; l <= mh.nsample; l++) {  // starting point + nsample proposals
+      {
+        KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
+        mh_fullsky_lnl_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials,
+                                                                 h->tickets, h->sums_local);
+        kt.done();
+      }
+      gather(h, 1);
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      mh_fullsky_step_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, 1);
+      ks.done();
+    }
+  } else {
+    const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+    const int cnt = nchunk * 3 * DG_SUFF_CHUNK;
+    const int grid = grid_for(h, h->P, DG_THREADS, 2);
+    {
+      KTimer kt(h, DANG_K_MH_SUFFSTAT, bytes_w(n_el * (2.0 * h->nbands + h->ncomp * 2.0)));
+      mh_suffstat_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets,
+                                                            h->sums_local);
+      kt.done();
+    }
+    gather(h, cnt);
+    KTimer ks(h, DANG_K_SCALAR, 0);
+    mh_suff_chain_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
+    ks.done();
+  }
+  {
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    mh_fullsky_store_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars);
+    kt.done();
+  }
+  MhScalars *hs = (MhScalars *)h->pinned;
+  CK(cudaMemcpyAsync(hs, h->mh_scalars, sizeof(MhScalars), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (accept) *accept = hs->accept;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- C ABI
+#define API_BEGIN                                   \
+  if (!h) return DANG_GPU_EINVAL;                   \
+  try {                                             \
+    set_device(h);
+#define API_END                                     \
+    return DANG_GPU_OK;                             \
+  } catch (const DgError &e) {                      \
+    h->err = e.what();                              \
+    return e.code;                                  \
+  } catch (const std::exception &e) {               \
+    h->err = e.what();                              \
+    return DANG_GPU_ECUDA;                          \
+  }
+
+extern "C" {
+
+const char *dang_gpu_last_error(const dang_gpu_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, int ncomp,
+                    int64_t pix_lo, int64_t pix_hi, dang_gpu_t **out) {
+  if (!out) return DANG_GPU_EINVAL;
+  *out = nullptr;
+  dang_gpu *h = nullptr;
+  try {
+    if (npix != 12LL * nside * nside) fail(DANG_GPU_EINVAL, "npix %lld /= 12*nside^2", (long long)npix);
+    if (nmaps < 1 || nmaps > 3) fail(DANG_GPU_EINVAL, "nmaps = %d", nmaps);
+    if (nbands < 1 || nbands > DG_MAX_BANDS) fail(DANG_GPU_EINVAL, "nbands = %d (max %d)", nbands, DG_MAX_BANDS);
+    if (ncomp < 1 || ncomp > DG_MAX_COMPS) fail(DANG_GPU_EINVAL, "ncomp = %d (max %d)", ncomp, DG_MAX_COMPS);
+    if (pix_lo < 0 || pix_hi > npix || pix_lo >= pix_hi) fail(DANG_GPU_EINVAL, "bad pixel range [%lld,%lld)", (long long)pix_lo, (long long)pix_hi);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      fail(DANG_GPU_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+           e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) fail(DANG_GPU_EINVAL, "device %d of %d", device, ndev);
+    h = new dang_gpu();
+    h->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->nside = nside;
+    h->npix = npix;
+    h->nmaps = nmaps;
+    h->nbands = nbands;
+    h->ncomp = ncomp;
+    h->lo = pix_lo;
+    h->hi = pix_hi;
+    h->P = pix_hi - pix_lo;
+    h->Ppad = (h->P + 63) / 64 * 64;
+    for (int j = 0; j < DG_MAX_BANDS; j++) {
+      h->gain[j] = 1.0;  // dang_data_mod.f90:127-128
+      h->offset[j] = 0.0;
+    }
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->grid_cap = h->num_sms * 8;
+    CK(cudaMalloc(&h->partials, (size_t)h->grid_cap * 32 * 4 * sizeof(double)));
+    CK(cudaMalloc(&h->tickets, 16 * sizeof(unsigned int)));
+    CK(cudaMemset(h->tickets, 0, 16 * sizeof(unsigned int)));
+    CK(cudaMalloc(&h->sums_local, GATHER_MAX * sizeof(double)));
+    CK(cudaMalloc(&h->gathered, (size_t)GATHER_MAX * 64 * sizeof(double)));
+    CK(cudaMalloc(&h->cg_scalars, sizeof(CgScalars)));
+    CK(cudaMalloc(&h->mh_scalars, sizeof(MhScalars)));
+    CK(cudaMallocHost(&h->pinned, 64 * 1024));
+    for (int i = 0; i < 16; i++) CK(cudaEventCreate(&h->ev[i]));
+    *out = h;
+    return DANG_GPU_OK;
+  } catch (const DgError &e) {
+    g_create_error = e.what();
+    delete h;
+    return e.code;
+  }
+}
+
+int dang_gpu_destroy(dang_gpu_t *h) {
+  if (!h) return DANG_GPU_EINVAL;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
+  dfree(h->sig); dfree(h->rms); dfree(h->mask); dfree(h->bp_nu0); dfree(h->bp_tau0);
+  for (auto &c : h->comp) { dfree(c.amp); dfree(c.idx[0]); dfree(c.idx[1]); }
+  for (auto &g : h->cg) for (auto &x : g.x) dfree(x);
+  dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
+  dfree(h->decisions); dfree(h->lnl_trace); dfree(h->stage); dfree(h->partials); dfree(h->tickets);
+  dfree(h->sums_local); dfree(h->gathered); dfree(h->cg_scalars); dfree(h->mh_scalars);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return DANG_GPU_OK;
+}
+
+int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
+  API_BEGIN
+  switch (option) {
+    case DANG_OPT_FIX_SAMPLE_VECTOR: h->fix_q1 = value != 0; break;
+    case DANG_OPT_CG_TWO_PASS: h->cg_two_pass = value != 0; break;
+    case DANG_OPT_FULLSKY_STREAM: h->fullsky_stream = value != 0; break;
+    case DANG_OPT_PROFILE: h->profile = value != 0; break;
+    case DANG_OPT_CG_CHUNK: h->cg_chunk = value < 1 ? 1 : (int)value; break;
+    case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
+    default: fail(DANG_GPU_EINVAL, "unknown option %d", option);
+  }
+  API_END
+}
+
+int dang_gpu_sync(dang_gpu_t *h) {
+  API_BEGIN
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_comm_unique_id(char id[128]) {
+  try {
+    nccl_load();
+    nccl_uid_t uid;
+    NCK(g_nccl.GetUniqueId(&uid));
+    memcpy(id, uid.internal, 128);
+    return DANG_GPU_OK;
+  } catch (const DgError &e) {
+    g_create_error = e.what();
+    return e.code;
+  }
+}
+
+int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]) {
+  API_BEGIN
+  if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) fail(DANG_GPU_EINVAL, "bad rank %d of %d", rank, nranks);
+  h->nranks = nranks;
+  h->rank = rank;
+  if (nranks > 1) {
+    nccl_load();
+    nccl_uid_t uid;
+    memcpy(uid.internal, id, 128);
+    NCK(g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
+  }
+  API_END
+}
+
+int dang_gpu_set_band(dang_gpu_t *h, int band, double nu_c_hz, int n_bp, const double *nu0_hz,
+                      const double *tau0) {
+  API_BEGIN
+  if (band < 0 || band >= h->nbands) fail(DANG_GPU_EINVAL, "band %d of %d", band, h->nbands);
+  if (n_bp < 0 || (n_bp > 0 && (!nu0_hz || !tau0))) fail(DANG_GPU_EINVAL, "bad bandpass table for band %d", band);
+  BandHost &b = h->band[band];
+  b.set = true;
+  b.nu_c = nu_c_hz;
+  b.n = n_bp;
+  b.nu0.assign(nu0_hz, nu0_hz + n_bp);
+  b.tau0.assign(tau0, tau0 + n_bp);
+  h->bp_dirty = true;
+  API_END
+}
+
+int dang_gpu_set_gain_offset(dang_gpu_t *h, const double *gain, const double *offset) {
+  API_BEGIN
+  for (int j = 0; j < h->nbands; j++) {
+    if (gain) h->gain[j] = gain[j];
+    if (offset) h->offset[j] = offset[j];
+  }
+  API_END
+}
+
+int dang_gpu_upload_maps(dang_gpu_t *h, const double *sig_map, const double *rms_map,
+                         const double *mask, const double *gain, const double *offset) {
+  API_BEGIN
+  if (!sig_map || !rms_map || !mask) fail(DANG_GPU_EINVAL, "null map pointer");
+  const size_t n3 = (size_t)h->nbands * h->nmaps * h->Ppad;
+  if (!h->sig) {
+    CK(cudaMalloc(&h->sig, n3 * sizeof(double)));
+    CK(cudaMalloc(&h->rms, n3 * sizeof(double)));
+    CK(cudaMalloc(&h->mask, h->Ppad));
+    CK(cudaMemsetAsync(h->sig, 0, n3 * sizeof(double), h->stream));
+    // padding lanes of rms hold 1 so that nothing divides by zero there
+    fill_kernel<<<h->num_sms * 4, DG_THREADS, 0, h->stream>>>(h->rms, (int64_t)n3, 1.0);
+    CK(cudaGetLastError());
+  }
+  h2d_planes(h, h->sig, sig_map, h->nbands * h->nmaps);
+  h2d_planes(h, h->rms, rms_map, h->nbands * h->nmaps);
+  ensure(h->stage, h->stage_len, (size_t)h->Ppad);
+  CK(cudaMemcpyAsync(h->stage, mask + h->lo, h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  mask_to_bytes_kernel<<<h->num_sms * 4, DG_THREADS, 0, h->stream>>>(h->stage, h->mask, h->P, h->Ppad);
+  CK(cudaGetLastError());
+  for (int j = 0; j < h->nbands; j++) {
+    if (gain) h->gain[j] = gain[j];
+    if (offset) h->offset[j] = offset[j];
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->maps_set = true;
+  API_END
+}
+
+int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, double nu_ref_hz,
+                           int cg_group, int sample_amplitude, const double *amplitude,
+                           const double *indices) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp) fail(DANG_GPU_EINVAL, "component %d of %d", ic, h->ncomp);
+  if (type != DANG_COMP_POWERLAW && type != DANG_COMP_MBB)
+    fail(DANG_GPU_EUNSUPPORTED, "component type %d: only power-law and mbb are built (DESIGN.md)", type);
+  CompHost &c = h->comp[ic];
+  c.set = true;
+  c.type = type;
+  c.label = label ? label : "";
+  c.nu_ref = nu_ref_hz;
+  c.cg_group = cg_group;
+  c.sample_amplitude = sample_amplitude != 0;
+  c.nind = type == DANG_COMP_MBB ? 2 : 1;
+  const size_t n2 = (size_t)h->nmaps * h->Ppad;
+  if (!c.amp) CK(cudaMalloc(&c.amp, n2 * sizeof(double)));
+  CK(cudaMemsetAsync(c.amp, 0, n2 * sizeof(double), h->stream));
+  if (amplitude) h2d_planes(h, c.amp, amplitude, h->nmaps);
+  for (int l = 0; l < c.nind; l++) {
+    if (!c.idx[l]) CK(cudaMalloc(&c.idx[l], n2 * sizeof(double)));
+    // padding lanes get a harmless finite index
+    fill_kernel<<<h->num_sms * 2, DG_THREADS, 0, h->stream>>>(c.idx[l], (int64_t)n2, 1.0);
+    CK(cudaGetLastError());
+    if (indices) h2d_planes(h, c.idx[l], indices + (size_t)l * h->nmaps * h->npix, h->nmaps);
+  }
+  for (int l = 0; l < DG_MAXIND; l++) {
+    c.index[l] = IndexHost();
+    c.index[l].sample_nside = h->nside;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_set_index(dang_gpu_t *h, int ic, int nind, int sample_index, int index_mode,
+                       int lnl_type, int prior_type, const double gauss_prior[2],
+                       const double uni_prior[2], double step_size, int sample_nside,
+                       const int *pol_flags, int nflag) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  CompHost &c = h->comp[ic];
+  if (nind < 0 || nind >= c.nind) fail(DANG_GPU_EINVAL, "component %d has no index %d", ic, nind);
+  if (nflag < 0 || nflag > 3) fail(DANG_GPU_EINVAL, "nflag = %d", nflag);
+  if (index_mode != DANG_INDEX_FULLSKY && index_mode != DANG_INDEX_PERPIXEL) fail(DANG_GPU_EINVAL, "index_mode = %d", index_mode);
+  IndexHost &ix = c.index[nind];
+  ix.sample_index = sample_index != 0;
+  ix.index_mode = index_mode;
+  ix.lnl_type = lnl_type;
+  ix.prior_type = prior_type;
+  if (gauss_prior) { ix.gauss[0] = gauss_prior[0]; ix.gauss[1] = gauss_prior[1]; }
+  if (uni_prior) { ix.uni[0] = uni_prior[0]; ix.uni[1] = uni_prior[1]; }
+  ix.step = step_size;
+  ix.sample_nside = sample_nside;
+  ix.nflag = nflag;
+  for (int k = 0; k < nflag; k++) ix.pol_flag[k] = pol_flags[k];
+  API_END
+}
+
+int dang_gpu_set_amplitude(dang_gpu_t *h, int ic, const double *amplitude) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !amplitude) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  h2d_planes(h, h->comp[ic].amp, amplitude, h->nmaps);
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_set_indices(dang_gpu_t *h, int ic, const double *indices) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !indices) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  for (int l = 0; l < h->comp[ic].nind; l++)
+    h2d_planes(h, h->comp[ic].idx[l], indices + (size_t)l * h->nmaps * h->npix, h->nmaps);
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_get_amplitude(dang_gpu_t *h, int ic, double *amplitude) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !amplitude) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  d2h_planes(h, amplitude, h->comp[ic].amp, h->nmaps);
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_get_indices(dang_gpu_t *h, int ic, double *indices) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !indices) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  for (int l = 0; l < h->comp[ic].nind; l++)
+    d2h_planes(h, indices + (size_t)l * h->nmaps * h->npix, h->comp[ic].idx[l], h->nmaps);
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_get_step_size(dang_gpu_t *h, int ic, int nind, double *step_size) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || nind < 0 || nind >= h->comp[ic].nind || !step_size)
+    fail(DANG_GPU_EINVAL, "bad component/index %d/%d", ic, nind);
+  *step_size = h->comp[ic].index[nind].step;
+  API_END
+}
+
+int dang_gpu_set_cg_group(dang_gpu_t *h, int cg_group, int i_max, double converge,
+                          const int *pol_flags, int nflag) {
+  API_BEGIN
+  if (nflag < 1 || nflag > 3 || !pol_flags) fail(DANG_GPU_EINVAL, "nflag = %d", nflag);
+  CgGroupHost *g = nullptr;
+  for (auto &gg : h->cg)
+    if (gg.cg_group == cg_group) g = &gg;
+  if (!g) {
+    h->cg.emplace_back();
+    g = &h->cg.back();
+  }
+  g->set = true;
+  g->cg_group = cg_group;
+  g->i_max = i_max;
+  g->converge = converge;
+  g->nflag = nflag;
+  for (int k = 0; k < nflag; k++) g->pol_flag[k] = pol_flags[k];
+  API_END
+}
+
+int dang_gpu_cg_solve(dang_gpu_t *h, int cg_group, int flag_n, int ml_mode, const double *eta,
+                      uint64_t seed, int *n_iter, double *delta_final) {
+  API_BEGIN
+  cg_solve(h, cg_group, flag_n, ml_mode, eta, seed, n_iter, delta_final);
+  API_END
+}
+
+int dang_gpu_cg_trace(dang_gpu_t *h, double *delta, int max_len, int *len) {
+  API_BEGIN
+  int n = (int)h->last_trace.size();
+  if (n > max_len) n = max_len;
+  for (int i = 0; i < n; i++) delta[i] = h->last_trace[i];
+  if (len) *len = n;
+  API_END
+}
+
+int dang_gpu_get_cg_x(dang_gpu_t *h, int cg_group, int flag_n, double *x) {
+  API_BEGIN
+  CgGroupHost *g = nullptr;
+  for (auto &gg : h->cg)
+    if (gg.set && gg.cg_group == cg_group) g = &gg;
+  if (!g || flag_n < 0 || flag_n >= g->nflag || !g->x[flag_n] || !x) fail(DANG_GPU_ESTATE, "no saved x for group %d flag %d", cg_group, flag_n);
+  const int nplanes = (int)(g->x_len[flag_n] / h->Ppad);
+  d2h_planes(h, x, g->x[flag_n], nplanes);
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsample, int ml_mode,
+                          const double *z, const double *u, uint64_t seed, double *accept) {
+  API_BEGIN
+  if (nsample < 0) fail(DANG_GPU_EINVAL, "nsample = %d", nsample);
+  MhView mh;
+  mh_view(h, ic, nind, map_n, nsample, ml_mode, mh);
+  if (h->comp[ic].index[nind].index_mode == DANG_INDEX_PERPIXEL) sample_perpixel(h, mh, z, u, seed, accept);
+  else sample_fullsky(h, mh, z, u, seed, accept);
+  API_END
+}
+
+int dang_gpu_get_decisions(dang_gpu_t *h, unsigned char *decisions, double *lnl) {
+  API_BEGIN
+  if (h->dec_mode == 0) fail(DANG_GPU_ESTATE, "no decisions recorded (per-pixel mode needs option 6)");
+  if (h->dec_mode == 1) {
+    if (decisions) CK(cudaMemcpyAsync(decisions, h->decisions, h->dec_nsample, cudaMemcpyDeviceToHost, h->stream));
+    if (lnl) CK(cudaMemcpyAsync(lnl, h->lnl_trace, h->dec_nsample * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    if (decisions)
+      CK(cudaMemcpy2DAsync(decisions + h->lo, h->npix, h->decisions, h->P, h->P, h->dec_nsample,
+                           cudaMemcpyDeviceToHost, h->stream));
+    if (lnl)
+      CK(cudaMemcpy2DAsync(lnl + h->lo, h->npix * sizeof(double), h->lnl_trace, h->P * sizeof(double),
+                           h->P * sizeof(double), h->dec_nsample, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_tune_index(dang_gpu_t *h, int, int, int, int, int, const double *, const double *,
+                        uint64_t, int, int *, double *) {
+  API_BEGIN
+  fail(DANG_GPU_EUNSUPPORTED, "tune_spectral_parameter_length is not built yet (DESIGN.md, next)");
+  API_END
+}
+
+int dang_gpu_chisq(dang_gpu_t *h, int pol_lo, int pol_hi, double *chisq_planes, int64_t *n_unmasked) {
+  API_BEGIN
+  double out4[4];
+  run_chisq(h, pol_lo, pol_hi, nullptr, nullptr, nullptr, out4);
+  if (chisq_planes)
+    for (int k = 0; k < h->nmaps; k++) chisq_planes[k] = out4[k];
+  if (n_unmasked) *n_unmasked = (int64_t)(out4[3] + 0.5);
+  API_END
+}
+
+int dang_gpu_get_sky_model(dang_gpu_t *h, int pol_lo, int pol_hi, double *sky_model, double *res_map,
+                           double *chi_map) {
+  API_BEGIN
+  const size_t n3 = (size_t)h->nbands * h->nmaps * h->Ppad, n2 = (size_t)h->nmaps * h->Ppad;
+  double *d_sky = nullptr, *d_res = nullptr, *d_chi = nullptr;
+  try {
+    CK(cudaMalloc(&d_sky, n3 * sizeof(double)));
+    CK(cudaMalloc(&d_res, n3 * sizeof(double)));
+    CK(cudaMalloc(&d_chi, n2 * sizeof(double)));
+    double out4[4];
+    run_chisq(h, pol_lo, pol_hi, d_sky, d_res, d_chi, out4);
+    if (sky_model) d2h_planes(h, sky_model, d_sky, h->nbands * h->nmaps);
+    if (res_map) d2h_planes(h, res_map, d_res, h->nbands * h->nmaps);
+    if (chi_map) d2h_planes(h, chi_map, d_chi, h->nmaps);
+    CK(cudaStreamSynchronize(h->stream));
+  } catch (...) {
+    cudaFree(d_sky); cudaFree(d_res); cudaFree(d_chi);
+    throw;
+  }
+  cudaFree(d_sky); cudaFree(d_res); cudaFree(d_chi);
+  API_END
+}
+
+int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || nind < 0 || nind >= h->comp[ic].nind || map_n < 1 || map_n > h->nmaps)
+    fail(DANG_GPU_EINVAL, "bad component/index/map %d/%d/%d", ic, nind, map_n);
+  model_view(h);
+  const int grid = grid_for(h, h->P, DG_THREADS, 4);
+  KTimer kt(h, DANG_K_SCALAR, 0);
+  masked_sum_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->comp[ic].idx[nind] + (size_t)(map_n - 1) * h->Ppad,
+                                                       h->mask, h->P, h->partials, h->tickets, h->sums_local);
+  kt.done();
+  gather(h, 4);
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double s = 0, n = 0;
+  for (int g = 0; g < h->nranks; g++) { s += hp[g * 4]; n += hp[g * 4 + 1]; }
+  if (mean) *mean = s / n;
+  API_END
+}
+
+int dang_gpu_host_alloc(void **ptr, uint64_t bytes) {
+  return cudaMallocHost(ptr, bytes) == cudaSuccess ? DANG_GPU_OK : DANG_GPU_ECUDA;
+}
+int dang_gpu_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DANG_GPU_OK : DANG_GPU_ECUDA; }
+
+int dang_gpu_event_record(dang_gpu_t *h, int slot) {
+  API_BEGIN
+  if (slot < 0 || slot >= 16) fail(DANG_GPU_EINVAL, "event slot %d", slot);
+  CK(cudaEventRecord(h->ev[slot], h->stream));
+  API_END
+}
+
+int dang_gpu_event_elapsed_ms(dang_gpu_t *h, int a, int b, float *ms) {
+  API_BEGIN
+  if (a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) fail(DANG_GPU_EINVAL, "event slots %d %d", a, b);
+  CK(cudaEventSynchronize(h->ev[b]));
+  CK(cudaEventElapsedTime(ms, h->ev[a], h->ev[b]));
+  API_END
+}
+
+int dang_gpu_launch_count(dang_gpu_t *h, int64_t *launches, int reset) {
+  API_BEGIN
+  if (launches) *launches = h->launches;
+  if (reset) h->launches = 0;
+  API_END
+}
+
+int dang_gpu_kernel_stats(dang_gpu_t *h, int kernel, int64_t *launches, double *total_ms, double *bytes,
+                          int reset) {
+  API_BEGIN
+  if (kernel < 0 || kernel >= DANG_K_COUNT) fail(DANG_GPU_EINVAL, "kernel id %d", kernel);
+  resolve_stats(h);
+  KStat &k = h->kstat[kernel];
+  if (launches) *launches = k.launches;
+  if (total_ms) *total_ms = k.ms;
+  if (bytes) *bytes = k.bytes;
+  if (reset) { k.launches = 0; k.ms = 0; k.bytes = 0; }
+  API_END
+}
+
+const char *dang_gpu_kernel_name(int kernel) {
+  static const char *names[DANG_K_COUNT] = {
+      "rhs_blocks_kernel", "cg_fused_pass_kernel", "cg_dq_pass_kernel", "cg_update_pass_kernel",
+      "chisq_kernel", "chisq_kernel(maps)", "mh_data_kernel", "mh_fullsky_lnl_kernel",
+      "mh_suffstat_kernel", "mh_perpixel_kernel", "scalar kernels"};
+  return (kernel >= 0 && kernel < DANG_K_COUNT) ? names[kernel] : "?";
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+// kernels_cg.cuh -- amplitude draw: compute_rhs + compute_sample_vector +
+// the block form of compute_Ax + cg_search, src/dang_cg_mod.f90:179-1100.
+//
+// The reference applies A = sum_nu T^t N^-1 T matrix-free, re-evaluating every SED twice per
+// band per CG iteration.  For diffuse components A is block diagonal per (pixel, Stokes) with a
+// CxC symmetric block M[c,c'] = sum_nu sed_c sed_c' / sigma^2, so K1 evaluates the SEDs once,
+// stores the C(C+1)/2 block entries, and every CG iteration is a pure HBM stream over
+// {M, x, r, d}: 15 doubles per (pixel, Stokes) for C = 2.
+#pragma once
+#include "common.cuh"
+
+template <int C>
+struct CgView {
+  int comp[C];               // indices into ModelView::comp, in component_list order
+  int S;                     // Stokes planes in this solve (1 or 2)
+  int plane[2];              // 0-based plane numbers
+  int nog;                   // components whose signal is subtracted from the data (:427-443)
+  int og[DG_MAX_COMPS];
+  int fluct;                 // 0: none (optimize), 1: reference indexing (Q1), 2: per-component
+  double *M;                 // [T][S][Ppad], T = C(C+1)/2, row-major upper triangle
+  double *x, *r, *d;         // [C][S][Ppad]
+  const double *eta;         // [S][Ppad] injected normals, or nullptr -> Philox
+  uint64_t seed;
+};
+
+// scalars of one solve, device resident (DESIGN.md "CG control")
+struct CgScalars {
+  double delta_new, delta_old, alpha, beta, dq;
+  double converge;
+  int iter, i_max, done, pad;
+  double trace[256];
+};
+
+template <int C>
+__device__ __forceinline__ int tri(int a, int b) {  // a <= b
+  return a * C - a * (a - 1) / 2 + (b - a);
+}
+
+// K1: one pass over sig/rms builds b2 = b + fluctuation, the blocks M, and the initial
+// residual r = b2 - M x (warm start x, Q10), d = r; reduces {r.r, r.M r}.
+// out[0] = sum r^2, out[1] = sum r.Mr
+template <int C>
+__global__ void __launch_bounds__(DG_THREADS)
+rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsigned int *ticket,
+                  double *out) {
+  constexpr int T = C * (C + 1) / 2;
+  __shared__ double smem[2 * 32];
+  double acc[2] = {0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
+    const bool use = mv.mask[p] != 0;
+    if (!use) {
+      // masked pixels: zero rows/cols (:474-485, :695); x keeps its initial value
+      for (int s = 0; s < cg.S; s++) {
+        const size_t e = (size_t)s * mv.Ppad + p;
+        for (int t = 0; t < T; t++) cg.M[(size_t)t * cg.S * mv.Ppad + e] = 0.0;
+        for (int c = 0; c < C; c++) {
+          cg.r[(size_t)c * cg.S * mv.Ppad + e] = 0.0;
+          cg.d[(size_t)c * cg.S * mv.Ppad + e] = 0.0;
+        }
+      }
+      continue;
+    }
+    // per-pixel parameters of the group components and of the subtracted components
+    double th[2][C][DG_MAXIND];
+    double oa[2][DG_MAX_COMPS], oth[2][DG_MAX_COMPS][DG_MAXIND];
+    #pragma unroll
+    for (int s = 0; s < 2; s++) {
+      if (s >= cg.S) continue;
+      const size_t kp = (size_t)cg.plane[s] * mv.Ppad + p;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const CompView &cv = mv.comp[cg.comp[c]];
+        th[s][c][0] = cv.nind > 0 ? cv.idx[0][kp] : 0.0;
+        th[s][c][1] = cv.nind > 1 ? cv.idx[1][kp] : 0.0;
+      }
+      for (int o = 0; o < cg.nog; o++) {
+        const CompView &cv = mv.comp[cg.og[o]];
+        oa[s][o] = cv.amp[kp];
+        oth[s][o][0] = cv.nind > 0 ? cv.idx[0][kp] : 0.0;
+        oth[s][o][1] = cv.nind > 1 ? cv.idx[1][kp] : 0.0;
+      }
+    }
+    double eta[2] = {0.0, 0.0};
+    if (cg.fluct)
+#pragma unroll
+      for (int s = 0; s < 2; s++)
+        if (s < cg.S) eta[s] = cg.eta ? cg.eta[(size_t)s * mv.Ppad + p]
+                        : philox_normal(cg.seed, DG_STREAM_ETA,
+                                        (uint64_t)s * (uint64_t)mv.npix + (uint64_t)(mv.pix_lo + p));
+    // Q and U share the SED whenever their index maps agree (always, after a Q+U draw)
+    bool same = cg.S == 2;
+    if (same) {
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        same = same && th[0][c][0] == th[1][c][0] && th[0][c][1] == th[1][c][1];
+      for (int o = 0; o < cg.nog; o++)
+        same = same && oth[0][o][0] == oth[1][o][0] && oth[0][o][1] == oth[1][o][1];
+    }
+
+    double b[2][C], f[2][C], M[2][T];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+#pragma unroll
+      for (int c = 0; c < C; c++) b[s][c] = f[s][c] = 0.0;
+#pragma unroll
+      for (int t = 0; t < T; t++) M[s][t] = 0.0;
+    }
+    for (int j = 0; j < mv.nbands; j++) {
+      double sed[2][C], osed[2][DG_MAX_COMPS];
+#pragma unroll
+      for (int c = 0; c < C; c++) sed[0][c] = sed_eval(mv, cg.comp[c], j, th[0][c][0], th[0][c][1]);
+      for (int o = 0; o < cg.nog; o++) osed[0][o] = sed_eval(mv, cg.og[o], j, oth[0][o][0], oth[0][o][1]);
+      if (cg.S == 2) {
+        if (same) {
+#pragma unroll
+          for (int c = 0; c < C; c++) sed[1][c] = sed[0][c];
+          for (int o = 0; o < cg.nog; o++) osed[1][o] = osed[0][o];
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; c++) sed[1][c] = sed_eval(mv, cg.comp[c], j, th[1][c][0], th[1][c][1]);
+          for (int o = 0; o < cg.nog; o++) osed[1][o] = sed_eval(mv, cg.og[o], j, oth[1][o][0], oth[1][o][1]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (s >= cg.S) continue;
+        const int k = cg.plane[s];
+        const size_t off = plane_off(mv, j, k) + p;
+        double data = ldg_stream(mv.sig + off);
+        const double rms = ldg_stream(mv.rms + off);
+        if (k == 0) data = data / mv.gain[j];  // :369-373 (no offset here, unlike update_sky_model)
+        for (int o = 0; o < cg.nog; o++) data = data - oa[s][o] * osed[s][o];
+        const double w = 1.0 / (rms * rms);
+        const double tn = eta[s] / rms;  // N^{-1/2} eta, :1005-1017
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          b[s][c] += data * sed[s][c] * w;       // :489-494
+          f[s][c] += tn * sed[s][c];             // :1030-1042
+#pragma unroll
+          for (int c2 = c; c2 < C; c2++) M[s][tri<C>(c, c2)] += sed[s][c] * sed[s][c2] * w;
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      if (s >= cg.S) continue;
+      const size_t e = (size_t)s * mv.Ppad + p;
+      if (cg.fluct == 1) {
+        b[s][0] += f[s][C - 1];  // Q1: last diffuse component's term lands in slot 1 only
+      } else if (cg.fluct == 2) {
+#pragma unroll
+        for (int c = 0; c < C; c++) b[s][c] += f[s][c];
+      }
+      double xv[C], rv[C], Mr[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) xv[c] = cg.x[(size_t)c * cg.S * mv.Ppad + e];
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        double ax = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < C; c2++) ax += M[s][c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)] * xv[c2];
+        rv[c] = b[s][c] - ax;
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        double a = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < C; c2++) a += M[s][c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)] * rv[c2];
+        Mr[c] = a;
+      }
+#pragma unroll
+      for (int t = 0; t < T; t++) cg.M[(size_t)t * cg.S * mv.Ppad + e] = M[s][t];
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        cg.r[(size_t)c * cg.S * mv.Ppad + e] = rv[c];
+        cg.d[(size_t)c * cg.S * mv.Ppad + e] = rv[c];
+        acc[0] += rv[c] * rv[c];
+        acc[1] += rv[c] * Mr[c];
+      }
+    }
+  }
+  grid_reduce<2>(acc, smem, partials, ticket, out);
+}
+
+// ---------------------------------------------------------------- scalar control
+// After K1: sums = {r.r, r.Mr} (gathered over ranks, rank order).  d_1 = r_1 so d.q = r.Mr.
+__global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, int nranks,
+                                       int i_max, double converge) {
+  double rr = 0.0, rMr = 0.0;
+  for (int g = 0; g < nranks; g++) {
+    rr += gathered[g * 4 + 0];
+    rMr += gathered[g * 4 + 1];
+  }
+  st->delta_new = rr;
+  st->delta_old = rr;
+  st->dq = rMr;
+  st->alpha = rr / rMr;
+  st->beta = 0.0;
+  st->iter = 1;  // the reference's loop counter starts at 1 (:287, Q3)
+  st->i_max = i_max;
+  st->converge = converge;
+  st->done = !(1 < i_max && rr > converge);
+  st->trace[0] = rr;
+}
+
+// After a fused pass: sums = {r'.r', r'.Mr', r'.q, d.q} with q = M d.
+// delta' = r'.r'; beta' = delta'/delta; d' = r' + beta' d  =>  d'.Md' = r'.Mr' + 2 beta' r'.q + beta'^2 d.q
+__global__ void cg_fused_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
+  if (st->done) return;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int g = 0; g < nranks; g++)
+    for (int i = 0; i < 4; i++) s[i] += gathered[g * 4 + i];
+  const double delta_old = st->delta_new;
+  const double delta_new = s[0];
+  const double beta = delta_new / delta_old;
+  const double dq = s[1] + 2.0 * beta * s[2] + beta * beta * s[3];
+  st->delta_old = delta_old;
+  st->delta_new = delta_new;
+  st->beta = beta;
+  st->dq = dq;
+  st->alpha = delta_new / dq;
+  const int it = st->iter + 1;
+  st->iter = it;
+  if (it - 1 < 256) st->trace[it - 1] = delta_new;
+  st->done = !(it < st->i_max && delta_new > st->converge);
+}
+
+// two-pass form: after the d.q pass
+__global__ void cg_dq_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
+  if (st->done) return;
+  double dq = 0.0;
+  for (int g = 0; g < nranks; g++) dq += gathered[g * 4 + 0];
+  st->dq = dq;
+  st->alpha = st->delta_new / dq;  // :297
+}
+// two-pass form: after the update pass
+__global__ void cg_rr_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
+  if (st->done) return;
+  double rr = 0.0;
+  for (int g = 0; g < nranks; g++) rr += gathered[g * 4 + 0];
+  st->delta_old = st->delta_new;  // :302-304
+  st->delta_new = rr;
+  st->beta = rr / st->delta_old;
+  const int it = st->iter + 1;
+  st->iter = it;
+  if (it - 1 < 256) st->trace[it - 1] = rr;
+  st->done = !(it < st->i_max && rr > st->converge);
+}
+
+// ---------------------------------------------------------------- K2: fused CG pass
+// One HBM pass per CG iteration over vec2 elements e of the flattened [S][Ppad] index:
+//   d <- r + beta d (beta = 0 on the first pass: d = r was stored by K1)
+//   q  = M d;  x += alpha d;  r' = r - alpha q
+//   sums {r'.r', r'.M r', r'.q, d.q}
+// reads T + 3C, writes 3C doubles per element: the compulsory traffic of SURVEY 8d bytes_cg_it.
+template <int C>
+__global__ void __launch_bounds__(DG_THREADS)
+cg_fused_pass_kernel(const CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
+                     double *__restrict__ r, double *__restrict__ d, int64_t n2 /* vec2 count per plane-set */,
+                     double *partials, unsigned int *ticket, double *out) {
+  constexpr int T = C * (C + 1) / 2;
+  if (st->done) return;
+  const double alpha = st->alpha, beta = st->beta;
+  __shared__ double smem[4 * 32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const size_t vs = (size_t)n2 * 2;  // doubles per component / block-entry plane-set
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    double2 m[T], xv[C], rv[C], dv[C];
+#pragma unroll
+    for (int t = 0; t < T; t++) m[t] = ldg_stream2(M + t * vs + 2 * e);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      rv[c] = *reinterpret_cast<const double2 *>(r + c * vs + 2 * e);
+      dv[c] = *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
+      xv[c] = *reinterpret_cast<const double2 *>(x + c * vs + 2 * e);
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      dv[c].x = rv[c].x + beta * dv[c].x;  // :305 (of the previous iteration)
+      dv[c].y = rv[c].y + beta * dv[c].y;
+    }
+    double2 q[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      double qx = 0.0, qy = 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < C; c2++) {
+        const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+        qx += mm.x * dv[c2].x;
+        qy += mm.y * dv[c2].y;
+      }
+      q[c].x = qx;
+      q[c].y = qy;
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      xv[c].x = xv[c].x + alpha * dv[c].x;  // :298
+      xv[c].y = xv[c].y + alpha * dv[c].y;
+      rv[c].x = rv[c].x - alpha * q[c].x;   // :300
+      rv[c].y = rv[c].y - alpha * q[c].y;
+      acc[3] += dv[c].x * q[c].x + dv[c].y * q[c].y;
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      double mx = 0.0, my = 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < C; c2++) {
+        const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+        mx += mm.x * rv[c2].x;
+        my += mm.y * rv[c2].y;
+      }
+      acc[0] += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
+      acc[1] += rv[c].x * mx + rv[c].y * my;
+      acc[2] += rv[c].x * q[c].x + rv[c].y * q[c].y;
+      *reinterpret_cast<double2 *>(d + c * vs + 2 * e) = dv[c];
+      *reinterpret_cast<double2 *>(x + c * vs + 2 * e) = xv[c];
+      *reinterpret_cast<double2 *>(r + c * vs + 2 * e) = rv[c];
+    }
+  }
+  grid_reduce<4>(acc, smem, partials, ticket, out);
+}
+
+// ---------------------------------------------------------------- classic two-pass form
+// pass A: d <- r + beta d (skipped on the first iteration), sum d.(M d)      (:296-297)
+template <int C>
+__global__ void __launch_bounds__(DG_THREADS)
+cg_dq_pass_kernel(const CgScalars *st, const double *__restrict__ M, const double *__restrict__ r,
+                  double *__restrict__ d, int64_t n2, double *partials, unsigned int *ticket,
+                  double *out) {
+  constexpr int T = C * (C + 1) / 2;
+  if (st->done) return;
+  const double beta = st->beta;
+  const bool first = st->iter == 1;
+  __shared__ double smem[4 * 32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const size_t vs = (size_t)n2 * 2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    double2 m[T], rv[C], dv[C];
+#pragma unroll
+    for (int t = 0; t < T; t++) m[t] = ldg_stream2(M + t * vs + 2 * e);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      dv[c] = *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
+      if (!first) {
+        rv[c] = *reinterpret_cast<const double2 *>(r + c * vs + 2 * e);
+        dv[c].x = rv[c].x + beta * dv[c].x;
+        dv[c].y = rv[c].y + beta * dv[c].y;
+        *reinterpret_cast<double2 *>(d + c * vs + 2 * e) = dv[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      double qx = 0.0, qy = 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < C; c2++) {
+        const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+        qx += mm.x * dv[c2].x;
+        qy += mm.y * dv[c2].y;
+      }
+      acc[0] += dv[c].x * qx + dv[c].y * qy;
+    }
+  }
+  grid_reduce<4>(acc, smem, partials, ticket, out);
+}
+
+// pass B: x += alpha d; r -= alpha (M d); sum r.r                            (:298-303)
+template <int C>
+__global__ void __launch_bounds__(DG_THREADS)
+cg_update_pass_kernel(const CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
+                      double *__restrict__ r, const double *__restrict__ d, int64_t n2,
+                      double *partials, unsigned int *ticket, double *out) {
+  constexpr int T = C * (C + 1) / 2;
+  if (st->done) return;
+  const double alpha = st->alpha;
+  __shared__ double smem[4 * 32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const size_t vs = (size_t)n2 * 2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    double2 m[T], xv[C], rv[C], dv[C];
+#pragma unroll
+    for (int t = 0; t < T; t++) m[t] = ldg_stream2(M + t * vs + 2 * e);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      rv[c] = *reinterpret_cast<const double2 *>(r + c * vs + 2 * e);
+      dv[c] = *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
+      xv[c] = *reinterpret_cast<const double2 *>(x + c * vs + 2 * e);
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      double qx = 0.0, qy = 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < C; c2++) {
+        const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+        qx += mm.x * dv[c2].x;
+        qy += mm.y * dv[c2].y;
+      }
+      xv[c].x = xv[c].x + alpha * dv[c].x;
+      xv[c].y = xv[c].y + alpha * dv[c].y;
+      rv[c].x = rv[c].x - alpha * qx;
+      rv[c].y = rv[c].y - alpha * qy;
+      acc[0] += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
+      *reinterpret_cast<double2 *>(x + c * vs + 2 * e) = xv[c];
+      *reinterpret_cast<double2 *>(r + c * vs + 2 * e) = rv[c];
+    }
+  }
+  grid_reduce<4>(acc, smem, partials, ticket, out);
+}
+
+// initialize_x / unpack_amplitudes, src/dang_cg_mod.f90:1173-1282, 1284-1396: plane copies
+__global__ void copy_planes_kernel(double *dst, const double *src, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}

@@ -1,0 +1,118 @@
+// kernels_data.cuh -- K6: update_sky_model + compute_chisq,
+// src/dang_data_mod.f90:339-396, 494-526, fused into one pass over sig/rms.
+// sky_model / res_map / chi_map are only materialised when the host asks for them
+// (write_maps cadence, src/dang.f90:119-121); the per-iteration call just reduces chi-square.
+#pragma once
+#include "common.cuh"
+
+struct ChisqView {
+  int k_lo, k_hi;     // 0-based plane range of ddata%pol_type
+  double *sky, *res;  // [nbands][nmaps][Ppad] or nullptr
+  double *chi_map;    // [nmaps][Ppad] or nullptr
+};
+
+// out[0..2] = sum over unmasked pixels of chi_map(:,k) (already / nbands), out[3] = #unmasked
+template <int NC>
+__global__ void __launch_bounds__(DG_THREADS)
+chisq_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned int *ticket,
+             double *out) {
+  __shared__ double smem[4 * 32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool maps = cv.sky != nullptr || cv.res != nullptr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
+    const bool use = mv.mask[p] != 0;
+    if (use) acc[3] += 1.0;
+    if (!use && !maps) {
+      if (cv.chi_map)
+        for (int k = 0; k < mv.nmaps; k++) cv.chi_map[(size_t)k * mv.Ppad + p] = 0.0;
+      continue;
+    }
+    // update_sky_model covers every plane and every pixel; compute_chisq only pol_type planes
+    const int ka = maps ? 0 : cv.k_lo, kb = maps ? mv.nmaps - 1 : cv.k_hi;
+    double a[3][NC], th[3][NC][DG_MAXIND];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (k < ka || k > kb) continue;
+      const size_t kp = (size_t)k * mv.Ppad + p;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        if (c < mv.ncomp) {
+          const CompView &cc = mv.comp[c];
+          a[k][c] = cc.amp[kp];
+          th[k][c][0] = cc.nind > 0 ? cc.idx[0][kp] : 0.0;
+          th[k][c][1] = cc.nind > 1 ? cc.idx[1][kp] : 0.0;
+        }
+      }
+    }
+    double chi[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < mv.nbands; j++) {
+      double sed[3][NC];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (k < ka || k > kb) continue;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          if (c < mv.ncomp) {
+            if (k > ka && th[k][c][0] == th[k > 0 ? k - 1 : 0][c][0] && th[k][c][1] == th[k > 0 ? k - 1 : 0][c][1])
+              sed[k][c] = sed[k > 0 ? k - 1 : 0][c];
+            else
+              sed[k][c] = sed_eval(mv, c, j, th[k][c][0], th[k][c][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (k < ka || k > kb) continue;
+        const size_t off = plane_off(mv, j, k) + p;
+        double sky = 0.0;  // :354, :367
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+          if (c < mv.ncomp) sky = sky + a[k][c] * sed[k][c];
+        const double sig = ldg_stream(mv.sig + off);
+        const double t = (k == 0) ? (sig - mv.offset[j]) / mv.gain[j] - sky : sig - sky;  // :384-387
+        if (cv.sky) cv.sky[off] = sky;
+        if (cv.res) cv.res[off] = t;
+        if (use && k >= cv.k_lo && k <= cv.k_hi) {
+          const double rms = ldg_stream(mv.rms + off);
+          chi[k] = chi[k] + (t * t) / (rms * rms);  // :510-516
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (k >= mv.nmaps) continue;
+      const double v = (use && k >= cv.k_lo && k <= cv.k_hi) ? chi[k] / mv.nbands : 0.0;  // :523
+      if (cv.chi_map) cv.chi_map[(size_t)k * mv.Ppad + p] = v;
+      acc[k] += v;
+    }
+  }
+  grid_reduce<4>(acc, smem, partials, ticket, out);
+}
+
+// mask_avg, src/dang_util_mod.f90:186-206: out[0] = sum over unmasked of map, out[1] = count
+__global__ void __launch_bounds__(DG_THREADS)
+masked_sum_kernel(const double *map, const unsigned char *mask, int64_t P, double *partials,
+                  unsigned int *ticket, double *out) {
+  __shared__ double smem[4 * 32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride)
+    if (mask[p]) {
+      acc[0] += map[p];
+      acc[1] += 1.0;
+    }
+  grid_reduce<4>(acc, smem, partials, ticket, out);
+}
+
+__global__ void fill_kernel(double *dst, int64_t n, double v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+
+// mask (double, 0 / missval = masked) -> bytes, src/dang_data_mod.f90:153-161
+__global__ void mask_to_bytes_kernel(const double *mask, unsigned char *out, int64_t P, int64_t Ppad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Ppad; i += stride)
+    out[i] = (i < P && mask[i] != 0.0 && mask[i] != -1.6375e30) ? 1 : 0;
+}

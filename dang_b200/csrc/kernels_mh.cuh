@@ -1,0 +1,411 @@
+// kernels_mh.cuh -- spectral-parameter draw: sample_index_mh,
+// src/dang_sample_mod.f90:88-485, with update_sample_model (:520-568), evaluate_lnL /
+// evaluate_marginal_lnL / eval_jeffreys_prior (src/dang_lnl_mod.f90) and eval_normal_prior
+// (src/dang_util_mod.f90:112-121) fused in.
+//
+// Per-pixel mode (K5): one thread owns one pixel's chain; the pixel's residual data, rms and
+// the proposal's SED live in shared memory; no communication.
+// Full-sky mode (K4): the chain itself runs in a single-thread scalar kernel on the device;
+// the likelihood comes either from per-band sufficient statistics gathered in ONE pass over the
+// maps (default) or from one streaming pass per proposal (the reference's structure).
+#pragma once
+#include "common.cuh"
+
+#define DG_MH_THREADS 128
+#define DG_SUFF_CHUNK 8   // bands per register-resident accumulator chunk
+
+struct MhView {
+  int ic;          // component being sampled
+  int nind;        // which of its indices
+  int S;           // planes map_inds(1)..map_inds(2)
+  int plane[2];    // 0-based
+  int nsample, ml_mode, lnl_type, prior_type;
+  int is_synch;    // label == 'synch' (eval_jeffreys_prior, src/dang_lnl_mod.f90:289)
+  double gauss[2], uni[2], step;
+  const double *z, *u;        // injected deviates (device copies) or nullptr -> Philox(seed)
+  uint64_t seed;
+  unsigned char *decisions;   // optional instrumentation
+  double *lnl_trace;
+};
+
+struct MhScalars {
+  double sample[DG_MAXIND], theta[DG_MAXIND];
+  double lnl_old, accept;
+  int l, phase, skip, pad;
+  double sed[DG_MAX_BANDS];  // SED of the proposal per band (streaming lnL kernel)
+  double s0[DG_MAX_BANDS];   // SED at the chain's starting point (sufficient statistics)
+};
+
+// log(eval_normal_prior(x, mean, std)), src/dang_util_mod.f90:112-121 + dang_sample_mod.f90:261
+__device__ __forceinline__ double log_normal_prior(double x, double mean, double sd) {
+  const double var = sd * sd;
+  const double num = exp(-((x - mean) * (x - mean)) / (2 * var));
+  const double denom = sd * sqrt(2.0 * DG_PI);
+  return log(num / denom);
+}
+
+// data_raw(i,k,j) = sig - sum_{c2 /= c} signal_c2, src/dang_sample_mod.f90:173-196
+__device__ __forceinline__ double mh_data_value(const ModelView &mv, int ic, int j, int k,
+                                                int64_t p) {
+  const size_t off = plane_off(mv, j, k) + p;
+  double v = ldg_stream(mv.sig + off);
+  if (k == 0) v = (v - mv.offset[j]) / mv.gain[j];
+  const size_t kp = (size_t)k * mv.Ppad + p;
+  for (int c2 = 0; c2 < mv.ncomp; c2++) {
+    if (c2 == ic) continue;
+    const CompView &cc = mv.comp[c2];
+    const double t0 = cc.nind > 0 ? cc.idx[0][kp] : 0.0;
+    const double t1 = cc.nind > 1 ? cc.idx[1][kp] : 0.0;
+    v = v - cc.amp[kp] * sed_eval(mv, c2, j, t0, t1);
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------- K5: per-pixel chains
+// dynamic smem: sD[B][S][T], sR[B][S][T] (rms), sS[B][T] (proposal SED)
+__global__ void __launch_bounds__(DG_MH_THREADS)
+mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsigned int *ticket,
+                   double *out) {
+  extern __shared__ double dyn[];
+  const int T = DG_MH_THREADS, tid = threadIdx.x, B = mv.nbands, S = mh.S;
+  double *sD = dyn, *sR = dyn + (size_t)B * S * T, *sS = dyn + (size_t)2 * B * S * T;
+  __shared__ double smem[32];
+  double acc[1] = {0.0};
+  const CompView &cv = mv.comp[mh.ic];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + tid; p < mv.P; p += stride) {
+    const uint64_t gpix = (uint64_t)(mv.pix_lo + p);
+    if (!mv.mask[p]) {  // :362; index_map stays 0 for masked pixels (:223, :465, :483)
+      for (int s = 0; s < S; s++) cv.idx[mh.nind][(size_t)mh.plane[s] * mv.Ppad + p] = 0.0;
+      if (mh.decisions)
+        for (int l = 0; l < mh.nsample; l++) mh.decisions[(size_t)l * mv.P + p] = 3;
+      continue;
+    }
+    const size_t kp0 = (size_t)mh.plane[0] * mv.Ppad + p;
+    double sample[DG_MAXIND], theta[DG_MAXIND], amp[2];
+    sample[0] = cv.nind > 0 ? cv.idx[0][kp0] : 0.0;  // :372-374
+    sample[1] = cv.nind > 1 ? cv.idx[1][kp0] : 0.0;
+    theta[0] = sample[0];
+    theta[1] = sample[1];
+    for (int s = 0; s < S; s++) amp[s] = cv.amp[(size_t)mh.plane[s] * mv.Ppad + p];
+    for (int j = 0; j < B; j++)
+      for (int s = 0; s < S; s++) {
+        sD[((size_t)j * S + s) * T + tid] = mh_data_value(mv, mh.ic, j, mh.plane[s], p);
+        sR[((size_t)j * S + s) * T + tid] = ldg_stream(mv.rms + plane_off(mv, j, mh.plane[s]) + p);
+      }
+
+    // lnL of theta; order of accumulation as evaluate_lnL: Stokes outer, band inner (:172-176)
+    auto eval_lnl = [&](const double *th) -> double {
+      for (int j = 0; j < B; j++) sS[(size_t)j * T + tid] = sed_eval(mv, mh.ic, j, th[0], th[1]);
+      double lnl = 0.0;
+      if (mh.lnl_type == 0) {
+        for (int s = 0; s < S; s++)
+          for (int j = 0; j < B; j++) {
+            const double model = amp[s] * sS[(size_t)j * T + tid];  // eval_signal :773
+            const double t = (sD[((size_t)j * S + s) * T + tid] - model) / sR[((size_t)j * S + s) * T + tid];
+            lnl = lnl - 0.5 * (t * t);
+          }
+      } else {  // marginal, src/dang_lnl_mod.f90:113-122 (band outer, Stokes inner)
+        for (int j = 0; j < B; j++)
+          for (int s = 0; s < S; s++) {
+            const double model = amp[s] * sS[(size_t)j * T + tid];
+            const double rms = sR[((size_t)j * S + s) * T + tid];
+            const double TN = model / (rms * rms);
+            const double TNd = TN * sD[((size_t)j * S + s) * T + tid];
+            const double TNT = TN * model;
+            const double invTNT = 1.0 / TNT;
+            lnl = lnl - 0.5 * TNd * invTNT * TNd;
+          }
+      }
+      return lnl;
+    };
+    auto eval_prior = [&](double val, double prev) -> double {
+      if (mh.prior_type == 1) return log_normal_prior(val, mh.gauss[0], mh.gauss[1]);
+      if (mh.prior_type == 2) {  // eval_jeffreys_prior, src/dang_lnl_mod.f90:242-304
+        double sum = 0.0;
+        if (mh.is_synch) {
+          for (int s = 0; s < S; s++)
+            for (int j = 0; j < B; j++) {
+              const double ss = amp[s] * sed_eval(mv, mh.ic, j, val, 0.0);
+              const double ir = 1.0 / sR[((size_t)j * S + s) * T + tid];
+              const double t = (ir * ir) * (ss / amp[s]) * log(mv.band[j].nu_c / cv.nu_ref);
+              sum = sum + t * t;
+            }
+        }
+        return log(sqrt(sum));
+      }
+      if (mh.prior_type == 0) return 0.0;
+      return prev;
+    };
+
+    double lnl = 0.0, lnl_prior = 0.0, lnl_old, lnl_new;
+    bool sample_it = true;
+    if (mh.lnl_type == 2) {  // 'prior': draw from the Gaussian prior (:389-391)
+      sample_it = false;
+      const double zz = mh.z ? mh.z[p] : philox_normal(mh.seed, DG_STREAM_MH_Z, gpix);
+      sample[mh.nind] = mh.gauss[0] + mh.gauss[1] * zz;
+    } else {
+      lnl = eval_lnl(sample);
+    }
+    lnl_prior = eval_prior(sample[mh.nind], lnl_prior);
+    lnl_old = lnl + lnl_prior;
+    if (sample_it) {
+      for (int l = 0; l < mh.nsample; l++) {  // :410-455
+        const size_t slot = (size_t)l * mv.P + p;
+        const uint64_t gslot = (uint64_t)l * (uint64_t)mv.npix + gpix;
+        const double zz = mh.z ? mh.z[slot] : philox_normal(mh.seed, DG_STREAM_MH_Z, gslot);
+        theta[mh.nind] = sample[mh.nind] + (0.0 + mh.step * zz);
+        if (theta[mh.nind] < mh.uni[0] || theta[mh.nind] > mh.uni[1]) {  // :415, Q5
+          if (mh.decisions) mh.decisions[slot] = 2;
+          continue;
+        }
+        lnl = eval_lnl(theta);
+        lnl_prior = eval_prior(theta[mh.nind], lnl_prior);
+        lnl_new = lnl + lnl_prior;
+        if (mh.lnl_trace) mh.lnl_trace[slot] = lnl_new;
+        const double diff = lnl_new - lnl_old;
+        bool accept;
+        if (mh.ml_mode == 0) {
+          accept = diff > 0.0;
+        } else {
+          double uu;
+          if (mh.u) {
+            uu = mh.u[slot];
+          } else {
+            double u2;
+            philox_uniform2(mh.seed, DG_STREAM_MH_U, gslot, uu, u2);
+          }
+          accept = diff > log(uu);  // :450, Q4
+        }
+        if (accept) {
+          sample[mh.nind] = theta[mh.nind];
+          lnl_old = lnl_new;
+          acc[0] += 1.0;
+        }
+        if (mh.decisions) mh.decisions[slot] = accept ? 1 : 0;
+      }
+    }
+    for (int s = 0; s < S; s++)  // :465, :483
+      cv.idx[mh.nind][(size_t)mh.plane[s] * mv.Ppad + p] = sample[mh.nind];
+  }
+  grid_reduce<1>(acc, smem, partials, ticket, out);
+}
+
+// ---------------------------------------------------------------- K4: full-sky chain
+// start of the chain: sample(:) = c%indices(0, map_inds(1), :) (:240-243), broadcast from the
+// rank that owns global pixel 0 (gathered[0..1] of rank 0)
+__global__ void mh_fullsky_init_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
+                                       const double *gathered, int cnt) {
+  ms->sample[0] = gathered[0];
+  ms->sample[1] = gathered[1];
+  ms->theta[0] = ms->sample[0];
+  ms->theta[1] = ms->sample[1];
+  ms->lnl_old = 0.0;
+  ms->accept = 0.0;
+  ms->l = 0;
+  ms->phase = 0;
+  ms->skip = 0;
+  for (int j = 0; j < mv.nbands; j++) {
+    const double s = sed_eval(mv, mh.ic, j, ms->sample[0], ms->sample[1]);
+    ms->sed[j] = s;
+    ms->s0[j] = s;
+  }
+  (void)cnt;
+}
+
+// local values of the index maps at this handle's first pixel (rank 0 owns global pixel 0)
+__global__ void mh_first_pixel_kernel(const ModelView mv, const MhView mh, double *out) {
+  const CompView &cv = mv.comp[mh.ic];
+  const size_t kp0 = (size_t)mh.plane[0] * mv.Ppad;
+  out[0] = cv.nind > 0 ? cv.idx[0][kp0] : 0.0;
+  out[1] = cv.nind > 1 ? cv.idx[1][kp0] : 0.0;
+}
+
+__device__ __forceinline__ double mh_draw_z(const MhView &mh, int l) {
+  return mh.z ? mh.z[l] : philox_normal(mh.seed, DG_STREAM_MH_Z, (uint64_t)l);
+}
+__device__ __forceinline__ double mh_draw_u(const MhView &mh, int l) {
+  if (mh.u) return mh.u[l];
+  double u1, u2;
+  philox_uniform2(mh.seed, DG_STREAM_MH_U, (uint64_t)l, u1, u2);
+  return u1;
+}
+
+// advance to the next in-bounds proposal (out-of-bounds ones consume z but not u, Q5)
+__device__ __forceinline__ void mh_next_proposal(const ModelView &mv, const MhView &mh,
+                                                 MhScalars *ms) {
+  while (ms->l < mh.nsample) {
+    const double th = ms->sample[mh.nind] + (0.0 + mh.step * mh_draw_z(mh, ms->l));  // :286
+    ms->theta[mh.nind] = th;
+    if (th < mh.uni[0] || th > mh.uni[1]) {  // :287
+      if (mh.decisions) mh.decisions[ms->l] = 2;
+      ms->l++;
+      continue;
+    }
+    for (int j = 0; j < mv.nbands; j++) ms->sed[j] = sed_eval(mv, mh.ic, j, ms->theta[0], ms->theta[1]);
+    return;
+  }
+  ms->skip = 1;
+}
+
+__device__ __forceinline__ void mh_accept_step(const MhView &mh, MhScalars *ms, double lnl) {
+  double prior = 0.0;
+  if (mh.prior_type == 1) prior = log_normal_prior(ms->theta[mh.nind], mh.gauss[0], mh.gauss[1]);
+  const double lnl_new = lnl + prior;  // :306
+  const int l = ms->l;
+  if (mh.lnl_trace) mh.lnl_trace[l] = lnl_new;
+  const double diff = lnl_new - ms->lnl_old;
+  const double ratio = exp(diff);  // :310, Q4
+  const bool accept = (mh.ml_mode == 0) ? (ratio > 1.0) : (ratio > mh_draw_u(mh, l));
+  if (accept) {
+    ms->sample[mh.nind] = ms->theta[mh.nind];
+    ms->lnl_old = lnl_new;
+    ms->accept += 1.0;
+  }
+  if (mh.decisions) mh.decisions[l] = accept ? 1 : 0;
+  ms->l = l + 1;
+}
+
+// streaming mode: consume the lnL just reduced (gathered over ranks), decide, propose next
+__global__ void mh_fullsky_step_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
+                                       const double *gathered, int nranks, int cnt) {
+  if (ms->skip) return;
+  double lnl = 0.0;
+  for (int g = 0; g < nranks; g++) lnl += gathered[g * cnt];
+  if (ms->phase == 0) {  // lnL of the starting point (:250, :261, :268)
+    double prior = 0.0;
+    if (mh.prior_type == 1) prior = log_normal_prior(ms->sample[mh.nind], mh.gauss[0], mh.gauss[1]);
+    ms->lnl_old = lnl + prior;
+    ms->phase = 1;
+  } else {
+    mh_accept_step(mh, ms, lnl);
+  }
+  mh_next_proposal(mv, mh, ms);
+}
+
+// D[j][s][Ppad] = data_raw for the sampled planes (streaming mode only)
+__global__ void __launch_bounds__(DG_THREADS)
+mh_data_kernel(const ModelView mv, const MhView mh, double *D) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride)
+    for (int j = 0; j < mv.nbands; j++)
+      for (int s = 0; s < mh.S; s++)
+        D[((size_t)j * mh.S + s) * mv.Ppad + p] = mh_data_value(mv, mh.ic, j, mh.plane[s], p);
+}
+
+// evaluate_lnL full sky, src/dang_lnl_mod.f90:126-182, for model = amplitude * ms->sed[j]
+__global__ void __launch_bounds__(DG_THREADS)
+mh_fullsky_lnl_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, const double *D,
+                      double *partials, unsigned int *ticket, double *out) {
+  if (ms->skip) return;
+  __shared__ double smem[32];
+  __shared__ double ssed[DG_MAX_BANDS];
+  if (threadIdx.x < mv.nbands) ssed[threadIdx.x] = ms->sed[threadIdx.x];
+  __syncthreads();
+  double acc[1] = {0.0};
+  const CompView &cv = mv.comp[mh.ic];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
+    if (!mv.mask[p]) continue;
+    double lnl = 0.0;
+    for (int s = 0; s < mh.S; s++) {
+      const double a = cv.amp[(size_t)mh.plane[s] * mv.Ppad + p];
+      for (int j = 0; j < mv.nbands; j++) {
+        const double d = ldg_stream(D + ((size_t)j * mh.S + s) * mv.Ppad + p);
+        const double rms = ldg_stream(mv.rms + plane_off(mv, j, mh.plane[s]) + p);
+        const double t = (d - a * ssed[j]) / rms;
+        lnl = lnl - 0.5 * (t * t);
+      }
+    }
+    acc[0] += lnl;
+  }
+  grid_reduce<1>(acc, smem, partials, ticket, out);
+}
+
+// Sufficient statistics of the full-sky chi-square about the chain's starting SED s0:
+//   R = data - a s0,  t = R / sigma,  u = a / sigma
+//   X_j = sum t^2,  Y_j = sum t u,  Z_j = sum u^2      (unmasked pixels, sampled planes)
+// so that for a proposal with SED s0 + delta:  sum ((data - a s)/sigma)^2 = X - 2 delta Y + delta^2 Z.
+// Expanding about s0 (not about 0) keeps X at the chi-square itself: no cancellation.
+// out[chunk*24 + 3*jj + {0,1,2}]
+__global__ void __launch_bounds__(DG_THREADS)
+mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, double *partials,
+                   unsigned int *tickets, double *out) {
+  constexpr int NV = 3 * DG_SUFF_CHUNK;
+  __shared__ double smem[NV * 32];
+  const CompView &cv = mv.comp[mh.ic];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int nchunk = (mv.nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  for (int ch = 0; ch < nchunk; ch++) {
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    double s0[DG_SUFF_CHUNK];
+#pragma unroll
+    for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
+      const int j = ch * DG_SUFF_CHUNK + jj;
+      s0[jj] = j < mv.nbands ? ms->s0[j] : 0.0;
+    }
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
+      if (!mv.mask[p]) continue;
+      for (int s = 0; s < mh.S; s++) {
+        const int k = mh.plane[s];
+        const double a = cv.amp[(size_t)k * mv.Ppad + p];
+#pragma unroll
+        for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
+          const int j = ch * DG_SUFF_CHUNK + jj;
+          if (j < mv.nbands) {
+            const double d = mh_data_value(mv, mh.ic, j, k, p);
+            const double rms = ldg_stream(mv.rms + plane_off(mv, j, k) + p);
+            const double t = (d - a * s0[jj]) / rms;
+            const double u = a / rms;
+            acc[3 * jj + 0] += t * t;
+            acc[3 * jj + 1] += t * u;
+            acc[3 * jj + 2] += u * u;
+          }
+        }
+      }
+    }
+    grid_reduce<NV>(acc, smem, partials + (size_t)ch * NV * gridDim.x, tickets + ch, out + ch * NV);
+    __syncthreads();
+  }
+}
+
+// the whole full-sky chain from the statistics: one thread, no map traffic (:282-324)
+__global__ void mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
+                                     const double *gathered, int nranks, int cnt) {
+  const int B = mv.nbands;
+  // lnL(theta) = -1/2 sum_j (X_j - 2 delta_j Y_j + delta_j^2 Z_j), delta_j = sed_j(theta) - s0_j
+  auto lnl_of = [&](const double *sed) -> double {
+    double lnl = 0.0;
+    for (int j = 0; j < B; j++) {
+      double X = 0.0, Y = 0.0, Z = 0.0;
+      for (int g = 0; g < nranks; g++) {
+        X += gathered[g * cnt + 3 * j + 0];
+        Y += gathered[g * cnt + 3 * j + 1];
+        Z += gathered[g * cnt + 3 * j + 2];
+      }
+      const double dl = sed[j] - ms->s0[j];
+      lnl = lnl - 0.5 * (X - 2.0 * dl * Y + dl * dl * Z);
+    }
+    return lnl;
+  };
+  double prior = 0.0;
+  if (mh.prior_type == 1) prior = log_normal_prior(ms->sample[mh.nind], mh.gauss[0], mh.gauss[1]);
+  ms->lnl_old = lnl_of(ms->s0) + prior;
+  ms->phase = 1;
+  mh_next_proposal(mv, mh, ms);
+  while (!ms->skip) {
+    mh_accept_step(mh, ms, lnl_of(ms->sed));
+    mh_next_proposal(mv, mh, ms);
+  }
+}
+
+// index_full_res(:, map_inds) = sample(nind) -> c%indices (:329, :483)
+__global__ void mh_fullsky_store_kernel(const ModelView mv, const MhView mh, const MhScalars *ms) {
+  const CompView &cv = mv.comp[mh.ic];
+  const double v = ms->sample[mh.nind];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride)
+    for (int s = 0; s < mh.S; s++) cv.idx[mh.nind][(size_t)mh.plane[s] * mv.Ppad + p] = v;
+}

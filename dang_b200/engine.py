@@ -1,0 +1,306 @@
+"""Host-side mirror of the reference's Gibbs-loop operators over the C ABI.
+
+`Engine` plays the role of the Fortran host (`dang.f90` + the thin shim in
+fortran/dang_gpu_mod.f90): it keeps the run description (RunConfig) as the source of truth,
+pushes bands / maps / components / CG groups through include/dang_gpu.h exactly as the shim
+does, and exposes the reference's own operator names:
+
+    sample_cg_groups            src/dang_cg_mod.f90:142-177
+    sample_spectral_parameters  src/dang_sample_mod.f90:21-86
+    sample_index_mh             src/dang_sample_mod.f90:88-485
+    update_sky_model            src/dang_data_mod.f90:339-396
+    compute_chisq               src/dang_data_mod.f90:494-526
+
+All computation happens in libdang_gpu.so on the GPU; nothing here falls back to numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .config import (COMP_TYPES, INDEX_MODES, LNL_TYPES, ML_MODES, PRIOR_TYPES, RunConfig,
+                     flag_to_map_n, return_poltype_flag)
+
+OPT_FIX_SAMPLE_VECTOR, OPT_CG_TWO_PASS, OPT_FULLSKY_STREAM, OPT_PROFILE, OPT_CG_CHUNK, OPT_RECORD = 1, 2, 3, 4, 5, 6
+KERNEL_COUNT = 11
+
+
+class DangGpuError(RuntimeError):
+    pass
+
+
+def _dp(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("expected a C-contiguous float64 array")
+    return a.ctypes.data_as(_lib.c_dp)
+
+
+def init_bandpass(band) -> Tuple[float, np.ndarray, np.ndarray]:
+    """Host part of init_bp_mod / read_bandpass / normalize_bandpass
+    (src/dang_bp_mod.f90:19-81,138): nu_c GHz -> Hz if < 1e9, nu0 GHz -> Hz, tau0 / sum(tau0)."""
+    nu_c = band.nu_ghz
+    if nu_c < 1e9:
+        nu_c = nu_c * 1e9
+    if band.is_delta:
+        return nu_c, np.zeros(0), np.zeros(0)
+    nu0 = np.ascontiguousarray(band.bp_nu_ghz, dtype=np.float64) * 1.0e9
+    tau = np.ascontiguousarray(band.bp_tau, dtype=np.float64)
+    total = 0.0
+    for t in tau:  # Fortran sum(): sequential
+        total = total + t
+    return nu_c, nu0, tau / total
+
+
+class Engine:
+    def __init__(self, cfg: RunConfig, sky, device: int = 0,
+                 pix_range: Optional[Tuple[int, int]] = None):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.npix, self.nmaps, self.nbands = cfg.npix, cfg.nmaps, cfg.nbands
+        self.lo, self.hi = pix_range if pix_range is not None else (0, cfg.npix)
+        self.h = _lib.vp()
+        rc = self.lib.dang_gpu_create(device, cfg.nside, cfg.npix, cfg.nmaps, cfg.nbands,
+                                      len(cfg.comps), self.lo, self.hi, C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.dang_gpu_last_error(None).decode()
+            self.h = None
+            raise DangGpuError(f"dang_gpu_create failed (rc={rc}): {msg}")
+        self.nranks, self.rank = 1, 0
+        # init_bp_mod
+        for j, b in enumerate(cfg.bands):
+            nu_c, nu0, tau0 = init_bandpass(b)
+            self._ck(self.lib.dang_gpu_set_band(self.h, j, nu_c, len(nu0), _dp(nu0) if len(nu0) else None,
+                                                _dp(tau0) if len(tau0) else None))
+        # initialize_data_module
+        self.upload_maps(sky)
+        # initialize_components
+        for ic, c in enumerate(cfg.comps):
+            nu_ref = c.nu_ref_ghz * 1e9 if c.nu_ref_ghz < 1e7 else c.nu_ref_ghz  # dang_param_mod.f90:571-573
+            amp = np.ascontiguousarray(sky.amplitude[c.label], dtype=np.float64)
+            idx = np.ascontiguousarray(sky.indices[c.label], dtype=np.float64)
+            self._ck(self.lib.dang_gpu_set_component(self.h, ic, COMP_TYPES[c.type], c.label.encode(), nu_ref,
+                                                     c.cg_group, int(c.amp_sample), _dp(amp), _dp(idx)))
+            for k, s in enumerate(c.indices):
+                flags = return_poltype_flag(s.poltype)
+                fl = (C.c_int * max(len(flags), 1))(*flags)
+                g = np.asarray(s.gauss, dtype=np.float64)
+                u = np.asarray(s.uni, dtype=np.float64)
+                self._ck(self.lib.dang_gpu_set_index(self.h, ic, k, int(s.sample), INDEX_MODES[s.region],
+                                                     LNL_TYPES[s.lnl_type], PRIOR_TYPES[s.prior], _dp(g), _dp(u),
+                                                     s.step, s.samp_nside or cfg.nside, fl, len(flags)))
+        # initialize_cg_groups
+        for ig, g in enumerate(cfg.cg_groups):
+            flags = return_poltype_flag(g.poltype)
+            fl = (C.c_int * len(flags))(*flags)
+            self._ck(self.lib.dang_gpu_set_cg_group(self.h, ig + 1, g.max_iter, g.converge, fl, len(flags)))
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise DangGpuError(f"libdang_gpu rc={rc}: {self.lib.dang_gpu_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dang_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, opt: int, value: float):
+        self._ck(self.lib.dang_gpu_set_option(self.h, opt, float(value)))
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        self._ck(self.lib.dang_gpu_comm_init(self.h, nranks, rank, uid))
+        self.nranks, self.rank = nranks, rank
+
+    def upload_maps(self, sky):
+        """ddata%sig_map / rms_map / masks / gain / offset -> device (also after swap_cg_maps)."""
+        self._ck(self.lib.dang_gpu_upload_maps(self.h, _dp(sky.sig), _dp(sky.rms), _dp(sky.mask),
+                                               _dp(np.ascontiguousarray(sky.gain, dtype=np.float64)),
+                                               _dp(np.ascontiguousarray(sky.offset, dtype=np.float64))))
+
+    # ------------------------------------------------------------------ state access
+    def amplitude(self, ic: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.zeros((self.nmaps, self.npix)) if out is None else out
+        self._ck(self.lib.dang_gpu_get_amplitude(self.h, ic, _dp(out)))
+        return out
+
+    def indices(self, ic: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        nind = len(self.cfg.comps[ic].indices)
+        out = np.zeros((nind, self.nmaps, self.npix)) if out is None else out
+        self._ck(self.lib.dang_gpu_get_indices(self.h, ic, _dp(out)))
+        return out
+
+    def set_amplitude(self, ic: int, amp: np.ndarray):
+        self._ck(self.lib.dang_gpu_set_amplitude(self.h, ic, _dp(np.ascontiguousarray(amp, dtype=np.float64))))
+
+    def set_indices(self, ic: int, idx: np.ndarray):
+        self._ck(self.lib.dang_gpu_set_indices(self.h, ic, _dp(np.ascontiguousarray(idx, dtype=np.float64))))
+
+    def cg_x(self, ig: int = 0, flag_n: int = 0) -> np.ndarray:
+        g = self.cfg.cg_groups[ig]
+        S = 2 if return_poltype_flag(g.poltype)[flag_n] & 8 else 1
+        ncg = sum(1 for c in self.cfg.comps if c.cg_group == ig + 1 and c.amp_sample)
+        out = np.zeros((ncg * S, self.npix))
+        self._ck(self.lib.dang_gpu_get_cg_x(self.h, ig + 1, flag_n, _dp(out)))
+        return out.reshape(-1)
+
+    # ------------------------------------------------------------------ operators
+    def cg_solve(self, ig: int = 0, flag_n: int = 0, ml_mode: str = "sample",
+                 eta: Optional[np.ndarray] = None, seed: int = 0) -> Tuple[int, float]:
+        """compute_rhs + cg_search + unpack_amplitudes for one (group, flag)."""
+        n_iter = C.c_int()
+        delta = C.c_double()
+        e = None if eta is None else np.ascontiguousarray(eta, dtype=np.float64)
+        self._ck(self.lib.dang_gpu_cg_solve(self.h, ig + 1, flag_n, ML_MODES[ml_mode], _dp(e), seed,
+                                            C.byref(n_iter), C.byref(delta)))
+        return n_iter.value, delta.value
+
+    def cg_trace(self) -> np.ndarray:
+        buf = np.zeros(256)
+        n = C.c_int()
+        self._ck(self.lib.dang_gpu_cg_trace(self.h, _dp(buf), 256, C.byref(n)))
+        return buf[: n.value].copy()
+
+    def sample_cg_groups(self, ml_mode: Optional[str] = None, eta: Optional[np.ndarray] = None,
+                         seed: int = 0, stats: bool = True):
+        """sample_cg_groups: per sampled group, per flag: rhs -> CG -> unpack; then the chi-square
+        print of write_stats_to_term.  `eta` holds the normals of all solves back to back."""
+        ml_mode = ml_mode or self.cfg.ml_mode
+        out = []
+        off = 0
+        for ig, g in enumerate(self.cfg.cg_groups):
+            if not g.sample:
+                continue
+            flags = return_poltype_flag(g.poltype)
+            for f, flag in enumerate(flags):
+                m = (2 if flag & 8 else 1) * self.npix
+                e = None if eta is None else eta[off: off + m]
+                off += m
+                out.append(self.cg_solve(ig, f, ml_mode, e, seed + 1000003 * (ig * 3 + f)))
+            if stats:
+                out.append(self.compute_chisq())
+        return out
+
+    def sample_index_mh(self, ic: int, nind: int, map_n: int, nsample: Optional[int] = None,
+                        ml_mode: Optional[str] = None, z: Optional[np.ndarray] = None,
+                        u: Optional[np.ndarray] = None, seed: int = 0) -> float:
+        nsample = self.cfg.nsample if nsample is None else nsample
+        ml_mode = ml_mode or self.cfg.ml_mode
+        acc = C.c_double()
+        zz = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        self._ck(self.lib.dang_gpu_sample_index(self.h, ic, nind, map_n, nsample, ML_MODES[ml_mode],
+                                                _dp(zz), _dp(uu), seed, C.byref(acc)))
+        return acc.value
+
+    def sample_spectral_parameters(self, nsample: Optional[int] = None, ml_mode: Optional[str] = None,
+                                   z: Optional[np.ndarray] = None, u: Optional[np.ndarray] = None,
+                                   seed: int = 0, stats: bool = True):
+        """sample_spectral_parameters: components -> indices -> pol flags, in reference order.
+        Deviate arrays are consumed call by call with stride nsample*npix (as the oracle does)."""
+        nsample = self.cfg.nsample if nsample is None else nsample
+        stride = nsample * self.npix
+        ncall, sampled, acc = 0, False, []
+        for ic, c in enumerate(self.cfg.comps):
+            if not c.indices or not any(s.sample for s in c.indices):
+                continue
+            sampled = True
+            for j, s in enumerate(c.indices):
+                if not s.sample:
+                    continue
+                for flag in return_poltype_flag(s.poltype):
+                    zz = None if z is None else z[stride * ncall: stride * (ncall + 1)]
+                    uu = None if u is None else u[stride * ncall: stride * (ncall + 1)]
+                    acc.append(self.sample_index_mh(ic, j, flag_to_map_n(flag), nsample, ml_mode, zz, uu,
+                                                    seed + 7919 * ncall))
+                    ncall += 1
+        chisq = self.compute_chisq() if (sampled and stats) else None
+        return acc, chisq
+
+    def decisions(self, nsample: int, fullsky: bool):
+        n = nsample if fullsky else nsample * self.npix
+        dec = np.full(n, 255, dtype=np.uint8)
+        lnl = np.full(n, np.nan)
+        self._ck(self.lib.dang_gpu_get_decisions(self.h, dec.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(lnl)))
+        return dec, lnl
+
+    def chisq_planes(self) -> Tuple[np.ndarray, int]:
+        planes = np.zeros(self.nmaps)
+        n = C.c_int64()
+        lo, hi = self.cfg.pol_type
+        self._ck(self.lib.dang_gpu_chisq(self.h, lo, hi, _dp(planes), C.byref(n)))
+        return planes, n.value
+
+    def compute_chisq(self) -> float:
+        """compute_chisq: sum(chi_map)/nump with nump = nmaps * #unmasked (SURVEY Q9 convention)."""
+        planes, n = self.chisq_planes()
+        total = 0.0
+        for k in range(self.nmaps):
+            total = total + planes[k]
+        return total / float(self.nmaps * n)
+
+    def update_sky_model(self):
+        """update_sky_model (+ chi_map): downloads sky_model, res_map, chi_map for this handle's pixels."""
+        sky = np.zeros((self.nbands, self.nmaps, self.npix))
+        res = np.zeros((self.nbands, self.nmaps, self.npix))
+        chi = np.zeros((self.nmaps, self.npix))
+        lo, hi = self.cfg.pol_type
+        self._ck(self.lib.dang_gpu_get_sky_model(self.h, lo, hi, _dp(sky), _dp(res), _dp(chi)))
+        return sky, res, chi
+
+    def index_mean(self, ic: int, nind: int, map_n: int) -> float:
+        m = C.c_double()
+        self._ck(self.lib.dang_gpu_index_mean(self.h, ic, nind, map_n, C.byref(m)))
+        return m.value
+
+    def gibbs_iteration(self, it: int, eta=None, z=None, u=None, seed: int = 0):
+        """Loop body of src/dang.f90:87-126 restricted to the hot path: sample_cg_groups, then
+        (iter > 1) sample_spectral_parameters.  Returns the chi-square after each block."""
+        r1 = self.sample_cg_groups(eta=eta, seed=seed + 2 * it)
+        r2 = None
+        if it > 1:
+            r2 = self.sample_spectral_parameters(z=z, u=u, seed=seed + 2 * it + 1)
+        return r1, r2
+
+    # ------------------------------------------------------------------ instrumentation
+    def sync(self):
+        self._ck(self.lib.dang_gpu_sync(self.h))
+
+    def event_record(self, slot: int):
+        self._ck(self.lib.dang_gpu_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.dang_gpu_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self, reset: bool = False) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.dang_gpu_launch_count(self.h, C.byref(n), int(reset)))
+        return n.value
+
+    def kernel_stats(self, reset: bool = False):
+        out = {}
+        for k in range(KERNEL_COUNT):
+            n, ms, by = C.c_int64(), C.c_double(), C.c_double()
+            self._ck(self.lib.dang_gpu_kernel_stats(self.h, k, C.byref(n), C.byref(ms), C.byref(by), int(reset)))
+            out[self.lib.dang_gpu_kernel_name(k).decode()] = dict(launches=n.value, ms=ms.value, bytes=by.value)
+        return out
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = _lib.load().dang_gpu_comm_unique_id(buf)
+    if rc != 0:
+        raise DangGpuError(f"dang_gpu_comm_unique_id rc={rc}: {_lib.load().dang_gpu_last_error(None).decode()}")
+    return buf.raw

@@ -1,0 +1,189 @@
+/*
+ * dang_gpu.h -- C ABI of the B200-native replacement for hermda02/dang's Gibbs hot path.
+ *
+ * The reference has no plugin/FFI layer; its "interface" for this path is the set of Fortran
+ * call sites in the Gibbs loop (src/dang.f90:87-126) and the three objects they take
+ * (dang_params, dang_data, dang_comps).  Each entry point below names the reference routine
+ * or call site it replaces; fortran/dang_gpu_mod.f90 is the iso_c_binding shim a maintainer
+ * adds, and dang_b200/engine.py is the same binding through ctypes.
+ *
+ * Conventions
+ *   - real(dp) <-> double, integer(i4b) <-> int32_t (int), logical(lgt) <-> int (0/1).
+ *   - Host arrays are the reference's own allocatables, passed by c_loc, in Fortran layout
+ *     A(0:npix-1, nmaps [, nbands]) == C [band][stokes][pix]; FULL-SKY size even when the
+ *     handle owns only a pixel slice.  Host memory stays owned by the caller; every call copies.
+ *   - Plane / map numbers are the reference's 1-based values (1=I, 2=Q, 3=U; map_n -1 = Q+U);
+ *     pol flags are the bit flags of return_poltype_flag (src/dang_util_mod.f90:228-292);
+ *     component / band / index / cg-group numbers are 0-based except `cg_group`, which is the
+ *     value of COMP_CG_GROUPnn (1-based) as stored in c%cg_group.
+ *   - One handle == one process == one GPU == one contiguous RING-ordered pixel range
+ *     [pix_lo, pix_hi).  Multi-GPU runs use one handle per rank plus dang_gpu_comm_init; the
+ *     only cross-rank traffic is the CG / lnL / chi-square scalars (NCCL all-gather).
+ *   - Every function returns 0 on success.  On failure it returns a DANG_GPU_E* code and
+ *     dang_gpu_last_error() holds the message; the shim prints it and STOPs, mirroring the
+ *     reference's `write(*,*) ...; stop` convention (e.g. src/dang_cg_mod.f90:97-101).
+ *     There is no CPU fallback anywhere in the library.
+ *   - Not thread-safe per handle; call from outside any OpenMP region.
+ */
+#ifndef DANG_GPU_H
+#define DANG_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dang_gpu dang_gpu_t;
+
+enum {
+  DANG_GPU_OK = 0,
+  DANG_GPU_EINVAL = 1,      /* bad argument                                   */
+  DANG_GPU_ECUDA = 2,       /* CUDA runtime error (no device, OOM, launch...) */
+  DANG_GPU_EUNSUPPORTED = 3,/* valid in the reference, not built yet (DESIGN.md "Out of scope") */
+  DANG_GPU_ENCCL = 4,       /* NCCL could not be loaded / failed              */
+  DANG_GPU_ESTATE = 5       /* call order violated (e.g. solve before upload) */
+};
+
+/* c%type, src/dang_component_mod.f90:791-809 */
+enum { DANG_COMP_POWERLAW = 1, DANG_COMP_MBB = 2 };
+/* c%lnl_type, src/dang_sample_mod.f90:249-258 */
+enum { DANG_LNL_CHISQ = 0, DANG_LNL_MARGINAL = 1, DANG_LNL_PRIOR = 2 };
+/* c%prior_type, src/dang_sample_mod.f90:260-266 */
+enum { DANG_PRIOR_UNIFORM = 0, DANG_PRIOR_GAUSSIAN = 1, DANG_PRIOR_JEFFREYS = 2 };
+/* ml_mode, src/dang_cg_mod.f90:254,265 */
+enum { DANG_ML_OPTIMIZE = 0, DANG_ML_SAMPLE = 1 };
+/* c%index_mode, src/dang_component_mod.f90:166-170 */
+enum { DANG_INDEX_FULLSKY = 1, DANG_INDEX_PERPIXEL = 2 };
+
+/* options for dang_gpu_set_option */
+enum {
+  /* 0 (default): reproduce compute_sample_vector's indexing (every diffuse
+   * component writes slot 1, src/dang_cg_mod.f90:1033-1034).  1: offset per component. */
+  DANG_OPT_FIX_SAMPLE_VECTOR = 1,
+  /* CG iteration form.  0 (default): one fused pass per iteration (d.q from a recurrence);
+   * 1: classic two-pass form with d.q summed directly, as cg_search writes it (:296-305). */
+  DANG_OPT_CG_TWO_PASS = 2,
+  /* Full-sky Metropolis likelihood.  0 (default): per-band sufficient statistics gathered in
+   * one pass, proposals evaluated from them; 1: stream the maps once per proposal, the
+   * reference's own structure (src/dang_sample_mod.f90:282-324). */
+  DANG_OPT_FULLSKY_STREAM = 3,
+  /* 1: record CUDA events around every kernel launch (dang_gpu_kernel_stats). */
+  DANG_OPT_PROFILE = 4,
+  /* CG iterations enqueued between host checks of the convergence flag (default 8). */
+  DANG_OPT_CG_CHUNK = 5,
+  /* 1: per-pixel chains record every decision / lnL (dang_gpu_get_decisions); parity tests. */
+  DANG_OPT_RECORD_DECISIONS = 6
+};
+
+/* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
+int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, int ncomp,
+                    int64_t pix_lo, int64_t pix_hi, dang_gpu_t **h);
+int dang_gpu_destroy(dang_gpu_t *h);
+const char *dang_gpu_last_error(const dang_gpu_t *h); /* h may be NULL: last create() error */
+int dang_gpu_set_option(dang_gpu_t *h, int option, double value);
+int dang_gpu_sync(dang_gpu_t *h);
+
+/* ---- multi-GPU: replaces the reference's unused MPI (src/dang_util_mod.f90:48-57) ----
+ * Rank 0 calls dang_gpu_comm_unique_id and broadcasts the 128 bytes with whatever the host
+ * has (MPI_Bcast in Fortran, torch.distributed here); then every rank calls comm_init. */
+int dang_gpu_comm_unique_id(char id[128]);
+int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]);
+
+/* ---- bp(j): type bandinfo, src/dang_bp_mod.f90:7-15 (as left by init_bp_mod :19-60) ----
+ * nu_c [Hz]; n_bp == 0 <=> bp%id == 'delta'; nu0 [Hz]; tau0 already normalised (:62-81). */
+int dang_gpu_set_band(dang_gpu_t *h, int band, double nu_c_hz, int n_bp, const double *nu0_hz,
+                      const double *tau0);
+
+/* ---- ddata: sig_map, rms_map, masks(:,1), gain, offset, src/dang_data_mod.f90:23-34 ----
+ * Call after initialize_data_module (:68-86) and again after swap_cg_maps (dang.f90:92-97). */
+int dang_gpu_upload_maps(dang_gpu_t *h, const double *sig_map, const double *rms_map,
+                         const double *mask, const double *gain, const double *offset);
+int dang_gpu_set_gain_offset(dang_gpu_t *h, const double *gain, const double *offset);
+
+/* ---- component_list(ic): type dang_comps, src/dang_component_mod.f90:12-55 ---- */
+int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label,
+                           double nu_ref_hz, int cg_group, int sample_amplitude,
+                           const double *amplitude /* (npix,nmaps) */,
+                           const double *indices /* (npix,nmaps,nindices) */);
+int dang_gpu_set_index(dang_gpu_t *h, int ic, int nind, int sample_index, int index_mode,
+                       int lnl_type, int prior_type, const double gauss_prior[2],
+                       const double uni_prior[2], double step_size, int sample_nside,
+                       const int *pol_flags, int nflag);
+int dang_gpu_set_amplitude(dang_gpu_t *h, int ic, const double *amplitude);
+int dang_gpu_set_indices(dang_gpu_t *h, int ic, const double *indices);
+int dang_gpu_get_amplitude(dang_gpu_t *h, int ic, double *amplitude); /* -> c%amplitude */
+int dang_gpu_get_indices(dang_gpu_t *h, int ic, double *indices);     /* -> c%indices   */
+int dang_gpu_get_step_size(dang_gpu_t *h, int ic, int nind, double *step_size);
+
+/* ---- cg_groups(i): constructor_cg, src/dang_cg_mod.f90:57-120 ---- */
+int dang_gpu_set_cg_group(dang_gpu_t *h, int cg_group, int i_max, double converge,
+                          const int *pol_flags, int nflag);
+
+/* ---- amplitude draw: compute_rhs + cg_search + unpack_amplitudes for one (group, flag),
+ * src/dang_cg_mod.f90:167-169 (bodies :326-596, :179-324, :598-911, :913-1100, :1284-1396).
+ * eta: the S*npix standard normals cg_search draws (:256-262), full-sky, [stokes][pix];
+ * NULL => generated on the device from `seed` (Philox4x32-10, DESIGN.md "RNG").
+ * n_iter: final value of the reference's loop counter i; delta_final: last sum(r*r). */
+int dang_gpu_cg_solve(dang_gpu_t *h, int cg_group, int flag_n, int ml_mode, const double *eta,
+                      uint64_t seed, int *n_iter, double *delta_final);
+/* per-iteration delta trace of the last solve (delta after init, then after each pass) */
+int dang_gpu_cg_trace(dang_gpu_t *h, double *delta, int max_len, int *len);
+/* the saved solution vector self%x of one (group, flag), full-sky layout [comp][stokes][pix] */
+int dang_gpu_get_cg_x(dang_gpu_t *h, int cg_group, int flag_n, double *x);
+
+/* ---- spectral-parameter draw: sample_index_mh(ddata,c,nind,map_n),
+ * src/dang_sample_mod.f90:88-485 (+ update_sample_model :520-568, evaluate_lnL etc. in
+ * src/dang_lnl_mod.f90, priors src/dang_util_mod.f90:112-121).
+ * z, u: injected deviates, slot-indexed (a slot is used only if the reference would draw it):
+ *   full-sky: z[l], u[l], l < nsample;  per-pixel: z[l*npix + pix], u[l*npix + pix] (full sky).
+ *   NULL => device RNG from `seed`.
+ * accept: number of accepted proposals (summed over this handle's pixels in per-pixel mode). */
+int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsample, int ml_mode,
+                          const double *z, const double *u, uint64_t seed, double *accept);
+/* decisions of the last dang_gpu_sample_index call (parity instrumentation):
+ * 0 rejected, 1 accepted, 2 out of prior bounds, 3 masked; full-sky: nsample entries,
+ * per-pixel: [l*npix + pix] for this handle's pixels (other entries untouched).
+ * lnl: lnl_new of every evaluated proposal, same indexing (may be NULL). */
+int dang_gpu_get_decisions(dang_gpu_t *h, unsigned char *decisions, double *lnl);
+/* tune_spectral_parameter_length, src/dang_sample_mod.f90:623-717 (full-sky chain).
+ * z, u hold max_blocks*nsample slots, [block*nsample + l]. */
+int dang_gpu_tune_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsample, int ml_mode,
+                        const double *z, const double *u, uint64_t seed, int max_blocks,
+                        int *blocks_run, double *step_size);
+
+/* ---- chi-square: update_sky_model + compute_chisq, src/dang_data_mod.f90:339-396,494-526
+ * (called from write_stats_to_term :528-570).  pol_lo..pol_hi = ddata%pol_type(1)..(size).
+ * chisq_planes[nmaps]: un-normalised sum over this handle's... all ranks' pixels of
+ * chi_map(:,k) (already divided by nbands, :523); n_unmasked: unmasked pixel count (all ranks).
+ * The host forms chisq = sum(chisq_planes)/nump with its own nump. */
+int dang_gpu_chisq(dang_gpu_t *h, int pol_lo, int pol_hi, double *chisq_planes,
+                   int64_t *n_unmasked);
+/* sky_model, res_map (npix,nmaps,nbands) and chi_map (npix,nmaps): only this handle's pixels
+ * are written; any pointer may be NULL.  Needed only when write_maps is due (dang.f90:119). */
+int dang_gpu_get_sky_model(dang_gpu_t *h, int pol_lo, int pol_hi, double *sky_model,
+                           double *res_map, double *chi_map);
+/* mask_avg(c%indices(:,map_n,nind), masks(:,1)), src/dang_util_mod.f90:186-206 */
+int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean);
+
+/* ---- instrumentation (bench.py) ---- */
+int dang_gpu_host_alloc(void **ptr, uint64_t bytes); /* pinned host memory */
+int dang_gpu_host_free(void *ptr);
+int dang_gpu_event_record(dang_gpu_t *h, int slot);  /* slot 0..15, on the handle's stream */
+int dang_gpu_event_elapsed_ms(dang_gpu_t *h, int slot_a, int slot_b, float *ms);
+int dang_gpu_launch_count(dang_gpu_t *h, int64_t *launches, int reset);
+/* per-kernel totals since the last reset (needs DANG_OPT_PROFILE): kernel ids in dang_gpu.h
+ * order below; bytes = algorithmic HBM bytes of those launches (DESIGN.md "Kernels"). */
+enum {
+  DANG_K_RHS_BLOCKS = 0, DANG_K_CG_PASS = 1, DANG_K_CG_DQ = 2, DANG_K_CG_UPDATE = 3,
+  DANG_K_CHISQ = 4, DANG_K_SKYMODEL = 5, DANG_K_MH_DATA = 6, DANG_K_MH_FULLSKY_LNL = 7,
+  DANG_K_MH_SUFFSTAT = 8, DANG_K_MH_PERPIXEL = 9, DANG_K_SCALAR = 10, DANG_K_COUNT = 11
+};
+int dang_gpu_kernel_stats(dang_gpu_t *h, int kernel, int64_t *launches, double *total_ms,
+                          double *bytes, int reset);
+const char *dang_gpu_kernel_name(int kernel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

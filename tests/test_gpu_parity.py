@@ -1,0 +1,282 @@
+"""GPU parity tests: every call goes through the C ABI (dang_b200.engine -> libdang_gpu.so) and
+is compared with the CPU oracle on the same seeded inputs and injected deviates.
+
+Bars (BASELINE.json north_star): accept/reject decisions and pixel indexing bit-exact;
+amplitude maps, index maps, chi-square and lnL within 1e-10 relative (norm-wise) in fp64.
+"""
+import numpy as np
+import pytest
+
+from conftest import TOL, rel_err
+from helpers import clone_sky, deviates, small_case
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(name="c1", nside=16, **kw):
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case(name, nside, **kw)
+    return cfg, sky, Oracle(cfg, sky), Engine(cfg, sky)
+
+
+# ------------------------------------------------------------------ chi-square / sky model
+@pytest.mark.parametrize("name,nside", [("c1", 16), ("c2", 16), ("c3", 8), ("c4", 8)])
+def test_chisq_and_sky_model(name, nside):
+    cfg, sky, ora, eng = make_pair(name, nside)
+    ora.update_sky_model()
+    chisq_o, planes_o = ora.compute_chisq()
+    planes_g, n_unmasked = eng.chisq_planes()
+    assert n_unmasked == int((sky.mask != 0).sum())
+    assert rel_err(planes_g, planes_o) < TOL
+    assert abs(eng.compute_chisq() - chisq_o) <= TOL * abs(chisq_o)
+    sky_g, res_g, chi_g = eng.update_sky_model()
+    assert rel_err(sky_g, ora.sky_model()) < TOL
+    assert rel_err(res_g, ora.res_map()) < TOL
+    assert rel_err(chi_g, ora.chi_map()) < TOL
+    # pixel indexing: masked pixels carry exactly zero chi-square
+    assert np.all(chi_g[:, sky.mask == 0] == 0.0)
+
+
+def test_chisq_missval_mask_and_ragged_size():
+    # nside=4 -> 192 pixels (not a multiple of the 64-pixel plane padding once sliced);
+    # mask uses the reference's missval sentinel as well as zeros
+    from dang_b200.config import MISSVAL
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c1", 4)
+    sky.mask[::7] = MISSVAL
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    ora.update_sky_model()
+    chisq_o, planes_o = ora.compute_chisq()
+    planes_g, n = eng.chisq_planes()
+    assert n == int(((sky.mask != 0) & (sky.mask != MISSVAL)).sum())
+    assert rel_err(planes_g, planes_o) < TOL
+
+
+# ------------------------------------------------------------------ amplitude draw
+@pytest.mark.parametrize("two_pass", [0, 1])
+@pytest.mark.parametrize("ml_mode", ["optimize", "sample"])
+def test_cg_solve_matches_oracle(two_pass, ml_mode):
+    from dang_b200.engine import OPT_CG_TWO_PASS
+    cfg, sky, ora, eng = make_pair("c1", 16)
+    eng.set_option(OPT_CG_TWO_PASS, two_pass)
+    eta = np.random.default_rng(5).standard_normal(2 * cfg.npix)
+    it_o, delta_o, trace_o = ora.cg_search_trace(ml_mode=1 if ml_mode == "sample" else 0, eta=eta)
+    it_g, delta_g = eng.cg_solve(0, 0, ml_mode, eta=eta)
+    trace_g = eng.cg_trace()
+    assert it_g == it_o, (it_g, it_o, trace_g, trace_o)
+    # the residual norm follows the oracle's trajectory iteration by iteration
+    assert np.allclose(trace_g, trace_o, rtol=1e-6, atol=0)
+    for ic in range(len(cfg.comps)):
+        assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
+    assert rel_err(eng.cg_x(), ora.cg_x()) < TOL
+    # masked pixels keep their initial amplitude exactly (zero rows / columns)
+    m = sky.mask == 0
+    for ic, c in enumerate(cfg.comps):
+        assert np.array_equal(eng.amplitude(ic)[:, m], sky.amplitude[c.label][:, m])
+
+
+def test_cg_sample_vector_quirk_and_fix():
+    """with two diffuse components the reference's fluctuation lands in slot 1 only;
+    DANG_OPT_FIX_SAMPLE_VECTOR switches to the per-component form.  Both match the oracle."""
+    from dang_b200.engine import OPT_FIX_SAMPLE_VECTOR
+    eta = np.random.default_rng(6).standard_normal(2 * 12 * 8 * 8)
+    res = {}
+    for fix in (0, 1):
+        cfg, sky, ora, eng = make_pair("c1", 8)
+        eng.set_option(OPT_FIX_SAMPLE_VECTOR, fix)
+        ora.cg_search_trace(ml_mode=1, eta=eta, fix_q1=bool(fix))
+        eng.cg_solve(0, 0, "sample", eta=eta)
+        for ic in range(2):
+            assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
+        res[fix] = eng.amplitude(1).copy()
+    assert rel_err(res[0], res[1]) > 1e-3  # the two conventions really differ
+
+
+def test_cg_warm_start_across_iterations():
+    """Q10: x is seeded from c%amplitude once and then warm-started from the saved x."""
+    cfg, sky, ora, eng = make_pair("c1", 8)
+    rng = np.random.default_rng(7)
+    for it in range(3):
+        eta = rng.standard_normal(2 * cfg.npix)
+        it_o, _, _ = ora.cg_search_trace(ml_mode=1, eta=eta)
+        it_g, _ = eng.cg_solve(0, 0, "sample", eta=eta)
+        assert it_g == it_o
+        for ic in range(2):
+            assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
+
+
+@pytest.mark.parametrize("poltype", ["Q", "U", "Q,U"])
+def test_cg_single_plane_flags(poltype):
+    from dang_b200.config import return_poltype_flag
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c1", 8)
+    cfg.cg_groups[0].poltype = poltype
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    rng = np.random.default_rng(8)
+    for f, _ in enumerate(return_poltype_flag(poltype)):
+        eta = rng.standard_normal(cfg.npix)
+        it_o, _, _ = ora.cg_search_trace(flag_n=f, ml_mode=1, eta=eta)
+        it_g, _ = eng.cg_solve(0, f, "sample", eta=eta)
+        assert it_g == it_o
+    for ic in range(2):
+        assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
+
+
+def test_cg_one_component_with_out_of_group_subtraction():
+    """Only synch is solved for; dust is not amplitude-sampled, so its signal is subtracted
+    from the data first (compute_rhs :427-443)."""
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c1", 8)
+    cfg.comps[1].amp_sample = False
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    eta = np.random.default_rng(9).standard_normal(2 * cfg.npix)
+    it_o, _, _ = ora.cg_search_trace(ml_mode=1, eta=eta)
+    it_g, _ = eng.cg_solve(0, 0, "sample", eta=eta)
+    assert it_g == it_o
+    for ic in range(2):
+        assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
+
+
+def test_cg_recovers_noiseless_sky():
+    """Known answer: noiseless data, indices at truth => optimize-mode CG returns the input sky."""
+    from dang_b200.engine import Engine
+    from dang_b200.synth import TRUE_THETA, make_config, make_sky, band_sed
+    cfg = make_config("c1", nside=8)
+    sky = make_sky(cfg)
+    sky.sig[:] = 0.0
+    for c in cfg.comps:
+        for k, v in enumerate(TRUE_THETA[c.label]):
+            sky.indices[c.label][k][:] = v
+        for j, b in enumerate(cfg.bands):
+            sky.sig[j, 1:3] += sky.truth[c.label][1:3] * band_sed(b, c, *TRUE_THETA[c.label])
+    eng = Engine(cfg, sky)
+    eng.cg_solve(0, 0, "optimize")
+    m = sky.mask != 0
+    for ic, c in enumerate(cfg.comps):
+        a = eng.amplitude(ic)
+        assert np.max(np.abs(a[1:3][:, m] - sky.truth[c.label][1:3][:, m])) < 1e-6
+    assert eng.compute_chisq() < 1e-12
+
+
+def test_device_rng_eta_matches_philox_definition():
+    """eta == NULL: the device draws eta from Philox4x32-10; feeding the oracle the same stream
+    (restated independently in oracle/dang_oracle.c) gives the same amplitudes."""
+    from oracle.binding import philox_normals
+    cfg, sky, ora, eng = make_pair("c1", 8)
+    seed = 1234567
+    eta = philox_normals(seed, 1, 0, 2 * cfg.npix)
+    assert abs(eta.mean()) < 0.1 and abs(eta.std() - 1.0) < 0.1
+    it_o, _, _ = ora.cg_search_trace(ml_mode=1, eta=eta)
+    it_g, _ = eng.cg_solve(0, 0, "sample", eta=None, seed=seed)
+    assert it_g == it_o
+    for ic in range(2):
+        assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < 1e-9
+
+
+# ------------------------------------------------------------------ spectral-parameter draw
+def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11):
+    from dang_b200.engine import OPT_RECORD, Engine
+    from oracle.binding import Oracle
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    eng.set_option(OPT_RECORD, 1)
+    z, u = deviates(cfg, nsample, seed=seed)
+    acc_o, dec_o, lnl_o = ora.sample_index_mh(ic, nind, -1, nsample, 1 if ml_mode == "sample" else 0, z, u,
+                                              want_trace=True)
+    acc_g = eng.sample_index_mh(ic, nind, -1, nsample, ml_mode, z, u)
+    dec_g, lnl_g = eng.decisions(nsample, fullsky=False)
+    return ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g)
+
+
+@pytest.mark.parametrize("name,ic,nind,nside", [("c1", 0, 0, 16), ("c3", 1, 0, 4), ("c4", 1, 0, 8), ("c4", 1, 1, 8)])
+def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside):
+    cfg, sky = small_case(name, nside)
+    cfg.comps[ic].indices[nind].sample = True
+    cfg.comps[ic].indices[nind].region = "per-pixel"
+    nsample = 12
+    ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(cfg, sky, ic, nind, nsample)
+    assert np.array_equal(dec_g, dec_o), f"{(dec_g != dec_o).sum()} decisions differ"
+    assert acc_g == acc_o
+    ev = dec_o < 2
+    assert rel_err(lnl_g[ev], lnl_o[ev]) < TOL
+    # accepted proposals are stored verbatim => index maps agree to the last bit up to the
+    # 1-ulp regrouping of step*z; masked pixels are zeroed exactly as index_map is (:223,:465)
+    idx_g, idx_o = eng.indices(ic), ora.indices(ic)
+    assert rel_err(idx_g, idx_o) < 1e-14
+    assert np.all(idx_g[nind][1:3][:, sky.mask == 0] == 0.0)
+    assert np.array_equal(idx_g[nind][0], idx_o[nind][0])  # I plane untouched
+
+
+def test_perpixel_optimize_mode_and_uniform_prior():
+    cfg, sky = small_case("c1", 8)
+    cfg.comps[0].indices[0].prior = "uniform"
+    cfg.comps[0].indices[0].uni = (-3.2, -2.9)  # tight bounds => many out-of-bounds proposals (Q5)
+    ora, eng, (acc_o, dec_o, _), (acc_g, dec_g, _) = run_perpixel(cfg, sky, 0, 0, 16, ml_mode="optimize")
+    assert (dec_o == 2).sum() > 0
+    assert np.array_equal(dec_g, dec_o)
+    assert acc_g == acc_o
+    assert rel_err(eng.indices(0), ora.indices(0)) < 1e-14
+
+
+def test_perpixel_marginal_lnl():
+    cfg, sky = small_case("c1", 8)
+    cfg.comps[0].indices[0].lnl_type = "marginal"
+    ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(cfg, sky, 0, 0, 8)
+    assert np.array_equal(dec_g, dec_o)
+    ev = dec_o < 2
+    assert rel_err(lnl_g[ev], lnl_o[ev]) < TOL
+
+
+@pytest.mark.parametrize("stream", [0, 1])
+@pytest.mark.parametrize("name,ic,nind", [("c2", 1, 0), ("c4", 1, 1), ("c1", 0, 0)])
+def test_fullsky_metropolis(stream, name, ic, nind):
+    from dang_b200.engine import OPT_FULLSKY_STREAM, Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case(name, 16)
+    spec = cfg.comps[ic].indices[nind]
+    spec.sample, spec.region = True, "fullsky"
+    for c in cfg.comps:  # full-sky indices are uniform maps
+        for k, s in enumerate(c.indices):
+            sky.indices[c.label][k][:] = s.init
+    spec.step = {0: 0.002, 1: 0.02}[nind]
+    nsample = 24
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    eng.set_option(OPT_FULLSKY_STREAM, stream)
+    rng = np.random.default_rng(13)
+    z, u = rng.standard_normal(nsample), rng.random(nsample)
+    acc_o, dec_o, lnl_o = ora.sample_index_mh(ic, nind, -1, nsample, 1, z, u, want_trace=True)
+    acc_g = eng.sample_index_mh(ic, nind, -1, nsample, "sample", z, u)
+    dec_g, lnl_g = eng.decisions(nsample, fullsky=True)
+    assert np.array_equal(dec_g, dec_o[:nsample]), (dec_g, dec_o[:nsample])
+    assert acc_g == acc_o
+    ev = dec_o[:nsample] < 2
+    assert ev.sum() > 0 and 0 < acc_o < ev.sum()  # a non-trivial chain
+    assert rel_err(lnl_g[ev], lnl_o[:nsample][ev]) < TOL
+    assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-14
+
+
+def test_full_gibbs_chain_c1():
+    """Three Gibbs iterations of config c1 (CG amplitudes + per-pixel beta_s) with injected
+    deviates: amplitudes, indices and chi-square follow the oracle throughout."""
+    cfg, sky, ora, eng = make_pair("c1", 8, perturb=False)
+    rng = np.random.default_rng(21)
+    nsample = 10
+    for it in range(1, 4):
+        eta = rng.standard_normal(2 * cfg.npix)
+        its_o, _ = ora.sample_cg_group(0, 1, eta)
+        r = eng.sample_cg_groups(eta=eta)
+        assert r[0][0] == its_o[0]
+        chisq_o, _ = ora.compute_chisq()
+        assert abs(r[1] - chisq_o) <= TOL * chisq_o
+        if it > 1:
+            z, u = rng.standard_normal(nsample * cfg.npix), rng.random(nsample * cfg.npix)
+            ora.sample_spectral_parameters(nsample, 1, z, u)
+            acc, chisq_g = eng.sample_spectral_parameters(nsample=nsample, z=z, u=u)
+            chisq_o, _ = ora.compute_chisq()
+            assert abs(chisq_g - chisq_o) <= TOL * chisq_o
+        for ic in range(2):
+            assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
+            assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-13
