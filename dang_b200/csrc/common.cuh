@@ -26,6 +26,15 @@ struct BandView {
   int off;      // offset into bp_nu0 / bp_tau0
 };
 
+// Device-resident per-handle tables (refreshed whenever an index map changes)
+struct SedTable {
+  int nonuni[DG_MAX_COMPS * 3][DG_MAXIND];     // scratch of uniform_check_kernel
+  int uni[DG_MAX_COMPS * 3];                   // all index maps of comp c constant on plane k
+  double sed[DG_MAX_COMPS * 3][DG_MAX_BANDS];  // tabulated SED for uniform (c, k)
+  double lnr_hi[DG_MAX_COMPS][DG_MAX_BANDS];   // ln(nu_c / nu_ref) as a double-double
+  double lnr_lo[DG_MAX_COMPS][DG_MAX_BANDS];
+};
+
 struct CompView {
   int type;     // DANG_COMP_*
   int nind;
@@ -43,7 +52,10 @@ struct ModelView {
   int64_t pix_lo, npix;  // global offset / full-sky size (RNG slots are global)
   BandView band[DG_MAX_BANDS];
   CompView comp[DG_MAX_COMPS];
-  const double *bp_nu0, *bp_tau0;
+  const double *bp_nu0, *bp_tau0;          // flattened bandpass tables, nbp samples in total
+  const double *bp_lnr_hi, *bp_lnr_lo;     // [ncomp][nbp] ln(nu0 / nu_ref)
+  int nbp;
+  const SedTable *tab;
   const double *sig, *rms;   // [nbands][nmaps][Ppad]
   const unsigned char *mask; // [Ppad], 1 = use pixel (mask /= 0 and /= missval)
   double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
@@ -69,40 +81,69 @@ __device__ __forceinline__ double2 ldg_stream2(const double *p) {
 
 // ---------------------------------------------------------------- SEDs
 // eval_sed, src/dang_component_mod.f90:778-813; evaluate_powerlaw :886-918; evaluate_mbb :920-958.
-// The arithmetic keeps the reference's form (pow / exp()-1, same operation order) so that the
-// only difference to glibc is the last-ulp behaviour of CUDA's pow/exp.
-__device__ __forceinline__ double sed_powerlaw(const ModelView &mv, const BandView &b,
-                                               double nu_ref, double beta) {
-  if (b.n == 0) return pow(b.nu_c / nu_ref, beta);
+//
+// (nu/nu_ref)**beta is evaluated as exp(beta * ln(nu/nu_ref)) with the logarithm precomputed on
+// the host in extended precision and carried as a double-double (hi, lo), so the result is
+// within ~1 ulp of a correctly rounded pow at a third of its cost; the Planck factor keeps the
+// reference's exp()-1 form and operation order.
+__device__ __forceinline__ double exp_scaled(double beta, double l_hi, double l_lo) {
+  const double p = beta * l_hi;
+  const double e = fma(beta, l_hi, -p) + beta * l_lo;
+  const double r = exp(p);
+  return fma(r, e, r);
+}
+
+__device__ __forceinline__ double sed_powerlaw(const ModelView &mv, int ic, int band, double beta) {
+  const BandView &b = mv.band[band];
+  const SedTable &t = *mv.tab;
+  if (b.n == 0) return exp_scaled(beta, t.lnr_hi[ic][band], t.lnr_lo[ic][band]);
+  const double *lh = mv.bp_lnr_hi + (size_t)ic * mv.nbp, *ll = mv.bp_lnr_lo + (size_t)ic * mv.nbp;
   double spectrum = 0.0;
   for (int i = 0; i < b.n; i++) {
-    const double nu0 = mv.bp_nu0[b.off + i];
-    if (nu0 == 0.0) continue;
-    spectrum = spectrum + mv.bp_tau0[b.off + i] * pow(nu0 / nu_ref, beta);
+    if (mv.bp_nu0[b.off + i] == 0.0) continue;
+    spectrum = spectrum + mv.bp_tau0[b.off + i] * exp_scaled(beta, lh[b.off + i], ll[b.off + i]);
   }
   return spectrum;
 }
 
-__device__ __forceinline__ double sed_mbb(const ModelView &mv, const BandView &b, double nu_ref,
-                                          double beta, double td) {
+__device__ __forceinline__ double sed_mbb(const ModelView &mv, int ic, int band, double beta,
+                                          double td) {
+  const BandView &b = mv.band[band];
+  const SedTable &t = *mv.tab;
+  const double nu_ref = mv.comp[ic].nu_ref;
   const double z = DG_H / (DG_KB * td);
   const double eref = exp(z * nu_ref) - 1.0;
-  if (b.n == 0) return eref / (exp(z * b.nu_c) - 1.0) * pow(b.nu_c / nu_ref, beta + 1.0);
+  if (b.n == 0)
+    return eref / (exp(z * b.nu_c) - 1.0) * exp_scaled(beta + 1.0, t.lnr_hi[ic][band], t.lnr_lo[ic][band]);
+  const double *lh = mv.bp_lnr_hi + (size_t)ic * mv.nbp, *ll = mv.bp_lnr_lo + (size_t)ic * mv.nbp;
   double spectrum = 0.0;
   for (int i = 0; i < b.n; i++) {
     const double nu0 = mv.bp_nu0[b.off + i];
     if (nu0 == 0.0) continue;
-    spectrum = spectrum +
-               mv.bp_tau0[b.off + i] * eref / (exp(z * nu0) - 1.0) * pow(nu0 / nu_ref, beta + 1.0);
+    spectrum = spectrum + mv.bp_tau0[b.off + i] * eref / (exp(z * nu0) - 1.0) *
+                              exp_scaled(beta + 1.0, lh[b.off + i], ll[b.off + i]);
   }
   return spectrum;
 }
 
-__device__ __forceinline__ double sed_eval(const ModelView &mv, int ic, int band, double t0,
+// SED of component ic in `band` for explicit parameters (a Metropolis proposal, or a pixel)
+__device__ __forceinline__ double sed_theta(const ModelView &mv, int ic, int band, double t0,
+                                            double t1) {
+  if (mv.comp[ic].type == 1) return sed_powerlaw(mv, ic, band, t0);
+  return sed_mbb(mv, ic, band, t0, t1);
+}
+
+// SED of component ic at a pixel of plane k.  When every index map of the component is constant
+// over this handle's pixels of that plane (always true for full-sky-sampled or never-sampled
+// indices) the per-band value was tabulated once by sed_table_kernel with the very same
+// arithmetic, and the pixel kernels become pure HBM streams.
+__device__ __forceinline__ bool sed_uniform(const ModelView &mv, int ic, int k) {
+  return mv.tab->uni[ic * 3 + k] != 0;
+}
+__device__ __forceinline__ double sed_eval(const ModelView &mv, int ic, int k, int band, double t0,
                                            double t1) {
-  const CompView &c = mv.comp[ic];
-  if (c.type == 1) return sed_powerlaw(mv, mv.band[band], c.nu_ref, t0);
-  return sed_mbb(mv, mv.band[band], c.nu_ref, t0, t1);
+  if (sed_uniform(mv, ic, k)) return mv.tab->sed[ic * 3 + k][band];
+  return sed_theta(mv, ic, band, t0, t1);
 }
 
 // ---------------------------------------------------------------- Philox4x32-10

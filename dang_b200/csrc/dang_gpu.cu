@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -21,6 +22,7 @@
 #include "kernels_cg.cuh"
 #include "kernels_data.cuh"
 #include "kernels_mh.cuh"
+#include "kernels_uni.cuh"
 
 // ---------------------------------------------------------------- errors
 namespace {
@@ -150,8 +152,12 @@ struct dang_gpu {
   double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
 
   BandHost band[DG_MAX_BANDS];
-  double *bp_nu0 = nullptr, *bp_tau0 = nullptr;
-  bool bp_dirty = true;
+  double *bp_nu0 = nullptr, *bp_tau0 = nullptr, *bp_lnr_hi = nullptr, *bp_lnr_lo = nullptr;
+  int nbp = 0;
+  bool bp_dirty = true;   // band / component constants changed: rebuild the static tables
+  bool tab_dirty = true;  // an index map changed: re-check uniformity, re-tabulate SEDs
+  SedTable *tab = nullptr;
+  int uni_host[DG_MAX_COMPS * 3] = {};  // host copy of SedTable::uni (refreshed with the tables)
   CompHost comp[DG_MAX_COMPS];
   std::vector<CgGroupHost> cg;
 
@@ -256,6 +262,14 @@ void d2h_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
                        h->P * sizeof(double), nplanes, cudaMemcpyDeviceToHost, h->stream));
 }
 
+// ln(a/b) as a double-double from an extended-precision logarithm
+void dd_log_ratio(double a, double b, double &hi, double &lo) {
+  const long double L = logl((long double)a / (long double)b);
+  hi = (double)L;
+  lo = (double)(L - (long double)hi);
+}
+
+// static tables: flattened bandpasses, ln(nu/nu_ref) per (component, band [, bandpass sample])
 void upload_bandpasses(dang_gpu *h) {
   if (!h->bp_dirty) return;
   std::vector<double> nu0, tau0;
@@ -263,16 +277,34 @@ void upload_bandpasses(dang_gpu *h) {
     nu0.insert(nu0.end(), h->band[j].nu0.begin(), h->band[j].nu0.end());
     tau0.insert(tau0.end(), h->band[j].tau0.begin(), h->band[j].tau0.end());
   }
-  dfree(h->bp_nu0);
-  dfree(h->bp_tau0);
-  if (!nu0.empty()) {
+  dfree(h->bp_nu0); dfree(h->bp_tau0); dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo);
+  h->nbp = (int)nu0.size();
+  std::vector<double> lhi((size_t)h->ncomp * h->nbp + 1), llo((size_t)h->ncomp * h->nbp + 1);
+  std::vector<double> thi(DG_MAX_COMPS * DG_MAX_BANDS, 0.0), tlo(DG_MAX_COMPS * DG_MAX_BANDS, 0.0);
+  for (int c = 0; c < h->ncomp; c++) {
+    if (!h->comp[c].set) continue;
+    for (int j = 0; j < h->nbands; j++)
+      if (h->band[j].set) dd_log_ratio(h->band[j].nu_c, h->comp[c].nu_ref, thi[c * DG_MAX_BANDS + j], tlo[c * DG_MAX_BANDS + j]);
+    for (int i = 0; i < h->nbp; i++)
+      if (nu0[i] != 0.0) dd_log_ratio(nu0[i], h->comp[c].nu_ref, lhi[(size_t)c * h->nbp + i], llo[(size_t)c * h->nbp + i]);
+  }
+  if (h->nbp) {
     CK(cudaMalloc(&h->bp_nu0, nu0.size() * sizeof(double)));
     CK(cudaMalloc(&h->bp_tau0, tau0.size() * sizeof(double)));
+    CK(cudaMalloc(&h->bp_lnr_hi, lhi.size() * sizeof(double)));
+    CK(cudaMalloc(&h->bp_lnr_lo, llo.size() * sizeof(double)));
     CK(cudaMemcpyAsync(h->bp_nu0, nu0.data(), nu0.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->bp_tau0, tau0.data(), tau0.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(h->bp_lnr_hi, lhi.data(), lhi.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bp_lnr_lo, llo.data(), llo.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
+  CK(cudaMemcpyAsync((char *)h->tab + offsetof(SedTable, lnr_hi), thi.data(), sizeof(double) * thi.size(),
+                     cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync((char *)h->tab + offsetof(SedTable, lnr_lo), tlo.data(), sizeof(double) * tlo.size(),
+                     cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
   h->bp_dirty = false;
+  h->tab_dirty = true;
 }
 
 ModelView model_view(dang_gpu *h) {
@@ -307,9 +339,31 @@ ModelView model_view(dang_gpu *h) {
   }
   mv.bp_nu0 = h->bp_nu0;
   mv.bp_tau0 = h->bp_tau0;
+  mv.bp_lnr_hi = h->bp_lnr_hi;
+  mv.bp_lnr_lo = h->bp_lnr_lo;
+  mv.nbp = h->nbp;
+  mv.tab = h->tab;
   mv.sig = h->sig;
   mv.rms = h->rms;
   mv.mask = h->mask;
+  if (h->tab_dirty) {  // an index map changed since the SED tables were built
+    CK(cudaMemsetAsync((char *)h->tab + offsetof(SedTable, nonuni), 0, sizeof(((SedTable *)0)->nonuni), h->stream));
+    {
+      KTimer kt(h, DANG_K_SCALAR, 0);
+      dim3 grid(grid_for(h, h->P, DG_THREADS, 1), h->ncomp * 3 * DG_MAXIND);
+      uniform_check_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, h->tab);
+      kt.done();
+    }
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    sed_table_kernel<<<h->ncomp * 3, 32, 0, h->stream>>>(mv, h->tab);
+    kt.done();
+    // the host picks the streaming (tabulated-SED) kernel variants from these flags
+    int *hu = (int *)((char *)h->pinned + 32 * 1024);
+    CK(cudaMemcpyAsync(hu, (char *)h->tab + offsetof(SedTable, uni), sizeof(h->uni_host), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(h->uni_host, hu, sizeof(h->uni_host));
+    h->tab_dirty = false;
+  }
   return mv;
 }
 
@@ -339,6 +393,8 @@ int flag_planes(int flag, int plane[2]) {  // 0-based planes; returns S
 }
 
 double bytes_w(double n) { return n * 8.0; }
+
+bool comp_uniform(const dang_gpu *h, int c, int k) { return h->uni_host[c * 3 + k] != 0; }
 
 // ---------------------------------------------------------------- amplitude draw
 template <int C>
@@ -412,7 +468,17 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     const double n_el = (double)S * h->P;
     KTimer kt(h, DANG_K_RHS_BLOCKS,
               bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + 2.0 * C)) + bytes_w((double)h->P * 3));
-    rhs_blocks_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    bool uni = true;
+    for (int s = 0; s < S; s++) {
+      for (int c = 0; c < C; c++) uni = uni && comp_uniform(h, comps[c], cv.plane[s]);
+      for (int o = 0; o < nog; o++) uni = uni && comp_uniform(h, og[o], cv.plane[s]);
+    }
+    if (uni) {
+      const int g2 = grid_for(h, h->Ppad / 2, DG_THREADS, 3);
+      rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    } else {
+      rhs_blocks_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    }
     kt.done();
   }
   gather(h, 4);
@@ -541,7 +607,17 @@ void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, do
   double bytes = bytes_w((double)h->P * nk * (2.0 * h->nbands + h->ncomp * 2.0));
   if (maps) bytes += bytes_w((double)h->P * h->nmaps * h->nbands * ((sky ? 1 : 0) + (res ? 1 : 0)));
   KTimer kt(h, maps ? DANG_K_SKYMODEL : DANG_K_CHISQ, bytes);
-  if (h->ncomp <= 1) launch_chisq<1>(h, mv, cv, grid);
+  bool uni = !maps && !chi_map && h->ncomp <= 4;
+  for (int k = cv.k_lo; k <= cv.k_hi && uni; k++)
+    for (int c = 0; c < h->ncomp; c++) uni = uni && comp_uniform(h, c, k);
+  if (uni) {
+    const int g2 = grid_for(h, h->Ppad / 2, DG_THREADS, 4);
+    if (h->ncomp <= 1) chisq_uni_kernel<1><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    else if (h->ncomp == 2) chisq_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    else if (h->ncomp == 3) chisq_uni_kernel<3><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    else chisq_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+  }
+  else if (h->ncomp <= 1) launch_chisq<1>(h, mv, cv, grid);
   else if (h->ncomp == 2) launch_chisq<2>(h, mv, cv, grid);
   else if (h->ncomp == 3) launch_chisq<3>(h, mv, cv, grid);
   else if (h->ncomp == 4) launch_chisq<4>(h, mv, cv, grid);
@@ -725,8 +801,18 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
     const int grid = grid_for(h, h->P, DG_THREADS, 2);
     {
       KTimer kt(h, DANG_K_MH_SUFFSTAT, bytes_w(n_el * (2.0 * h->nbands + h->ncomp * 2.0)));
-      mh_suffstat_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets,
-                                                            h->sums_local);
+      bool uni = h->ncomp <= 4;
+      for (int s = 0; s < mh.S && uni; s++)
+        for (int c = 0; c < h->ncomp; c++)
+          if (c != mh.ic) uni = uni && comp_uniform(h, c, mh.plane[s]);
+      if (uni) {
+        const int g2 = grid_for(h, h->Ppad / 2, DG_THREADS, 2);
+        if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+        else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+      } else {
+        mh_suffstat_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets,
+                                                              h->sums_local);
+      }
       kt.done();
     }
     gather(h, cnt);
@@ -812,6 +898,8 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaMalloc(&h->gathered, (size_t)GATHER_MAX * 64 * sizeof(double)));
     CK(cudaMalloc(&h->cg_scalars, sizeof(CgScalars)));
     CK(cudaMalloc(&h->mh_scalars, sizeof(MhScalars)));
+    CK(cudaMalloc(&h->tab, sizeof(SedTable)));
+    CK(cudaMemset(h->tab, 0, sizeof(SedTable)));
     CK(cudaMallocHost(&h->pinned, 64 * 1024));
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&h->ev[i]));
     *out = h;
@@ -833,7 +921,8 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   for (auto &g : h->cg) for (auto &x : g.x) dfree(x);
   dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
   dfree(h->decisions); dfree(h->lnl_trace); dfree(h->stage); dfree(h->partials); dfree(h->tickets);
-  dfree(h->sums_local); dfree(h->gathered); dfree(h->cg_scalars); dfree(h->mh_scalars);
+  dfree(h->sums_local); dfree(h->gathered); dfree(h->cg_scalars); dfree(h->mh_scalars); dfree(h->tab);
+  dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -973,6 +1062,8 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
     c.index[l].sample_nside = h->nside;
   }
   CK(cudaStreamSynchronize(h->stream));
+  h->bp_dirty = true;
+  h->tab_dirty = true;
   API_END
 }
 
@@ -1014,6 +1105,7 @@ int dang_gpu_set_indices(dang_gpu_t *h, int ic, const double *indices) {
   for (int l = 0; l < h->comp[ic].nind; l++)
     h2d_planes(h, h->comp[ic].idx[l], indices + (size_t)l * h->nmaps * h->npix, h->nmaps);
   CK(cudaStreamSynchronize(h->stream));
+  h->tab_dirty = true;
   API_END
 }
 
@@ -1096,8 +1188,10 @@ int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsampl
   if (nsample < 0) fail(DANG_GPU_EINVAL, "nsample = %d", nsample);
   MhView mh;
   mh_view(h, ic, nind, map_n, nsample, ml_mode, mh);
+  h->tab_dirty = true;  // set before the draw so an error path cannot leave stale tables
   if (h->comp[ic].index[nind].index_mode == DANG_INDEX_PERPIXEL) sample_perpixel(h, mh, z, u, seed, accept);
   else sample_fullsky(h, mh, z, u, seed, accept);
+  h->tab_dirty = true;
   API_END
 }
 

@@ -93,6 +93,11 @@ rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsi
     if (same) {
 #pragma unroll
       for (int c = 0; c < C; c++)
+        same = same && sed_uniform(mv, cg.comp[c], cg.plane[0]) == sed_uniform(mv, cg.comp[c], cg.plane[1]);
+      for (int o = 0; o < cg.nog; o++)
+        same = same && sed_uniform(mv, cg.og[o], cg.plane[0]) == sed_uniform(mv, cg.og[o], cg.plane[1]);
+#pragma unroll
+      for (int c = 0; c < C; c++)
         same = same && th[0][c][0] == th[1][c][0] && th[0][c][1] == th[1][c][1];
       for (int o = 0; o < cg.nog; o++)
         same = same && oth[0][o][0] == oth[1][o][0] && oth[0][o][1] == oth[1][o][1];
@@ -109,8 +114,8 @@ rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsi
     for (int j = 0; j < mv.nbands; j++) {
       double sed[2][C], osed[2][DG_MAX_COMPS];
 #pragma unroll
-      for (int c = 0; c < C; c++) sed[0][c] = sed_eval(mv, cg.comp[c], j, th[0][c][0], th[0][c][1]);
-      for (int o = 0; o < cg.nog; o++) osed[0][o] = sed_eval(mv, cg.og[o], j, oth[0][o][0], oth[0][o][1]);
+      for (int c = 0; c < C; c++) sed[0][c] = sed_eval(mv, cg.comp[c], cg.plane[0], j, th[0][c][0], th[0][c][1]);
+      for (int o = 0; o < cg.nog; o++) osed[0][o] = sed_eval(mv, cg.og[o], cg.plane[0], j, oth[0][o][0], oth[0][o][1]);
       if (cg.S == 2) {
         if (same) {
 #pragma unroll
@@ -118,8 +123,8 @@ rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsi
           for (int o = 0; o < cg.nog; o++) osed[1][o] = osed[0][o];
         } else {
 #pragma unroll
-          for (int c = 0; c < C; c++) sed[1][c] = sed_eval(mv, cg.comp[c], j, th[1][c][0], th[1][c][1]);
-          for (int o = 0; o < cg.nog; o++) osed[1][o] = sed_eval(mv, cg.og[o], j, oth[1][o][0], oth[1][o][1]);
+          for (int c = 0; c < C; c++) sed[1][c] = sed_eval(mv, cg.comp[c], cg.plane[1], j, th[1][c][0], th[1][c][1]);
+          for (int o = 0; o < cg.nog; o++) osed[1][o] = sed_eval(mv, cg.og[o], cg.plane[1], j, oth[1][o][0], oth[1][o][1]);
         }
       }
 #pragma unroll

@@ -54,10 +54,10 @@ chisq_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned 
 #pragma unroll
         for (int c = 0; c < NC; c++) {
           if (c < mv.ncomp) {
-            if (k > ka && th[k][c][0] == th[k > 0 ? k - 1 : 0][c][0] && th[k][c][1] == th[k > 0 ? k - 1 : 0][c][1])
+            if (k > ka && sed_uniform(mv, c, k) == sed_uniform(mv, c, k > 0 ? k - 1 : 0) && th[k][c][0] == th[k > 0 ? k - 1 : 0][c][0] && th[k][c][1] == th[k > 0 ? k - 1 : 0][c][1])
               sed[k][c] = sed[k > 0 ? k - 1 : 0][c];
             else
-              sed[k][c] = sed_eval(mv, c, j, th[k][c][0], th[k][c][1]);
+              sed[k][c] = sed_eval(mv, c, k, j, th[k][c][0], th[k][c][1]);
           }
         }
       }
@@ -115,4 +115,39 @@ __global__ void mask_to_bytes_kernel(const double *mask, unsigned char *out, int
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Ppad; i += stride)
     out[i] = (i < P && mask[i] != 0.0 && mask[i] != -1.6375e30) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- SED tables
+// uniform_check_kernel: does index map (c, l) hold one value on plane k (over ALL local pixels)?
+// grid = (blocks, ncomp * 3 * DG_MAXIND); tab->nonuni must be zero on entry.
+__global__ void __launch_bounds__(DG_THREADS)
+uniform_check_kernel(const ModelView mv, SedTable *tab) {
+  const int m = blockIdx.y;
+  const int l = m % DG_MAXIND, k = (m / DG_MAXIND) % 3, c = m / (DG_MAXIND * 3);
+  if (c >= mv.ncomp || k >= mv.nmaps || l >= mv.comp[c].nind) return;
+  const double *map = mv.comp[c].idx[l] + (size_t)k * mv.Ppad;
+  const double first = map[0];
+  bool bad = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride)
+    bad = bad || !(map[p] == first);  // NaN counts as non-uniform
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&tab->nonuni[c * 3 + k][l], 1);
+}
+
+// sed_table_kernel<<<ncomp*3, 32>>>: tabulate the per-band SED of every uniform (component, plane)
+__global__ void sed_table_kernel(const ModelView mv, SedTable *tab) {
+  const int ck = blockIdx.x, c = ck / 3, k = ck % 3;
+  if (c >= mv.ncomp || k >= mv.nmaps) {
+    if (threadIdx.x == 0) tab->uni[ck] = 0;
+    return;
+  }
+  const CompView &cv = mv.comp[c];
+  bool uni = true;
+  for (int l = 0; l < cv.nind; l++) uni = uni && tab->nonuni[ck][l] == 0;
+  if (uni) {
+    const double t0 = cv.nind > 0 ? cv.idx[0][(size_t)k * mv.Ppad] : 0.0;
+    const double t1 = cv.nind > 1 ? cv.idx[1][(size_t)k * mv.Ppad] : 0.0;
+    for (int j = threadIdx.x; j < mv.nbands; j += blockDim.x) tab->sed[ck][j] = sed_theta(mv, c, j, t0, t1);
+  }
+  if (threadIdx.x == 0) tab->uni[ck] = uni ? 1 : 0;
 }

@@ -56,7 +56,7 @@ __device__ __forceinline__ double mh_data_value(const ModelView &mv, int ic, int
     const CompView &cc = mv.comp[c2];
     const double t0 = cc.nind > 0 ? cc.idx[0][kp] : 0.0;
     const double t1 = cc.nind > 1 ? cc.idx[1][kp] : 0.0;
-    v = v - cc.amp[kp] * sed_eval(mv, c2, j, t0, t1);
+    v = v - cc.amp[kp] * sed_eval(mv, c2, k, j, t0, t1);
   }
   return v;
 }
@@ -96,7 +96,7 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
 
     // lnL of theta; order of accumulation as evaluate_lnL: Stokes outer, band inner (:172-176)
     auto eval_lnl = [&](const double *th) -> double {
-      for (int j = 0; j < B; j++) sS[(size_t)j * T + tid] = sed_eval(mv, mh.ic, j, th[0], th[1]);
+      for (int j = 0; j < B; j++) sS[(size_t)j * T + tid] = sed_theta(mv, mh.ic, j, th[0], th[1]);
       double lnl = 0.0;
       if (mh.lnl_type == 0) {
         for (int s = 0; s < S; s++)
@@ -126,7 +126,7 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
         if (mh.is_synch) {
           for (int s = 0; s < S; s++)
             for (int j = 0; j < B; j++) {
-              const double ss = amp[s] * sed_eval(mv, mh.ic, j, val, 0.0);
+              const double ss = amp[s] * sed_theta(mv, mh.ic, j, val, 0.0);
               const double ir = 1.0 / sR[((size_t)j * S + s) * T + tid];
               const double t = (ir * ir) * (ss / amp[s]) * log(mv.band[j].nu_c / cv.nu_ref);
               sum = sum + t * t;
@@ -206,7 +206,7 @@ __global__ void mh_fullsky_init_kernel(const ModelView mv, const MhView mh, MhSc
   ms->phase = 0;
   ms->skip = 0;
   for (int j = 0; j < mv.nbands; j++) {
-    const double s = sed_eval(mv, mh.ic, j, ms->sample[0], ms->sample[1]);
+    const double s = sed_theta(mv, mh.ic, j, ms->sample[0], ms->sample[1]);
     ms->sed[j] = s;
     ms->s0[j] = s;
   }
@@ -242,7 +242,7 @@ __device__ __forceinline__ void mh_next_proposal(const ModelView &mv, const MhVi
       ms->l++;
       continue;
     }
-    for (int j = 0; j < mv.nbands; j++) ms->sed[j] = sed_eval(mv, mh.ic, j, ms->theta[0], ms->theta[1]);
+    for (int j = 0; j < mv.nbands; j++) ms->sed[j] = sed_theta(mv, mh.ic, j, ms->theta[0], ms->theta[1]);
     return;
   }
   ms->skip = 1;

@@ -1,0 +1,278 @@
+// kernels_uni.cuh -- streaming variants of K1 (rhs + blocks), K6 (chi-square) and the full-sky
+// sufficient statistics for the case where every component involved has spatially constant
+// spectral indices on the planes in play (full-sky-sampled or never-sampled indices: the
+// BASELINE headline config c2).  The per-band SEDs then come from the SedTable that
+// sed_table_kernel built with the same arithmetic as the per-pixel path, so these kernels do
+// no transcendental work at all: they are pure HBM streams over sig/rms with 16-byte loads,
+// two pixels per thread, the band loop unrolled for memory-level parallelism.
+// Element-wise arithmetic (operation order) is identical to the general kernels.
+#pragma once
+#include "common.cuh"
+#include "kernels_cg.cuh"
+#include "kernels_data.cuh"
+#include "kernels_mh.cuh"
+
+// band loops are unrolled x4: 16 independent 16-byte loads in flight per thread
+
+__device__ __forceinline__ double2 ld2(const double *p) { return ldg_stream2(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+// K1, uniform-SED form.  Same outputs as rhs_blocks_kernel.
+template <int C>
+__global__ void __launch_bounds__(DG_THREADS)
+rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
+                      unsigned int *ticket, double *out) {
+  constexpr int T = C * (C + 1) / 2;
+  __shared__ double smem[2 * 32];
+  __shared__ double ssed[2][C][DG_MAX_BANDS];
+  __shared__ double sog[2][DG_MAX_COMPS][DG_MAX_BANDS];
+  const int B = mv.nbands;
+  for (int i = threadIdx.x; i < 2 * C * B; i += blockDim.x) {
+    const int s = i / (C * B), c = (i / B) % C, j = i % B;
+    if (s < cg.S) ssed[s][c][j] = mv.tab->sed[cg.comp[c] * 3 + cg.plane[s]][j];
+  }
+  for (int i = threadIdx.x; i < 2 * cg.nog * B; i += blockDim.x) {
+    const int s = i / (cg.nog * B), o = (i / B) % cg.nog, j = i % B;
+    if (s < cg.S) sog[s][o][j] = mv.tab->sed[cg.og[o] * 3 + cg.plane[s]][j];
+  }
+  __syncthreads();
+
+  double acc[2] = {0.0, 0.0};
+  const int64_t n2 = mv.Ppad / 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const size_t vs = (size_t)cg.S * mv.Ppad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    const int64_t p = 2 * e;
+    const uchar2 mk = *reinterpret_cast<const uchar2 *>(mv.mask + p);
+    const bool use0 = mk.x != 0, use1 = mk.y != 0;
+    for (int s = 0; s < cg.S; s++) {
+      const int k = cg.plane[s];
+      const size_t es = (size_t)s * mv.Ppad + p;
+      double2 b[C], f[C], M[T];
+#pragma unroll
+      for (int c = 0; c < C; c++) b[c] = f[c] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int t = 0; t < T; t++) M[t] = make_double2(0.0, 0.0);
+      double2 eta = make_double2(0.0, 0.0);
+      if (cg.fluct) {
+        if (cg.eta) {
+          eta = ld2(cg.eta + es);
+        } else {
+          const uint64_t g0 = (uint64_t)s * (uint64_t)mv.npix + (uint64_t)(mv.pix_lo + p);
+          eta.x = use0 ? philox_normal(cg.seed, DG_STREAM_ETA, g0) : 0.0;
+          eta.y = use1 ? philox_normal(cg.seed, DG_STREAM_ETA, g0 + 1) : 0.0;
+        }
+      }
+      double2 oa[DG_MAX_COMPS];
+      for (int o = 0; o < cg.nog; o++) oa[o] = ld2(mv.comp[cg.og[o]].amp + (size_t)k * mv.Ppad + p);
+#pragma unroll 4
+      for (int j = 0; j < B; j++) {
+        const size_t off = plane_off(mv, j, k) + p;
+        double2 data = ld2(mv.sig + off);
+        const double2 rms = ld2(mv.rms + off);
+        if (k == 0) {
+          data.x = data.x / mv.gain[j];
+          data.y = data.y / mv.gain[j];
+        }
+        for (int o = 0; o < cg.nog; o++) {
+          data.x = data.x - oa[o].x * sog[s][o][j];
+          data.y = data.y - oa[o].y * sog[s][o][j];
+        }
+        const double wx = 1.0 / (rms.x * rms.x), wy = 1.0 / (rms.y * rms.y);
+        const double tx = eta.x / rms.x, ty = eta.y / rms.y;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const double sc = ssed[s][c][j];
+          b[c].x += data.x * sc * wx;
+          b[c].y += data.y * sc * wy;
+          f[c].x += tx * sc;
+          f[c].y += ty * sc;
+#pragma unroll
+          for (int c2 = c; c2 < C; c2++) {
+            const double sc2 = ssed[s][c2][j];
+            M[tri<C>(c, c2)].x += sc * sc2 * wx;
+            M[tri<C>(c, c2)].y += sc * sc2 * wy;
+          }
+        }
+      }
+      if (cg.fluct == 1) {
+        b[0].x += f[C - 1].x;
+        b[0].y += f[C - 1].y;
+      } else if (cg.fluct == 2) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          b[c].x += f[c].x;
+          b[c].y += f[c].y;
+        }
+      }
+      // masked lanes: zero rows / columns (rms may be anything there, so select, do not scale)
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        if (!use0) M[t].x = 0.0;
+        if (!use1) M[t].y = 0.0;
+      }
+      double2 xv[C], rv[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) xv[c] = *reinterpret_cast<const double2 *>(cg.x + c * vs + es);
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        double ax = 0.0, ay = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < C; c2++) {
+          const double2 mm = M[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+          ax += mm.x * xv[c2].x;
+          ay += mm.y * xv[c2].y;
+        }
+        rv[c].x = use0 ? b[c].x - ax : 0.0;
+        rv[c].y = use1 ? b[c].y - ay : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        double mx = 0.0, my = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < C; c2++) {
+          const double2 mm = M[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+          mx += mm.x * rv[c2].x;
+          my += mm.y * rv[c2].y;
+        }
+        acc[0] += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
+        acc[1] += rv[c].x * mx + rv[c].y * my;
+      }
+#pragma unroll
+      for (int t = 0; t < T; t++) st2(cg.M + t * vs + es, M[t]);
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        st2(cg.r + c * vs + es, rv[c]);
+        st2(cg.d + c * vs + es, rv[c]);
+      }
+    }
+  }
+  grid_reduce<2>(acc, smem, partials, ticket, out);
+}
+
+// K6, uniform-SED form (chi-square reduction only; map output stays in chisq_kernel).
+template <int NC>
+__global__ void __launch_bounds__(DG_THREADS)
+chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned int *ticket,
+                 double *out) {
+  __shared__ double smem[4 * 32];
+  __shared__ double ssed[3][NC][DG_MAX_BANDS];
+  const int B = mv.nbands;
+  for (int i = threadIdx.x; i < 3 * NC * B; i += blockDim.x) {
+    const int k = i / (NC * B), c = (i / B) % NC, j = i % B;
+    ssed[k][c][j] = (c < mv.ncomp && k < mv.nmaps) ? mv.tab->sed[c * 3 + k][j] : 0.0;
+  }
+  __syncthreads();
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t n2 = mv.Ppad / 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    const int64_t p = 2 * e;
+    const uchar2 mk = *reinterpret_cast<const uchar2 *>(mv.mask + p);
+    const bool use0 = mk.x != 0, use1 = mk.y != 0;
+    acc[3] += (use0 ? 1.0 : 0.0) + (use1 ? 1.0 : 0.0);
+    if (!use0 && !use1) continue;
+    for (int k = cv.k_lo; k <= cv.k_hi; k++) {
+      double2 a[NC];
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+        a[c] = c < mv.ncomp ? ld2(mv.comp[c].amp + (size_t)k * mv.Ppad + p) : make_double2(0.0, 0.0);
+      double2 chi = make_double2(0.0, 0.0);
+#pragma unroll 4
+      for (int j = 0; j < B; j++) {
+        const size_t off = plane_off(mv, j, k) + p;
+        const double2 sig = ld2(mv.sig + off);
+        const double2 rms = ld2(mv.rms + off);
+        double skx = 0.0, sky = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+          if (c < mv.ncomp) {
+            skx = skx + a[c].x * ssed[k][c][j];
+            sky = sky + a[c].y * ssed[k][c][j];
+          }
+        double tx, ty;
+        if (k == 0) {
+          tx = (sig.x - mv.offset[j]) / mv.gain[j] - skx;
+          ty = (sig.y - mv.offset[j]) / mv.gain[j] - sky;
+        } else {
+          tx = sig.x - skx;
+          ty = sig.y - sky;
+        }
+        chi.x = chi.x + (tx * tx) / (rms.x * rms.x);
+        chi.y = chi.y + (ty * ty) / (rms.y * rms.y);
+      }
+      acc[k] += (use0 ? chi.x / B : 0.0) + (use1 ? chi.y / B : 0.0);
+    }
+  }
+  grid_reduce<4>(acc, smem, partials, ticket, out);
+}
+
+// Full-sky sufficient statistics, uniform-SED form: every component other than the sampled one
+// has tabulated SEDs, so data_raw = sig - sum_c2 a_c2 sed_c2 needs no transcendental either.
+template <int NC>
+__global__ void __launch_bounds__(DG_THREADS)
+mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, double *partials,
+                       unsigned int *tickets, double *out) {
+  constexpr int NV = 3 * DG_SUFF_CHUNK;
+  __shared__ double smem[NV * 32];
+  __shared__ double ssed[2][NC][DG_MAX_BANDS];
+  __shared__ double s0s[DG_MAX_BANDS];
+  const int B = mv.nbands;
+  for (int i = threadIdx.x; i < 2 * NC * B; i += blockDim.x) {
+    const int s = i / (NC * B), c = (i / B) % NC, j = i % B;
+    ssed[s][c][j] = (c < mv.ncomp && c != mh.ic && s < mh.S) ? mv.tab->sed[c * 3 + mh.plane[s]][j] : 0.0;
+  }
+  if (threadIdx.x < B) s0s[threadIdx.x] = ms->s0[threadIdx.x];
+  __syncthreads();
+  const int64_t n2 = mv.Ppad / 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  for (int ch = 0; ch < nchunk; ch++) {
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+      const int64_t p = 2 * e;
+      const uchar2 mk = *reinterpret_cast<const uchar2 *>(mv.mask + p);
+      const bool use0 = mk.x != 0, use1 = mk.y != 0;
+      if (!use0 && !use1) continue;
+      for (int s = 0; s < mh.S; s++) {
+        const int k = mh.plane[s];
+        double2 a[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+          a[c] = c < mv.ncomp ? ld2(mv.comp[c].amp + (size_t)k * mv.Ppad + p) : make_double2(0.0, 0.0);
+        double2 am = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+          if (c == mh.ic) am = a[c];
+#pragma unroll
+        for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
+          const int j = ch * DG_SUFF_CHUNK + jj;
+          if (j < B) {
+            const size_t off = plane_off(mv, j, k) + p;
+            double2 d = ld2(mv.sig + off);
+            const double2 rms = ld2(mv.rms + off);
+            if (k == 0) {
+              d.x = (d.x - mv.offset[j]) / mv.gain[j];
+              d.y = (d.y - mv.offset[j]) / mv.gain[j];
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+              if (c < mv.ncomp && c != mh.ic) {
+                d.x = d.x - a[c].x * ssed[s][c][j];
+                d.y = d.y - a[c].y * ssed[s][c][j];
+              }
+            const double tx = (d.x - am.x * s0s[j]) / rms.x, ty = (d.y - am.y * s0s[j]) / rms.y;
+            const double ux = am.x / rms.x, uy = am.y / rms.y;
+            acc[3 * jj + 0] += (use0 ? tx * tx : 0.0) + (use1 ? ty * ty : 0.0);
+            acc[3 * jj + 1] += (use0 ? tx * ux : 0.0) + (use1 ? ty * uy : 0.0);
+            acc[3 * jj + 2] += (use0 ? ux * ux : 0.0) + (use1 ? uy * uy : 0.0);
+          }
+        }
+      }
+    }
+    grid_reduce<NV>(acc, smem, partials + (size_t)ch * NV * gridDim.x, tickets + ch, out + ch * NV);
+    __syncthreads();
+  }
+}

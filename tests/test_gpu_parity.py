@@ -55,11 +55,12 @@ def test_chisq_missval_mask_and_ragged_size():
 
 
 # ------------------------------------------------------------------ amplitude draw
+@pytest.mark.parametrize("name", ["c1", "c2"])  # c1: per-pixel SEDs; c2: tabulated (uniform) SEDs
 @pytest.mark.parametrize("two_pass", [0, 1])
 @pytest.mark.parametrize("ml_mode", ["optimize", "sample"])
-def test_cg_solve_matches_oracle(two_pass, ml_mode):
+def test_cg_solve_matches_oracle(name, two_pass, ml_mode):
     from dang_b200.engine import OPT_CG_TWO_PASS
-    cfg, sky, ora, eng = make_pair("c1", 16)
+    cfg, sky, ora, eng = make_pair(name, 16)
     eng.set_option(OPT_CG_TWO_PASS, two_pass)
     eta = np.random.default_rng(5).standard_normal(2 * cfg.npix)
     it_o, delta_o, trace_o = ora.cg_search_trace(ml_mode=1 if ml_mode == "sample" else 0, eta=eta)
@@ -231,16 +232,18 @@ def test_perpixel_marginal_lnl():
 
 
 @pytest.mark.parametrize("stream", [0, 1])
-@pytest.mark.parametrize("name,ic,nind", [("c2", 1, 0), ("c4", 1, 1), ("c1", 0, 0)])
-def test_fullsky_metropolis(stream, name, ic, nind):
+@pytest.mark.parametrize("name,ic,nind,others_uniform", [("c2", 1, 0, True), ("c4", 1, 1, True), ("c1", 0, 0, True),
+                                                        ("c1", 1, 0, False)])
+def test_fullsky_metropolis(stream, name, ic, nind, others_uniform):
     from dang_b200.engine import OPT_FULLSKY_STREAM, Engine
     from oracle.binding import Oracle
     cfg, sky = small_case(name, 16)
     spec = cfg.comps[ic].indices[nind]
     spec.sample, spec.region = True, "fullsky"
-    for c in cfg.comps:  # full-sky indices are uniform maps
+    for i2, c in enumerate(cfg.comps):  # the sampled component's indices are uniform maps
         for k, s in enumerate(c.indices):
-            sky.indices[c.label][k][:] = s.init
+            if others_uniform or i2 == ic:
+                sky.indices[c.label][k][:] = s.init
     spec.step = {0: 0.002, 1: 0.02}[nind]
     nsample = 24
     ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
