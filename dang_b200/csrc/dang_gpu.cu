@@ -124,6 +124,7 @@ struct CgGroupHost {
   double converge = 0;
   double *x[3] = {nullptr, nullptr, nullptr};  // Q10: persists across Gibbs iterations
   size_t x_len[3] = {0, 0, 0};
+  int last_iter[3] = {0, 0, 0};  // iterations of the previous solve (sizes the first batch)
 };
 
 struct KStat {
@@ -172,7 +173,7 @@ struct dang_gpu {
   double *stage = nullptr; size_t stage_len = 0; // device staging for strided host copies
   double *partials = nullptr; unsigned int *tickets = nullptr;
   int grid_cap = 0;
-  double *sums_local = nullptr, *gathered = nullptr;
+  double *sums_local = nullptr, *gathered = nullptr, *gathered_buf = nullptr;
   CgScalars *cg_scalars = nullptr;
   MhScalars *mh_scalars = nullptr;
   void *pinned = nullptr;  // small pinned buffer for scalar read-back
@@ -205,6 +206,20 @@ void ensure(double *&buf, size_t &len, size_t need) {
   buf = nullptr;
   CK(cudaMalloc(&buf, need * sizeof(double)));
   len = need;
+}
+
+// Persistent-style launch: exactly as many blocks as are resident at once (blocks/SM from the
+// occupancy calculator x SM count), or fewer when the work is small; grid-stride loops inside.
+template <typename K>
+int occ_grid(dang_gpu *h, K kernel, int64_t work, int threads, size_t smem = 0) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t need = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)h->num_sms * per_sm;
+  if (cap > h->grid_cap) cap = h->grid_cap;
+  int64_t g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
 }
 
 int grid_for(dang_gpu *h, int64_t work, int threads, int blocks_per_sm) {
@@ -371,7 +386,7 @@ ModelView model_view(dang_gpu *h) {
 void gather(dang_gpu *h, int cnt) {
   if (cnt > GATHER_MAX) fail(DANG_GPU_EINVAL, "gather of %d doubles exceeds %d", cnt, GATHER_MAX);
   if (h->nranks == 1) {
-    CK(cudaMemcpyAsync(h->gathered, h->sums_local, cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return;  // h->gathered aliases h->sums_local (set in create / comm_init)
   } else {
     NCK(g_nccl.AllGather(h->sums_local, h->gathered, cnt, NCCL_DOUBLE, h->comm, h->stream));
   }
@@ -474,10 +489,11 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       for (int o = 0; o < nog; o++) uni = uni && comp_uniform(h, og[o], cv.plane[s]);
     }
     if (uni) {
-      const int g2 = grid_for(h, h->Ppad / 2, DG_THREADS, 3);
+      const int g2 = occ_grid(h, rhs_blocks_uni_kernel<C>, h->Ppad / 2, DG_THREADS);
       rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
     } else {
-      rhs_blocks_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+      const int g1 = occ_grid(h, rhs_blocks_kernel<C>, h->P, DG_THREADS);
+      rhs_blocks_kernel<C><<<g1, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
     }
     kt.done();
   }
@@ -496,52 +512,70 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     return Snap{hs->delta_new, hs->iter, hs->done};
   };
 
-  const int grid = grid_for(h, n2, DG_THREADS, 4);
+  const int fold = h->nranks == 1 ? 1 : 0;
+  const int grid = h->cg_two_pass ? occ_grid(h, cg_update_pass_kernel<C>, n2, DG_THREADS)
+                                  : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
   const double el = (double)vs;
-  int enq = 0;  // passes enqueued
-  Snap sn = read_state();
-  while (!sn.done && enq < g.i_max - 1) {
-    int chunk = h->cg_chunk;
-    if (chunk > g.i_max - 1 - enq) chunk = g.i_max - 1 - enq;
-    for (int it = 0; it < chunk; it++) {
-      if (!h->cg_two_pass) {
-        {
-          KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * (T + 6.0 * C)));
-          cg_fused_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-              h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local);
-          kt.done();
-        }
+  auto enqueue_pass = [&](int pass_no) {
+    if (!h->cg_two_pass) {
+      {
+        // compulsory traffic of this launch: x is touched on even passes only
+        const double per_el = (pass_no & 1) ? (T + 4.0 * C) : (T + 6.0 * C);
+        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
+        cg_fused_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold);
+        kt.done();
+      }
+      if (!fold) {
         gather(h, 4);
         KTimer ks(h, DANG_K_SCALAR, 0);
         cg_fused_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
         ks.done();
-      } else {
-        {
-          KTimer kt(h, DANG_K_CG_DQ, bytes_w(el * (T + 3.0 * C)));
-          cg_dq_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, h->M, h->r, h->d, n2,
-                                                                    h->partials, h->tickets, h->sums_local);
-          kt.done();
-        }
-        gather(h, 4);
-        {
-          KTimer ks(h, DANG_K_SCALAR, 0);
-          cg_dq_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
-          ks.done();
-        }
-        {
-          KTimer kt(h, DANG_K_CG_UPDATE, bytes_w(el * (T + 5.0 * C)));
-          cg_update_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-              h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local);
-          kt.done();
-        }
-        gather(h, 4);
+      }
+    } else {
+      {
+        KTimer kt(h, DANG_K_CG_DQ, bytes_w(el * (T + 3.0 * C)));
+        cg_dq_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, h->M, h->r, h->d, n2,
+                                                                  h->partials, h->tickets, h->sums_local);
+        kt.done();
+      }
+      gather(h, 4);
+      {
         KTimer ks(h, DANG_K_SCALAR, 0);
-        cg_rr_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+        cg_dq_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
         ks.done();
       }
+      {
+        KTimer kt(h, DANG_K_CG_UPDATE, bytes_w(el * (T + 5.0 * C)));
+        cg_update_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local);
+        kt.done();
+      }
+      gather(h, 4);
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      cg_rr_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+      ks.done();
     }
-    enq += chunk;
+  };
+  // Passes are enqueued without waiting for the convergence flag: a pass launched after the
+  // solve is done returns at once (device-side early exit).  The first batch is sized from the
+  // previous solve of this (group, flag) -- successive Gibbs iterations converge in almost the
+  // same number of steps -- and further batches of cg_chunk follow until the flag is seen.
+  const int max_pass = g.i_max - 1;
+  int enq = 0;
+  int batch = g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : h->cg_chunk;
+  Snap sn{0.0, 1, max_pass < 1};
+  while (!sn.done && enq < max_pass) {
+    if (batch > max_pass - enq) batch = max_pass - enq;
+    for (int it = 0; it < batch; it++) enqueue_pass(enq + it + 1);
+    enq += batch;
     sn = read_state();
+    batch = h->cg_chunk;
+  }
+  if (!h->cg_two_pass) {
+    KTimer kt(h, DANG_K_CG_PASS, 0);
+    cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
+    kt.done();
   }
 
   // unpack_amplitudes :1327-1335: x -> c%amplitude planes
@@ -556,6 +590,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     CK(cudaStreamSynchronize(h->stream));
     int n = hs->iter < 256 ? hs->iter : 256;
     h->last_trace.assign(hs->trace, hs->trace + n);
+    g.last_iter[flag_n] = hs->iter;
     if (n_iter) *n_iter = hs->iter;
     if (delta_final) *delta_final = hs->delta_new;
   }
@@ -587,7 +622,8 @@ void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *
 
 // ---------------------------------------------------------------- chi-square
 template <int NC>
-void launch_chisq(dang_gpu *h, const ModelView &mv, const ChisqView &cv, int grid) {
+void launch_chisq(dang_gpu *h, const ModelView &mv, const ChisqView &cv, int) {
+  const int grid = occ_grid(h, chisq_kernel<NC>, h->P, DG_THREADS);
   chisq_kernel<NC><<<grid, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
 }
 
@@ -611,7 +647,7 @@ void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, do
   for (int k = cv.k_lo; k <= cv.k_hi && uni; k++)
     for (int c = 0; c < h->ncomp; c++) uni = uni && comp_uniform(h, c, k);
   if (uni) {
-    const int g2 = grid_for(h, h->Ppad / 2, DG_THREADS, 4);
+    const int g2 = occ_grid(h, chisq_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
     if (h->ncomp <= 1) chisq_uni_kernel<1><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
     else if (h->ncomp == 2) chisq_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
     else if (h->ncomp == 3) chisq_uni_kernel<3><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
@@ -806,7 +842,7 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
         for (int c = 0; c < h->ncomp; c++)
           if (c != mh.ic) uni = uni && comp_uniform(h, c, mh.plane[s]);
       if (uni) {
-        const int g2 = grid_for(h, h->Ppad / 2, DG_THREADS, 2);
+        const int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
         if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
         else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
       } else {
@@ -895,7 +931,8 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaMalloc(&h->tickets, 16 * sizeof(unsigned int)));
     CK(cudaMemset(h->tickets, 0, 16 * sizeof(unsigned int)));
     CK(cudaMalloc(&h->sums_local, GATHER_MAX * sizeof(double)));
-    CK(cudaMalloc(&h->gathered, (size_t)GATHER_MAX * 64 * sizeof(double)));
+    CK(cudaMalloc(&h->gathered_buf, (size_t)GATHER_MAX * 64 * sizeof(double)));
+    h->gathered = h->sums_local;  // single rank: no exchange
     CK(cudaMalloc(&h->cg_scalars, sizeof(CgScalars)));
     CK(cudaMalloc(&h->mh_scalars, sizeof(MhScalars)));
     CK(cudaMalloc(&h->tab, sizeof(SedTable)));
@@ -921,7 +958,7 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   for (auto &g : h->cg) for (auto &x : g.x) dfree(x);
   dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
   dfree(h->decisions); dfree(h->lnl_trace); dfree(h->stage); dfree(h->partials); dfree(h->tickets);
-  dfree(h->sums_local); dfree(h->gathered); dfree(h->cg_scalars); dfree(h->mh_scalars); dfree(h->tab);
+  dfree(h->sums_local); dfree(h->gathered_buf); dfree(h->cg_scalars); dfree(h->mh_scalars); dfree(h->tab);
   dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -969,6 +1006,7 @@ int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]) 
   if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) fail(DANG_GPU_EINVAL, "bad rank %d of %d", rank, nranks);
   h->nranks = nranks;
   h->rank = rank;
+  h->gathered = nranks > 1 ? h->gathered_buf : h->sums_local;
   if (nranks > 1) {
     nccl_load();
     nccl_uid_t uid;

@@ -26,6 +26,7 @@ struct CgView {
 // scalars of one solve, device resident (DESIGN.md "CG control")
 struct CgScalars {
   double delta_new, delta_old, alpha, beta, dq;
+  double alpha_prev;  // alpha of the pass that ran last (deferred x update, see cg_fused_pass_kernel)
   double converge;
   int iter, i_max, done, pad;
   double trace[256];
@@ -189,18 +190,20 @@ rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsi
 }
 
 // ---------------------------------------------------------------- scalar control
-// After K1: sums = {r.r, r.Mr} (gathered over ranks, rank order).  d_1 = r_1 so d.q = r.Mr.
-__global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, int nranks,
-                                       int i_max, double converge) {
+// `sums` holds one row of 4 doubles per rank (rank order => identical bits on every rank).
+// After K1: {r.r, r.Mr}.  d_1 = r_1 so d.q = r.Mr.
+__device__ __forceinline__ void cg_init_update(CgScalars *st, const double *sums, int nranks,
+                                               int i_max, double converge) {
   double rr = 0.0, rMr = 0.0;
   for (int g = 0; g < nranks; g++) {
-    rr += gathered[g * 4 + 0];
-    rMr += gathered[g * 4 + 1];
+    rr += sums[g * 4 + 0];
+    rMr += sums[g * 4 + 1];
   }
   st->delta_new = rr;
   st->delta_old = rr;
   st->dq = rMr;
   st->alpha = rr / rMr;
+  st->alpha_prev = 0.0;
   st->beta = 0.0;
   st->iter = 1;  // the reference's loop counter starts at 1 (:287, Q3)
   st->i_max = i_max;
@@ -209,13 +212,12 @@ __global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, in
   st->trace[0] = rr;
 }
 
-// After a fused pass: sums = {r'.r', r'.Mr', r'.q, d.q} with q = M d.
+// After a fused pass: {r'.r', r'.Mr', r'.q, d.q} with q = M d.
 // delta' = r'.r'; beta' = delta'/delta; d' = r' + beta' d  =>  d'.Md' = r'.Mr' + 2 beta' r'.q + beta'^2 d.q
-__global__ void cg_fused_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
-  if (st->done) return;
+__device__ __forceinline__ void cg_fused_update(CgScalars *st, const double *sums, int nranks) {
   double s[4] = {0.0, 0.0, 0.0, 0.0};
   for (int g = 0; g < nranks; g++)
-    for (int i = 0; i < 4; i++) s[i] += gathered[g * 4 + i];
+    for (int i = 0; i < 4; i++) s[i] += sums[g * 4 + i];
   const double delta_old = st->delta_new;
   const double delta_new = s[0];
   const double beta = delta_new / delta_old;
@@ -224,11 +226,21 @@ __global__ void cg_fused_scalars_kernel(CgScalars *st, const double *gathered, i
   st->delta_new = delta_new;
   st->beta = beta;
   st->dq = dq;
+  st->alpha_prev = st->alpha;
   st->alpha = delta_new / dq;
   const int it = st->iter + 1;
   st->iter = it;
   if (it - 1 < 256) st->trace[it - 1] = delta_new;
   st->done = !(it < st->i_max && delta_new > st->converge);
+}
+
+__global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, int nranks,
+                                       int i_max, double converge) {
+  cg_init_update(st, gathered, nranks, i_max, converge);
+}
+__global__ void cg_fused_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
+  if (st->done) return;
+  cg_fused_update(st, gathered, nranks);
 }
 
 // two-pass form: after the d.q pass
@@ -256,35 +268,41 @@ __global__ void cg_rr_scalars_kernel(CgScalars *st, const double *gathered, int 
 // ---------------------------------------------------------------- K2: fused CG pass
 // One HBM pass per CG iteration over vec2 elements e of the flattened [S][Ppad] index:
 //   d <- r + beta d (beta = 0 on the first pass: d = r was stored by K1)
-//   q  = M d;  x += alpha d;  r' = r - alpha q
-//   sums {r'.r', r'.M r', r'.q, d.q}
-// reads T + 3C, writes 3C doubles per element: the compulsory traffic of SURVEY 8d bytes_cg_it.
+//   q  = M d;  r' = r - alpha q;  sums {r'.r', r'.M r', r'.q, d.q}
+//   x: on even passes  x <- (x + alpha_prev d_prev) + alpha d  -- the two updates the reference
+//      performs in consecutive iterations (:298), in the same order and therefore bit-identical,
+//      but with x read and written every other pass only; cg_x_fixup_kernel applies the pending
+//      term if the solve ends on an odd pass.
+// Compulsory traffic per element: T + 2C reads + 2C writes, plus C + C for x on even passes
+// (11 / 15 doubles for C = 2) against the 15 of SURVEY 8d's bytes_cg_it.
+// fold = 1 (single rank): the last block also advances the scalars, saving a launch.
 template <int C>
 __global__ void __launch_bounds__(DG_THREADS)
-cg_fused_pass_kernel(const CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
-                     double *__restrict__ r, double *__restrict__ d, int64_t n2 /* vec2 count per plane-set */,
-                     double *partials, unsigned int *ticket, double *out) {
+cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
+                     double *__restrict__ r, double *__restrict__ d, int64_t n2 /* vec2 elements */,
+                     double *partials, unsigned int *ticket, double *out, int fold) {
   constexpr int T = C * (C + 1) / 2;
   if (st->done) return;
-  const double alpha = st->alpha, beta = st->beta;
+  const double alpha = st->alpha, beta = st->beta, alpha_prev = st->alpha_prev;
+  const bool with_x = (st->iter & 1) == 0;  // passes are numbered by the loop counter, from 1
   __shared__ double smem[4 * 32];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const size_t vs = (size_t)n2 * 2;  // doubles per component / block-entry plane-set
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
-    double2 m[T], xv[C], rv[C], dv[C];
+    double2 m[T], xv[C], rv[C], dv[C], dp[C];
 #pragma unroll
     for (int t = 0; t < T; t++) m[t] = ldg_stream2(M + t * vs + 2 * e);
 #pragma unroll
     for (int c = 0; c < C; c++) {
       rv[c] = *reinterpret_cast<const double2 *>(r + c * vs + 2 * e);
-      dv[c] = *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
-      xv[c] = *reinterpret_cast<const double2 *>(x + c * vs + 2 * e);
+      dp[c] = *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
+      if (with_x) xv[c] = *reinterpret_cast<const double2 *>(x + c * vs + 2 * e);
     }
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      dv[c].x = rv[c].x + beta * dv[c].x;  // :305 (of the previous iteration)
-      dv[c].y = rv[c].y + beta * dv[c].y;
+      dv[c].x = rv[c].x + beta * dp[c].x;  // :305 (of the previous iteration)
+      dv[c].y = rv[c].y + beta * dp[c].y;
     }
     double2 q[C];
 #pragma unroll
@@ -301,8 +319,10 @@ cg_fused_pass_kernel(const CgScalars *st, const double *__restrict__ M, double *
     }
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      xv[c].x = xv[c].x + alpha * dv[c].x;  // :298
-      xv[c].y = xv[c].y + alpha * dv[c].y;
+      if (with_x) {
+        xv[c].x = (xv[c].x + alpha_prev * dp[c].x) + alpha * dv[c].x;  // :298, twice
+        xv[c].y = (xv[c].y + alpha_prev * dp[c].y) + alpha * dv[c].y;
+      }
       rv[c].x = rv[c].x - alpha * q[c].x;   // :300
       rv[c].y = rv[c].y - alpha * q[c].y;
       acc[3] += dv[c].x * q[c].x + dv[c].y * q[c].y;
@@ -320,11 +340,27 @@ cg_fused_pass_kernel(const CgScalars *st, const double *__restrict__ M, double *
       acc[1] += rv[c].x * mx + rv[c].y * my;
       acc[2] += rv[c].x * q[c].x + rv[c].y * q[c].y;
       *reinterpret_cast<double2 *>(d + c * vs + 2 * e) = dv[c];
-      *reinterpret_cast<double2 *>(x + c * vs + 2 * e) = xv[c];
+      if (with_x) *reinterpret_cast<double2 *>(x + c * vs + 2 * e) = xv[c];
       *reinterpret_cast<double2 *>(r + c * vs + 2 * e) = rv[c];
     }
   }
-  grid_reduce<4>(acc, smem, partials, ticket, out);
+  const bool last = grid_reduce<4>(acc, smem, partials, ticket, out);
+  if (fold && last && threadIdx.x == 0) cg_fused_update(st, out, 1);
+}
+
+// pending x update when the solve stopped after an odd number of passes
+__global__ void __launch_bounds__(DG_THREADS)
+cg_x_fixup_kernel(const CgScalars *st, double *__restrict__ x, const double *__restrict__ d, int64_t n) {
+  if (((st->iter - 1) & 1) == 0) return;
+  const double a = st->alpha_prev;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n / 2; e += stride) {
+    double2 xv = *reinterpret_cast<const double2 *>(x + 2 * e);
+    const double2 dv = *reinterpret_cast<const double2 *>(d + 2 * e);
+    xv.x = xv.x + a * dv.x;
+    xv.y = xv.y + a * dv.y;
+    *reinterpret_cast<double2 *>(x + 2 * e) = xv;
+  }
 }
 
 // ---------------------------------------------------------------- classic two-pass form

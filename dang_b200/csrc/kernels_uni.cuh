@@ -12,7 +12,24 @@
 #include "kernels_data.cuh"
 #include "kernels_mh.cuh"
 
-// band loops are unrolled x4: 16 independent 16-byte loads in flight per thread
+// Band loops run in batches of DG_UB bands: all 2*DG_UB 16-byte loads of a batch are issued
+// before any arithmetic (indices clamped so the loads are unconditional), which is what keeps
+// enough bytes in flight per SM to reach the HBM roofline at 1-2 resident blocks per SM.
+#define DG_UB 4
+
+// 1/x without the IEEE slow-path branches of the compiler's fp64 division (those BSSY/BSYNC
+// regions stop the scheduler from hoisting the next loads): hardware seed + two Newton steps,
+// <= 1 ulp for the O(1) noise levels it is applied to.  Inf/NaN lanes (masked pixels, rms = 0)
+// are discarded by the callers.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
 
 __device__ __forceinline__ double2 ld2(const double *p) { return ldg_stream2(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
@@ -65,33 +82,46 @@ rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
       }
       double2 oa[DG_MAX_COMPS];
       for (int o = 0; o < cg.nog; o++) oa[o] = ld2(mv.comp[cg.og[o]].amp + (size_t)k * mv.Ppad + p);
-#pragma unroll 4
-      for (int j = 0; j < B; j++) {
-        const size_t off = plane_off(mv, j, k) + p;
-        double2 data = ld2(mv.sig + off);
-        const double2 rms = ld2(mv.rms + off);
-        if (k == 0) {
-          data.x = data.x / mv.gain[j];
-          data.y = data.y / mv.gain[j];
-        }
-        for (int o = 0; o < cg.nog; o++) {
-          data.x = data.x - oa[o].x * sog[s][o][j];
-          data.y = data.y - oa[o].y * sog[s][o][j];
-        }
-        const double wx = 1.0 / (rms.x * rms.x), wy = 1.0 / (rms.y * rms.y);
-        const double tx = eta.x / rms.x, ty = eta.y / rms.y;
+      for (int j0 = 0; j0 < B; j0 += DG_UB) {
+        double2 sg[DG_UB], rm[DG_UB];
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-          const double sc = ssed[s][c][j];
-          b[c].x += data.x * sc * wx;
-          b[c].y += data.y * sc * wy;
-          f[c].x += tx * sc;
-          f[c].y += ty * sc;
+        for (int u = 0; u < DG_UB; u++) {
+          const int j = min(j0 + u, B - 1);
+          const size_t off = plane_off(mv, j, k) + p;
+          sg[u] = ld2(mv.sig + off);
+          rm[u] = ld2(mv.rms + off);
+        }
 #pragma unroll
-          for (int c2 = c; c2 < C; c2++) {
-            const double sc2 = ssed[s][c2][j];
-            M[tri<C>(c, c2)].x += sc * sc2 * wx;
-            M[tri<C>(c, c2)].y += sc * sc2 * wy;
+        for (int u = 0; u < DG_UB; u++) {
+          const int j = j0 + u;
+          if (j < B) {
+            double2 data = sg[u];
+            if (k == 0) {
+              data.x = data.x / mv.gain[j];
+              data.y = data.y / mv.gain[j];
+            }
+            for (int o = 0; o < cg.nog; o++) {
+              data.x = data.x - oa[o].x * sog[s][o][j];
+              data.y = data.y - oa[o].y * sog[s][o][j];
+            }
+            // one reciprocal per lane: 1/sigma, then 1/sigma^2 and eta/sigma by multiplication
+            const double ix = fast_rcp(rm[u].x), iy = fast_rcp(rm[u].y);
+            const double wx = ix * ix, wy = iy * iy;
+            const double tx = eta.x * ix, ty = eta.y * iy;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+              const double sc = ssed[s][c][j];
+              b[c].x += data.x * sc * wx;
+              b[c].y += data.y * sc * wy;
+              f[c].x += tx * sc;
+              f[c].y += ty * sc;
+#pragma unroll
+              for (int c2 = c; c2 < C; c2++) {
+                const double sc2 = ssed[s][c2][j];
+                M[tri<C>(c, c2)].x += sc * sc2 * wx;
+                M[tri<C>(c, c2)].y += sc * sc2 * wy;
+              }
+            }
           }
         }
       }
@@ -178,28 +208,38 @@ chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsig
       for (int c = 0; c < NC; c++)
         a[c] = c < mv.ncomp ? ld2(mv.comp[c].amp + (size_t)k * mv.Ppad + p) : make_double2(0.0, 0.0);
       double2 chi = make_double2(0.0, 0.0);
-#pragma unroll 4
-      for (int j = 0; j < B; j++) {
-        const size_t off = plane_off(mv, j, k) + p;
-        const double2 sig = ld2(mv.sig + off);
-        const double2 rms = ld2(mv.rms + off);
-        double skx = 0.0, sky = 0.0;
+      for (int j0 = 0; j0 < B; j0 += DG_UB) {
+        double2 sg[DG_UB], rm[DG_UB];
 #pragma unroll
-        for (int c = 0; c < NC; c++)
-          if (c < mv.ncomp) {
-            skx = skx + a[c].x * ssed[k][c][j];
-            sky = sky + a[c].y * ssed[k][c][j];
-          }
-        double tx, ty;
-        if (k == 0) {
-          tx = (sig.x - mv.offset[j]) / mv.gain[j] - skx;
-          ty = (sig.y - mv.offset[j]) / mv.gain[j] - sky;
-        } else {
-          tx = sig.x - skx;
-          ty = sig.y - sky;
+        for (int u = 0; u < DG_UB; u++) {
+          const int j = min(j0 + u, B - 1);
+          const size_t off = plane_off(mv, j, k) + p;
+          sg[u] = ld2(mv.sig + off);
+          rm[u] = ld2(mv.rms + off);
         }
-        chi.x = chi.x + (tx * tx) / (rms.x * rms.x);
-        chi.y = chi.y + (ty * ty) / (rms.y * rms.y);
+#pragma unroll
+        for (int u = 0; u < DG_UB; u++) {
+          const int j = j0 + u;
+          if (j < B) {
+            double skx = 0.0, sky = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+              if (c < mv.ncomp) {
+                skx = skx + a[c].x * ssed[k][c][j];
+                sky = sky + a[c].y * ssed[k][c][j];
+              }
+            double tx, ty;
+            if (k == 0) {
+              tx = (sg[u].x - mv.offset[j]) / mv.gain[j] - skx;
+              ty = (sg[u].y - mv.offset[j]) / mv.gain[j] - sky;
+            } else {
+              tx = sg[u].x - skx;
+              ty = sg[u].y - sky;
+            }
+            chi.x = chi.x + (tx * tx) * fast_rcp(rm[u].x * rm[u].x);
+            chi.y = chi.y + (ty * ty) * fast_rcp(rm[u].y * rm[u].y);
+          }
+        }
       }
       acc[k] += (use0 ? chi.x / B : 0.0) + (use1 ? chi.y / B : 0.0);
     }
@@ -246,13 +286,19 @@ mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms,
 #pragma unroll
         for (int c = 0; c < NC; c++)
           if (c == mh.ic) am = a[c];
+        double2 sg[DG_SUFF_CHUNK], rm[DG_SUFF_CHUNK];
+#pragma unroll
+        for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
+          const int j = min(ch * DG_SUFF_CHUNK + jj, B - 1);
+          const size_t off = plane_off(mv, j, k) + p;
+          sg[jj] = ld2(mv.sig + off);
+          rm[jj] = ld2(mv.rms + off);
+        }
 #pragma unroll
         for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
           const int j = ch * DG_SUFF_CHUNK + jj;
           if (j < B) {
-            const size_t off = plane_off(mv, j, k) + p;
-            double2 d = ld2(mv.sig + off);
-            const double2 rms = ld2(mv.rms + off);
+            double2 d = sg[jj];
             if (k == 0) {
               d.x = (d.x - mv.offset[j]) / mv.gain[j];
               d.y = (d.y - mv.offset[j]) / mv.gain[j];
@@ -263,8 +309,9 @@ mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms,
                 d.x = d.x - a[c].x * ssed[s][c][j];
                 d.y = d.y - a[c].y * ssed[s][c][j];
               }
-            const double tx = (d.x - am.x * s0s[j]) / rms.x, ty = (d.y - am.y * s0s[j]) / rms.y;
-            const double ux = am.x / rms.x, uy = am.y / rms.y;
+            const double ix = fast_rcp(rm[jj].x), iy = fast_rcp(rm[jj].y);
+            const double tx = (d.x - am.x * s0s[j]) * ix, ty = (d.y - am.y * s0s[j]) * iy;
+            const double ux = am.x * ix, uy = am.y * iy;
             acc[3 * jj + 0] += (use0 ? tx * tx : 0.0) + (use1 ? ty * ty : 0.0);
             acc[3 * jj + 1] += (use0 ? tx * ux : 0.0) + (use1 ? ty * uy : 0.0);
             acc[3 * jj + 2] += (use0 ? ux * ux : 0.0) + (use1 ? uy * uy : 0.0);
