@@ -156,7 +156,8 @@ struct dang_gpu {
   double *bp_nu0 = nullptr, *bp_tau0 = nullptr, *bp_lnr_hi = nullptr, *bp_lnr_lo = nullptr;
   int nbp = 0;
   bool bp_dirty = true;   // band / component constants changed: rebuild the static tables
-  bool tab_dirty = true;  // an index map changed: re-check uniformity, re-tabulate SEDs
+  bool tab_dirty = true;  // an index map changed: re-tabulate SEDs
+  unsigned long long check_mask = ~0ull;  // index maps whose uniformity must be re-scanned
   SedTable *tab = nullptr;
   int uni_host[DG_MAX_COMPS * 3] = {};  // host copy of SedTable::uni (refreshed with the tables)
   CompHost comp[DG_MAX_COMPS];
@@ -362,12 +363,18 @@ ModelView model_view(dang_gpu *h) {
   mv.rms = h->rms;
   mv.mask = h->mask;
   if (h->tab_dirty) {  // an index map changed since the SED tables were built
-    CK(cudaMemsetAsync((char *)h->tab + offsetof(SedTable, nonuni), 0, sizeof(((SedTable *)0)->nonuni), h->stream));
-    {
+    if (h->check_mask) {
+      // maps uploaded by the host are scanned once; maps written by the samplers are not (their
+      // uniformity is known by construction and was recorded by set_nonuni)
+      const int nmap = h->ncomp * 3 * DG_MAXIND;
+      for (int m = 0; m < nmap; m++)
+        if ((h->check_mask >> m) & 1ull)
+          CK(cudaMemsetAsync((char *)h->tab + offsetof(SedTable, nonuni) + m * sizeof(int), 0, sizeof(int), h->stream));
       KTimer kt(h, DANG_K_SCALAR, 0);
-      dim3 grid(grid_for(h, h->P, DG_THREADS, 1), h->ncomp * 3 * DG_MAXIND);
-      uniform_check_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, h->tab);
+      dim3 grid(grid_for(h, h->P, DG_THREADS, 1), nmap);
+      uniform_check_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, h->tab, h->check_mask);
       kt.done();
+      h->check_mask = 0;
     }
     KTimer kt(h, DANG_K_SCALAR, 0);
     sed_table_kernel<<<h->ncomp * 3, 32, 0, h->stream>>>(mv, h->tab);
@@ -408,6 +415,14 @@ int flag_planes(int flag, int plane[2]) {  // 0-based planes; returns S
 }
 
 double bytes_w(double n) { return n * 8.0; }
+
+// record that index map (c, l) on plane k is known constant (val = 0) or varying (val = 1)
+void set_nonuni(dang_gpu *h, int c, int k, int l, int val) {
+  const int m = (c * 3 + k) * DG_MAXIND + l;
+  CK(cudaMemsetAsync((char *)h->tab + offsetof(SedTable, nonuni) + m * sizeof(int), val ? 1 : 0, sizeof(int), h->stream));
+  h->check_mask &= ~(1ull << m);
+  h->tab_dirty = true;
+}
 
 bool comp_uniform(const dang_gpu *h, int c, int k) { return h->uni_host[c * 3 + k] != 0; }
 
@@ -853,7 +868,7 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
     }
     gather(h, cnt);
     KTimer ks(h, DANG_K_SCALAR, 0);
-    mh_suff_chain_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
+    mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
     ks.done();
   }
   {
@@ -1102,6 +1117,8 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   CK(cudaStreamSynchronize(h->stream));
   h->bp_dirty = true;
   h->tab_dirty = true;
+  for (int k = 0; k < 3; k++)
+    for (int l = 0; l < DG_MAXIND; l++) h->check_mask |= 1ull << ((ic * 3 + k) * DG_MAXIND + l);
   API_END
 }
 
@@ -1144,6 +1161,8 @@ int dang_gpu_set_indices(dang_gpu_t *h, int ic, const double *indices) {
     h2d_planes(h, h->comp[ic].idx[l], indices + (size_t)l * h->nmaps * h->npix, h->nmaps);
   CK(cudaStreamSynchronize(h->stream));
   h->tab_dirty = true;
+  for (int k = 0; k < 3; k++)
+    for (int l = 0; l < DG_MAXIND; l++) h->check_mask |= 1ull << ((ic * 3 + k) * DG_MAXIND + l);
   API_END
 }
 
@@ -1226,10 +1245,13 @@ int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsampl
   if (nsample < 0) fail(DANG_GPU_EINVAL, "nsample = %d", nsample);
   MhView mh;
   mh_view(h, ic, nind, map_n, nsample, ml_mode, mh);
-  h->tab_dirty = true;  // set before the draw so an error path cannot leave stale tables
-  if (h->comp[ic].index[nind].index_mode == DANG_INDEX_PERPIXEL) sample_perpixel(h, mh, z, u, seed, accept);
+  const bool perpix = h->comp[ic].index[nind].index_mode == DANG_INDEX_PERPIXEL;
+  if (perpix) sample_perpixel(h, mh, z, u, seed, accept);
   else sample_fullsky(h, mh, z, u, seed, accept);
-  h->tab_dirty = true;
+  // the written planes are varying after a per-pixel draw (masked pixels are zeroed, so even a
+  // chain that never moved leaves a non-constant plane unless nothing is masked -- treating it as
+  // varying is always safe) and constant after a full-sky draw
+  for (int s = 0; s < mh.S; s++) set_nonuni(h, ic, mh.plane[s], nind, perpix ? 1 : 0);
   API_END
 }
 

@@ -119,12 +119,15 @@ __global__ void mask_to_bytes_kernel(const double *mask, unsigned char *out, int
 
 // ---------------------------------------------------------------- SED tables
 // uniform_check_kernel: does index map (c, l) hold one value on plane k (over ALL local pixels)?
-// grid = (blocks, ncomp * 3 * DG_MAXIND); tab->nonuni must be zero on entry.
+// grid = (blocks, ncomp * 3 * DG_MAXIND); the nonuni flags of the maps selected by check_mask must
+// be zero on entry.  Maps written by the samplers are never re-scanned: a full-sky draw leaves a
+// constant plane, a per-pixel draw a varying one, and the host sets their flags directly.
 __global__ void __launch_bounds__(DG_THREADS)
-uniform_check_kernel(const ModelView mv, SedTable *tab) {
+uniform_check_kernel(const ModelView mv, SedTable *tab, unsigned long long check_mask) {
   const int m = blockIdx.y;
   const int l = m % DG_MAXIND, k = (m / DG_MAXIND) % 3, c = m / (DG_MAXIND * 3);
   if (c >= mv.ncomp || k >= mv.nmaps || l >= mv.comp[c].nind) return;
+  if (!((check_mask >> m) & 1ull)) return;  // this map's flag is already known
   const double *map = mv.comp[c].idx[l] + (size_t)k * mv.Ppad;
   const double first = map[0];
   bool bad = false;

@@ -371,33 +371,66 @@ mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, dou
   }
 }
 
-// the whole full-sky chain from the statistics: one thread, no map traffic (:282-324)
-__global__ void mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
-                                     const double *gathered, int nranks, int cnt) {
-  const int B = mv.nbands;
-  // lnL(theta) = -1/2 sum_j (X_j - 2 delta_j Y_j + delta_j^2 Z_j), delta_j = sed_j(theta) - s0_j
-  auto lnl_of = [&](const double *sed) -> double {
-    double lnl = 0.0;
-    for (int j = 0; j < B; j++) {
-      double X = 0.0, Y = 0.0, Z = 0.0;
-      for (int g = 0; g < nranks; g++) {
-        X += gathered[g * cnt + 3 * j + 0];
-        Y += gathered[g * cnt + 3 * j + 1];
-        Z += gathered[g * cnt + 3 * j + 2];
-      }
-      const double dl = sed[j] - ms->s0[j];
-      lnl = lnl - 0.5 * (X - 2.0 * dl * Y + dl * dl * Z);
+// The whole full-sky chain from the statistics (:282-324), no map traffic.  One warp: lane j owns
+// band j (its statistics, s0 and the proposal's SED), lnL is a fixed-order butterfly over lanes;
+// every lane carries the same chain state, lane 0 publishes it.
+__global__ void __launch_bounds__(32)
+mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const double *gathered,
+                     int nranks, int cnt) {
+  const int B = mv.nbands, j = threadIdx.x;
+  double X = 0.0, Y = 0.0, Z = 0.0, s0 = 0.0;
+  if (j < B) {
+    for (int g = 0; g < nranks; g++) {
+      X += gathered[g * cnt + 3 * j + 0];
+      Y += gathered[g * cnt + 3 * j + 1];
+      Z += gathered[g * cnt + 3 * j + 2];
     }
-    return lnl;
+    s0 = ms->s0[j];
+  }
+  double sample[DG_MAXIND] = {ms->sample[0], ms->sample[1]};
+  double theta[DG_MAXIND] = {sample[0], sample[1]};
+  // lnL(theta) = -1/2 sum_j (X_j - 2 delta_j Y_j + delta_j^2 Z_j), delta_j = sed_j(theta) - s0_j
+  auto lnl_of = [&](double sed) -> double {
+    const double dl = sed - s0;
+    double v = (j < B) ? -0.5 * (X - 2.0 * dl * Y + dl * dl * Z) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
   };
-  double prior = 0.0;
-  if (mh.prior_type == 1) prior = log_normal_prior(ms->sample[mh.nind], mh.gauss[0], mh.gauss[1]);
-  ms->lnl_old = lnl_of(ms->s0) + prior;
-  ms->phase = 1;
-  mh_next_proposal(mv, mh, ms);
-  while (!ms->skip) {
-    mh_accept_step(mh, ms, lnl_of(ms->sed));
-    mh_next_proposal(mv, mh, ms);
+  auto prior_of = [&](double val) -> double {
+    return mh.prior_type == 1 ? log_normal_prior(val, mh.gauss[0], mh.gauss[1]) : 0.0;
+  };
+  double lnl_old = lnl_of(s0) + prior_of(sample[mh.nind]);  // :250, :261, :268
+  double accept = 0.0;
+  for (int l = 0; l < mh.nsample; l++) {
+    theta[mh.nind] = sample[mh.nind] + (0.0 + mh.step * mh_draw_z(mh, l));  // :286
+    if (theta[mh.nind] < mh.uni[0] || theta[mh.nind] > mh.uni[1]) {          // :287, Q5
+      if (mh.decisions && j == 0) mh.decisions[l] = 2;
+      continue;
+    }
+    const double sed = (j < B) ? sed_theta(mv, mh.ic, j, theta[0], theta[1]) : 0.0;
+    const double lnl_new = lnl_of(sed) + prior_of(theta[mh.nind]);  // :306
+    const double diff = lnl_new - lnl_old;
+    const double ratio = exp(diff);  // :310, Q4
+    const bool acc = (mh.ml_mode == 0) ? (ratio > 1.0) : (ratio > mh_draw_u(mh, l));
+    if (acc) {
+      sample[mh.nind] = theta[mh.nind];
+      lnl_old = lnl_new;
+      accept += 1.0;
+    }
+    if (j == 0) {
+      if (mh.lnl_trace) mh.lnl_trace[l] = lnl_new;
+      if (mh.decisions) mh.decisions[l] = acc ? 1 : 0;
+    }
+  }
+  if (j == 0) {
+    ms->sample[0] = sample[0];
+    ms->sample[1] = sample[1];
+    ms->lnl_old = lnl_old;
+    ms->accept = accept;
+    ms->l = mh.nsample;
+    ms->phase = 1;
+    ms->skip = 1;
   }
 }
 
