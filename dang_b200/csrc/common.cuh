@@ -183,7 +183,7 @@ __host__ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t
   return r * sin(2.0 * DG_PI * u2);
 }
 
-enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3 };
+enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3, DG_STREAM_TUNE_Z = 4, DG_STREAM_TUNE_U = 5 };
 
 // ---------------------------------------------------------------- deterministic reductions
 // Two-stage tree: per-thread serial partial -> warp shuffle -> shared-memory tree over warps

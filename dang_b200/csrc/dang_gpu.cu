@@ -784,34 +784,8 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
   if (accept) *accept = a;
 }
 
-void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
-                    double *accept) {
-  if (mh.lnl_type != DANG_LNL_CHISQ)
-    fail(DANG_GPU_EUNSUPPORTED, "full-sky sampling supports lnl_type 'chisq' only (DESIGN.md)");
-  if (mh.prior_type == DANG_PRIOR_JEFFREYS)
-    fail(DANG_GPU_EUNSUPPORTED, "full-sky Jeffreys prior is not built (DESIGN.md)");
-  ModelView mv = model_view(h);
-  mh.seed = seed;
-  const size_t n = (size_t)mh.nsample;
-  if (z) {
-    ensure_zu(h, n > 0 ? n : 1);
-    CK(cudaMemcpyAsync(h->zbuf, z, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    mh.z = h->zbuf;
-    if (u) {
-      CK(cudaMemcpyAsync(h->ubuf, u, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      mh.u = h->ubuf;
-    } else if (mh.ml_mode == DANG_ML_SAMPLE) {
-      fail(DANG_GPU_EINVAL, "z injected without u");
-    }
-  }
-  ensure_decisions(h, n > 0 ? n : 1);
-  CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
-  CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));
-  mh.decisions = h->decisions;
-  mh.lnl_trace = h->lnl_trace;
-  h->dec_mode = 1;
-  h->dec_nsample = mh.nsample;
-
+// chain start (sample <- indices at global pixel 0) + sufficient statistics, gathered over ranks
+int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
   CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
   {
     KTimer kt(h, DANG_K_SCALAR, 0);
@@ -824,6 +798,64 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
     mh_fullsky_init_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, 2);
     kt.done();
   }
+  if (h->fullsky_stream) return 0;
+  const double n_el = (double)mh.S * h->P;
+  const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  const int cnt = nchunk * 3 * DG_SUFF_CHUNK;
+  KTimer kt(h, DANG_K_MH_SUFFSTAT, bytes_w(n_el * (2.0 * h->nbands + h->ncomp)));
+  bool uni = h->ncomp <= 4;
+  for (int s = 0; s < mh.S && uni; s++)
+    for (int c = 0; c < h->ncomp; c++)
+      if (c != mh.ic) uni = uni && comp_uniform(h, c, mh.plane[s]);
+  if (uni) {
+    const int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
+    if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+    else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+  } else {
+    const int grid = occ_grid(h, mh_suffstat_kernel, h->P, DG_THREADS);
+    mh_suffstat_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+  }
+  kt.done();
+  gather(h, cnt);
+  return cnt;
+}
+
+void check_fullsky_supported(const MhView &mh) {
+  if (mh.lnl_type != DANG_LNL_CHISQ)
+    fail(DANG_GPU_EUNSUPPORTED, "full-sky sampling supports lnl_type 'chisq' only (DESIGN.md)");
+  if (mh.prior_type == DANG_PRIOR_JEFFREYS)
+    fail(DANG_GPU_EUNSUPPORTED, "full-sky Jeffreys prior is not built (DESIGN.md)");
+}
+
+void upload_fullsky_deviates(dang_gpu *h, MhView &mh, const double *z, const double *u, size_t n) {
+  if (!z) return;
+  ensure_zu(h, n > 0 ? n : 1);
+  CK(cudaMemcpyAsync(h->zbuf, z, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  mh.z = h->zbuf;
+  if (u) {
+    CK(cudaMemcpyAsync(h->ubuf, u, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    mh.u = h->ubuf;
+  } else if (mh.ml_mode == DANG_ML_SAMPLE) {
+    fail(DANG_GPU_EINVAL, "z injected without u");
+  }
+}
+
+void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
+                    double *accept) {
+  check_fullsky_supported(mh);
+  ModelView mv = model_view(h);
+  mh.seed = seed;
+  const size_t n = (size_t)mh.nsample;
+  upload_fullsky_deviates(h, mh, z, u, n);
+  ensure_decisions(h, n > 0 ? n : 1);
+  CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
+  CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));
+  mh.decisions = h->decisions;
+  mh.lnl_trace = h->lnl_trace;
+  h->dec_mode = 1;
+  h->dec_nsample = mh.nsample;
+
+  const int cnt = fullsky_statistics(h, mv, mh);
   const double n_el = (double)mh.S * h->P;
   if (h->fullsky_stream) {
     const size_t dl = (size_t)h->nbands * mh.S * h->Ppad;
@@ -847,26 +879,6 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
       ks.done();
     }
   } else {
-    const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
-    const int cnt = nchunk * 3 * DG_SUFF_CHUNK;
-    const int grid = grid_for(h, h->P, DG_THREADS, 2);
-    {
-      KTimer kt(h, DANG_K_MH_SUFFSTAT, bytes_w(n_el * (2.0 * h->nbands + h->ncomp * 2.0)));
-      bool uni = h->ncomp <= 4;
-      for (int s = 0; s < mh.S && uni; s++)
-        for (int c = 0; c < h->ncomp; c++)
-          if (c != mh.ic) uni = uni && comp_uniform(h, c, mh.plane[s]);
-      if (uni) {
-        const int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
-        if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
-        else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
-      } else {
-        mh_suffstat_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets,
-                                                              h->sums_local);
-      }
-      kt.done();
-    }
-    gather(h, cnt);
     KTimer ks(h, DANG_K_SCALAR, 0);
     mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
     ks.done();
@@ -881,6 +893,37 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
   CK(cudaMemcpyAsync(hs, h->mh_scalars, sizeof(MhScalars), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (accept) *accept = hs->accept;
+}
+
+void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
+                  int max_blocks, int *blocks_run, double *step_size) {
+  check_fullsky_supported(mh);
+  if (max_blocks < 0) fail(DANG_GPU_EINVAL, "max_blocks = %d", max_blocks);
+  ModelView mv = model_view(h);
+  mh.seed = seed;
+  upload_fullsky_deviates(h, mh, z, u, (size_t)mh.nsample * max_blocks);
+  const int saved_stream = h->fullsky_stream;
+  h->fullsky_stream = 0;  // the tuner always runs on the sufficient statistics
+  int cnt = 0;
+  try {
+    cnt = fullsky_statistics(h, mv, mh);
+  } catch (...) {
+    h->fullsky_stream = saved_stream;
+    throw;
+  }
+  h->fullsky_stream = saved_stream;
+  double *d_out = h->sums_local + 100;  // scratch beyond the statistics rows
+  {
+    KTimer ks(h, DANG_K_SCALAR, 0);
+    mh_suff_tune_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt, max_blocks, d_out);
+    ks.done();
+  }
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->comp[ic].index[nind].step = hp[0];  // c%step_size(nind), :708-710
+  if (blocks_run) *blocks_run = (int)hp[1];
+  if (step_size) *step_size = hp[0];
 }
 
 }  // namespace
@@ -1273,10 +1316,14 @@ int dang_gpu_get_decisions(dang_gpu_t *h, unsigned char *decisions, double *lnl)
   API_END
 }
 
-int dang_gpu_tune_index(dang_gpu_t *h, int, int, int, int, int, const double *, const double *,
-                        uint64_t, int, int *, double *) {
+int dang_gpu_tune_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsample, int ml_mode,
+                        const double *z, const double *u, uint64_t seed, int max_blocks, int *blocks_run,
+                        double *step_size) {
   API_BEGIN
-  fail(DANG_GPU_EUNSUPPORTED, "tune_spectral_parameter_length is not built yet (DESIGN.md, next)");
+  if (nsample < 0) fail(DANG_GPU_EINVAL, "nsample = %d", nsample);
+  MhView mh;
+  mh_view(h, ic, nind, map_n, nsample, ml_mode, mh);
+  tune_fullsky(h, ic, nind, mh, z, u, seed, max_blocks, blocks_run, step_size);
   API_END
 }
 

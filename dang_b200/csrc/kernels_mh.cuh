@@ -434,6 +434,80 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
   }
 }
 
+// tune_spectral_parameter_length, src/dang_sample_mod.f90:623-717, on the same statistics:
+// blocks of nsample proposals; halve the step if accept/(nsample+1) < 0.4, x1.5 if > 0.6
+// (single-precision literals as in the source), stop when it lands in between.
+// out[0] = tuned step, out[1] = blocks run, out[2] = tuned flag.  Deviate slots: blk*nsample + l.
+__global__ void __launch_bounds__(32)
+mh_suff_tune_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, const double *gathered,
+                    int nranks, int cnt, int max_blocks, double *out) {
+  const int B = mv.nbands, j = threadIdx.x;
+  double X = 0.0, Y = 0.0, Z = 0.0, s0 = 0.0;
+  if (j < B) {
+    for (int g = 0; g < nranks; g++) {
+      X += gathered[g * cnt + 3 * j + 0];
+      Y += gathered[g * cnt + 3 * j + 1];
+      Z += gathered[g * cnt + 3 * j + 2];
+    }
+    s0 = ms->s0[j];
+  }
+  double sample[DG_MAXIND] = {ms->sample[0], ms->sample[1]};
+  double theta[DG_MAXIND] = {sample[0], sample[1]};
+  auto lnl_of = [&](double sed) -> double {
+    const double dl = sed - s0;
+    double v = (j < B) ? -0.5 * (X - 2.0 * dl * Y + dl * dl * Z) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  double lnl_old = 0.0, lnl_new = 0.0;
+  {
+    const double lnl = lnl_of(s0);
+    if (mh.prior_type == 1) lnl_old = lnl + log_normal_prior(sample[mh.nind], mh.gauss[0], mh.gauss[1]);  // :658-662
+    else if (mh.prior_type == 0) lnl_old = lnl;
+  }
+  double step = mh.step;
+  int blk = 0, tuned = 0;
+  while (!tuned && blk < max_blocks) {
+    double accept = 0.0;
+    for (int l = 0; l < mh.nsample; l++) {
+      const int slot = blk * mh.nsample + l;
+      const double zz = mh.z ? mh.z[slot] : philox_normal(mh.seed, DG_STREAM_TUNE_Z, (uint64_t)slot);
+      theta[mh.nind] = sample[mh.nind] + (0.0 + step * zz);  // :668
+      if (theta[mh.nind] < mh.uni[0] || theta[mh.nind] > mh.uni[1]) continue;
+      const double sed = (j < B) ? sed_theta(mv, mh.ic, j, theta[0], theta[1]) : 0.0;
+      const double lnl = lnl_of(sed);
+      if (mh.prior_type == 1) lnl_new = lnl + log_normal_prior(theta[mh.nind], mh.gauss[0], mh.gauss[1]);
+      else if (mh.prior_type == 0) lnl_new = lnl;
+      const double ratio = exp(lnl_new - lnl_old);
+      bool acc;
+      if (mh.ml_mode == 0) {
+        acc = ratio > 1.0;
+      } else {
+        double uu, u2;
+        if (mh.u) uu = mh.u[slot];
+        else philox_uniform2(mh.seed, DG_STREAM_TUNE_U, (uint64_t)slot, uu, u2);
+        acc = ratio > uu;
+      }
+      if (acc) {
+        sample[mh.nind] = theta[mh.nind];
+        lnl_old = lnl_new;
+        accept = accept + 1;
+      }
+    }
+    const double rate = accept / (double)(mh.nsample + 1);  // Fortran loop counter after the loop (:707)
+    if (rate < (double)0.4f) step = step - (double)0.5f * step;
+    else if (rate > (double)0.6f) step = step + (double)0.5f * step;
+    else tuned = 1;
+    blk++;
+  }
+  if (j == 0) {
+    out[0] = step;
+    out[1] = (double)blk;
+    out[2] = (double)tuned;
+  }
+}
+
 // index_full_res(:, map_inds) = sample(nind) -> c%indices (:329, :483)
 __global__ void mh_fullsky_store_kernel(const ModelView mv, const MhView mh, const MhScalars *ms) {
   const CompView &cv = mv.comp[mh.ic];

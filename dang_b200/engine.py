@@ -203,6 +203,20 @@ class Engine:
                                                 _dp(zz), _dp(uu), seed, C.byref(acc)))
         return acc.value
 
+    def tune_index(self, ic: int, nind: int, map_n: int, nsample: Optional[int] = None,
+                   ml_mode: Optional[str] = None, z: Optional[np.ndarray] = None,
+                   u: Optional[np.ndarray] = None, seed: int = 0, max_blocks: int = 20) -> Tuple[int, float]:
+        """tune_spectral_parameter_length (src/dang_sample_mod.f90:623-717): returns
+        (blocks run, tuned step size); the step is stored in the component for later draws."""
+        nsample = self.cfg.nsample if nsample is None else nsample
+        ml_mode = ml_mode or self.cfg.ml_mode
+        zz = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        nb, step = C.c_int(), C.c_double()
+        self._ck(self.lib.dang_gpu_tune_index(self.h, ic, nind, map_n, nsample, ML_MODES[ml_mode], _dp(zz),
+                                              _dp(uu), seed, max_blocks, C.byref(nb), C.byref(step)))
+        return nb.value, step.value
+
     def sample_spectral_parameters(self, nsample: Optional[int] = None, ml_mode: Optional[str] = None,
                                    z: Optional[np.ndarray] = None, u: Optional[np.ndarray] = None,
                                    seed: int = 0, stats: bool = True):

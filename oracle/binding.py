@@ -84,6 +84,7 @@ def load(omp: bool = False) -> C.CDLL:
         "ora_philox_uniform2": (None, [C.c_ulonglong, C.c_uint, C.c_ulonglong, c_dp, c_dp]),
         "ora_philox_normals": (None, [C.c_ulonglong, C.c_uint, C.c_ulonglong, ll, c_dp]),
         "ora_philox_uniforms": (None, [C.c_ulonglong, C.c_uint, C.c_ulonglong, ll, c_dp]),
+        "ora_philox_raw": (None, [C.POINTER(C.c_uint), C.c_uint, C.c_uint]),
         "ora_num_threads": (i, []),
     }
     for name_, (res, args) in sigs.items():

@@ -1239,6 +1239,8 @@ static void philox4x32_10(unsigned int c[4], unsigned int k0, unsigned int k1) {
   }
 }
 
+void ora_philox_raw(unsigned int ctr[4], unsigned int k0, unsigned int k1) { philox4x32_10(ctr, k0, k1); }
+
 void ora_philox_uniform2(unsigned long long seed, unsigned int stream, unsigned long long slot,
                          double *u1, double *u2) {
   unsigned int c[4] = {(unsigned int)slot, (unsigned int)(slot >> 32), stream, 0x44414e47u};

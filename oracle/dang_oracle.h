@@ -145,6 +145,7 @@ double ora_fit_band_gain(ora_state *st, int map_n, int band, int ml_mode, double
  * Stream definition (DESIGN.md "RNG"): uniform pair for (seed, stream, slot) is taken from
  * philox4x32_10(counter = {slot_lo, slot_hi, stream, 0x44414e47}, key = {seed_lo, seed_hi});
  * u1 = (x0*2^32 + x1 + 0.5) * 2^-64 ... see ora_philox_uniform2. */
+void ora_philox_raw(unsigned int ctr[4], unsigned int k0, unsigned int k1); /* Random123 KATs */
 void ora_philox_uniform2(unsigned long long seed, unsigned int stream, unsigned long long slot,
                          double *u1, double *u2);
 void ora_philox_normals(unsigned long long seed, unsigned int stream, unsigned long long slot0,

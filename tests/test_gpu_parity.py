@@ -261,6 +261,32 @@ def test_fullsky_metropolis(stream, name, ic, nind, others_uniform):
     assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-14
 
 
+@pytest.mark.parametrize("step0", [0.2, 0.0005, 0.004])
+def test_step_size_tuner(step0):
+    """tune_spectral_parameter_length: same blocks, same halving / x1.5 sequence, same final step."""
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c2", 16, perturb=False)
+    spec = cfg.comps[1].indices[0]
+    spec.step, spec.tune = step0, True
+    nsample, max_blocks = 20, 8
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    rng = np.random.default_rng(31)
+    z, u = rng.standard_normal(nsample * max_blocks), rng.random(nsample * max_blocks)
+    nb_o, step_o = ora.tune_step(1, 0, -1, nsample, 1, z, u, max_blocks)
+    nb_g, step_g = eng.tune_index(1, 0, -1, nsample, "sample", z, u, max_blocks=max_blocks)
+    assert nb_g == nb_o and nb_o >= 1
+    assert step_g == step_o
+    if nb_o == max_blocks:
+        return  # never settled inside 0.4..0.6 within max_blocks: the oracle still counts as untuned
+    # the tuned step is the one the next draw uses
+    z2, u2 = rng.standard_normal(nsample), rng.random(nsample)
+    acc_o, dec_o, _ = ora.sample_index_mh(1, 0, -1, nsample, 1, z2, u2)
+    acc_g = eng.sample_index_mh(1, 0, -1, nsample, "sample", z2, u2)
+    dec_g, _ = eng.decisions(nsample, fullsky=True)
+    assert np.array_equal(dec_g, dec_o[:nsample]) and acc_g == acc_o
+
+
 def test_full_gibbs_chain_c1():
     """Three Gibbs iterations of config c1 (CG amplitudes + per-pixel beta_s) with injected
     deviates: amplitudes, indices and chi-square follow the oracle throughout."""
