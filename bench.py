@@ -172,16 +172,20 @@ def run_gpu(args):
     # --- end to end through the C ABI with host buffers: deviates in, maps out, every step
     npix = cfg.npix
     eta_h = pinned_array(eng.lib, (2 * npix,))
-    z_h = pinned_array(eng.lib, (cfg.nsample,))
-    u_h = pinned_array(eng.lib, (cfg.nsample,))
+    # one (z, u) pair per sample_index_mh call: nsample slots for a full-sky index,
+    # nsample*npix for a per-pixel one
+    calls = [s for c in cfg.comps for s in c.indices if s.sample for _ in s.poltype.split(",")]
+    z_h = [pinned_array(eng.lib, (cfg.nsample * (1 if s.region == "fullsky" else npix),)) for s in calls]
+    u_h = [pinned_array(eng.lib, (cfg.nsample * (1 if s.region == "fullsky" else npix),)) for s in calls]
     amp_h = [pinned_array(eng.lib, (cfg.nmaps, npix)) for _ in cfg.comps]
     idx_h = [pinned_array(eng.lib, (len(c.indices), cfg.nmaps, npix)) for c in cfg.comps]
     rng = np.random.default_rng(20260103 + rank * 0)
     eta_h[:] = rng.standard_normal(2 * npix)
-    z_h[:] = rng.standard_normal(cfg.nsample)
-    u_h[:] = rng.random(cfg.nsample)
+    for zz, uu in zip(z_h, u_h):
+        zz[:] = rng.standard_normal(zz.size)
+        uu[:] = rng.random(uu.size)
     P = hi - lo
-    h2d = 8 * (2 * P + 2 * cfg.nsample)
+    h2d = 8 * (2 * P + sum(2 * cfg.nsample * (1 if s.region == "fullsky" else P) for s in calls))
     d2h = 8 * P * cfg.nmaps * (len(cfg.comps) + sum(len(c.indices) for c in cfg.comps)) + 8 * 8
 
     def e2e_step(it):

@@ -180,7 +180,11 @@ __host__ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t
   double u1, u2;
   philox_uniform2(seed, stream, slot, u1, u2);
   const double r = sqrt(-2.0 * log(u1));
+#ifdef __CUDA_ARCH__
+  return r * sinpi(2.0 * u2);  // == sin(2 pi u2) up to rounding, without reducing by an inexact pi
+#else
   return r * sin(2.0 * DG_PI * u2);
+#endif
 }
 
 enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3, DG_STREAM_TUNE_Z = 4, DG_STREAM_TUNE_U = 5 };

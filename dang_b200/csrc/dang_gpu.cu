@@ -144,7 +144,7 @@ struct dang_gpu {
   std::string err;
 
   // options
-  int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0;
+  int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
 
   // ddata
   bool maps_set = false;
@@ -767,14 +767,53 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
     h->dec_mode = 2;
     h->dec_nsample = mh.nsample;
   }
-  const size_t smem = (size_t)(2 * h->nbands * mh.S + h->nbands) * DG_MH_THREADS * sizeof(double);
-  if (smem > 200 * 1024) fail(DANG_GPU_EUNSUPPORTED, "per-pixel chain needs %zu B of shared memory", smem);
-  CK(cudaFuncSetAttribute(mh_perpixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = grid_for(h, h->P, DG_MH_THREADS, 8);
   const double n_el = (double)mh.S * h->P;
-  KTimer kt(h, DANG_K_MH_PERPIXEL, bytes_w(n_el * (2.0 * h->nbands + h->ncomp + 1) + (double)h->P * 4));
-  mh_perpixel_kernel<<<grid, DG_MH_THREADS, smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local);
-  kt.done();
+  const double kbytes = bytes_w(n_el * (2.0 * h->nbands + h->ncomp + 1) + (double)h->P * 4);
+  // the lane-cooperative kernel covers the chisq likelihood with uniform / Gaussian prior;
+  // marginal lnL, 'prior' draws and the Jeffreys prior run on the strict kernel
+  const bool strict = h->perpixel_serial || mh.lnl_type != DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS;
+  if (strict) {
+    const size_t smem = (size_t)(2 * h->nbands * mh.S + 2 * h->nbands) * DG_MH_THREADS * sizeof(double);
+    if (smem > 200 * 1024) fail(DANG_GPU_EUNSUPPORTED, "per-pixel chain needs %zu B of shared memory", smem);
+    CK(cudaFuncSetAttribute(mh_perpixel_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = occ_grid(h, mh_perpixel_serial_kernel, h->P, DG_MH_THREADS, smem);
+    KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
+    mh_perpixel_serial_kernel<<<grid, DG_MH_THREADS, smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local);
+    kt.done();
+  } else {
+    const size_t smem = (size_t)2 * (DG_MH_THREADS / DG_MH_LANES) * (mh.nsample > 0 ? mh.nsample : 1) * sizeof(double);
+    if (smem > 160 * 1024) fail(DANG_GPU_EUNSUPPORTED, "nsample = %d needs %zu B of shared memory", mh.nsample, smem);
+    const int bpl = (h->nbands + DG_MH_LANES - 1) / DG_MH_LANES;
+    const int64_t work = h->P * DG_MH_LANES;
+    bool any_bp = false;
+    for (int j = 0; j < h->nbands; j++) any_bp = any_bp || h->band[j].n != 0;
+    int mode = MH_SED_GENERIC;
+    if (!any_bp) {
+      if (h->comp[mh.ic].type == DANG_COMP_POWERLAW) mode = MH_SED_POWERLAW;
+      else mode = mh.nind == 0 ? MH_SED_MBB_BETA : MH_SED_MBB_T;
+    }
+    KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
+#define LAUNCH_PP(BPL, MODE)                                                                               \
+    {                                                                                                      \
+      CK(cudaFuncSetAttribute(mh_perpixel_kernel<BPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      const int grid = occ_grid(h, mh_perpixel_kernel<BPL, MODE>, work, DG_MH_THREADS, smem);              \
+      mh_perpixel_kernel<BPL, MODE><<<grid, DG_MH_THREADS, smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local); \
+    }
+#define LAUNCH_PP_MODE(BPL)                                     \
+    {                                                           \
+      if (mode == MH_SED_POWERLAW) LAUNCH_PP(BPL, MH_SED_POWERLAW) \
+      else if (mode == MH_SED_MBB_BETA) LAUNCH_PP(BPL, MH_SED_MBB_BETA) \
+      else if (mode == MH_SED_MBB_T) LAUNCH_PP(BPL, MH_SED_MBB_T)  \
+      else LAUNCH_PP(BPL, MH_SED_GENERIC)                       \
+    }
+    if (bpl <= 2) LAUNCH_PP_MODE(2)
+    else if (bpl <= 3) LAUNCH_PP_MODE(3)
+    else if (bpl <= 5) LAUNCH_PP_MODE(5)
+    else LAUNCH_PP_MODE(8)
+#undef LAUNCH_PP_MODE
+#undef LAUNCH_PP
+    kt.done();
+  }
   gather(h, 1);
   double *hp = (double *)h->pinned;
   CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1035,6 +1074,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_PROFILE: h->profile = value != 0; break;
     case DANG_OPT_CG_CHUNK: h->cg_chunk = value < 1 ? 1 : (int)value; break;
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
+    case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
     default: fail(DANG_GPU_EINVAL, "unknown option %d", option);
   }
   API_END

@@ -61,17 +61,40 @@ __device__ __forceinline__ double mh_data_value(const ModelView &mv, int ic, int
   return v;
 }
 
-// ---------------------------------------------------------------- K5: per-pixel chains
-// dynamic smem: sD[B][S][T], sR[B][S][T] (rms), sS[B][T] (proposal SED)
+// ---------------------------------------------------------------- K5 (strict order): per-pixel chains
+// Selected by DANG_OPT_PERPIXEL_SERIAL: lnL accumulated in exactly the reference's order.
+// One thread owns one pixel's chain (:353-470).  Shared memory per thread: the residual data
+// sD[B][S], the inverse noise sW[B][S], the proposal's SED sS[B] and sF[B], the factor of the SED
+// that does not depend on the index being sampled:
+//     power-law            sed_j = exp((beta) L_j)                      F_j = 1
+//     mbb, beta sampled    sed_j = [eref/(exp(z nu_j)-1)] exp((beta+1) L_j)   F_j = Planck ratio (T fixed)
+//     mbb, T sampled       sed_j = eref(T)/(exp(z nu_j)-1) [exp((beta+1) L_j)] F_j = power law (beta fixed)
+// so a proposal costs one exp per band (+1 for T) instead of three transcendentals; the products
+// are formed in the same order as sed_mbb, i.e. the same bits.  Bandpass-integrated bands keep
+// the full sum over bandpass samples.  This kernel is FP64-pipe bound (nsample*B exp per pixel
+// against 2*B*S*8 bytes of traffic), not HBM bound.
+__device__ __forceinline__ double mh_fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
 __global__ void __launch_bounds__(DG_MH_THREADS)
-mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsigned int *ticket,
-                   double *out) {
+mh_perpixel_serial_kernel(const ModelView mv, const MhView mh, double *partials, unsigned int *ticket,
+                          double *out) {
   extern __shared__ double dyn[];
   const int T = DG_MH_THREADS, tid = threadIdx.x, B = mv.nbands, S = mh.S;
-  double *sD = dyn, *sR = dyn + (size_t)B * S * T, *sS = dyn + (size_t)2 * B * S * T;
+  double *sD = dyn, *sW = dyn + (size_t)B * S * T, *sS = dyn + (size_t)2 * B * S * T,
+         *sF = dyn + (size_t)(2 * S + 1) * B * T;
   __shared__ double smem[32];
   double acc[1] = {0.0};
   const CompView &cv = mv.comp[mh.ic];
+  const SedTable &tab = *mv.tab;
+  const bool is_mbb = cv.type != 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + tid; p < mv.P; p += stride) {
     const uint64_t gpix = (uint64_t)(mv.pix_lo + p);
@@ -91,25 +114,61 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
     for (int j = 0; j < B; j++)
       for (int s = 0; s < S; s++) {
         sD[((size_t)j * S + s) * T + tid] = mh_data_value(mv, mh.ic, j, mh.plane[s], p);
-        sR[((size_t)j * S + s) * T + tid] = ldg_stream(mv.rms + plane_off(mv, j, mh.plane[s]) + p);
+        sW[((size_t)j * S + s) * T + tid] = ldg_stream(mv.rms + plane_off(mv, j, mh.plane[s]) + p);
       }
+    // the factor of each delta band's SED that stays fixed during this chain
+    if (is_mbb) {
+      if (mh.nind == 0) {
+        const double z = DG_H / (DG_KB * sample[1]);
+        const double eref = exp(z * cv.nu_ref) - 1.0;
+        for (int j = 0; j < B; j++)
+          if (mv.band[j].n == 0) sF[(size_t)j * T + tid] = eref / (exp(z * mv.band[j].nu_c) - 1.0);
+      } else {
+        for (int j = 0; j < B; j++)
+          if (mv.band[j].n == 0)
+            sF[(size_t)j * T + tid] = exp_scaled(sample[0] + 1.0, tab.lnr_hi[mh.ic][j], tab.lnr_lo[mh.ic][j]);
+      }
+    }
 
+    // SED of the proposal, band by band, into sS
+    auto eval_sed = [&](const double *th) {
+      if (!is_mbb) {
+#pragma unroll 4
+        for (int j = 0; j < B; j++)
+          sS[(size_t)j * T + tid] = sed_powerlaw(mv, mh.ic, j, th[0]);
+      } else if (mh.nind == 0) {
+#pragma unroll 4
+        for (int j = 0; j < B; j++)
+          sS[(size_t)j * T + tid] =
+              mv.band[j].n == 0 ? sF[(size_t)j * T + tid] * exp_scaled(th[0] + 1.0, tab.lnr_hi[mh.ic][j], tab.lnr_lo[mh.ic][j])
+                                : sed_mbb(mv, mh.ic, j, th[0], th[1]);
+      } else {
+        const double z = DG_H / (DG_KB * th[1]);
+        const double eref = exp(z * cv.nu_ref) - 1.0;
+#pragma unroll 4
+        for (int j = 0; j < B; j++)
+          sS[(size_t)j * T + tid] = mv.band[j].n == 0
+                                        ? eref / (exp(z * mv.band[j].nu_c) - 1.0) * sF[(size_t)j * T + tid]
+                                        : sed_mbb(mv, mh.ic, j, th[0], th[1]);
+      }
+    };
     // lnL of theta; order of accumulation as evaluate_lnL: Stokes outer, band inner (:172-176)
     auto eval_lnl = [&](const double *th) -> double {
-      for (int j = 0; j < B; j++) sS[(size_t)j * T + tid] = sed_theta(mv, mh.ic, j, th[0], th[1]);
+      eval_sed(th);
       double lnl = 0.0;
       if (mh.lnl_type == 0) {
         for (int s = 0; s < S; s++)
+#pragma unroll 4
           for (int j = 0; j < B; j++) {
             const double model = amp[s] * sS[(size_t)j * T + tid];  // eval_signal :773
-            const double t = (sD[((size_t)j * S + s) * T + tid] - model) / sR[((size_t)j * S + s) * T + tid];
+            const double t = (sD[((size_t)j * S + s) * T + tid] - model) / sW[((size_t)j * S + s) * T + tid];
             lnl = lnl - 0.5 * (t * t);
           }
       } else {  // marginal, src/dang_lnl_mod.f90:113-122 (band outer, Stokes inner)
         for (int j = 0; j < B; j++)
           for (int s = 0; s < S; s++) {
             const double model = amp[s] * sS[(size_t)j * T + tid];
-            const double rms = sR[((size_t)j * S + s) * T + tid];
+            const double rms = sW[((size_t)j * S + s) * T + tid];
             const double TN = model / (rms * rms);
             const double TNd = TN * sD[((size_t)j * S + s) * T + tid];
             const double TNT = TN * model;
@@ -127,7 +186,7 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
           for (int s = 0; s < S; s++)
             for (int j = 0; j < B; j++) {
               const double ss = amp[s] * sed_theta(mv, mh.ic, j, val, 0.0);
-              const double ir = 1.0 / sR[((size_t)j * S + s) * T + tid];
+              const double ir = 1.0 / sW[((size_t)j * S + s) * T + tid];
               const double t = (ir * ir) * (ss / amp[s]) * log(mv.band[j].nu_c / cv.nu_ref);
               sum = sum + t * t;
             }
@@ -187,6 +246,190 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
     }
     for (int s = 0; s < S; s++)  // :465, :483
       cv.idx[mh.nind][(size_t)mh.plane[s] * mv.Ppad + p] = sample[mh.nind];
+  }
+  grid_reduce<1>(acc, smem, partials, ticket, out);
+}
+
+// ---------------------------------------------------------------- K5 (default): per-pixel chains
+// chisq likelihood with uniform / Gaussian prior (every BASELINE config); the rare variants
+// (marginal lnL, 'prior' draws, Jeffreys prior) run on the strict kernel above.
+//
+// DG_MH_LANES lanes cooperate on one pixel's chain: lane r owns bands r, r+L, r+2L, ... with their
+// residual data, inverse noise, ln(nu/nu_ref) and fixed SED factor in REGISTERS (BPL = bands per
+// lane and the SED form are template parameters), evaluates its share of the proposal's SED and
+// chi-square, and the group forms lnL with a fixed-order butterfly.  The chain's deviates
+// (z_l, ln u_l) for the warp's 8 pixels are generated by all 32 lanes and parked in shared memory.
+// Compared with the strict kernel the numerical differences are the (fixed, tree) summation order
+// over bands, 1/sigma by multiplication and the Gaussian log-prior evaluated as
+// -(x-mu)^2/(2 sigma^2) - ln(sigma sqrt(2 pi)): lnL agrees to ~1e-16 relative, so a decision can
+// differ from the reference's only when |diff - ln u| < ~1e-14.
+#define DG_MH_LANES 4
+enum { MH_SED_POWERLAW = 0, MH_SED_MBB_BETA = 1, MH_SED_MBB_T = 2, MH_SED_GENERIC = 3 };
+
+template <int BPL, int MODE>
+__global__ void __launch_bounds__(DG_MH_THREADS)
+mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsigned int *ticket,
+                   double *out) {
+  constexpr int L = DG_MH_LANES;
+  constexpr int PB = DG_MH_THREADS / L;  // pixels per block iteration
+  constexpr int PW = 32 / L;             // pixels per warp
+  extern __shared__ double dyn[];        // zs[PB][nsample], lus[PB][nsample]
+  __shared__ double smem[32];
+  const int tid = threadIdx.x, lane = tid & 31, r = tid % L, g = tid / L, B = mv.nbands, S = mh.S;
+  const int nsample = mh.nsample;
+  const unsigned full = 0xffffffffu;
+  double *zs = dyn + (size_t)g * nsample, *lus = dyn + (size_t)(PB + g) * nsample;
+  double *wzs = dyn + (size_t)(g - lane / L) * nsample;  // first pixel of this warp
+  double *wlus = wzs + (size_t)PB * nsample;
+  double acc[1] = {0.0};
+  const CompView &cv = mv.comp[mh.ic];
+  const SedTable &tab = *mv.tab;
+  const double nu_ref = cv.nu_ref;
+  const double ln_denom = log(mh.gauss[1] * sqrt(2.0 * DG_PI));
+  const double inv2var = 1.0 / (2 * (mh.gauss[1] * mh.gauss[1]));
+
+  // per-lane band constants
+  double Lh[BPL], Ll[BPL], nuc[BPL];
+  bool bp[BPL];
+#pragma unroll
+  for (int i = 0; i < BPL; i++) {
+    const int j = r + i * L;
+    Lh[i] = j < B ? tab.lnr_hi[mh.ic][j] : 0.0;
+    Ll[i] = j < B ? tab.lnr_lo[mh.ic][j] : 0.0;
+    nuc[i] = j < B ? mv.band[j].nu_c : 1.0;
+    bp[i] = j < B && mv.band[j].n != 0;
+  }
+
+  const int64_t ngroups = (int64_t)gridDim.x * PB;
+  const int64_t niter = (mv.P + ngroups - 1) / ngroups;
+  for (int64_t itp = 0; itp < niter; itp++) {
+    const int64_t p = itp * ngroups + (int64_t)blockIdx.x * PB + g;
+    const bool valid = p < mv.P;
+    const bool use = valid && mv.mask[p] != 0;
+    if (!use && valid && r == 0) {  // :362; index_map stays 0 for masked pixels (:223, :465, :483)
+      for (int s = 0; s < S; s++) cv.idx[mh.nind][(size_t)mh.plane[s] * mv.Ppad + p] = 0.0;
+      if (mh.decisions)
+        for (int l = 0; l < nsample; l++) mh.decisions[(size_t)l * mv.P + p] = 3;
+    }
+    // a warp leaves only if all of its 8 pixels are idle; otherwise idle groups run along on
+    // pixel 0's data so the shuffles stay convergent (use == false guards every store)
+    if (!__any_sync(full, use)) continue;
+    const int64_t pp = use ? p : 0;
+    const size_t kp0 = (size_t)mh.plane[0] * mv.Ppad + pp;
+    const double idx0 = cv.nind > 0 ? cv.idx[0][kp0] : 0.0;  // :372-374
+    const double idx1 = cv.nind > 1 ? cv.idx[1][kp0] : 0.0;
+    double cur = mh.nind == 0 ? idx0 : idx1;
+    const double amp0 = cv.amp[(size_t)mh.plane[0] * mv.Ppad + pp];
+    const double amp1 = S > 1 ? cv.amp[(size_t)mh.plane[1] * mv.Ppad + pp] : 0.0;
+
+    double D0[BPL], D1[BPL], W0[BPL], W1[BPL], F[BPL];
+#pragma unroll
+    for (int i = 0; i < BPL; i++) {
+      const int j = r + i * L;
+      D0[i] = D1[i] = W0[i] = W1[i] = 0.0;
+      F[i] = 1.0;
+      if (j < B) {
+        D0[i] = mh_data_value(mv, mh.ic, j, mh.plane[0], pp);
+        W0[i] = 1.0 / ldg_stream(mv.rms + plane_off(mv, j, mh.plane[0]) + pp);
+        if (S > 1) {
+          D1[i] = mh_data_value(mv, mh.ic, j, mh.plane[1], pp);
+          W1[i] = 1.0 / ldg_stream(mv.rms + plane_off(mv, j, mh.plane[1]) + pp);
+        }
+        if (MODE == MH_SED_MBB_BETA) {
+          const double z = DG_H / (DG_KB * idx1);
+          F[i] = (exp(z * nu_ref) - 1.0) / (exp(z * nuc[i]) - 1.0);
+        } else if (MODE == MH_SED_MBB_T) {
+          F[i] = exp_scaled(idx0 + 1.0, Lh[i], Ll[i]);
+        }
+      }
+    }
+    // deviates of this warp's PW chains, slot-indexed (Q5), generated by all 32 lanes
+    __syncwarp();
+    {
+      const int64_t p_first = itp * ngroups + (int64_t)blockIdx.x * PB + (g - lane / L);
+      for (int q = lane; q < PW * nsample; q += 32) {
+        const int gq = q / nsample, l = q - gq * nsample;
+        int64_t pq = p_first + gq;
+        if (pq >= mv.P) pq = 0;
+        const size_t slot = (size_t)l * mv.P + pq;
+        const uint64_t gslot = (uint64_t)l * (uint64_t)mv.npix + (uint64_t)(mv.pix_lo + pq);
+        wzs[(size_t)gq * nsample + l] = mh.z ? mh.z[slot] : philox_normal(mh.seed, DG_STREAM_MH_Z, gslot);
+        double uu = 1.0, u2;
+        if (mh.ml_mode != 0) {
+          if (mh.u) uu = mh.u[slot];
+          else philox_uniform2(mh.seed, DG_STREAM_MH_U, gslot, uu, u2);
+        }
+        wlus[(size_t)gq * nsample + l] = log(uu);  // :450
+      }
+    }
+    __syncwarp();
+
+    double lnl_old = 0.0, naccept = 0.0;
+    for (int l = -1; l < nsample; l++) {  // l = -1: lnL of the starting point (:380-402)
+      double x = cur;
+      bool oob = false;
+      if (l >= 0) {
+        x = cur + (0.0 + mh.step * zs[l]);             // :414
+        oob = x < mh.uni[0] || x > mh.uni[1];          // :415, Q5
+      }
+      const double xe = oob ? cur : x;  // out-of-bounds groups evaluate a harmless value, discarded
+      // ---- this lane's share of lnL(xe)
+      double zT = 0.0, eref = 0.0;
+      if (MODE == MH_SED_MBB_T) {
+        zT = DG_H / (DG_KB * xe);
+        eref = exp(zT * nu_ref) - 1.0;
+      }
+      double part = 0.0;
+#pragma unroll
+      for (int i = 0; i < BPL; i++) {
+        const int j = r + i * L;
+        if (j < B) {
+          double sed;
+          if (MODE == MH_SED_POWERLAW) sed = exp_scaled(xe, Lh[i], Ll[i]);
+          else if (MODE == MH_SED_MBB_BETA) sed = F[i] * exp_scaled(xe + 1.0, Lh[i], Ll[i]);
+          else if (MODE == MH_SED_MBB_T) sed = eref * mh_fast_rcp(exp(zT * nuc[i]) - 1.0) * F[i];
+          else sed = sed_theta(mv, mh.ic, j, mh.nind == 0 ? xe : idx0, mh.nind == 0 ? idx1 : xe);
+          const double t0 = (D0[i] - amp0 * sed) * W0[i];
+          part = part - 0.5 * (t0 * t0);
+          if (S > 1) {
+            const double t1 = (D1[i] - amp1 * sed) * W1[i];
+            part = part - 0.5 * (t1 * t1);
+          }
+        }
+      }
+      part += __shfl_xor_sync(full, part, 1);
+      part += __shfl_xor_sync(full, part, 2);
+      double prior = 0.0;
+      if (mh.prior_type == 1) {
+        const double a = ((xe - mh.gauss[0]) * (xe - mh.gauss[0])) * inv2var;
+        prior = a < 700.0 ? -a - ln_denom : log_normal_prior(xe, mh.gauss[0], mh.gauss[1]);
+      }
+      const double lnl_new = part + prior;
+      if (l < 0) {
+        lnl_old = lnl_new;
+        continue;
+      }
+      const size_t slot = (size_t)l * mv.P + pp;
+      if (oob) {
+        if (use && r == 0 && mh.decisions) mh.decisions[slot] = 2;
+        continue;
+      }
+      const double diff = lnl_new - lnl_old;
+      const bool accept = (mh.ml_mode == 0) ? (diff > 0.0) : (diff > lus[l]);  // :444, :450 (Q4)
+      if (accept) {
+        cur = x;
+        lnl_old = lnl_new;
+        naccept += 1.0;
+      }
+      if (use && r == 0) {
+        if (mh.lnl_trace) mh.lnl_trace[slot] = lnl_new;
+        if (mh.decisions) mh.decisions[slot] = accept ? 1 : 0;
+      }
+    }
+    if (use && r == 0) {
+      for (int s = 0; s < S; s++) cv.idx[mh.nind][(size_t)mh.plane[s] * mv.Ppad + p] = cur;  // :465, :483
+      acc[0] += naccept;
+    }
   }
   grid_reduce<1>(acc, smem, partials, ticket, out);
 }

@@ -25,6 +25,7 @@ from .config import (COMP_TYPES, INDEX_MODES, LNL_TYPES, ML_MODES, PRIOR_TYPES, 
                      flag_to_map_n, return_poltype_flag)
 
 OPT_FIX_SAMPLE_VECTOR, OPT_CG_TWO_PASS, OPT_FULLSKY_STREAM, OPT_PROFILE, OPT_CG_CHUNK, OPT_RECORD = 1, 2, 3, 4, 5, 6
+OPT_PERPIXEL_SERIAL = 7
 KERNEL_COUNT = 11
 
 
@@ -221,9 +222,11 @@ class Engine:
                                    z: Optional[np.ndarray] = None, u: Optional[np.ndarray] = None,
                                    seed: int = 0, stats: bool = True):
         """sample_spectral_parameters: components -> indices -> pol flags, in reference order.
-        Deviate arrays are consumed call by call with stride nsample*npix (as the oracle does)."""
+        Deviate arrays are consumed call by call with stride nsample*npix (as the oracle does);
+        alternatively `z` / `u` may be lists holding one array per sample_index_mh call."""
         nsample = self.cfg.nsample if nsample is None else nsample
         stride = nsample * self.npix
+        per_call = isinstance(z, (list, tuple))
         ncall, sampled, acc = 0, False, []
         for ic, c in enumerate(self.cfg.comps):
             if not c.indices or not any(s.sample for s in c.indices):
@@ -233,8 +236,11 @@ class Engine:
                 if not s.sample:
                     continue
                 for flag in return_poltype_flag(s.poltype):
-                    zz = None if z is None else z[stride * ncall: stride * (ncall + 1)]
-                    uu = None if u is None else u[stride * ncall: stride * (ncall + 1)]
+                    if per_call:
+                        zz, uu = z[ncall], (None if u is None else u[ncall])
+                    else:
+                        zz = None if z is None else z[stride * ncall: stride * (ncall + 1)]
+                        uu = None if u is None else u[stride * ncall: stride * (ncall + 1)]
                     acc.append(self.sample_index_mh(ic, j, flag_to_map_n(flag), nsample, ml_mode, zz, uu,
                                                     seed + 7919 * ncall))
                     ncall += 1

@@ -73,7 +73,11 @@ enum {
   /* CG iterations enqueued between host checks of the convergence flag (default 8). */
   DANG_OPT_CG_CHUNK = 5,
   /* 1: per-pixel chains record every decision / lnL (dang_gpu_get_decisions); parity tests. */
-  DANG_OPT_RECORD_DECISIONS = 6
+  DANG_OPT_RECORD_DECISIONS = 6,
+  /* Per-pixel Metropolis.  0 (default): four lanes share a pixel's bands, lnL summed in a fixed
+   * tree order; 1: one thread per pixel, lnL accumulated in exactly the reference's order
+   * (Stokes outer, band inner, src/dang_lnl_mod.f90:172-176) -- several times slower. */
+  DANG_OPT_PERPIXEL_SERIAL = 7
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */

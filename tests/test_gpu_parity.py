@@ -179,11 +179,12 @@ def test_device_rng_eta_matches_philox_definition():
 
 
 # ------------------------------------------------------------------ spectral-parameter draw
-def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11):
-    from dang_b200.engine import OPT_RECORD, Engine
+def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11, serial=0):
+    from dang_b200.engine import OPT_PERPIXEL_SERIAL, OPT_RECORD, Engine
     from oracle.binding import Oracle
     ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
     eng.set_option(OPT_RECORD, 1)
+    eng.set_option(OPT_PERPIXEL_SERIAL, serial)
     z, u = deviates(cfg, nsample, seed=seed)
     acc_o, dec_o, lnl_o = ora.sample_index_mh(ic, nind, -1, nsample, 1 if ml_mode == "sample" else 0, z, u,
                                               want_trace=True)
@@ -192,13 +193,15 @@ def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11):
     return ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g)
 
 
-@pytest.mark.parametrize("name,ic,nind,nside", [("c1", 0, 0, 16), ("c3", 1, 0, 4), ("c4", 1, 0, 8), ("c4", 1, 1, 8)])
-def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside):
+@pytest.mark.parametrize("serial", [0, 1])  # lane-cooperative (default) and strict-order kernels
+@pytest.mark.parametrize("name,ic,nind,nside", [("c1", 0, 0, 16), ("c3", 1, 0, 4), ("c3", 0, 0, 4), ("c4", 1, 0, 8),
+                                                ("c4", 1, 1, 8), ("c2", 1, 1, 8)])
+def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside, serial):
     cfg, sky = small_case(name, nside)
     cfg.comps[ic].indices[nind].sample = True
     cfg.comps[ic].indices[nind].region = "per-pixel"
     nsample = 12
-    ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(cfg, sky, ic, nind, nsample)
+    ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(cfg, sky, ic, nind, nsample, serial=serial)
     assert np.array_equal(dec_g, dec_o), f"{(dec_g != dec_o).sum()} decisions differ"
     assert acc_g == acc_o
     ev = dec_o < 2
