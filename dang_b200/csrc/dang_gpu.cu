@@ -498,14 +498,20 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     const double n_el = (double)S * h->P;
     KTimer kt(h, DANG_K_RHS_BLOCKS,
               bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + 2.0 * C)) + bytes_w((double)h->P * 3));
-    bool uni = true;
+    // streaming kernel: out-of-group components must have tabulated SEDs; group components with
+    // varying indices get their SEDs staged per thread in dynamic shared memory
+    bool og_uni = true;
+    unsigned nu_mask = 0;
     for (int s = 0; s < S; s++) {
-      for (int c = 0; c < C; c++) uni = uni && comp_uniform(h, comps[c], cv.plane[s]);
-      for (int o = 0; o < nog; o++) uni = uni && comp_uniform(h, og[o], cv.plane[s]);
+      for (int c = 0; c < C; c++)
+        if (!comp_uniform(h, comps[c], cv.plane[s])) nu_mask |= 1u << c;
+      for (int o = 0; o < nog; o++) og_uni = og_uni && comp_uniform(h, og[o], cv.plane[s]);
     }
-    if (uni) {
-      const int g2 = occ_grid(h, rhs_blocks_uni_kernel<C>, h->Ppad / 2, DG_THREADS);
-      rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    const size_t dsm = (size_t)__builtin_popcount(nu_mask) * h->nbands * 2 * DG_THREADS * sizeof(double);
+    if (og_uni && dsm <= 160 * 1024) {
+      if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(rhs_blocks_uni_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      const int g2 = occ_grid(h, rhs_blocks_uni_kernel<C>, h->Ppad / 2, DG_THREADS, dsm);
+      rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask);
     } else {
       const int g1 = occ_grid(h, rhs_blocks_kernel<C>, h->P, DG_THREADS);
       rhs_blocks_kernel<C><<<g1, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
@@ -659,14 +665,24 @@ void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, do
   if (maps) bytes += bytes_w((double)h->P * h->nmaps * h->nbands * ((sky ? 1 : 0) + (res ? 1 : 0)));
   KTimer kt(h, maps ? DANG_K_SKYMODEL : DANG_K_CHISQ, bytes);
   bool uni = !maps && !chi_map && h->ncomp <= 4;
+  unsigned nu_mask = 0;
   for (int k = cv.k_lo; k <= cv.k_hi && uni; k++)
-    for (int c = 0; c < h->ncomp; c++) uni = uni && comp_uniform(h, c, k);
+    for (int c = 0; c < h->ncomp; c++)
+      if (!comp_uniform(h, c, k)) nu_mask |= 1u << c;
+  const size_t dsm = (size_t)__builtin_popcount(nu_mask) * h->nbands * 2 * DG_THREADS * sizeof(double);
+  if (dsm > 160 * 1024) uni = false;
   if (uni) {
-    const int g2 = occ_grid(h, chisq_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
-    if (h->ncomp <= 1) chisq_uni_kernel<1><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
-    else if (h->ncomp == 2) chisq_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
-    else if (h->ncomp == 3) chisq_uni_kernel<3><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
-    else chisq_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+#define LAUNCH_CHISQ_UNI(NC)                                                                                  \
+    {                                                                                                         \
+      if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(chisq_uni_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); \
+      const int g2 = occ_grid(h, chisq_uni_kernel<NC>, h->Ppad / 2, DG_THREADS, dsm);                         \
+      chisq_uni_kernel<NC><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask); \
+    }
+    if (h->ncomp <= 1) LAUNCH_CHISQ_UNI(1)
+    else if (h->ncomp == 2) LAUNCH_CHISQ_UNI(2)
+    else if (h->ncomp == 3) LAUNCH_CHISQ_UNI(3)
+    else LAUNCH_CHISQ_UNI(4)
+#undef LAUNCH_CHISQ_UNI
   }
   else if (h->ncomp <= 1) launch_chisq<1>(h, mv, cv, grid);
   else if (h->ncomp == 2) launch_chisq<2>(h, mv, cv, grid);

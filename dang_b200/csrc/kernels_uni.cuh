@@ -32,21 +32,73 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 __device__ __forceinline__ double2 ld2(const double *p) { return ldg_stream2(p); }
+
+// Per-thread SED staging for components whose indices vary from pixel to pixel: the SEDs of the
+// thread's two pixels, all bands, go to dynamic shared memory dst[(j*2 + lane)*nthr + tid] (one
+// exp per band for a power law, two for a modified blackbody with the reference-frequency Planck
+// term hoisted), after which the band loop streams exactly as in the all-uniform case.
+__device__ __forceinline__ void sed_pair_to_smem(const ModelView &mv, int ic, int k, int64_t p,
+                                                 double *dst, int nthr, int tid) {
+  const CompView &cv = mv.comp[ic];
+  const size_t kp = (size_t)k * mv.Ppad + p;
+  const double2 t0 = cv.nind > 0 ? *reinterpret_cast<const double2 *>(cv.idx[0] + kp) : make_double2(0.0, 0.0);
+  const double2 t1 = cv.nind > 1 ? *reinterpret_cast<const double2 *>(cv.idx[1] + kp) : make_double2(0.0, 0.0);
+  const bool same = t0.x == t0.y && t1.x == t1.y;
+  const SedTable &tab = *mv.tab;
+  if (cv.type == 1) {
+    for (int j = 0; j < mv.nbands; j++) {
+      const double a = sed_powerlaw(mv, ic, j, t0.x);
+      dst[(size_t)(j * 2 + 0) * nthr + tid] = a;
+      dst[(size_t)(j * 2 + 1) * nthr + tid] = same ? a : sed_powerlaw(mv, ic, j, t0.y);
+    }
+  } else {
+    const double zx = DG_H / (DG_KB * t1.x), zy = DG_H / (DG_KB * t1.y);
+    const double ex = exp(zx * cv.nu_ref) - 1.0, ey = same ? ex : exp(zy * cv.nu_ref) - 1.0;
+    for (int j = 0; j < mv.nbands; j++) {
+      double a, b;
+      if (mv.band[j].n == 0) {  // same operation order as sed_mbb
+        a = ex / (exp(zx * mv.band[j].nu_c) - 1.0) * exp_scaled(t0.x + 1.0, tab.lnr_hi[ic][j], tab.lnr_lo[ic][j]);
+        b = same ? a : ey / (exp(zy * mv.band[j].nu_c) - 1.0) * exp_scaled(t0.y + 1.0, tab.lnr_hi[ic][j], tab.lnr_lo[ic][j]);
+      } else {
+        a = sed_mbb(mv, ic, j, t0.x, t1.x);
+        b = same ? a : sed_mbb(mv, ic, j, t0.y, t1.y);
+      }
+      dst[(size_t)(j * 2 + 0) * nthr + tid] = a;
+      dst[(size_t)(j * 2 + 1) * nthr + tid] = b;
+    }
+  }
+}
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+// do the thread's two pixels carry the same indices of component ic on planes k and k2?
+// (always true after a Q+U draw: then the staged SEDs are reused instead of recomputed)
+__device__ __forceinline__ bool same_indices(const ModelView &mv, int ic, int k, int k2, int64_t p) {
+  const CompView &cv = mv.comp[ic];
+  if (sed_uniform(mv, ic, k) != sed_uniform(mv, ic, k2)) return false;
+  bool same = true;
+  for (int l = 0; l < cv.nind; l++) {
+    const double2 a = *reinterpret_cast<const double2 *>(cv.idx[l] + (size_t)k * mv.Ppad + p);
+    const double2 b = *reinterpret_cast<const double2 *>(cv.idx[l] + (size_t)k2 * mv.Ppad + p);
+    same = same && a.x == b.x && a.y == b.y;
+  }
+  return same;
+}
 
 // K1, uniform-SED form.  Same outputs as rhs_blocks_kernel.
 template <int C>
 __global__ void __launch_bounds__(DG_THREADS)
 rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
-                      unsigned int *ticket, double *out) {
+                      unsigned int *ticket, double *out, unsigned nu_mask) {
   constexpr int T = C * (C + 1) / 2;
+  extern __shared__ double dsed[];  // [slot][band][2][blockDim] for the components in nu_mask
+  const int nthr = blockDim.x, tid = threadIdx.x;
   __shared__ double smem[2 * 32];
   __shared__ double ssed[2][C][DG_MAX_BANDS];
   __shared__ double sog[2][DG_MAX_COMPS][DG_MAX_BANDS];
   const int B = mv.nbands;
   for (int i = threadIdx.x; i < 2 * C * B; i += blockDim.x) {
     const int s = i / (C * B), c = (i / B) % C, j = i % B;
-    if (s < cg.S) ssed[s][c][j] = mv.tab->sed[cg.comp[c] * 3 + cg.plane[s]][j];
+    if (s < cg.S && !((nu_mask >> c) & 1u)) ssed[s][c][j] = mv.tab->sed[cg.comp[c] * 3 + cg.plane[s]][j];
   }
   for (int i = threadIdx.x; i < 2 * cg.nog * B; i += blockDim.x) {
     const int s = i / (cg.nog * B), o = (i / B) % cg.nog, j = i % B;
@@ -65,6 +117,16 @@ rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
     for (int s = 0; s < cg.S; s++) {
       const int k = cg.plane[s];
       const size_t es = (size_t)s * mv.Ppad + p;
+      if (nu_mask) {  // stage this pixel pair's SEDs of the varying-index components
+        int slot = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++)
+          if ((nu_mask >> c) & 1u) {
+            if (s == 0 || !same_indices(mv, cg.comp[c], k, cg.plane[0], p))
+              sed_pair_to_smem(mv, cg.comp[c], k, p, dsed + (size_t)slot * B * 2 * nthr, nthr, tid);
+            slot++;
+          }
+      }
       double2 b[C], f[C], M[T];
 #pragma unroll
       for (int c = 0; c < C; c++) b[c] = f[c] = make_double2(0.0, 0.0);
@@ -108,18 +170,30 @@ rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
             const double ix = fast_rcp(rm[u].x), iy = fast_rcp(rm[u].y);
             const double wx = ix * ix, wy = iy * iy;
             const double tx = eta.x * ix, ty = eta.y * iy;
+            double2 sc[C];
+            {
+              int slot = 0;
+#pragma unroll
+              for (int c = 0; c < C; c++) {
+                if ((nu_mask >> c) & 1u) {
+                  const double *q = dsed + ((size_t)slot * B + j) * 2 * nthr + tid;
+                  sc[c] = make_double2(q[0], q[nthr]);
+                  slot++;
+                } else {
+                  sc[c] = make_double2(ssed[s][c][j], ssed[s][c][j]);
+                }
+              }
+            }
 #pragma unroll
             for (int c = 0; c < C; c++) {
-              const double sc = ssed[s][c][j];
-              b[c].x += data.x * sc * wx;
-              b[c].y += data.y * sc * wy;
-              f[c].x += tx * sc;
-              f[c].y += ty * sc;
+              b[c].x += data.x * sc[c].x * wx;
+              b[c].y += data.y * sc[c].y * wy;
+              f[c].x += tx * sc[c].x;
+              f[c].y += ty * sc[c].y;
 #pragma unroll
               for (int c2 = c; c2 < C; c2++) {
-                const double sc2 = ssed[s][c2][j];
-                M[tri<C>(c, c2)].x += sc * sc2 * wx;
-                M[tri<C>(c, c2)].y += sc * sc2 * wy;
+                M[tri<C>(c, c2)].x += sc[c].x * sc[c2].x * wx;
+                M[tri<C>(c, c2)].y += sc[c].y * sc[c2].y * wy;
               }
             }
           }
@@ -184,7 +258,9 @@ rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
 template <int NC>
 __global__ void __launch_bounds__(DG_THREADS)
 chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned int *ticket,
-                 double *out) {
+                 double *out, unsigned nu_mask) {
+  extern __shared__ double dsed[];  // [slot][band][2][blockDim] for the components in nu_mask
+  const int nthr = blockDim.x, tid = threadIdx.x;
   __shared__ double smem[4 * 32];
   __shared__ double ssed[3][NC][DG_MAX_BANDS];
   const int B = mv.nbands;
@@ -203,6 +279,25 @@ chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsig
     acc[3] += (use0 ? 1.0 : 0.0) + (use1 ? 1.0 : 0.0);
     if (!use0 && !use1) continue;
     for (int k = cv.k_lo; k <= cv.k_hi; k++) {
+      if (nu_mask) {
+        int slot = 0;
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+          if (c < mv.ncomp && ((nu_mask >> c) & 1u)) {
+            // components whose index maps vary on this plane; planes with a tabulated SED just copy
+            if (k > cv.k_lo && same_indices(mv, c, k, k - 1, p)) {
+              // staged values of the previous plane are still valid
+            } else if (sed_uniform(mv, c, k)) {
+              for (int j = 0; j < B; j++) {
+                dsed[((size_t)slot * B + j) * 2 * nthr + tid] = ssed[k][c][j];
+                dsed[((size_t)slot * B + j) * 2 * nthr + nthr + tid] = ssed[k][c][j];
+              }
+            } else {
+              sed_pair_to_smem(mv, c, k, p, dsed + (size_t)slot * B * 2 * nthr, nthr, tid);
+            }
+            slot++;
+          }
+      }
       double2 a[NC];
 #pragma unroll
       for (int c = 0; c < NC; c++)
@@ -222,12 +317,22 @@ chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsig
           const int j = j0 + u;
           if (j < B) {
             double skx = 0.0, sky = 0.0;
+            {
+              int slot = 0;
 #pragma unroll
-            for (int c = 0; c < NC; c++)
-              if (c < mv.ncomp) {
-                skx = skx + a[c].x * ssed[k][c][j];
-                sky = sky + a[c].y * ssed[k][c][j];
-              }
+              for (int c = 0; c < NC; c++)
+                if (c < mv.ncomp) {
+                  if ((nu_mask >> c) & 1u) {
+                    const double *q = dsed + ((size_t)slot * B + j) * 2 * nthr + tid;
+                    skx = skx + a[c].x * q[0];
+                    sky = sky + a[c].y * q[nthr];
+                    slot++;
+                  } else {
+                    skx = skx + a[c].x * ssed[k][c][j];
+                    sky = sky + a[c].y * ssed[k][c][j];
+                  }
+                }
+            }
             double tx, ty;
             if (k == 0) {
               tx = (sg[u].x - mv.offset[j]) / mv.gain[j] - skx;
