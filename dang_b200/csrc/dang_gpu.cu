@@ -145,6 +145,7 @@ struct dang_gpu {
 
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
+  int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
 
   // ddata
   bool maps_set = false;
@@ -524,6 +525,9 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     cg_init_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks, g.i_max, g.converge);
     kt.done();
   }
+  // recompute form needs the (alpha, beta) history: fall back to streaming for very long solves
+  const int ckpt_m = (!h->cg_two_pass && g.i_max < DG_CG_HIST) ? h->cg_ckpt : 0;
+  CK(cudaMemcpyAsync((char *)h->cg_scalars + offsetof(CgScalars, m), &ckpt_m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
 
   struct Snap { double delta_new; int iter, done; };
   auto read_state = [&]() -> Snap {
@@ -535,11 +539,19 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
 
   const int fold = h->nranks == 1 ? 1 : 0;
   const int grid = h->cg_two_pass ? occ_grid(h, cg_update_pass_kernel<C>, n2, DG_THREADS)
-                                  : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
+                   : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C>, n2, DG_THREADS)
+                                : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
   const double el = (double)vs;
   auto enqueue_pass = [&](int pass_no) {
     if (!h->cg_two_pass) {
-      {
+      if (ckpt_m) {
+        // compulsory traffic of this launch: M, r, d in; on checkpoint passes also x in, r, d, x out
+        const double per_el = (pass_no % ckpt_m == 0) ? (T + 6.0 * C) : (T + 2.0 * C);
+        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
+        cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0);
+        kt.done();
+      } else {
         // compulsory traffic of this launch: x is touched on even passes only
         const double per_el = (pass_no & 1) ? (T + 4.0 * C) : (T + 6.0 * C);
         KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
@@ -593,9 +605,13 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     sn = read_state();
     batch = h->cg_chunk;
   }
-  if (!h->cg_two_pass) {
-    KTimer kt(h, DANG_K_CG_PASS, 0);
-    cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
+  if (!h->cg_two_pass) {  // bring x up to date (pending term of the deferred / checkpointed update)
+    KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 4.0 * C : 3.0 * C)));
+    if (ckpt_m)
+      cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+          h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1);
+    else
+      cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
     kt.done();
   }
 
@@ -1091,6 +1107,9 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_CG_CHUNK: h->cg_chunk = value < 1 ? 1 : (int)value; break;
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
     case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
+    case DANG_OPT_CG_CHECKPOINT:
+      h->cg_ckpt = value < 0 ? 0 : (value > DG_CG_MAXM ? DG_CG_MAXM : (int)value);
+      break;
     default: fail(DANG_GPU_EINVAL, "unknown option %d", option);
   }
   API_END
@@ -1480,7 +1499,7 @@ const char *dang_gpu_kernel_name(int kernel) {
   static const char *names[DANG_K_COUNT] = {
       "rhs_blocks_kernel", "cg_fused_pass_kernel", "cg_dq_pass_kernel", "cg_update_pass_kernel",
       "chisq_kernel", "chisq_kernel(maps)", "mh_data_kernel", "mh_fullsky_lnl_kernel",
-      "mh_suffstat_kernel", "mh_perpixel_kernel", "scalar kernels"};
+      "mh_suffstat_kernel", "mh_perpixel_kernel", "scalar kernels", "cg_x_fixup"};
   return (kernel >= 0 && kernel < DANG_K_COUNT) ? names[kernel] : "?";
 }
 

@@ -24,12 +24,17 @@ struct CgView {
 };
 
 // scalars of one solve, device resident (DESIGN.md "CG control")
+#define DG_CG_HIST 1024   // passes whose (alpha, beta) are kept for the recompute form
+#define DG_CG_MAXM 32     // largest checkpoint interval
+
 struct CgScalars {
   double delta_new, delta_old, alpha, beta, dq;
   double alpha_prev;  // alpha of the pass that ran last (deferred x update, see cg_fused_pass_kernel)
   double converge;
   int iter, i_max, done, pad;
+  int ckpt, m;        // recompute form: pass whose state is stored in (r, d); checkpoint interval
   double trace[256];
+  double ah[DG_CG_HIST], bh[DG_CG_HIST];  // alpha_i, beta_i used IN pass i (1-based)
 };
 
 template <int C>
@@ -210,6 +215,9 @@ __device__ __forceinline__ void cg_init_update(CgScalars *st, const double *sums
   st->converge = converge;
   st->done = !(1 < i_max && rr > converge);
   st->trace[0] = rr;
+  st->ckpt = 0;
+  st->ah[1] = st->alpha;
+  st->bh[1] = 0.0;
 }
 
 // After a fused pass: {r'.r', r'.Mr', r'.q, d.q} with q = M d.
@@ -232,6 +240,11 @@ __device__ __forceinline__ void cg_fused_update(CgScalars *st, const double *sum
   st->iter = it;
   if (it - 1 < 256) st->trace[it - 1] = delta_new;
   st->done = !(it < st->i_max && delta_new > st->converge);
+  if (it < DG_CG_HIST) {
+    st->ah[it] = st->alpha;
+    st->bh[it] = beta;
+  }
+  if (st->m > 0 && (it - 1) - st->ckpt == st->m) st->ckpt = it - 1;  // pass it-1 stored its state
 }
 
 __global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, int nranks,
@@ -344,6 +357,110 @@ cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__rest
       *reinterpret_cast<double2 *>(r + c * vs + 2 * e) = rv[c];
     }
   }
+  const bool last = grid_reduce<4>(acc, smem, partials, ticket, out);
+  if (fold && last && threadIdx.x == 0) cg_fused_update(st, out, 1);
+}
+
+// ---------------------------------------------------------------- K2r: recompute form
+// The CG state of a block depends on the rest of the sky only through the scalars (alpha_i,
+// beta_i), so a pass does not have to STORE r and d: given the state after some earlier pass c
+// ("checkpoint") it re-runs the block-local recurrences for passes c+1..k in registers -- the
+// same operations in the same order, hence the same bits -- and only every m-th pass writes
+// r, d and x back.  HBM traffic per element and pass drops from T+4C / T+6C doubles to
+// T+2C reads, plus 2C (x) reads and 4C... writes on checkpoint passes: ~8 instead of 13 doubles
+// on average for C = 2, m = 8, paid for with ~m/2 extra 2x2 mat-vecs per element on an FP64 pipe
+// that the streaming form leaves idle.
+//   stored (r, d) = (r_{c+1}, d_c);   pass i:  d_i = r_i + beta_i d_{i-1};  q = M d_i;
+//   x += alpha_i d_i;  r_{i+1} = r_i - alpha_i q          (cg_search :296-305)
+// final = 1: the solve is over; bring x up to date from the last checkpoint (no reduction).
+template <int C>
+__global__ void __launch_bounds__(DG_THREADS)
+cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
+                         double *__restrict__ r, double *__restrict__ d, int64_t n2,
+                         double *partials, unsigned int *ticket, double *out, int fold, int final) {
+  constexpr int T = C * (C + 1) / 2;
+  if (st->done && !final) return;
+  const int c0 = st->ckpt;
+  const int k = final ? st->iter - 1 : st->iter;  // last pass to (re)run
+  const int nstep = k - c0;
+  if (final && nstep <= 0) return;
+  const bool store = !final && nstep == st->m;     // checkpoint pass
+  const bool with_x = store || final;
+  __shared__ double smem[4 * 32];
+  __shared__ double sa[DG_CG_MAXM + 1], sb[DG_CG_MAXM + 1];
+  if (threadIdx.x < nstep) {
+    sa[threadIdx.x] = st->ah[c0 + 1 + threadIdx.x];
+    sb[threadIdx.x] = st->bh[c0 + 1 + threadIdx.x];
+  }
+  __syncthreads();
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const size_t vs = (size_t)n2 * 2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    double2 m[T], xv[C], rv[C], dv[C], q[C];
+#pragma unroll
+    for (int t = 0; t < T; t++) m[t] = ldg_stream2(M + t * vs + 2 * e);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      rv[c] = *reinterpret_cast<const double2 *>(r + c * vs + 2 * e);
+      dv[c] = *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
+      if (with_x) xv[c] = *reinterpret_cast<const double2 *>(x + c * vs + 2 * e);
+    }
+    for (int i = 0; i < nstep; i++) {
+      const double alpha = sa[i], beta = sb[i];
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        dv[c].x = rv[c].x + beta * dv[c].x;  // :305
+        dv[c].y = rv[c].y + beta * dv[c].y;
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        double qx = 0.0, qy = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < C; c2++) {
+          const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+          qx += mm.x * dv[c2].x;
+          qy += mm.y * dv[c2].y;
+        }
+        q[c].x = qx;
+        q[c].y = qy;
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        if (with_x) {
+          xv[c].x = xv[c].x + alpha * dv[c].x;  // :298
+          xv[c].y = xv[c].y + alpha * dv[c].y;
+        }
+        rv[c].x = rv[c].x - alpha * q[c].x;     // :300
+        rv[c].y = rv[c].y - alpha * q[c].y;
+      }
+    }
+    if (!final) {
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        double mx = 0.0, my = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < C; c2++) {
+          const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+          mx += mm.x * rv[c2].x;
+          my += mm.y * rv[c2].y;
+        }
+        acc[0] += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
+        acc[1] += rv[c].x * mx + rv[c].y * my;
+        acc[2] += rv[c].x * q[c].x + rv[c].y * q[c].y;
+        acc[3] += dv[c].x * q[c].x + dv[c].y * q[c].y;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      if (store) {
+        *reinterpret_cast<double2 *>(r + c * vs + 2 * e) = rv[c];
+        *reinterpret_cast<double2 *>(d + c * vs + 2 * e) = dv[c];
+      }
+      if (with_x) *reinterpret_cast<double2 *>(x + c * vs + 2 * e) = xv[c];
+    }
+  }
+  if (final) return;
   const bool last = grid_reduce<4>(acc, smem, partials, ticket, out);
   if (fold && last && threadIdx.x == 0) cg_fused_update(st, out, 1);
 }

@@ -77,7 +77,11 @@ enum {
   /* Per-pixel Metropolis.  0 (default): four lanes share a pixel's bands, lnL summed in a fixed
    * tree order; 1: one thread per pixel, lnL accumulated in exactly the reference's order
    * (Stokes outer, band inner, src/dang_lnl_mod.f90:172-176) -- several times slower. */
-  DANG_OPT_PERPIXEL_SERIAL = 7
+  DANG_OPT_PERPIXEL_SERIAL = 7,
+  /* CG state checkpoint interval m of the recompute form (default 8): a pass re-runs the
+   * block-local recurrences since the last checkpoint in registers instead of reading and
+   * writing r, d, x every iteration; 0 selects the streaming form (one r/d/x update per pass). */
+  DANG_OPT_CG_CHECKPOINT = 8
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
@@ -181,7 +185,8 @@ int dang_gpu_launch_count(dang_gpu_t *h, int64_t *launches, int reset);
 enum {
   DANG_K_RHS_BLOCKS = 0, DANG_K_CG_PASS = 1, DANG_K_CG_DQ = 2, DANG_K_CG_UPDATE = 3,
   DANG_K_CHISQ = 4, DANG_K_SKYMODEL = 5, DANG_K_MH_DATA = 6, DANG_K_MH_FULLSKY_LNL = 7,
-  DANG_K_MH_SUFFSTAT = 8, DANG_K_MH_PERPIXEL = 9, DANG_K_SCALAR = 10, DANG_K_COUNT = 11
+  DANG_K_MH_SUFFSTAT = 8, DANG_K_MH_PERPIXEL = 9, DANG_K_SCALAR = 10, DANG_K_CG_FIXUP = 11,
+  DANG_K_COUNT = 12
 };
 int dang_gpu_kernel_stats(dang_gpu_t *h, int kernel, int64_t *launches, double *total_ms,
                           double *bytes, int reset);

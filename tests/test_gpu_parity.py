@@ -56,12 +56,15 @@ def test_chisq_missval_mask_and_ragged_size():
 
 # ------------------------------------------------------------------ amplitude draw
 @pytest.mark.parametrize("name", ["c1", "c2"])  # c1: per-pixel SEDs; c2: tabulated (uniform) SEDs
-@pytest.mark.parametrize("two_pass", [0, 1])
+@pytest.mark.parametrize("form", ["recompute8", "recompute3", "streaming", "two_pass"])
 @pytest.mark.parametrize("ml_mode", ["optimize", "sample"])
-def test_cg_solve_matches_oracle(name, two_pass, ml_mode):
-    from dang_b200.engine import OPT_CG_TWO_PASS
+def test_cg_solve_matches_oracle(name, form, ml_mode):
+    """All CG forms (checkpointed recompute, streaming fused pass, classic two-pass) follow the
+    oracle's cg_search: same iteration count, same residual trajectory, same amplitudes."""
+    from dang_b200.engine import OPT_CG_CHECKPOINT, OPT_CG_TWO_PASS
     cfg, sky, ora, eng = make_pair(name, 16)
-    eng.set_option(OPT_CG_TWO_PASS, two_pass)
+    eng.set_option(OPT_CG_TWO_PASS, int(form == "two_pass"))
+    eng.set_option(OPT_CG_CHECKPOINT, {"recompute8": 8, "recompute3": 3}.get(form, 0))
     eta = np.random.default_rng(5).standard_normal(2 * cfg.npix)
     it_o, delta_o, trace_o = ora.cg_search_trace(ml_mode=1 if ml_mode == "sample" else 0, eta=eta)
     it_g, delta_g = eng.cg_solve(0, 0, ml_mode, eta=eta)
