@@ -140,7 +140,10 @@ const int GATHER_MAX = 128;  // doubles per rank in one scalar exchange
 struct dang_gpu {
   int device = 0, nside = 0, nmaps = 0, nbands = 0, ncomp = 0, num_sms = 0;
   int64_t npix = 0, lo = 0, hi = 0, P = 0, Ppad = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, d2h_stream = nullptr, h2d_stream = nullptr;
+  cudaEvent_t ev_compute = nullptr, ev_amp_dl = nullptr, ev_idx_dl = nullptr, ev_eta = nullptr;
+  bool amp_dl_pending = false, idx_dl_pending = false, eta_staged = false;
+  double *eta_stage = nullptr; size_t eta_stage_len = 0; int eta_stage_planes = 0;
   std::string err;
 
   // options
@@ -490,6 +493,10 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       ensure(h->eta, h->eta_len, vs);
       h2d_planes(h, h->eta, eta, S);  // host eta is [stokes][npix]
       cv.eta = h->eta;
+    } else if (h->eta_staged && h->eta_stage_planes == S) {
+      CK(cudaStreamWaitEvent(h->stream, h->ev_eta, 0));  // uploaded by dang_gpu_stage_eta
+      cv.eta = h->eta_stage;
+      h->eta_staged = false;
     }
   }
 
@@ -615,7 +622,11 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     kt.done();
   }
 
-  // unpack_amplitudes :1327-1335: x -> c%amplitude planes
+  // unpack_amplitudes :1327-1335: x -> c%amplitude planes (after any download still reading them)
+  if (h->amp_dl_pending) {
+    CK(cudaStreamWaitEvent(h->stream, h->ev_amp_dl, 0));
+    h->amp_dl_pending = false;
+  }
   for (int c = 0; c < C; c++)
     for (int s = 0; s < S; s++)
       CK(cudaMemcpyAsync(h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
@@ -1055,6 +1066,12 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
       h->offset[j] = 0.0;
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_amp_dl, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_idx_dl, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_eta, cudaEventDisableTiming));
     h->grid_cap = h->num_sms * 8;
     CK(cudaMalloc(&h->partials, (size_t)h->grid_cap * 32 * 4 * sizeof(double)));
     CK(cudaMalloc(&h->tickets, 16 * sizeof(unsigned int)));
@@ -1092,6 +1109,12 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  cudaStreamSynchronize(h->d2h_stream);
+  cudaStreamSynchronize(h->h2d_stream);
+  dfree(h->eta_stage);
+  for (cudaEvent_t e : {h->ev_compute, h->ev_amp_dl, h->ev_idx_dl, h->ev_eta}) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->d2h_stream);
+  cudaStreamDestroy(h->h2d_stream);
   cudaStreamDestroy(h->stream);
   delete h;
   return DANG_GPU_OK;
@@ -1364,6 +1387,10 @@ int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsampl
   MhView mh;
   mh_view(h, ic, nind, map_n, nsample, ml_mode, mh);
   const bool perpix = h->comp[ic].index[nind].index_mode == DANG_INDEX_PERPIXEL;
+  if (h->idx_dl_pending) {  // the draw overwrites index planes a download may still be reading
+    CK(cudaStreamWaitEvent(h->stream, h->ev_idx_dl, 0));
+    h->idx_dl_pending = false;
+  }
   if (perpix) sample_perpixel(h, mh, z, u, seed, accept);
   else sample_fullsky(h, mh, z, u, seed, accept);
   // the written planes are varying after a per-pixel draw (masked pixels are zeroed, so even a
@@ -1452,6 +1479,58 @@ int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean
   double s = 0, n = 0;
   for (int g = 0; g < h->nranks; g++) { s += hp[g * 4]; n += hp[g * 4 + 1]; }
   if (mean) *mean = s / n;
+  API_END
+}
+
+int dang_gpu_get_amplitude_async(dang_gpu_t *h, int ic, int k_lo, int k_hi, double *amplitude) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !amplitude || k_lo < 1 || k_hi > h->nmaps || k_lo > k_hi)
+    fail(DANG_GPU_EINVAL, "bad component / plane range %d %d..%d", ic, k_lo, k_hi);
+  CK(cudaEventRecord(h->ev_compute, h->stream));
+  CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute, 0));
+  const size_t o = (size_t)(k_lo - 1);
+  CK(cudaMemcpy2DAsync(amplitude + o * h->npix + h->lo, h->npix * sizeof(double), h->comp[ic].amp + o * h->Ppad,
+                       h->Ppad * sizeof(double), h->P * sizeof(double), k_hi - k_lo + 1, cudaMemcpyDeviceToHost,
+                       h->d2h_stream));
+  CK(cudaEventRecord(h->ev_amp_dl, h->d2h_stream));
+  h->amp_dl_pending = true;
+  API_END
+}
+
+int dang_gpu_get_indices_async(dang_gpu_t *h, int ic, int nind, int k_lo, int k_hi, double *indices) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || nind < 0 || nind >= h->comp[ic].nind || !indices || k_lo < 1 ||
+      k_hi > h->nmaps || k_lo > k_hi)
+    fail(DANG_GPU_EINVAL, "bad component / index / plane range %d %d %d..%d", ic, nind, k_lo, k_hi);
+  CK(cudaEventRecord(h->ev_compute, h->stream));
+  CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute, 0));
+  const size_t o = (size_t)(k_lo - 1);
+  CK(cudaMemcpy2DAsync(indices + ((size_t)nind * h->nmaps + o) * h->npix + h->lo, h->npix * sizeof(double),
+                       h->comp[ic].idx[nind] + o * h->Ppad, h->Ppad * sizeof(double), h->P * sizeof(double),
+                       k_hi - k_lo + 1, cudaMemcpyDeviceToHost, h->d2h_stream));
+  CK(cudaEventRecord(h->ev_idx_dl, h->d2h_stream));
+  h->idx_dl_pending = true;
+  API_END
+}
+
+int dang_gpu_download_wait(dang_gpu_t *h) {
+  API_BEGIN
+  CK(cudaStreamSynchronize(h->d2h_stream));
+  h->amp_dl_pending = false;
+  h->idx_dl_pending = false;
+  API_END
+}
+
+int dang_gpu_stage_eta(dang_gpu_t *h, const double *eta, int nplanes) {
+  API_BEGIN
+  if (!eta || nplanes < 1 || nplanes > 2) fail(DANG_GPU_EINVAL, "stage_eta: nplanes = %d", nplanes);
+  ensure(h->eta_stage, h->eta_stage_len, (size_t)nplanes * h->Ppad);
+  // the previous consumer (K1 of the last solve) has finished: every solve ends with a sync
+  CK(cudaMemcpy2DAsync(h->eta_stage, h->Ppad * sizeof(double), eta + h->lo, h->npix * sizeof(double),
+                       h->P * sizeof(double), nplanes, cudaMemcpyHostToDevice, h->h2d_stream));
+  CK(cudaEventRecord(h->ev_eta, h->h2d_stream));
+  h->eta_staged = true;
+  h->eta_stage_planes = nplanes;
   API_END
 }
 

@@ -142,6 +142,20 @@ class Engine:
         self._ck(self.lib.dang_gpu_get_indices(self.h, ic, _dp(out)))
         return out
 
+    # asynchronous staging (copies overlap later calls; host arrays should be pinned)
+    def amplitude_async(self, ic: int, out: np.ndarray, k_lo: int = 2, k_hi: int = 3):
+        self._ck(self.lib.dang_gpu_get_amplitude_async(self.h, ic, k_lo, k_hi, _dp(out)))
+
+    def indices_async(self, ic: int, nind: int, out: np.ndarray, k_lo: int = 2, k_hi: int = 3):
+        self._ck(self.lib.dang_gpu_get_indices_async(self.h, ic, nind, k_lo, k_hi, _dp(out)))
+
+    def download_wait(self):
+        self._ck(self.lib.dang_gpu_download_wait(self.h))
+
+    def stage_eta(self, eta: np.ndarray, nplanes: int = 2):
+        """Upload the next cg_solve's normals in the background; call that solve with eta=None."""
+        self._ck(self.lib.dang_gpu_stage_eta(self.h, _dp(eta), nplanes))
+
     def set_amplitude(self, ic: int, amp: np.ndarray):
         self._ck(self.lib.dang_gpu_set_amplitude(self.h, ic, _dp(np.ascontiguousarray(amp, dtype=np.float64))))
 

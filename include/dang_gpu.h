@@ -174,6 +174,20 @@ int dang_gpu_get_sky_model(dang_gpu_t *h, int pol_lo, int pol_hi, double *sky_mo
 /* mask_avg(c%indices(:,map_n,nind), masks(:,1)), src/dang_util_mod.f90:186-206 */
 int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean);
 
+/* ---- output / input staging: copies on dedicated streams that overlap later calls.
+ * dang_gpu_get_*_async start a device->host copy of planes k_lo..k_hi (1-based) of c%amplitude /
+ * c%indices(:,:,nind) into the caller's arrays (same addressing as the synchronous getters) and
+ * return at once; the library orders them against its own later writes (a solve's unpack waits
+ * for a pending amplitude download, a sampler for a pending index download).
+ * dang_gpu_download_wait blocks until every pending download has landed.
+ * dang_gpu_stage_eta uploads the S*npix normals of the NEXT dang_gpu_cg_solve while other work
+ * runs; that solve is then called with eta == NULL and uses the staged deviates (once).
+ * Host buffers should be pinned (dang_gpu_host_alloc) or the copies serialise. */
+int dang_gpu_get_amplitude_async(dang_gpu_t *h, int ic, int k_lo, int k_hi, double *amplitude);
+int dang_gpu_get_indices_async(dang_gpu_t *h, int ic, int nind, int k_lo, int k_hi, double *indices);
+int dang_gpu_download_wait(dang_gpu_t *h);
+int dang_gpu_stage_eta(dang_gpu_t *h, const double *eta, int nplanes);
+
 /* ---- instrumentation (bench.py) ---- */
 int dang_gpu_host_alloc(void **ptr, uint64_t bytes); /* pinned host memory */
 int dang_gpu_host_free(void *ptr);
