@@ -487,6 +487,9 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   cv.seed = seed;
   cv.fluct = 0;
   cv.eta = nullptr;
+  // recompute form needs the (alpha, beta) history: fall back to streaming for very long solves
+  const int ckpt_m = (!h->cg_two_pass && g.i_max < DG_CG_HIST) ? h->cg_ckpt : 0;
+  cv.store_d = ckpt_m ? 0 : 1;
   if (ml_mode == DANG_ML_SAMPLE) {  // :254-264
     cv.fluct = h->fix_q1 ? 2 : 1;
     if (eta) {
@@ -505,7 +508,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     const int grid = grid_for(h, h->P, DG_THREADS, 4);
     const double n_el = (double)S * h->P;
     KTimer kt(h, DANG_K_RHS_BLOCKS,
-              bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + 2.0 * C)) + bytes_w((double)h->P * 3));
+              bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + (ckpt_m ? 1.0 : 2.0) * C)) + bytes_w((double)h->P * 3));
     // streaming kernel: out-of-group components must have tabulated SEDs; group components with
     // varying indices get their SEDs staged per thread in dynamic shared memory
     bool og_uni = true;
@@ -532,8 +535,6 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     cg_init_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks, g.i_max, g.converge);
     kt.done();
   }
-  // recompute form needs the (alpha, beta) history: fall back to streaming for very long solves
-  const int ckpt_m = (!h->cg_two_pass && g.i_max < DG_CG_HIST) ? h->cg_ckpt : 0;
   CK(cudaMemcpyAsync((char *)h->cg_scalars + offsetof(CgScalars, m), &ckpt_m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
 
   struct Snap { double delta_new; int iter, done; };
@@ -553,7 +554,8 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     if (!h->cg_two_pass) {
       if (ckpt_m) {
         // compulsory traffic of this launch: M, r, d in; on checkpoint passes also x in, r, d, x out
-        const double per_el = (pass_no % ckpt_m == 0) ? (T + 6.0 * C) : (T + 2.0 * C);
+        const double per_el = (pass_no % ckpt_m == 0) ? (T + (pass_no == ckpt_m ? 5.0 : 6.0) * C)
+                                                      : (T + (pass_no < ckpt_m ? 1.0 : 2.0) * C);
         KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
         cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
             h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0);

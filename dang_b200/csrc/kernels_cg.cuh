@@ -21,6 +21,7 @@ struct CgView {
   double *x, *r, *d;         // [C][S][Ppad]
   const double *eta;         // [S][Ppad] injected normals, or nullptr -> Philox
   uint64_t seed;
+  int store_d;               // 0: the recompute CG form never reads the initial d (= r)
 };
 
 // scalars of one solve, device resident (DESIGN.md "CG control")
@@ -185,7 +186,7 @@ rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsi
 #pragma unroll
       for (int c = 0; c < C; c++) {
         cg.r[(size_t)c * cg.S * mv.Ppad + e] = rv[c];
-        cg.d[(size_t)c * cg.S * mv.Ppad + e] = rv[c];
+        if (cg.store_d) cg.d[(size_t)c * cg.S * mv.Ppad + e] = rv[c];
         acc[0] += rv[c] * rv[c];
         acc[1] += rv[c] * Mr[c];
       }
@@ -403,7 +404,8 @@ cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__
 #pragma unroll
     for (int c = 0; c < C; c++) {
       rv[c] = *reinterpret_cast<const double2 *>(r + c * vs + 2 * e);
-      dv[c] = *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
+      // before the first checkpoint the stored direction is d_0 = r_1 itself (beta_1 = 0)
+      dv[c] = c0 == 0 ? rv[c] : *reinterpret_cast<const double2 *>(d + c * vs + 2 * e);
       if (with_x) xv[c] = *reinterpret_cast<const double2 *>(x + c * vs + 2 * e);
     }
     for (int i = 0; i < nstep; i++) {

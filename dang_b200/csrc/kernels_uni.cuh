@@ -247,7 +247,7 @@ rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
 #pragma unroll
       for (int c = 0; c < C; c++) {
         st2(cg.r + c * vs + es, rv[c]);
-        st2(cg.d + c * vs + es, rv[c]);
+        if (cg.store_d) st2(cg.d + c * vs + es, rv[c]);
       }
     }
   }

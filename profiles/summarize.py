@@ -1,0 +1,74 @@
+"""Turn ncu exports into the committed summaries under profiles/.
+
+  python profiles/summarize.py <launch-list.csv> <raw-page.csv> <out.md> [bench.json]
+
+launch-list.csv : ncu --metrics gpu__time_duration.sum --csv --log-file ...   (every launch)
+raw-page.csv    : ncu -i prof.ncu-rep --page raw --csv                        (--set full capture)
+"""
+import collections
+import csv
+import json
+import sys
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    for i, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, start = r, i + 1
+            break
+    kn, mv, mn = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+    d = collections.OrderedDict()
+    for r in rows[start:]:
+        if len(r) > mv and r[mn] == "gpu__time_duration.sum":
+            name = r[kn].split("(")[0].replace("void ", "")
+            d.setdefault(name, []).append(float(r[mv].replace(",", "")) / 1e3)  # ns -> us
+    return d
+
+
+def raw(path):
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "launch__grid_size",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+    out = []
+    for r in rows[2:]:
+        rec = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")}
+        for w in want:
+            if w in hdr:
+                rec[w] = r[hdr.index(w)]
+        out.append(rec)
+    return out, rows[1], hdr
+
+
+def main():
+    ll, rp, outp = sys.argv[1:4]
+    lines = ["# ncu summary\n"]
+    if len(sys.argv) > 4:
+        b = json.loads(open(sys.argv[4]).read().strip().splitlines()[-1])
+        lines += ["bench.py line of the same build (CUDA events, not under ncu):\n", "```json", json.dumps(b), "```\n"]
+    d = launches(ll)
+    tot = sum(sum(v) for v in d.values())
+    lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)\n",
+              "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
+    for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+        lines.append(f"| `{k}` | {len(v)} | {sum(v):.1f} | {sum(v) / len(v):.2f} | {sum(v) / tot:.3f} |")
+    recs, units, hdr = raw(rp)
+    lines += ["\n## `ncu --set full` captures (per launch)\n",
+              "| kernel | time us | DRAM read MB | DRAM write MB | DRAM % of ncu peak | warps active % | regs | FP64 pipe % | tensor pipe % | grid |",
+              "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    for r in recs:
+        g = lambda k: r.get(k, "")
+        lines.append(f"| `{r['kernel']}` | {g('gpu__time_duration.sum')} | {g('dram__bytes_read.sum')} | {g('dram__bytes_write.sum')} | "
+                     f"{g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} | {g('sm__warps_active.avg.pct_of_peak_sustained_active')} | "
+                     f"{g('launch__registers_per_thread')} | {g('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')} | "
+                     f"{g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} | {g('launch__grid_size')} |")
+    open(outp, "w").write("\n".join(lines) + "\n")
+    print("wrote", outp)
+
+
+if __name__ == "__main__":
+    main()
