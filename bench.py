@@ -100,7 +100,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from dang_b200.engine import OPT_PROFILE, Engine, comm_unique_id
+    from dang_b200.engine import OPT_PROFILE, Engine, setup_torch_comm
     from dang_b200.healpix import ring_partition
     from dang_b200.synth import make_config, make_sky
 
@@ -117,12 +117,9 @@ def run_gpu(args):
     bounds = ring_partition(cfg.nside, world, weights=(sky.mask != 0).astype(np.float64))
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
+    mailboxes = os.environ.get("DANG_GPU_MAILBOX", "1") != "0"
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(uid, 0)
-        eng.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        setup_torch_comm(eng, mailboxes=mailboxes)
 
     def barrier():
         eng.sync()
@@ -248,7 +245,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": f"{cfg.name}: nside={cfg.nside}, {cfg.nbands} delta bands, Q+U, synch+dust, "
                                    f"CG amplitudes + full-sky beta_d, NUMSAMPLE={cfg.nsample}",
-                       "npix": cfg.npix, "n_cg_iterations": n_cg, "parallelism": f"ring-range pixel shards x{world}",
+                       "npix": cfg.npix, "n_cg_iterations": n_cg, "parallelism": f"ring-range pixel shards x{world}" + ("" if world == 1 else (", scalar exchange over NVLink mailboxes" if mailboxes else ", scalar exchange by NCCL all-gather")),
                        "l2": "working set (sig+rms 1.2 GB, CG state 0.7 GB) >> 126 MB L2, no flush needed",
                        "rng": "device Philox4x32-10"},
             "pixel_band_updates_per_s": round(2 * cfg.npix * cfg.nbands * 1e3 / ms_per_step, 1),

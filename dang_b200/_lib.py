@@ -27,6 +27,9 @@ SIGNATURES = {
     "dang_gpu_sync": (C.c_int, [vp]),
     "dang_gpu_comm_unique_id": (C.c_int, [C.c_char_p]),
     "dang_gpu_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
+    "dang_gpu_comm_ipc_handle": (C.c_int, [vp, C.c_char_p]),
+    "dang_gpu_comm_open_peers": (C.c_int, [vp, C.c_char_p]),
+    "dang_gpu_comm_check": (C.c_int, [vp]),
     "dang_gpu_set_band": (C.c_int, [vp, C.c_int, C.c_double, C.c_int, c_dp, c_dp]),
     "dang_gpu_upload_maps": (C.c_int, [vp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "dang_gpu_set_gain_offset": (C.c_int, [vp, c_dp, c_dp]),

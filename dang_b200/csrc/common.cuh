@@ -189,6 +189,75 @@ __host__ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t
 
 enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3, DG_STREAM_TUNE_Z = 4, DG_STREAM_TUNE_U = 5 };
 
+// ---------------------------------------------------------------- cross-rank scalar exchange
+// Every rank owns a mailbox in its own HBM, mapped into all peers with CUDA IPC.  An exchange
+// is: write my row of <= DG_MAIL_VALS doubles into slot (seq mod DG_MAIL_SLOTS) of EVERY rank's
+// mailbox over NVLink, publish it with a release store of the sequence number, then wait for
+// every rank's row in my own mailbox and copy the rows out in rank order (=> the sums formed
+// from them are bit-identical everywhere).  One warp does it, lane = peer rank; it runs inside
+// the kernel that produced the partial sums, so a CG iteration on N GPUs is still ONE launch and
+// the collective costs one NVLink round trip instead of an NCCL launch.
+// All ranks execute the same sequence of exchanges (they take identical decisions from
+// identical sums), so sequence numbers stay aligned; a rank can lead by at most one exchange.
+#define DG_MAIL_VALS 128
+#define DG_MAIL_SLOTS 4
+#define DG_MAX_RANKS 32
+
+struct Mail {
+  double vals[DG_MAIL_VALS];
+  unsigned long long seq;
+  unsigned long long pad[15];
+};
+
+struct PeerComm {
+  int nranks, rank;
+  unsigned long long *seq;       // device counter of exchanges done by this rank
+  int *error;                    // set on timeout
+  Mail *box[DG_MAX_RANKS];       // box[g]: rank g's mailbox [DG_MAIL_SLOTS][nranks] (peer-mapped)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by ONE full warp.  local[cnt] -> gathered[nranks][cnt] (rank order).
+__device__ __forceinline__ void peer_exchange(const PeerComm &pc, const double *local, int cnt,
+                                              double *gathered) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();  // `local` was written by one lane of this warp
+  const unsigned long long seq = *pc.seq + 1;
+  const int slot = (int)(seq % DG_MAIL_SLOTS);
+  if (lane < pc.nranks) {
+    Mail *dst = pc.box[lane] + (size_t)slot * pc.nranks + pc.rank;  // my row in rank `lane`'s box
+    for (int i = 0; i < cnt; i++) dst->vals[i] = local[i];
+    __threadfence_system();
+    st_release_sys(&dst->seq, seq);
+    const Mail *src = pc.box[pc.rank] + (size_t)slot * pc.nranks + lane;  // rank `lane`'s row in my box
+    const long long t0 = clock64();
+    bool ok = true;
+    while (ld_acquire_sys(&src->seq) != seq) {
+      if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; fail loudly instead of hanging
+        ok = false;
+        break;
+      }
+    }
+    if (!ok) atomicExch(pc.error, 1);
+    for (int i = 0; i < cnt; i++) gathered[lane * cnt + i] = ok ? src->vals[i] : 0.0;
+  }
+  __syncwarp();
+  if (lane == 0) *pc.seq = seq;
+  __syncwarp();
+}
+
+__global__ void peer_exchange_kernel(PeerComm pc, const double *local, int cnt, double *gathered) {
+  peer_exchange(pc, local, cnt, gathered);
+}
+
 // ---------------------------------------------------------------- deterministic reductions
 // Two-stage tree: per-thread serial partial -> warp shuffle -> shared-memory tree over warps
 // -> one partial per block in global memory -> fixed-order final sum by the block that

@@ -187,6 +187,11 @@ struct dang_gpu {
   // comm
   int nranks = 1, rank = 0;
   nccl_comm_t comm = nullptr;
+  // NVLink mailboxes (CUDA IPC); peer.nranks == 1 until dang_gpu_comm_open_peers succeeds
+  Mail *mailbox = nullptr;
+  void *peer_ptr[DG_MAX_RANKS] = {};
+  PeerComm peer{};
+  bool use_mail = false;
 
   // instrumentation
   int64_t launches = 0;
@@ -398,6 +403,9 @@ void gather(dang_gpu *h, int cnt) {
   if (cnt > GATHER_MAX) fail(DANG_GPU_EINVAL, "gather of %d doubles exceeds %d", cnt, GATHER_MAX);
   if (h->nranks == 1) {
     return;  // h->gathered aliases h->sums_local (set in create / comm_init)
+  } else if (h->use_mail) {
+    peer_exchange_kernel<<<1, 32, 0, h->stream>>>(h->peer, h->sums_local, cnt, h->gathered);
+    CK(cudaGetLastError());
   } else {
     NCK(g_nccl.AllGather(h->sums_local, h->gathered, cnt, NCCL_DOUBLE, h->comm, h->stream));
   }
@@ -545,7 +553,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     return Snap{hs->delta_new, hs->iter, hs->done};
   };
 
-  const int fold = h->nranks == 1 ? 1 : 0;
+  const int fold = (h->nranks == 1 || h->use_mail) ? 1 : 0;
   const int grid = h->cg_two_pass ? occ_grid(h, cg_update_pass_kernel<C>, n2, DG_THREADS)
                    : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C>, n2, DG_THREADS)
                                 : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
@@ -558,14 +566,14 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
                                                       : (T + (pass_no < ckpt_m ? 1.0 : 2.0) * C);
         KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
         cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0);
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0, h->peer, h->gathered);
         kt.done();
       } else {
         // compulsory traffic of this launch: x is touched on even passes only
         const double per_el = (pass_no & 1) ? (T + 4.0 * C) : (T + 6.0 * C);
         KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
         cg_fused_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold);
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, h->peer, h->gathered);
         kt.done();
       }
       if (!fold) {
@@ -618,7 +626,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 4.0 * C : 3.0 * C)));
     if (ckpt_m)
       cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-          h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1);
+          h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1, h->peer, h->gathered);
     else
       cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
     kt.done();
@@ -1086,6 +1094,8 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaMalloc(&h->tab, sizeof(SedTable)));
     CK(cudaMemset(h->tab, 0, sizeof(SedTable)));
     CK(cudaMallocHost(&h->pinned, 64 * 1024));
+    h->peer.nranks = 1;
+    h->peer.rank = 0;
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&h->ev[i]));
     *out = h;
     return DANG_GPU_OK;
@@ -1101,6 +1111,11 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->comm) g_nccl.CommDestroy(h->comm);
+  for (int g = 0; g < DG_MAX_RANKS; g++)
+    if (h->peer_ptr[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_ptr[g]);
+  if (h->peer.seq) cudaFree(h->peer.seq);
+  if (h->peer.error) cudaFree(h->peer.error);
+  if (h->mailbox) cudaFree(h->mailbox);
   dfree(h->sig); dfree(h->rms); dfree(h->mask); dfree(h->bp_nu0); dfree(h->bp_tau0);
   for (auto &c : h->comp) { dfree(c.amp); dfree(c.idx[0]); dfree(c.idx[1]); }
   for (auto &g : h->cg) for (auto &x : g.x) dfree(x);
@@ -1170,6 +1185,57 @@ int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]) 
     nccl_uid_t uid;
     memcpy(uid.internal, id, 128);
     NCK(g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
+  }
+  API_END
+}
+
+int dang_gpu_comm_ipc_handle(dang_gpu_t *h, char handle[64]) {
+  API_BEGIN
+  if (h->nranks < 2) fail(DANG_GPU_ESTATE, "dang_gpu_comm_init with nranks > 1 comes first");
+  if (h->nranks > DG_MAX_RANKS) fail(DANG_GPU_EUNSUPPORTED, "mailboxes support up to %d ranks", DG_MAX_RANKS);
+  if (!h->mailbox) {
+    const size_t n = (size_t)DG_MAIL_SLOTS * h->nranks * sizeof(Mail);
+    CK(cudaMalloc(&h->mailbox, n));
+    CK(cudaMemset(h->mailbox, 0, n));
+    CK(cudaMalloc(&h->peer.seq, sizeof(unsigned long long)));
+    CK(cudaMemset(h->peer.seq, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc(&h->peer.error, sizeof(int)));
+    CK(cudaMemset(h->peer.error, 0, sizeof(int)));
+    CK(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t ih;
+  CK(cudaIpcGetMemHandle(&ih, h->mailbox));
+  static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle, &ih, 64);
+  API_END
+}
+
+int dang_gpu_comm_open_peers(dang_gpu_t *h, const char *handles) {
+  API_BEGIN
+  if (!h->mailbox || !handles) fail(DANG_GPU_ESTATE, "dang_gpu_comm_ipc_handle comes first");
+  for (int g = 0; g < h->nranks; g++) {
+    if (g == h->rank) {
+      h->peer_ptr[g] = h->mailbox;
+    } else {
+      cudaIpcMemHandle_t ih;
+      memcpy(&ih, handles + (size_t)g * 64, 64);
+      CK(cudaIpcOpenMemHandle(&h->peer_ptr[g], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->peer.box[g] = (Mail *)h->peer_ptr[g];
+  }
+  h->peer.nranks = h->nranks;
+  h->peer.rank = h->rank;
+  h->use_mail = true;
+  API_END
+}
+
+int dang_gpu_comm_check(dang_gpu_t *h) {
+  API_BEGIN
+  if (h->use_mail) {
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, h->peer.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (err) fail(DANG_GPU_ENCCL, "a peer rank did not answer a scalar exchange within the timeout");
   }
   API_END
 }

@@ -294,7 +294,8 @@ template <int C>
 __global__ void __launch_bounds__(DG_THREADS)
 cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
                      double *__restrict__ r, double *__restrict__ d, int64_t n2 /* vec2 elements */,
-                     double *partials, unsigned int *ticket, double *out, int fold) {
+                     double *partials, unsigned int *ticket, double *out, int fold, PeerComm pc,
+                     double *gathered) {
   constexpr int T = C * (C + 1) / 2;
   if (st->done) return;
   const double alpha = st->alpha, beta = st->beta, alpha_prev = st->alpha_prev;
@@ -378,7 +379,8 @@ template <int C>
 __global__ void __launch_bounds__(DG_THREADS)
 cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
                          double *__restrict__ r, double *__restrict__ d, int64_t n2,
-                         double *partials, unsigned int *ticket, double *out, int fold, int final) {
+                         double *partials, unsigned int *ticket, double *out, int fold, int final,
+                         PeerComm pc, double *gathered) {
   constexpr int T = C * (C + 1) / 2;
   if (st->done && !final) return;
   const int c0 = st->ckpt;
@@ -464,7 +466,10 @@ cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__
   }
   if (final) return;
   const bool last = grid_reduce<4>(acc, smem, partials, ticket, out);
-  if (fold && last && threadIdx.x == 0) cg_fused_update(st, out, 1);
+  if (fold && last) {  // warp 0 of the last block: exchange over NVLink (if any), advance the scalars
+    if (pc.nranks > 1) peer_exchange(pc, out, 4, gathered);
+    if (threadIdx.x == 0) cg_fused_update(st, pc.nranks > 1 ? gathered : out, pc.nranks);
+  }
 }
 
 // pending x update when the solve stopped after an odd number of passes

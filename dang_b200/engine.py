@@ -124,6 +124,18 @@ class Engine:
         self._ck(self.lib.dang_gpu_comm_init(self.h, nranks, rank, uid))
         self.nranks, self.rank = nranks, rank
 
+    def comm_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.dang_gpu_comm_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def comm_open_peers(self, handles: bytes):
+        """handles: the nranks 64-byte IPC handles, rank-major; enables the NVLink mailbox path."""
+        self._ck(self.lib.dang_gpu_comm_open_peers(self.h, handles))
+
+    def comm_check(self):
+        self._ck(self.lib.dang_gpu_comm_check(self.h))
+
     def upload_maps(self, sky):
         """ddata%sig_map / rms_map / masks / gain / offset -> device (also after swap_cg_maps)."""
         self._ck(self.lib.dang_gpu_upload_maps(self.h, _dp(sky.sig), _dp(sky.rms), _dp(sky.mask),
@@ -331,6 +343,28 @@ class Engine:
             self._ck(self.lib.dang_gpu_kernel_stats(self.h, k, C.byref(n), C.byref(ms), C.byref(by), int(reset)))
             out[self.lib.dang_gpu_kernel_name(k).decode()] = dict(launches=n.value, ms=ms.value, bytes=by.value)
         return out
+
+
+def setup_torch_comm(eng: "Engine", mailboxes: bool = True):
+    """Wire an Engine into an initialised torch.distributed NCCL process group (one process per
+    GPU): broadcast the NCCL unique id, then (optionally) all-gather the CUDA-IPC mailbox handles
+    for the NVLink scalar-exchange path.  torch.distributed is plumbing only."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    eng.comm_init(world, rank, uid.cpu().numpy().tobytes())
+    if mailboxes:
+        mine = torch.frombuffer(bytearray(eng.comm_ipc_handle()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        eng.comm_open_peers(b"".join(t.cpu().numpy().tobytes() for t in allh))
+        dist.barrier()
 
 
 def comm_unique_id() -> bytes:

@@ -97,6 +97,14 @@ int dang_gpu_sync(dang_gpu_t *h);
  * has (MPI_Bcast in Fortran, torch.distributed here); then every rank calls comm_init. */
 int dang_gpu_comm_unique_id(char id[128]);
 int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]);
+/* Optional NVLink fast path for the scalar exchanges (one process per GPU on one node): every
+ * rank exports its mailbox (64-byte CUDA IPC handle), the host all-gathers the handles
+ * (rank-major, nranks*64 bytes) and every rank opens them.  From then on the exchanges are peer
+ * stores + flag waits inside the compute kernels instead of NCCL calls; a CG iteration on N GPUs
+ * is a single kernel launch.  dang_gpu_comm_check reports a peer that stopped answering. */
+int dang_gpu_comm_ipc_handle(dang_gpu_t *h, char handle[64]);
+int dang_gpu_comm_open_peers(dang_gpu_t *h, const char *handles);
+int dang_gpu_comm_check(dang_gpu_t *h);
 
 /* ---- bp(j): type bandinfo, src/dang_bp_mod.f90:7-15 (as left by init_bp_mod :19-60) ----
  * nu_c [Hz]; n_bp == 0 <=> bp%id == 'delta'; nu0 [Hz]; tau0 already normalised (:62-81). */

@@ -21,7 +21,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from dang_b200.engine import Engine, comm_unique_id
+    from dang_b200.engine import Engine, setup_torch_comm
     from dang_b200.healpix import ring_partition
     from helpers import small_case
     from oracle.binding import Oracle
@@ -35,11 +35,7 @@ def main():
         bounds = ring_partition(cfg.nside, world, weights=(sky.mask != 0).astype(np.float64))
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(uid, 0)
-        eng.comm_init(world, rank, uid.cpu().numpy().tobytes())
+        setup_torch_comm(eng, mailboxes=os.environ.get("DANG_GPU_MAILBOX", "1") != "0")
         ora = Oracle(cfg, sky)
         rng = np.random.default_rng(77)
         nsample = 8
@@ -63,6 +59,7 @@ def main():
                 assert e < 1e-10, (rank, name, it, ic, e)
                 ia, ib = eng.indices(ic)[:, :, lo:hi], ora.indices(ic)[:, :, lo:hi]
                 assert np.max(np.abs(ia - ib)) < 1e-12, (rank, name, it, ic)
+        eng.comm_check()
         eng.close()
         dist.barrier()
     print(f"rank {rank}/{world}: multi-GPU parity ok (pixels [{lo},{hi}), worst amplitude error {worst:.2e})", flush=True)
