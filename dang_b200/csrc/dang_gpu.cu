@@ -164,6 +164,7 @@ struct dang_gpu {
   unsigned long long check_mask = ~0ull;  // index maps whose uniformity must be re-scanned
   SedTable *tab = nullptr;
   int uni_host[DG_MAX_COMPS * 3] = {};  // host copy of SedTable::uni (refreshed with the tables)
+  int nonuni_host[DG_MAX_COMPS * 3][DG_MAXIND] = {};  // host mirror of SedTable::nonuni
   CompHost comp[DG_MAX_COMPS];
   std::vector<CgGroupHost> cg;
 
@@ -372,6 +373,7 @@ ModelView model_view(dang_gpu *h) {
   mv.rms = h->rms;
   mv.mask = h->mask;
   if (h->tab_dirty) {  // an index map changed since the SED tables were built
+    const bool scanned = h->check_mask != 0;
     if (h->check_mask) {
       // maps uploaded by the host are scanned once; maps written by the samplers are not (their
       // uniformity is known by construction and was recorded by set_nonuni)
@@ -388,11 +390,20 @@ ModelView model_view(dang_gpu *h) {
     KTimer kt(h, DANG_K_SCALAR, 0);
     sed_table_kernel<<<h->ncomp * 3, 32, 0, h->stream>>>(mv, h->tab);
     kt.done();
-    // the host picks the streaming (tabulated-SED) kernel variants from these flags
-    int *hu = (int *)((char *)h->pinned + 32 * 1024);
-    CK(cudaMemcpyAsync(hu, (char *)h->tab + offsetof(SedTable, uni), sizeof(h->uni_host), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    memcpy(h->uni_host, hu, sizeof(h->uni_host));
+    // the host picks the streaming (tabulated-SED) kernel variants from these flags; they are read
+    // back only after a scan, otherwise the host mirror (kept by set_nonuni) already has them
+    if (scanned) {
+      int *hu = (int *)((char *)h->pinned + 32 * 1024);
+      CK(cudaMemcpyAsync(hu, (char *)h->tab + offsetof(SedTable, nonuni), sizeof(h->nonuni_host), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      memcpy(h->nonuni_host, hu, sizeof(h->nonuni_host));
+    }
+    for (int c = 0; c < DG_MAX_COMPS; c++)
+      for (int k = 0; k < 3; k++) {
+        bool uni = c < h->ncomp && k < h->nmaps;
+        for (int l = 0; uni && l < h->comp[c].nind; l++) uni = h->nonuni_host[c * 3 + k][l] == 0;
+        h->uni_host[c * 3 + k] = uni ? 1 : 0;
+      }
     h->tab_dirty = false;
   }
   return mv;
@@ -432,6 +443,7 @@ double bytes_w(double n) { return n * 8.0; }
 void set_nonuni(dang_gpu *h, int c, int k, int l, int val) {
   const int m = (c * 3 + k) * DG_MAXIND + l;
   CK(cudaMemsetAsync((char *)h->tab + offsetof(SedTable, nonuni) + m * sizeof(int), val ? 1 : 0, sizeof(int), h->stream));
+  h->nonuni_host[c * 3 + k][l] = val ? 1 : 0;
   h->check_mask &= ~(1ull << m);
   h->tab_dirty = true;
 }
@@ -546,10 +558,12 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   CK(cudaMemcpyAsync((char *)h->cg_scalars + offsetof(CgScalars, m), &ckpt_m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
 
   struct Snap { double delta_new; int iter, done; };
-  auto read_state = [&]() -> Snap {
+  bool have_state = false;
+  auto read_state = [&]() -> Snap {  // scalars + residual trace in one small copy
     CgScalars *hs = (CgScalars *)h->pinned;
-    CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, trace), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    have_state = true;
     return Snap{hs->delta_new, hs->iter, hs->done};
   };
 
@@ -643,9 +657,11 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
                          g.x[flag_n] + c * vs + (size_t)s * h->Ppad, h->P * sizeof(double),
                          cudaMemcpyDeviceToDevice, h->stream));
   {
-    CgScalars *hs = (CgScalars *)h->pinned;
-    CK(cudaMemcpyAsync(hs, h->cg_scalars, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CgScalars *hs = (CgScalars *)h->pinned;  // filled by the last read_state (the solve was done then)
+    if (!sn.done || !have_state) {  // ran out of passes (i_max) without seeing the flag: read the final state
+      CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
     int n = hs->iter < 256 ? hs->iter : 256;
     h->last_trace.assign(hs->trace, hs->trace + n);
     g.last_iter[flag_n] = hs->iter;
