@@ -38,6 +38,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by profiles/summarize.py)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel)
+
+
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -49,7 +58,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -161,7 +170,7 @@ def run_gpu(args):
     # --- per-kernel timing for the roofline: same steps with CUDA events around every launch
     eng.kernel_stats(reset=True)
     eng.set_option(OPT_PROFILE, 1)
-    for k in range(max(1, min(args.steps, 3))):
+    for k in range(max(1, min(args.steps, 5))):
         step(2 + args.warmup + args.steps + k)
     stats = eng.kernel_stats(reset=True)
     eng.set_option(OPT_PROFILE, 0)
@@ -211,7 +220,7 @@ def run_gpu(args):
     barrier()
     eng.event_record(2)
     t0 = time.perf_counter()
-    ke = max(1, min(args.steps, 10))
+    ke = max(1, min(args.steps, 50))
     for k in range(ke):
         e2e_step(k)
     eng.download_wait()
@@ -232,7 +241,8 @@ def run_gpu(args):
             ach = s["bytes"] / (s["ms"] * 1e-3) / 1e9
             tot = sum(v["ms"] for v in stats.values())
             roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / peak, 4), "traffic": ncu_traffic(top), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": round(s["bytes"] / max(s["launches"], 1)),
                     "avg_launch_us": round(1e3 * s["ms"] / max(s["launches"], 1), 2),
                     "share_of_kernel_time": round(s["ms"] / tot, 3),
                     "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
@@ -326,8 +336,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--nside", type=int, default=None, help="override the map size (tests only)")

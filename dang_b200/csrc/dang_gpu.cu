@@ -1660,7 +1660,7 @@ int dang_gpu_kernel_stats(dang_gpu_t *h, int kernel, int64_t *launches, double *
 
 const char *dang_gpu_kernel_name(int kernel) {
   static const char *names[DANG_K_COUNT] = {
-      "rhs_blocks_kernel", "cg_fused_pass_kernel", "cg_dq_pass_kernel", "cg_update_pass_kernel",
+      "rhs_blocks_kernel", "cg_pass_kernel", "cg_dq_pass_kernel", "cg_update_pass_kernel",
       "chisq_kernel", "chisq_kernel(maps)", "mh_data_kernel", "mh_fullsky_lnl_kernel",
       "mh_suffstat_kernel", "mh_perpixel_kernel", "scalar kernels", "cg_x_fixup"};
   return (kernel >= 0 && kernel < DANG_K_COUNT) ? names[kernel] : "?";

@@ -12,7 +12,7 @@
 #include "common.cuh"
 
 #define DG_MH_THREADS 128
-#define DG_SUFF_CHUNK 8   // bands per register-resident accumulator chunk
+#define DG_SUFF_CHUNK 4   // bands per register-resident accumulator chunk
 
 struct MhView {
   int ic;          // component being sampled

@@ -86,7 +86,7 @@ __device__ __forceinline__ bool same_indices(const ModelView &mv, int ic, int k,
 
 // K1, uniform-SED form.  Same outputs as rhs_blocks_kernel.
 template <int C>
-__global__ void __launch_bounds__(DG_THREADS)
+__global__ void __launch_bounds__(DG_THREADS, (C <= 2 ? 2 : 1))
 rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
                       unsigned int *ticket, double *out, unsigned nu_mask) {
   constexpr int T = C * (C + 1) / 2;
@@ -256,7 +256,7 @@ rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
 
 // K6, uniform-SED form (chi-square reduction only; map output stays in chisq_kernel).
 template <int NC>
-__global__ void __launch_bounds__(DG_THREADS)
+__global__ void __launch_bounds__(DG_THREADS, 3)
 chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned int *ticket,
                  double *out, unsigned nu_mask) {
   extern __shared__ double dsed[];  // [slot][band][2][blockDim] for the components in nu_mask
@@ -355,7 +355,7 @@ chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsig
 // Full-sky sufficient statistics, uniform-SED form: every component other than the sampled one
 // has tabulated SEDs, so data_raw = sig - sum_c2 a_c2 sed_c2 needs no transcendental either.
 template <int NC>
-__global__ void __launch_bounds__(DG_THREADS)
+__global__ void __launch_bounds__(DG_THREADS, 2)
 mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, double *partials,
                        unsigned int *tickets, double *out) {
   constexpr int NV = 3 * DG_SUFF_CHUNK;

@@ -68,6 +68,27 @@ def main():
                      f"{g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} | {g('launch__grid_size')} |")
     open(outp, "w").write("\n".join(lines) + "\n")
     print("wrote", outp)
+    # per-launch DRAM traffic (read + write, bytes) keyed by bench.py's kernel names
+    alias = {"rhs_blocks": "rhs_blocks_kernel", "cg_recompute_pass": "cg_pass_kernel", "cg_fused_pass": "cg_pass_kernel",
+             "chisq": "chisq_kernel", "mh_suffstat": "mh_suffstat_kernel", "mh_perpixel": "mh_perpixel_kernel"}
+    acc = collections.defaultdict(list)
+    for r in recs:
+        try:
+            t = float(r["gpu__time_duration.sum"])
+            by = (float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])) * 1e6
+        except (KeyError, ValueError):
+            continue
+        if t < 10.0:
+            continue  # passes launched after convergence return at once
+        for pre, name in alias.items():
+            if r["kernel"].startswith(pre):
+                acc[name].append(by)
+    import os
+    tp = os.path.join(os.path.dirname(os.path.abspath(outp)), "ncu_traffic.json")
+    old = json.load(open(tp)) if os.path.exists(tp) else {}
+    old.update({k: round(sum(v) / len(v)) for k, v in acc.items()})
+    json.dump(old, open(tp, "w"), indent=1, sort_keys=True)
+    print("wrote", tp)
 
 
 if __name__ == "__main__":
