@@ -928,11 +928,10 @@ int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
   return cnt;
 }
 
-void check_fullsky_supported(const MhView &mh) {
-  if (mh.lnl_type != DANG_LNL_CHISQ)
-    fail(DANG_GPU_EUNSUPPORTED, "full-sky sampling supports lnl_type 'chisq' only (DESIGN.md)");
-  if (mh.prior_type == DANG_PRIOR_JEFFREYS)
-    fail(DANG_GPU_EUNSUPPORTED, "full-sky Jeffreys prior is not built (DESIGN.md)");
+// the sufficient-statistics form covers the chisq likelihood with uniform / Gaussian prior; the
+// marginal likelihood, the Jeffreys prior and 'prior' draws stream the maps per proposal
+bool fullsky_needs_stream(const MhView &mh) {
+  return mh.lnl_type != DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS;
 }
 
 void upload_fullsky_deviates(dang_gpu *h, MhView &mh, const double *z, const double *u, size_t n) {
@@ -950,7 +949,12 @@ void upload_fullsky_deviates(dang_gpu *h, MhView &mh, const double *z, const dou
 
 void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
                     double *accept) {
-  check_fullsky_supported(mh);
+  const int saved_stream = h->fullsky_stream;
+  struct Restore {
+    dang_gpu *h; int v;
+    ~Restore() { h->fullsky_stream = v; }
+  } restore{h, saved_stream};
+  if (fullsky_needs_stream(mh)) h->fullsky_stream = 1;
   ModelView mv = model_view(h);
   mh.seed = seed;
   const size_t n = (size_t)mh.nsample;
@@ -974,16 +978,31 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
       mh_data_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->D);
       kt.done();
     }
-    for (int l = 0; l <= mh.nsample; l++) {  // starting point + nsample proposals
-      {
+    const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+    const int cnt = mh.lnl_type == DANG_LNL_MARGINAL ? 2 + 4 * DG_SUFF_CHUNK * nchunk : 2;
+    if (cnt > GATHER_MAX) fail(DANG_GPU_EUNSUPPORTED, "full-sky marginal lnL with %d bands", h->nbands);
+    if (mh.lnl_type == DANG_LNL_PRIOR) {  // :255-257: no chain, draw the index from its Gaussian prior
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      mh_fullsky_prior_draw_kernel<<<1, 1, 0, h->stream>>>(mh, h->mh_scalars);
+      ks.done();
+    }
+    for (int l = 0; l <= mh.nsample && mh.lnl_type != DANG_LNL_PRIOR; l++) {  // starting point + proposals
+      CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+      if (mh.lnl_type == DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS) {
         KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
         mh_fullsky_lnl_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials,
                                                                  h->tickets, h->sums_local);
         kt.done();
       }
-      gather(h, 1);
+      if (mh.lnl_type == DANG_LNL_MARGINAL) {
+        KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
+        mh_fullsky_marginal_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials,
+                                                                      h->tickets, h->sums_local);
+        kt.done();
+      }
+      gather(h, cnt);
       KTimer ks(h, DANG_K_SCALAR, 0);
-      mh_fullsky_step_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, 1);
+      mh_fullsky_step_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
       ks.done();
     }
   } else {
@@ -1005,7 +1024,8 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
 
 void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
                   int max_blocks, int *blocks_run, double *step_size) {
-  check_fullsky_supported(mh);
+  if (fullsky_needs_stream(mh))
+    fail(DANG_GPU_EUNSUPPORTED, "the step-size tuner is built for the chisq likelihood with uniform / Gaussian prior");
   if (max_blocks < 0) fail(DANG_GPU_EINVAL, "max_blocks = %d", max_blocks);
   ModelView mv = model_view(h);
   mh.seed = seed;

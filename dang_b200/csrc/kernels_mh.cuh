@@ -491,9 +491,7 @@ __device__ __forceinline__ void mh_next_proposal(const ModelView &mv, const MhVi
   ms->skip = 1;
 }
 
-__device__ __forceinline__ void mh_accept_step(const MhView &mh, MhScalars *ms, double lnl) {
-  double prior = 0.0;
-  if (mh.prior_type == 1) prior = log_normal_prior(ms->theta[mh.nind], mh.gauss[0], mh.gauss[1]);
+__device__ __forceinline__ void mh_accept_step(const MhView &mh, MhScalars *ms, double lnl, double prior) {
   const double lnl_new = lnl + prior;  // :306
   const int l = ms->l;
   if (mh.lnl_trace) mh.lnl_trace[l] = lnl_new;
@@ -509,21 +507,48 @@ __device__ __forceinline__ void mh_accept_step(const MhView &mh, MhScalars *ms, 
   ms->l = l + 1;
 }
 
-// streaming mode: consume the lnL just reduced (gathered over ranks), decide, propose next
+// streaming mode: consume the sums just reduced (gathered over ranks), decide, propose next.
+// Row layout: [0] chi-square lnL, [1] Jeffreys sum, [2 + 4*j + 2*s + {0,1}] = TNd, TNT (marginal).
 __global__ void mh_fullsky_step_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
                                        const double *gathered, int nranks, int cnt) {
   if (ms->skip) return;
   double lnl = 0.0;
-  for (int g = 0; g < nranks; g++) lnl += gathered[g * cnt];
+  if (mh.lnl_type == 0) {
+    for (int g = 0; g < nranks; g++) lnl += gathered[g * cnt];
+  } else if (mh.lnl_type == 1) {  // evaluate_marginal_lnL, src/dang_lnl_mod.f90:113-122
+    for (int j = 0; j < mv.nbands; j++)
+      for (int s = 0; s < mh.S; s++) {
+        double TNd = 0.0, TNT = 0.0;
+        for (int g = 0; g < nranks; g++) {
+          TNd += gathered[g * cnt + 2 + 4 * j + 2 * s];
+          TNT += gathered[g * cnt + 2 + 4 * j + 2 * s + 1];
+        }
+        const double invTNT = 1.0 / TNT;
+        lnl = lnl - 0.5 * TNd * invTNT * TNd;
+      }
+  }
+  const double val = ms->phase == 0 ? ms->sample[mh.nind] : ms->theta[mh.nind];
+  double prior = 0.0;
+  if (mh.prior_type == 1) {
+    prior = log_normal_prior(val, mh.gauss[0], mh.gauss[1]);
+  } else if (mh.prior_type == 2) {  // eval_jeffreys_prior, src/dang_lnl_mod.f90:242-304 (:263, :302)
+    double sum = 0.0;
+    for (int g = 0; g < nranks; g++) sum += gathered[g * cnt + 1];
+    prior = log(sqrt(sum));
+  }
   if (ms->phase == 0) {  // lnL of the starting point (:250, :261, :268)
-    double prior = 0.0;
-    if (mh.prior_type == 1) prior = log_normal_prior(ms->sample[mh.nind], mh.gauss[0], mh.gauss[1]);
     ms->lnl_old = lnl + prior;
     ms->phase = 1;
   } else {
-    mh_accept_step(mh, ms, lnl);
+    mh_accept_step(mh, ms, lnl, prior);
   }
   mh_next_proposal(mv, mh, ms);
+}
+
+// lnl_type 'prior' (:255-257): no chain, the index is drawn from its Gaussian prior
+__global__ void mh_fullsky_prior_draw_kernel(const MhView mh, MhScalars *ms) {
+  ms->sample[mh.nind] = mh.gauss[0] + mh.gauss[1] * mh_draw_z(mh, 0);
+  ms->skip = 1;
 }
 
 // D[j][s][Ppad] = data_raw for the sampled planes (streaming mode only)
@@ -541,28 +566,81 @@ __global__ void __launch_bounds__(DG_THREADS)
 mh_fullsky_lnl_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, const double *D,
                       double *partials, unsigned int *ticket, double *out) {
   if (ms->skip) return;
-  __shared__ double smem[32];
+  __shared__ double smem[2 * 32];
   __shared__ double ssed[DG_MAX_BANDS];
   if (threadIdx.x < mv.nbands) ssed[threadIdx.x] = ms->sed[threadIdx.x];
   __syncthreads();
-  double acc[1] = {0.0};
+  double acc[2] = {0.0, 0.0};
   const CompView &cv = mv.comp[mh.ic];
+  const bool jeff = mh.prior_type == 2 && mh.is_synch;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
     if (!mv.mask[p]) continue;
-    double lnl = 0.0;
+    double lnl = 0.0, js = 0.0;
     for (int s = 0; s < mh.S; s++) {
       const double a = cv.amp[(size_t)mh.plane[s] * mv.Ppad + p];
       for (int j = 0; j < mv.nbands; j++) {
-        const double d = ldg_stream(D + ((size_t)j * mh.S + s) * mv.Ppad + p);
         const double rms = ldg_stream(mv.rms + plane_off(mv, j, mh.plane[s]) + p);
-        const double t = (d - a * ssed[j]) / rms;
-        lnl = lnl - 0.5 * (t * t);
+        if (mh.lnl_type == 0) {
+          const double d = ldg_stream(D + ((size_t)j * mh.S + s) * mv.Ppad + p);
+          const double t = (d - a * ssed[j]) / rms;
+          lnl = lnl - 0.5 * (t * t);
+        }
+        if (jeff) {  // (((1/rms)**2) * (ss/amplitude) * log(nu_c/nu_ref))**2, :296-297
+          const double ir = 1.0 / rms;
+          const double t = (ir * ir) * ((a * ssed[j]) / a) * log(mv.band[j].nu_c / cv.nu_ref);
+          js = js + t * t;
+        }
       }
     }
     acc[0] += lnl;
+    acc[1] += js;
   }
-  grid_reduce<1>(acc, smem, partials, ticket, out);
+  grid_reduce<2>(acc, smem, partials, ticket, out);
+}
+
+// evaluate_marginal_lnL full sky (:113-122): per (band, Stokes) the sums over ALL pixels (the
+// source ignores the mask) of TN*data and TN*model, TN = model / rms^2, model = amplitude * sed.
+// out[2 + 4*j + 2*s + {0,1}]; bands in chunks of DG_SUFF_CHUNK.
+__global__ void __launch_bounds__(DG_THREADS)
+mh_fullsky_marginal_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, const double *D,
+                           double *partials, unsigned int *tickets, double *out) {
+  if (ms->skip) return;
+  constexpr int NV = 4 * DG_SUFF_CHUNK;  // (TNd, TNT) x 2 planes per band
+  __shared__ double smem[NV * 32];
+  __shared__ double ssed[DG_MAX_BANDS];
+  if (threadIdx.x < mv.nbands) ssed[threadIdx.x] = ms->sed[threadIdx.x];
+  __syncthreads();
+  const CompView &cv = mv.comp[mh.ic];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int nchunk = (mv.nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  for (int ch = 0; ch < nchunk; ch++) {
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (s >= mh.S) continue;
+        const double a = cv.amp[(size_t)mh.plane[s] * mv.Ppad + p];
+#pragma unroll
+        for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
+          const int j = ch * DG_SUFF_CHUNK + jj;
+          if (j < mv.nbands) {
+            const double d = ldg_stream(D + ((size_t)j * mh.S + s) * mv.Ppad + p);
+            const double rms = ldg_stream(mv.rms + plane_off(mv, j, mh.plane[s]) + p);
+            const double model = a * ssed[j];
+            const double TN = model / (rms * rms);
+            acc[4 * jj + 2 * s + 0] += TN * d;
+            acc[4 * jj + 2 * s + 1] += TN * model;
+          }
+        }
+      }
+    }
+    // chunk ch holds bands ch*CHUNK .. : slot 2 + 4*j + 2*s + {0,1}
+    grid_reduce<NV>(acc, smem, partials + (size_t)ch * NV * gridDim.x, tickets + ch, out + 2 + ch * NV);
+    __syncthreads();
+  }
 }
 
 // Sufficient statistics of the full-sky chi-square about the chain's starting SED s0:

@@ -267,6 +267,41 @@ def test_fullsky_metropolis(stream, name, ic, nind, others_uniform):
     assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-14
 
 
+@pytest.mark.parametrize("variant", ["marginal", "jeffreys", "prior_draw"])
+def test_fullsky_metropolis_rare_variants(variant):
+    """Full-sky chains with the marginal likelihood (dang_lnl_mod.f90:47-124), the Jeffreys prior
+    (:242-304, synchrotron only) and lnl_type 'prior' (a plain draw from the Gaussian prior)."""
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c1", 16, perturb=False)
+    spec = cfg.comps[0].indices[0]
+    spec.sample, spec.region, spec.step = True, "fullsky", 0.01
+    if variant == "marginal":
+        spec.lnl_type = "marginal"
+    elif variant == "jeffreys":
+        spec.prior = "jeffreys"
+    else:
+        spec.lnl_type = "prior"
+    # non-zero amplitudes (the Jeffreys term divides by them)
+    rng = np.random.default_rng(17)
+    for c in cfg.comps:
+        sky.amplitude[c.label][1:3] = sky.truth[c.label][1:3] * (1.0 + 0.05 * rng.standard_normal((2, cfg.npix)))
+    nsample = 16
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    z, u = rng.standard_normal(nsample), rng.random(nsample)
+    acc_o, dec_o, lnl_o = ora.sample_index_mh(0, 0, -1, nsample, 1, z, u, want_trace=True)
+    acc_g = eng.sample_index_mh(0, 0, -1, nsample, "sample", z, u)
+    assert rel_err(eng.indices(0), ora.indices(0)) < 1e-14
+    if variant == "prior_draw":
+        assert np.all(eng.indices(0)[0, 1] == spec.gauss[0] + spec.gauss[1] * z[0])
+        return
+    dec_g, lnl_g = eng.decisions(nsample, fullsky=True)
+    assert np.array_equal(dec_g, dec_o[:nsample])
+    assert acc_g == acc_o
+    ev = dec_o[:nsample] < 2
+    assert rel_err(lnl_g[ev], lnl_o[:nsample][ev]) < TOL
+
+
 @pytest.mark.parametrize("step0", [0.2, 0.0005, 0.004])
 def test_step_size_tuner(step0):
     """tune_spectral_parameter_length: same blocks, same halving / x1.5 sequence, same final step."""
@@ -375,3 +410,38 @@ def test_full_gibbs_chain_c1():
         for ic in range(2):
             assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
             assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-13
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_are_loud_and_specific():
+    """Everything outside the built scope fails with a nonzero code and a message (the Fortran
+    shim prints it and stops, like the reference's own `write(*,*) ...; stop`)."""
+    import ctypes as C
+    from dang_b200 import _lib
+    from dang_b200.engine import DangGpuError, Engine
+    cfg, sky = small_case("c1", 4)
+    # sample_nside /= nside needs HEALPix udgrade_ring (out of scope)
+    cfg.comps[0].indices[0].samp_nside = 2
+    eng = Engine(cfg, sky)
+    with pytest.raises(DangGpuError, match="udgrade"):
+        eng.sample_index_mh(0, 0, -1, 4)
+    with pytest.raises(DangGpuError, match="T\\+Q\\+U|unreachable"):
+        eng.sample_index_mh(0, 0, -2, 4)
+    with pytest.raises(DangGpuError, match="CG group"):
+        eng.cg_solve(ig=5)
+    lib = _lib.load()
+    # unsupported component type (template = 6 is not an enum value of the ABI)
+    rc = lib.dang_gpu_set_component(eng.h, 0, 6, b"tmpl", 30e9, 1, 1, None, None)
+    assert rc == 3 and b"power-law" in lib.dang_gpu_last_error(eng.h)
+    # bad geometry at creation
+    h = _lib.vp()
+    assert lib.dang_gpu_create(0, 4, 191, 3, 5, 2, 0, 191, C.byref(h)) == 1
+    assert lib.dang_gpu_create(0, 4, 192, 3, 5, 2, 10, 5, C.byref(h)) == 1
+    assert lib.dang_gpu_create(99, 4, 192, 3, 5, 2, 0, 192, C.byref(h)) == 1
+    # operators before the maps are uploaded
+    assert lib.dang_gpu_create(0, 4, 192, 3, 5, 2, 0, 192, C.byref(h)) == 0
+    planes = (C.c_double * 3)()
+    n = C.c_int64()
+    assert lib.dang_gpu_chisq(h, 2, 3, planes, C.byref(n)) == 5
+    assert b"upload_maps" in lib.dang_gpu_last_error(h)
+    lib.dang_gpu_destroy(h)
