@@ -126,11 +126,76 @@ __device__ __forceinline__ double sed_mbb(const ModelView &mv, int ic, int band,
   return spectrum;
 }
 
+// evaluate_freefree, src/dang_component_mod.f90:1001-1040 (T_e is the only index)
+__device__ __forceinline__ double ff_gaunt(double nu, double T_e) {
+  return log(exp(5.960 - sqrt(3.0) / DG_PI * log(1.0 * nu / 1.e9 * pow(T_e / 1.e4, -1.5))) + 2.71828);
+}
+__device__ __forceinline__ double sed_freefree(const ModelView &mv, int ic, int band, double T_e) {
+  const BandView &b = mv.band[band];
+  const double nu_ref = mv.comp[ic].nu_ref;
+  const double S_ref = ff_gaunt(nu_ref, T_e);
+  if (b.n == 0) {
+    const double r = b.nu_c / nu_ref;
+    return ff_gaunt(b.nu_c, T_e) / S_ref * (1.0 / (r * r));
+  }
+  double spectrum = 0.0;
+  for (int i = 0; i < b.n; i++) {
+    const double nu0 = mv.bp_nu0[b.off + i];
+    if (nu0 == 0.0) continue;
+    const double r = nu0 / nu_ref;
+    spectrum = spectrum + mv.bp_tau0[b.off + i] * ff_gaunt(nu0, T_e) / S_ref * (1.0 / (r * r));
+  }
+  return spectrum;
+}
+
+// evaluate_lognormal, src/dang_component_mod.f90:960-999 (nu_p [GHz], w_ame)
+__device__ __forceinline__ double sed_lognormal(const ModelView &mv, int ic, int band, double nu_p,
+                                                double w_ame) {
+  const BandView &b = mv.band[band];
+  const double nu_ref = mv.comp[ic].nu_ref;
+  if (b.n == 0) {
+    const double t = log(b.nu_c / (nu_p * 1e9)) / w_ame, r = nu_ref / b.nu_c;
+    return exp(-0.5 * (t * t)) * (r * r);
+  }
+  double spectrum = 0.0;
+  for (int i = 0; i < b.n; i++) {
+    const double nu0 = mv.bp_nu0[b.off + i];
+    if (nu0 == 0.0) continue;
+    const double t = log(nu0 / (nu_p * 1e9)) / w_ame, r = nu_ref / nu0;
+    spectrum = spectrum + mv.bp_tau0[b.off + i] * exp(-0.5 * (t * t)) * (r * r);
+  }
+  return spectrum;
+}
+
+// type 'cmb': 1/a2t(bp(band)), src/dang_component_mod.f90:799-800 with a2t from dang_bp_mod.f90:211-243
+__device__ __forceinline__ double sed_cmb(const ModelView &mv, int band) {
+  const BandView &b = mv.band[band];
+  const double T_CMB = 2.7255;  // src/dang_util_mod.f90:15
+  double sum = 0.0;
+  if (b.n == 0) {
+    const double y = (b.nu_c > 1e7) ? (DG_H * b.nu_c) / (DG_KB * T_CMB) : (DG_H * b.nu_c * 1e9) / (DG_KB * T_CMB);
+    sum = ((exp(y) - 1.0) * (exp(y) - 1.0)) / ((y * y) * exp(y));
+  } else {
+    for (int i = 0; i < b.n; i++) {
+      const double nu0 = mv.bp_nu0[b.off + i];
+      if (nu0 == 0.0) continue;
+      const double y = (nu0 > 1e7) ? (DG_H * nu0) / (DG_KB * T_CMB) : (DG_H * nu0 * 1e9) / (DG_KB * T_CMB);
+      sum = sum + mv.bp_tau0[b.off + i] * ((exp(y) - 1.0) * (exp(y) - 1.0)) / ((y * y) * exp(y));
+    }
+  }
+  return 1.0 / sum;
+}
+
 // SED of component ic in `band` for explicit parameters (a Metropolis proposal, or a pixel)
 __device__ __forceinline__ double sed_theta(const ModelView &mv, int ic, int band, double t0,
                                             double t1) {
-  if (mv.comp[ic].type == 1) return sed_powerlaw(mv, ic, band, t0);
-  return sed_mbb(mv, ic, band, t0, t1);
+  switch (mv.comp[ic].type) {
+    case 1: return sed_powerlaw(mv, ic, band, t0);
+    case 2: return sed_mbb(mv, ic, band, t0, t1);
+    case 3: return sed_freefree(mv, ic, band, t0);
+    case 4: return sed_lognormal(mv, ic, band, t0, t1);
+    default: return sed_cmb(mv, band);
+  }
 }
 
 // SED of component ic at a pixel of plane k.  When every index map of the component is constant

@@ -859,7 +859,7 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
     int mode = MH_SED_GENERIC;
     if (!any_bp) {
       if (h->comp[mh.ic].type == DANG_COMP_POWERLAW) mode = MH_SED_POWERLAW;
-      else mode = mh.nind == 0 ? MH_SED_MBB_BETA : MH_SED_MBB_T;
+      else if (h->comp[mh.ic].type == DANG_COMP_MBB) mode = mh.nind == 0 ? MH_SED_MBB_BETA : MH_SED_MBB_T;
     }
     KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
 #define LAUNCH_PP(BPL, MODE)                                                                               \
@@ -1334,8 +1334,10 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
                            const double *indices) {
   API_BEGIN
   if (ic < 0 || ic >= h->ncomp) fail(DANG_GPU_EINVAL, "component %d of %d", ic, h->ncomp);
-  if (type != DANG_COMP_POWERLAW && type != DANG_COMP_MBB)
-    fail(DANG_GPU_EUNSUPPORTED, "component type %d: only power-law and mbb are built (DESIGN.md)", type);
+  if (type < DANG_COMP_POWERLAW || type > DANG_COMP_CMB)
+    fail(DANG_GPU_EUNSUPPORTED,
+         "component type %d: power-law, mbb, freefree, lognormal and cmb are built; template / monopole / hi_fit / T_cmb "
+         "are not (DESIGN.md)", type);
   CompHost &c = h->comp[ic];
   c.set = true;
   c.type = type;
@@ -1343,7 +1345,7 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   c.nu_ref = nu_ref_hz;
   c.cg_group = cg_group;
   c.sample_amplitude = sample_amplitude != 0;
-  c.nind = type == DANG_COMP_MBB ? 2 : 1;
+  c.nind = (type == DANG_COMP_MBB || type == DANG_COMP_LOGNORMAL) ? 2 : (type == DANG_COMP_CMB ? 0 : 1);
   const size_t n2 = (size_t)h->nmaps * h->Ppad;
   if (!c.amp) CK(cudaMalloc(&c.amp, n2 * sizeof(double)));
   CK(cudaMemsetAsync(c.amp, 0, n2 * sizeof(double), h->stream));

@@ -94,7 +94,8 @@ mh_perpixel_serial_kernel(const ModelView mv, const MhView mh, double *partials,
   double acc[1] = {0.0};
   const CompView &cv = mv.comp[mh.ic];
   const SedTable &tab = *mv.tab;
-  const bool is_mbb = cv.type != 1;
+  const bool is_mbb = cv.type == 2;
+  const bool is_pl = cv.type == 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + tid; p < mv.P; p += stride) {
     const uint64_t gpix = (uint64_t)(mv.pix_lo + p);
@@ -132,10 +133,12 @@ mh_perpixel_serial_kernel(const ModelView mv, const MhView mh, double *partials,
 
     // SED of the proposal, band by band, into sS
     auto eval_sed = [&](const double *th) {
-      if (!is_mbb) {
+      if (is_pl) {
 #pragma unroll 4
         for (int j = 0; j < B; j++)
           sS[(size_t)j * T + tid] = sed_powerlaw(mv, mh.ic, j, th[0]);
+      } else if (!is_mbb) {
+        for (int j = 0; j < B; j++) sS[(size_t)j * T + tid] = sed_theta(mv, mh.ic, j, th[0], th[1]);
       } else if (mh.nind == 0) {
 #pragma unroll 4
         for (int j = 0; j < B; j++)

@@ -45,7 +45,13 @@ __device__ __forceinline__ void sed_pair_to_smem(const ModelView &mv, int ic, in
   const double2 t1 = cv.nind > 1 ? *reinterpret_cast<const double2 *>(cv.idx[1] + kp) : make_double2(0.0, 0.0);
   const bool same = t0.x == t0.y && t1.x == t1.y;
   const SedTable &tab = *mv.tab;
-  if (cv.type == 1) {
+  if (cv.type > 2) {  // free-free, lognormal, cmb: the generic per-band evaluation
+    for (int j = 0; j < mv.nbands; j++) {
+      const double a = sed_theta(mv, ic, j, t0.x, t1.x);
+      dst[(size_t)(j * 2 + 0) * nthr + tid] = a;
+      dst[(size_t)(j * 2 + 1) * nthr + tid] = same ? a : sed_theta(mv, ic, j, t0.y, t1.y);
+    }
+  } else if (cv.type == 1) {
     for (int j = 0; j < mv.nbands; j++) {
       const double a = sed_powerlaw(mv, ic, j, t0.x);
       dst[(size_t)(j * 2 + 0) * nthr + tid] = a;

@@ -124,12 +124,14 @@ def make_sky(cfg: RunConfig, seed: int = SEED_SKY, noise_seed: int = SEED_NOISE)
     sig = np.zeros((nb, nm, npix))
     for c in cfg.comps:
         a = np.zeros((nm, npix))
-        a[1:3] = rng.normal(0.0, TRUE_AMP_SIGMA[c.label], size=(2, npix))
-        truth[c.label] = a
         amp0[c.label] = np.zeros((nm, npix))
-        idx0[c.label] = np.stack([np.full((nm, npix), s.init) for s in c.indices])
-        for j, b in enumerate(cfg.bands):
-            sig[j, 1:3] += a[1:3] * band_sed(b, c, *TRUE_THETA[c.label])
+        idx0[c.label] = (np.stack([np.full((nm, npix), s.init) for s in c.indices]) if c.indices
+                         else np.zeros((0, nm, npix)))
+        if c.label in TRUE_THETA:  # synch / dust carry the simulated sky; other components start empty
+            a[1:3] = rng.normal(0.0, TRUE_AMP_SIGMA[c.label], size=(2, npix))
+            for j, b in enumerate(cfg.bands):
+                sig[j, 1:3] += a[1:3] * band_sed(b, c, *TRUE_THETA[c.label])
+        truth[c.label] = a
     rms = np.ones((nb, nm, npix))
     for j, b in enumerate(cfg.bands):
         rms[j, 1:3] = band_sigma(b.nu_ghz) * (1.0 + 0.3 * nrng.random(size=(2, npix)))

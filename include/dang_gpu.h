@@ -46,7 +46,7 @@ enum {
 };
 
 /* c%type, src/dang_component_mod.f90:791-809 */
-enum { DANG_COMP_POWERLAW = 1, DANG_COMP_MBB = 2 };
+enum { DANG_COMP_POWERLAW = 1, DANG_COMP_MBB = 2, DANG_COMP_FREEFREE = 3, DANG_COMP_LOGNORMAL = 4, DANG_COMP_CMB = 5 };
 /* c%lnl_type, src/dang_sample_mod.f90:249-258 */
 enum { DANG_LNL_CHISQ = 0, DANG_LNL_MARGINAL = 1, DANG_LNL_PRIOR = 2 };
 /* c%prior_type, src/dang_sample_mod.f90:260-266 */

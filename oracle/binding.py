@@ -205,6 +205,7 @@ class Oracle:
         return list(niter)[:nflag], delta[:nflag].copy()
 
     def cg_search_trace(self, ig=0, flag_n=0, ml_mode=1, eta=None, fix_q1=False, trace_len=256):
+        """compute_rhs -> cg_search -> unpack_amplitudes for one (group, flag), with the delta trace."""
         b = self.compute_rhs(ig, flag_n)
         trace = np.full(trace_len, np.nan)
         delta = C.c_double()

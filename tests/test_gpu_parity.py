@@ -412,6 +412,50 @@ def test_full_gibbs_chain_c1():
             assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-13
 
 
+def test_freefree_lognormal_cmb_components():
+    """The remaining diffuse SED types (evaluate_freefree :1001-1040, evaluate_lognormal :960-999,
+    'cmb' = 1/a2t) through chi-square, the CG amplitude draw (5x5 blocks split over two CG groups)
+    and a per-pixel draw of the free-free electron temperature."""
+    from dang_b200.config import CGGroup, Component, IndexSpec
+    from dang_b200.engine import OPT_RECORD, Engine
+    from oracle.binding import Oracle
+    cfg, sky0 = small_case("c1", 8)
+    cfg.comps += [
+        Component("ff", "freefree", 40.0, cg_group=2, indices=[
+            IndexSpec("T_e", 7000.0, sample=True, region="per-pixel", prior="uniform", uni=(4000.0, 11000.0), step=300.0)]),
+        Component("ame", "lognormal", 22.0, cg_group=2, indices=[IndexSpec("NU_P", 21.0), IndexSpec("W_AME", 0.55)]),
+        Component("cmb", "cmb", 100.0, cg_group=2, indices=[]),
+    ]
+    cfg.cg_groups.append(CGGroup(sample=True, max_iter=60, converge=1e-10, poltype="Q+U"))
+    from dang_b200.synth import make_sky
+    sky = make_sky(cfg)
+    rng = np.random.default_rng(23)
+    for c in cfg.comps:
+        sky.amplitude[c.label][1:3] = rng.normal(0.0, 5.0, size=(2, cfg.npix))
+    sky.indices["ff"][0][:] = 7000.0 + 500.0 * rng.standard_normal(cfg.npix)[None, :]
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    eng.set_option(OPT_RECORD, 1)
+    ora.update_sky_model()
+    chisq_o, planes_o = ora.compute_chisq()
+    assert rel_err(eng.chisq_planes()[0], planes_o) < TOL
+    sky_g, res_g, _ = eng.update_sky_model()
+    assert rel_err(sky_g, ora.sky_model()) < TOL
+    for ig in (0, 1):
+        eta = rng.standard_normal(2 * cfg.npix)
+        it_o, _, _ = ora.cg_search_trace(ig=ig, ml_mode=1, eta=eta)
+        it_g, _ = eng.cg_solve(ig, 0, "sample", eta=eta)
+        assert it_g == it_o
+    for ic in range(len(cfg.comps)):
+        assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
+    nsample = 8
+    z, u = deviates(cfg, nsample, seed=29)
+    acc_o, dec_o, lnl_o = ora.sample_index_mh(2, 0, -1, nsample, 1, z, u, want_trace=True)
+    acc_g = eng.sample_index_mh(2, 0, -1, nsample, "sample", z, u)
+    dec_g, lnl_g = eng.decisions(nsample, fullsky=False)
+    assert np.array_equal(dec_g, dec_o) and acc_g == acc_o
+    assert rel_err(eng.indices(2), ora.indices(2)) < 1e-14
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_are_loud_and_specific():
     """Everything outside the built scope fails with a nonzero code and a message (the Fortran
@@ -432,7 +476,7 @@ def test_errors_are_loud_and_specific():
     with pytest.raises(DangGpuError, match="CG group"):
         eng.cg_solve(ig=5)
     lib = _lib.load()
-    # unsupported component type (template = 6 is not an enum value of the ABI)
+    # unsupported component type (template / monopole / hi_fit have no enum value in the ABI)
     rc = lib.dang_gpu_set_component(eng.h, 0, 6, b"tmpl", 30e9, 1, 1, None, None)
     assert rc == 3 and b"power-law" in lib.dang_gpu_last_error(eng.h)
     # bad geometry at creation
