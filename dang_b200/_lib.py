@@ -53,6 +53,7 @@ SIGNATURES = {
                                       C.c_uint64, C.c_int, c_ip, c_dp]),
     "dang_gpu_chisq": (C.c_int, [vp, C.c_int, C.c_int, c_dp, c_i64p]),
     "dang_gpu_get_sky_model": (C.c_int, [vp, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
+    "dang_gpu_fit_band_gain": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp, C.c_uint64, c_dp]),
     "dang_gpu_index_mean": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp]),
     "dang_gpu_get_amplitude_async": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp]),
     "dang_gpu_get_indices_async": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp]),

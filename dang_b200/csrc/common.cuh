@@ -252,7 +252,7 @@ __host__ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t
 #endif
 }
 
-enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3, DG_STREAM_TUNE_Z = 4, DG_STREAM_TUNE_U = 5 };
+enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3, DG_STREAM_TUNE_Z = 4, DG_STREAM_TUNE_U = 5, DG_STREAM_GAIN = 6 };
 
 // ---------------------------------------------------------------- cross-rank scalar exchange
 // Every rank owns a mailbox in its own HBM, mapped into all peers with CUDA IPC.  An exchange

@@ -1640,6 +1640,38 @@ int dang_gpu_stage_eta(dang_gpu_t *h, const double *eta, int nplanes) {
   API_END
 }
 
+int dang_gpu_fit_band_gain(dang_gpu_t *h, int map_n, int band, int ml_mode, const double *z, uint64_t seed,
+                           double *gain) {
+  API_BEGIN
+  if (map_n < 1 || map_n > h->nmaps || band < 0 || band >= h->nbands) fail(DANG_GPU_EINVAL, "bad map / band %d / %d", map_n, band);
+  ModelView mv = model_view(h);
+  const int grid = occ_grid(h, band_gain_kernel, h->P, DG_THREADS);
+  {
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    band_gain_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, map_n - 1, band, h->partials, h->tickets, h->sums_local);
+    kt.done();
+  }
+  gather(h, 4);
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double mu = 0.0, sigma = 0.0;
+  for (int g = 0; g < h->nranks; g++) {
+    mu += hp[g * 4 + 0];
+    sigma += hp[g * 4 + 1];
+  }
+  mu = mu / sigma;               // :609-610
+  sigma = sqrt(1.0 / sigma);
+  double g = mu;
+  if (ml_mode != DANG_ML_OPTIMIZE) {
+    const double zz = z ? *z : philox_normal(seed, DG_STREAM_GAIN, (uint64_t)band);
+    g = mu + sigma * (0.0 + 1.0 * zz);  // rand_normal(0,1), :615
+  }
+  h->gain[band] = g;             // ddata%gain(band) = gain, :619
+  if (gain) *gain = g;
+  API_END
+}
+
 int dang_gpu_host_alloc(void **ptr, uint64_t bytes) {
   return cudaMallocHost(ptr, bytes) == cudaSuccess ? DANG_GPU_OK : DANG_GPU_ECUDA;
 }

@@ -154,3 +154,31 @@ __global__ void sed_table_kernel(const ModelView mv, SedTable *tab) {
   }
   if (threadIdx.x == 0) tab->uni[ck] = uni ? 1 : 0;
 }
+
+// fit_band_gain, src/dang_sample_mod.f90:570-621: the two masked, noise-weighted dot products of
+// one band against the current sky model.  out[0] = sum(map2*N_inv*map1), out[1] = sum(map1*N_inv*map1)
+// with map1 = sky_model, map2 = res_map + sky_model (update_sky_model :384-387 fused in).
+__global__ void __launch_bounds__(DG_THREADS)
+band_gain_kernel(const ModelView mv, int k, int band, double *partials, unsigned int *ticket, double *out) {
+  __shared__ double smem[4 * 32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
+    if (!mv.mask[p]) continue;
+    const size_t kp = (size_t)k * mv.Ppad + p;
+    double sky = 0.0;
+    for (int c = 0; c < mv.ncomp; c++) {
+      const CompView &cc = mv.comp[c];
+      const double t0 = cc.nind > 0 ? cc.idx[0][kp] : 0.0, t1 = cc.nind > 1 ? cc.idx[1][kp] : 0.0;
+      sky = sky + cc.amp[kp] * sed_eval(mv, c, k, band, t0, t1);
+    }
+    const size_t off = plane_off(mv, band, k) + p;
+    const double sig = mv.sig[off], noise = mv.rms[off];
+    const double res = (k == 0) ? (sig - mv.offset[band]) / mv.gain[band] - sky : sig - sky;
+    const double map1 = sky, map2 = res + sky;
+    const double N_inv = 1.0 / (noise * noise);
+    acc[0] += map2 * N_inv * map1;
+    acc[1] += map1 * N_inv * map1;
+  }
+  grid_reduce<4>(acc, smem, partials, ticket, out);
+}

@@ -305,6 +305,15 @@ class Engine:
         self._ck(self.lib.dang_gpu_get_sky_model(self.h, lo, hi, _dp(sky), _dp(res), _dp(chi)))
         return sky, res, chi
 
+    def fit_band_gain(self, map_n: int, band: int, ml_mode: Optional[str] = None, z: Optional[float] = None,
+                      seed: int = 0) -> float:
+        """fit_band_gain (src/dang_sample_mod.f90:570-621); the new gain stays in the handle."""
+        ml_mode = ml_mode or self.cfg.ml_mode
+        g = C.c_double()
+        zz = None if z is None else C.byref(C.c_double(z))
+        self._ck(self.lib.dang_gpu_fit_band_gain(self.h, map_n, band, ML_MODES[ml_mode], zz, seed, C.byref(g)))
+        return g.value
+
     def index_mean(self, ic: int, nind: int, map_n: int) -> float:
         m = C.c_double()
         self._ck(self.lib.dang_gpu_index_mean(self.h, ic, nind, map_n, C.byref(m)))

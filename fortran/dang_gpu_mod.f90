@@ -28,7 +28,7 @@ module dang_gpu_mod
 
   private
   public :: dang_gpu_init, dang_gpu_finalize, dang_gpu_upload_ddata
-  public :: sample_cg_groups_gpu, sample_spectral_parameters_gpu, compute_chisq_gpu
+  public :: sample_cg_groups_gpu, sample_spectral_parameters_gpu, compute_chisq_gpu, sample_calibrators_gpu
   public :: dang_gpu_download_components, dang_gpu_download_sky_model
 
   type(c_ptr), save :: handle = c_null_ptr
@@ -136,6 +136,14 @@ module dang_gpu_mod
        integer(c_int), value :: pol_lo, pol_hi
        real(c_double) :: sky(*), res(*), chi(*)
      end function dang_gpu_get_sky_model
+     integer(c_int) function dang_gpu_fit_band_gain(h, map_n, band, ml_mode, z, seed, gain) &
+          bind(C, name='dang_gpu_fit_band_gain')
+       import :: c_int, c_double, c_ptr, c_int64_t
+       type(c_ptr), value :: h, z             ! z = c_null_ptr: device RNG
+       integer(c_int), value :: map_n, band, ml_mode
+       integer(c_int64_t), value :: seed
+       real(c_double) :: gain
+     end function dang_gpu_fit_band_gain
      integer(c_int) function dang_gpu_index_mean(h, ic, nind, map_n, mean) bind(C, name='dang_gpu_index_mean')
        import :: c_int, c_double, c_ptr
        type(c_ptr), value :: h
@@ -304,6 +312,30 @@ contains
        call write_stats_gpu(ddata, iter)
     end if
   end subroutine sample_spectral_parameters_gpu
+
+  subroutine sample_calibrators_gpu(ddata)
+    ! Drop-in for sample_calibrators / fit_band_gain (dang_sample_mod.f90:487-518, 570-621)
+    type(dang_data), intent(inout) :: ddata
+    integer(i4b)   :: j
+    integer(c_int) :: mode
+    real(c_double) :: gain
+    logical(lgt)   :: sampled
+    mode = ML_OPTIMIZE; if (trim(ml_mode) == 'sample') mode = ML_SAMPLE
+    sampled = any(ddata%fit_gain(:))
+    if (sampled) write(*,*) "Sampling band calibrators"
+    do j = 1, nbands
+       if (ddata%fit_gain(j)) then
+          gpu_seed = gpu_seed + 1
+          call gpu_check(dang_gpu_fit_band_gain(handle, 1_c_int, int(j-1,c_int), mode, c_null_ptr, &
+               int(gpu_seed,c_int64_t), gain), 'fit_band_gain')
+          ddata%gain(j) = gain
+       end if
+    end do
+    if (sampled) then
+       call compute_chisq_gpu(ddata)
+       call write_stats_gpu(ddata, iter)
+    end if
+  end subroutine sample_calibrators_gpu
 
   subroutine compute_chisq_gpu(ddata)
     ! Drop-in for update_sky_model + compute_chisq (dang_data_mod.f90:339-396,494-526).

@@ -179,6 +179,12 @@ int dang_gpu_chisq(dang_gpu_t *h, int pol_lo, int pol_hi, double *chisq_planes,
  * are written; any pointer may be NULL.  Needed only when write_maps is due (dang.f90:119). */
 int dang_gpu_get_sky_model(dang_gpu_t *h, int pol_lo, int pol_hi, double *sky_model,
                            double *res_map, double *chi_map);
+/* ---- band calibration: fit_band_gain(ddata, map_n, band), src/dang_sample_mod.f90:570-621
+ * (called for Stokes I by sample_calibrators :487-518).  z: the N(0,1) deviate of :615 or NULL
+ * (device stream `seed`).  The fitted gain replaces the handle's gain(band) and is returned. */
+int dang_gpu_fit_band_gain(dang_gpu_t *h, int map_n, int band, int ml_mode, const double *z,
+                           uint64_t seed, double *gain);
+
 /* mask_avg(c%indices(:,map_n,nind), masks(:,1)), src/dang_util_mod.f90:186-206 */
 int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean);
 

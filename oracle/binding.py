@@ -241,6 +241,9 @@ class Oracle:
         u = np.ascontiguousarray(u, dtype=np.float64)
         return self.lib.ora_sample_spectral_parameters(self.st, nsample, ml_mode, _dp(z), _dp(u))
 
+    def fit_band_gain(self, map_n, band, ml_mode, z):
+        return self.lib.ora_fit_band_gain(self.st, map_n, band, ml_mode, z)
+
     def tune_step(self, ic, nind, map_n, nsample, ml_mode, z, u, max_blocks):
         z = np.ascontiguousarray(z, dtype=np.float64)
         u = np.ascontiguousarray(u, dtype=np.float64)

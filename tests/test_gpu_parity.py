@@ -456,6 +456,45 @@ def test_freefree_lognormal_cmb_components():
     assert rel_err(eng.indices(2), ora.indices(2)) < 1e-14
 
 
+def test_band_gain_fit_intensity():
+    """fit_band_gain on a Stokes-I run (TQU = T): gains and offsets enter the data, the fitted
+    gain matches the oracle and feeds the next chi-square."""
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c1", 8)
+    cfg.tqu = "T"
+    cfg.cg_groups[0].poltype = "T"
+    for c in cfg.comps:
+        for s in c.indices:
+            s.poltype = "T"
+    rng = np.random.default_rng(37)
+    sky.gain = 1.0 + 0.02 * rng.standard_normal(cfg.nbands)
+    sky.offset = rng.normal(0.0, 0.5, cfg.nbands)
+    sky.rms[:, 0] = sky.rms[:, 1]
+    for c in cfg.comps:
+        sky.amplitude[c.label][0] = sky.truth[c.label][1]
+        sky.indices[c.label][:, 0] = sky.indices[c.label][:, 1]
+    from dang_b200.synth import TRUE_THETA, band_sed
+    for j, b in enumerate(cfg.bands):
+        sky.sig[j, 0] = sum(sky.truth[c.label][1] * band_sed(b, c, *TRUE_THETA[c.label]) for c in cfg.comps)
+        sky.sig[j, 0] = sky.sig[j, 0] * sky.gain[j] + sky.offset[j] + sky.rms[j, 0] * rng.standard_normal(cfg.npix)
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    eta = rng.standard_normal(cfg.npix)
+    it_o, _, _ = ora.cg_search_trace(ml_mode=1, eta=eta)
+    it_g, _ = eng.cg_solve(0, 0, "sample", eta=eta)
+    assert it_g == it_o
+    ora.update_sky_model()
+    chisq_o, _ = ora.compute_chisq()
+    assert abs(eng.compute_chisq() - chisq_o) <= TOL * chisq_o
+    for band, z in ((0, 0.3), (3, -1.1)):
+        g_o = ora.fit_band_gain(1, band, 1, z)
+        g_g = eng.fit_band_gain(1, band, "sample", z)
+        assert abs(g_g - g_o) <= TOL * abs(g_o)
+    ora.update_sky_model()
+    chisq_o, _ = ora.compute_chisq()
+    assert abs(eng.compute_chisq() - chisq_o) <= TOL * chisq_o
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_are_loud_and_specific():
     """Everything outside the built scope fails with a nonzero code and a message (the Fortran
