@@ -35,7 +35,7 @@ module dang_gpu_mod
   integer(i8b), save :: gpu_seed = 20260101_i8b   ! device Philox seed, advanced every draw
 
   ! enums of include/dang_gpu.h
-  integer(c_int), parameter :: COMP_POWERLAW = 1, COMP_MBB = 2
+  integer(c_int), parameter :: COMP_POWERLAW = 1, COMP_MBB = 2, COMP_FREEFREE = 3, COMP_LOGNORMAL = 4, COMP_CMB = 5
   integer(c_int), parameter :: LNL_CHISQ = 0, LNL_MARGINAL = 1, LNL_PRIOR = 2
   integer(c_int), parameter :: PRIOR_UNIFORM = 0, PRIOR_GAUSSIAN = 1, PRIOR_JEFFREYS = 2
   integer(c_int), parameter :: ML_OPTIMIZE = 0, ML_SAMPLE = 1
@@ -176,6 +176,12 @@ contains
        comp_type_enum = COMP_POWERLAW
     else if (trim(ctype) == 'mbb') then
        comp_type_enum = COMP_MBB
+    else if (trim(ctype) == 'freefree') then
+       comp_type_enum = COMP_FREEFREE
+    else if (trim(ctype) == 'lognormal') then
+       comp_type_enum = COMP_LOGNORMAL
+    else if (trim(ctype) == 'cmb') then
+       comp_type_enum = COMP_CMB
     else
        write(*,*) 'dang_gpu: component type '//trim(ctype)//' is not on the GPU path yet'
        stop
