@@ -32,6 +32,7 @@ SIGNATURES = {
     "dang_gpu_comm_check": (C.c_int, [vp]),
     "dang_gpu_set_band": (C.c_int, [vp, C.c_int, C.c_double, C.c_int, c_dp, c_dp]),
     "dang_gpu_upload_maps": (C.c_int, [vp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "dang_gpu_share_maps": (C.c_int, [vp, vp]),
     "dang_gpu_set_gain_offset": (C.c_int, [vp, c_dp, c_dp]),
     "dang_gpu_set_component": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.c_double, C.c_int, C.c_int,
                                          c_dp, c_dp]),

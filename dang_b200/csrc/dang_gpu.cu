@@ -151,7 +151,7 @@ struct dang_gpu {
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
 
   // ddata
-  bool maps_set = false;
+  bool maps_set = false, maps_borrowed = false;  // borrowed: sig/rms/mask belong to another handle (ensembles)
   double *sig = nullptr, *rms = nullptr;
   unsigned char *mask = nullptr;
   double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
@@ -1152,7 +1152,8 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   if (h->peer.seq) cudaFree(h->peer.seq);
   if (h->peer.error) cudaFree(h->peer.error);
   if (h->mailbox) cudaFree(h->mailbox);
-  dfree(h->sig); dfree(h->rms); dfree(h->mask); dfree(h->bp_nu0); dfree(h->bp_tau0);
+  if (!h->maps_borrowed) { dfree(h->sig); dfree(h->rms); dfree(h->mask); }
+  dfree(h->bp_nu0); dfree(h->bp_tau0);
   for (auto &c : h->comp) { dfree(c.amp); dfree(c.idx[0]); dfree(c.idx[1]); }
   for (auto &g : h->cg) for (auto &x : g.x) dfree(x);
   dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
@@ -1304,6 +1305,7 @@ int dang_gpu_upload_maps(dang_gpu_t *h, const double *sig_map, const double *rms
                          const double *mask, const double *gain, const double *offset) {
   API_BEGIN
   if (!sig_map || !rms_map || !mask) fail(DANG_GPU_EINVAL, "null map pointer");
+  if (h->maps_borrowed) fail(DANG_GPU_ESTATE, "this handle borrows its maps (dang_gpu_share_maps): upload through the owner");
   const size_t n3 = (size_t)h->nbands * h->nmaps * h->Ppad;
   if (!h->sig) {
     CK(cudaMalloc(&h->sig, n3 * sizeof(double)));
@@ -1325,6 +1327,25 @@ int dang_gpu_upload_maps(dang_gpu_t *h, const double *sig_map, const double *rms
     if (offset) h->offset[j] = offset[j];
   }
   CK(cudaStreamSynchronize(h->stream));
+  h->maps_set = true;
+  API_END
+}
+
+int dang_gpu_share_maps(dang_gpu_t *h, dang_gpu_t *src) {
+  API_BEGIN
+  if (!src || !src->maps_set) fail(DANG_GPU_ESTATE, "the source handle has no maps");
+  if (src->device != h->device || src->npix != h->npix || src->nmaps != h->nmaps || src->nbands != h->nbands ||
+      src->lo != h->lo || src->hi != h->hi)
+    fail(DANG_GPU_EINVAL, "handles that share maps must have the same device, geometry and pixel range");
+  if (h->sig && !h->maps_borrowed) { dfree(h->sig); dfree(h->rms); dfree(h->mask); }
+  h->sig = src->sig;
+  h->rms = src->rms;
+  h->mask = src->mask;
+  for (int j = 0; j < h->nbands; j++) {
+    h->gain[j] = src->gain[j];
+    h->offset[j] = src->offset[j];
+  }
+  h->maps_borrowed = true;
   h->maps_set = true;
   API_END
 }

@@ -60,7 +60,7 @@ def init_bandpass(band) -> Tuple[float, np.ndarray, np.ndarray]:
 
 class Engine:
     def __init__(self, cfg: RunConfig, sky, device: int = 0,
-                 pix_range: Optional[Tuple[int, int]] = None):
+                 pix_range: Optional[Tuple[int, int]] = None, share_maps_with: Optional["Engine"] = None):
         self.lib = _lib.load()
         self.cfg = cfg
         self.npix, self.nmaps, self.nbands = cfg.npix, cfg.nmaps, cfg.nbands
@@ -78,8 +78,12 @@ class Engine:
             nu_c, nu0, tau0 = init_bandpass(b)
             self._ck(self.lib.dang_gpu_set_band(self.h, j, nu_c, len(nu0), _dp(nu0) if len(nu0) else None,
                                                 _dp(tau0) if len(tau0) else None))
-        # initialize_data_module
-        self.upload_maps(sky)
+        # initialize_data_module (an ensemble member borrows the owner's device maps instead)
+        self._owner = share_maps_with
+        if share_maps_with is None:
+            self.upload_maps(sky)
+        else:
+            self._ck(self.lib.dang_gpu_share_maps(self.h, share_maps_with.h))
         # initialize_components
         for ic, c in enumerate(cfg.comps):
             nu_ref = c.nu_ref_ghz * 1e9 if c.nu_ref_ghz < 1e7 else c.nu_ref_ghz  # dang_param_mod.f90:571-573

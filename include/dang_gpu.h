@@ -116,6 +116,10 @@ int dang_gpu_set_band(dang_gpu_t *h, int band, double nu_c_hz, int n_bp, const d
 int dang_gpu_upload_maps(dang_gpu_t *h, const double *sig_map, const double *rms_map,
                          const double *mask, const double *gain, const double *offset);
 int dang_gpu_set_gain_offset(dang_gpu_t *h, const double *gain, const double *offset);
+/* Ensembles of independent chains on one GPU (BASELINE config c5): `h` uses the device copies of
+ * sig_map / rms_map / masks that `src` uploaded instead of holding its own (64 chains at nside 512
+ * share 1.2 GB of maps and keep ~0.9 GB of state each).  `src` must outlive `h`. */
+int dang_gpu_share_maps(dang_gpu_t *h, dang_gpu_t *src);
 
 /* ---- component_list(ic): type dang_comps, src/dang_component_mod.f90:12-55 ---- */
 int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label,

@@ -495,6 +495,28 @@ def test_band_gain_fit_intensity():
     assert abs(eng.compute_chisq() - chisq_o) <= TOL * chisq_o
 
 
+def test_ensemble_of_chains_shares_one_copy_of_the_maps():
+    """BASELINE config c5 in miniature: independent chains (different deviates) on one GPU that
+    borrow one device copy of sig / rms / mask evolve exactly like chains with private copies."""
+    from dang_b200.engine import Engine
+    cfg, sky = small_case("c2", 16, perturb=False)
+    owner = Engine(cfg, sky)
+    members = [owner] + [Engine(cfg, sky, share_maps_with=owner) for _ in range(3)]
+    private = [Engine(cfg, sky) for _ in range(4)]
+    for it in (1, 2, 3):
+        for k, (a, b) in enumerate(zip(members, private)):  # interleaved: chains do not disturb each other
+            ra = a.gibbs_iteration(it, seed=1000 * k)
+            rb = b.gibbs_iteration(it, seed=1000 * k)
+            assert ra[0][0] == rb[0][0] and ra[0][1] == rb[0][1]
+    for a, b in zip(members, private):
+        for ic in range(2):
+            assert np.array_equal(a.amplitude(ic), b.amplitude(ic))
+            assert np.array_equal(a.indices(ic), b.indices(ic))
+    assert not np.array_equal(members[0].amplitude(0), members[1].amplitude(0))  # different chains
+    for e in members[1:] + private:
+        e.close()
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_are_loud_and_specific():
     """Everything outside the built scope fails with a nonzero code and a message (the Fortran
