@@ -126,6 +126,9 @@ def run_gpu(args):
     bounds = ring_partition(cfg.nside, world, weights=(sky.mask != 0).astype(np.float64))
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(int(k), float(v))
     mailboxes = os.environ.get("DANG_GPU_MAILBOX", "1") != "0"
     if world > 1:
         setup_torch_comm(eng, mailboxes=mailboxes)
@@ -343,6 +346,7 @@ def main():
     ap.add_argument("--nside", type=int, default=None, help="override the map size (tests only)")
     ap.add_argument("--cpu-nside", type=int, default=128, help="map size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option id=value (experiments), e.g. --opt 8=16")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -149,6 +149,7 @@ struct dang_gpu {
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int use_tma = 0;  // TMA-staged K1 (measured slower than the LDG form on B200: kept as an experiment)
 
   // ddata
   bool maps_set = false, maps_borrowed = false;  // borrowed: sig/rms/mask belong to another handle (ensembles)
@@ -539,7 +540,14 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       for (int o = 0; o < nog; o++) og_uni = og_uni && comp_uniform(h, og[o], cv.plane[s]);
     }
     const size_t dsm = (size_t)__builtin_popcount(nu_mask) * h->nbands * 2 * DG_THREADS * sizeof(double);
-    if (og_uni && dsm <= 160 * 1024) {
+    const size_t tma_smem = (size_t)DG_TMA_STAGES * DG_TMA_BANDS * 2 * 2 * DG_TMA_TILE * sizeof(double);
+    if (h->use_tma && nu_mask == 0 && nog == 0) {
+      // TMA-staged stream: one block per SM, 3-stage shared-memory ring filled by cp.async.bulk
+      CK(cudaFuncSetAttribute(rhs_blocks_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+      const int64_t ntiles = (h->Ppad + DG_TMA_TILE - 1) / DG_TMA_TILE;
+      const int g3 = (int)(ntiles < h->num_sms ? ntiles : h->num_sms);
+      rhs_blocks_tma_kernel<C><<<g3, DG_TMA_THREADS, tma_smem, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    } else if (og_uni && dsm <= 160 * 1024) {
       if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(rhs_blocks_uni_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       const int g2 = occ_grid(h, rhs_blocks_uni_kernel<C>, h->Ppad / 2, DG_THREADS, dsm);
       rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask);
@@ -1184,6 +1192,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_CG_CHUNK: h->cg_chunk = value < 1 ? 1 : (int)value; break;
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
     case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
+    case DANG_OPT_TMA: h->use_tma = value != 0; break;
     case DANG_OPT_CG_CHECKPOINT:
       h->cg_ckpt = value < 0 ? 0 : (value > DG_CG_MAXM ? DG_CG_MAXM : (int)value);
       break;

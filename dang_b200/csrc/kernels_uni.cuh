@@ -434,3 +434,242 @@ mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms,
     __syncthreads();
   }
 }
+
+// ======================================================================================
+// TMA-staged variants (Blackwell bulk-copy engine).  K1 and the sufficient-statistics pass keep
+// ~30 live accumulators per thread, which caps them at two resident blocks per SM -- too few
+// 16-byte loads in flight to saturate HBM.  Here one elected thread streams whole [band][plane]
+// rows of a 512-pixel tile into a 3-stage shared-memory ring with cp.async.bulk (1-D TMA,
+// completion counted on an mbarrier), so ~128 KB per SM are in flight independent of occupancy
+// and registers, and the 128 consumer threads read their pixel pair from shared memory.
+// The arithmetic is the same, in the same order, as in the LDG kernels above.
+// MEASURED (B200, nside 512, 8 bands): 313 us against 285 us for rhs_blocks_uni_kernel -- with the
+// loads decoupled from the registers the kernel turns out to be bound by FP64 / issue latency at
+// the 16 warps per SM its accumulators allow, not by loads in flight.  It is therefore OFF by
+// default (DANG_OPT_TMA) and kept as a measured experiment; parity is covered by
+// tests/test_gpu_parity.py::test_tma_staged_k1_matches.
+// ======================================================================================
+#define DG_TMA_TILE 1024    // pixels per tile (2 per consumer thread)
+#define DG_TMA_THREADS 512
+#define DG_TMA_STAGES 3
+#define DG_TMA_BANDS 2      // bands per stage
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// One work item = (tile, band chunk).  Rows of a stage: [(jj*S + s)*2 + {sig, rms}][DG_TMA_TILE].
+struct TmaRing {
+  double *buf;       // DG_TMA_STAGES * rows_max * DG_TMA_TILE doubles
+  uint64_t *full;    // DG_TMA_STAGES mbarriers
+  int rows_max;
+};
+
+__device__ __forceinline__ void tma_issue_item(const ModelView &mv, const TmaRing &ring, int stage, int64_t tile,
+                                               int chunk, int S, const int *plane) {
+  const int64_t p0 = tile * DG_TMA_TILE;
+  const int npx = (int)min((int64_t)DG_TMA_TILE, mv.Ppad - p0);
+  const int j0 = chunk * DG_TMA_BANDS, nb = min(DG_TMA_BANDS, mv.nbands - j0);
+  const uint32_t row_bytes = (uint32_t)npx * 8u;
+  double *base = ring.buf + (size_t)stage * ring.rows_max * DG_TMA_TILE;
+  mbar_expect_tx(&ring.full[stage], row_bytes * (uint32_t)(nb * S * 2));
+  for (int jj = 0; jj < nb; jj++)
+    for (int s = 0; s < S; s++) {
+      const size_t off = plane_off(mv, j0 + jj, plane[s]) + p0;
+      double *dst = base + (size_t)((jj * S + s) * 2) * DG_TMA_TILE;
+      bulk_g2s(dst, mv.sig + off, row_bytes, &ring.full[stage]);
+      bulk_g2s(dst + DG_TMA_TILE, mv.rms + off, row_bytes, &ring.full[stage]);
+    }
+}
+
+// K1, all SEDs tabulated, no subtracted components (the headline configuration).
+template <int C>
+__global__ void __launch_bounds__(DG_TMA_THREADS, 1)
+rhs_blocks_tma_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsigned int *ticket, double *out) {
+  constexpr int T = C * (C + 1) / 2;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ double smem[2 * 32];
+  __shared__ double ssed[2][C][DG_MAX_BANDS];
+  __shared__ __align__(8) uint64_t full[DG_TMA_STAGES];
+  const int B = mv.nbands, S = cg.S, tid = threadIdx.x;
+  TmaRing ring;
+  ring.buf = reinterpret_cast<double *>(tma_smem);
+  ring.full = full;
+  ring.rows_max = DG_TMA_BANDS * 2 * 2;
+  for (int i = tid; i < 2 * C * B; i += blockDim.x) {
+    const int s = i / (C * B), c = (i / B) % C, j = i % B;
+    if (s < S) ssed[s][c][j] = mv.tab->sed[cg.comp[c] * 3 + cg.plane[s]][j];
+  }
+  if (tid == 0) {
+    for (int st = 0; st < DG_TMA_STAGES; st++) mbar_init(&full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t ntiles = (mv.Ppad + DG_TMA_TILE - 1) / DG_TMA_TILE;
+  const int nchunk = (B + DG_TMA_BANDS - 1) / DG_TMA_BANDS;
+  const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t nitems = my_tiles * nchunk;
+  auto item_tile = [&](int64_t i) { return (int64_t)blockIdx.x + (i / nchunk) * gridDim.x; };
+  if (tid == 0)
+    for (int64_t i = 0; i < DG_TMA_STAGES - 1 && i < nitems; i++)
+      tma_issue_item(mv, ring, (int)(i % DG_TMA_STAGES), item_tile(i), (int)(i % nchunk), S, cg.plane);
+
+  double acc[2] = {0.0, 0.0};
+  const size_t vs = (size_t)S * mv.Ppad;
+  double2 b[2][C], f[2][C], M[2][T], eta[2];
+  for (int64_t i = 0; i < nitems; i++) {
+    const int stage = (int)(i % DG_TMA_STAGES);
+    const uint32_t parity = (uint32_t)((i / DG_TMA_STAGES) & 1);
+    const int64_t tile = item_tile(i);
+    const int chunk = (int)(i % nchunk);
+    if (tid == 0 && i + DG_TMA_STAGES - 1 < nitems) {
+      const int64_t n = i + DG_TMA_STAGES - 1;  // its stage was consumed in iteration i-1 (barrier below)
+      tma_issue_item(mv, ring, (int)(n % DG_TMA_STAGES), item_tile(n), (int)(n % nchunk), S, cg.plane);
+    }
+    const int64_t p = tile * DG_TMA_TILE + 2 * tid;
+    const bool inb = p < mv.Ppad;
+    uchar2 mk = make_uchar2(0, 0);
+    if (inb) mk = *reinterpret_cast<const uchar2 *>(mv.mask + p);
+    const bool use0 = mk.x != 0, use1 = mk.y != 0;
+    if (chunk == 0) {
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+#pragma unroll
+        for (int c = 0; c < C; c++) b[s][c] = f[s][c] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int t = 0; t < T; t++) M[s][t] = make_double2(0.0, 0.0);
+        eta[s] = make_double2(0.0, 0.0);
+        if (cg.fluct && s < S && inb) {
+          if (cg.eta) {
+            eta[s] = ld2(cg.eta + (size_t)s * mv.Ppad + p);
+          } else {
+            const uint64_t g0 = (uint64_t)s * (uint64_t)mv.npix + (uint64_t)(mv.pix_lo + p);
+            eta[s].x = use0 ? philox_normal(cg.seed, DG_STREAM_ETA, g0) : 0.0;
+            eta[s].y = use1 ? philox_normal(cg.seed, DG_STREAM_ETA, g0 + 1) : 0.0;
+          }
+        }
+      }
+    }
+    mbar_wait(&full[stage], parity);
+    const double *base = ring.buf + (size_t)stage * ring.rows_max * DG_TMA_TILE;
+    const int j0 = chunk * DG_TMA_BANDS, nb = min(DG_TMA_BANDS, B - j0);
+    if (inb) {
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (s >= S) continue;
+        const int k = cg.plane[s];
+#pragma unroll
+        for (int jj = 0; jj < DG_TMA_BANDS; jj++) {
+          if (jj >= nb) continue;
+          const int j = j0 + jj;
+          const double *row = base + (size_t)((jj * S + s) * 2) * DG_TMA_TILE + 2 * tid;
+          double2 data = *reinterpret_cast<const double2 *>(row);
+          const double2 rm = *reinterpret_cast<const double2 *>(row + DG_TMA_TILE);
+          if (k == 0) {
+            data.x = data.x / mv.gain[j];
+            data.y = data.y / mv.gain[j];
+          }
+          const double ix = fast_rcp(rm.x), iy = fast_rcp(rm.y);
+          const double wx = ix * ix, wy = iy * iy;
+          const double tx = eta[s].x * ix, ty = eta[s].y * iy;
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            const double sc = ssed[s][c][j];
+            b[s][c].x += data.x * sc * wx;
+            b[s][c].y += data.y * sc * wy;
+            f[s][c].x += tx * sc;
+            f[s][c].y += ty * sc;
+#pragma unroll
+            for (int c2 = c; c2 < C; c2++) {
+              const double sc2 = ssed[s][c2][j];
+              M[s][tri<C>(c, c2)].x += sc * sc2 * wx;
+              M[s][tri<C>(c, c2)].y += sc * sc2 * wy;
+            }
+          }
+        }
+      }
+    }
+    if (chunk == nchunk - 1 && inb) {
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (s >= S) continue;
+        const size_t es = (size_t)s * mv.Ppad + p;
+        if (cg.fluct == 1) {
+          b[s][0].x += f[s][C - 1].x;
+          b[s][0].y += f[s][C - 1].y;
+        } else if (cg.fluct == 2) {
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            b[s][c].x += f[s][c].x;
+            b[s][c].y += f[s][c].y;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+          if (!use0) M[s][t].x = 0.0;
+          if (!use1) M[s][t].y = 0.0;
+        }
+        double2 xv[C], rv[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) xv[c] = *reinterpret_cast<const double2 *>(cg.x + c * vs + es);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          double ax = 0.0, ay = 0.0;
+#pragma unroll
+          for (int c2 = 0; c2 < C; c2++) {
+            const double2 mm = M[s][c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+            ax += mm.x * xv[c2].x;
+            ay += mm.y * xv[c2].y;
+          }
+          rv[c].x = use0 ? b[s][c].x - ax : 0.0;
+          rv[c].y = use1 ? b[s][c].y - ay : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          double mx = 0.0, my = 0.0;
+#pragma unroll
+          for (int c2 = 0; c2 < C; c2++) {
+            const double2 mm = M[s][c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+            mx += mm.x * rv[c2].x;
+            my += mm.y * rv[c2].y;
+          }
+          acc[0] += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
+          acc[1] += rv[c].x * mx + rv[c].y * my;
+        }
+#pragma unroll
+        for (int t = 0; t < T; t++) st2(cg.M + t * vs + es, M[s][t]);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          st2(cg.r + c * vs + es, rv[c]);
+          if (cg.store_d) st2(cg.d + c * vs + es, rv[c]);
+        }
+      }
+    }
+    __syncthreads();  // every consumer is done with this stage before it is refilled
+  }
+  grid_reduce<2>(acc, smem, partials, ticket, out);
+}

@@ -27,6 +27,7 @@ from .config import (COMP_TYPES, INDEX_MODES, LNL_TYPES, ML_MODES, PRIOR_TYPES, 
 OPT_FIX_SAMPLE_VECTOR, OPT_CG_TWO_PASS, OPT_FULLSKY_STREAM, OPT_PROFILE, OPT_CG_CHUNK, OPT_RECORD = 1, 2, 3, 4, 5, 6
 OPT_PERPIXEL_SERIAL = 7
 OPT_CG_CHECKPOINT = 8
+OPT_TMA = 9
 KERNEL_COUNT = 12
 
 

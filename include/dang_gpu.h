@@ -81,7 +81,11 @@ enum {
   /* CG state checkpoint interval m of the recompute form (default 8): a pass re-runs the
    * block-local recurrences since the last checkpoint in registers instead of reading and
    * writing r, d, x every iteration; 0 selects the streaming form (one r/d/x update per pass). */
-  DANG_OPT_CG_CHECKPOINT = 8
+  DANG_OPT_CG_CHECKPOINT = 8,
+  /* 1: K1 streams sig/rms through a shared-memory ring filled by the TMA bulk-copy engine
+   * (cp.async.bulk + mbarrier) when all SEDs are tabulated; 0 (default): 16-byte LDG loads, which
+   * measured faster (285 vs 313 us at nside 512: K1 is issue-bound, not load-bound). */
+  DANG_OPT_TMA = 9
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */

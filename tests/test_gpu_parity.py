@@ -81,6 +81,21 @@ def test_cg_solve_matches_oracle(name, form, ml_mode):
         assert np.array_equal(eng.amplitude(ic)[:, m], sky.amplitude[c.label][:, m])
 
 
+def test_tma_staged_k1_matches():
+    """DANG_OPT_TMA: K1 fed by cp.async.bulk + mbarrier produces the same bits as the LDG form."""
+    from dang_b200.engine import OPT_TMA, Engine
+    cfg, sky = small_case("c2", 16, perturb=False)
+    eta = np.random.default_rng(4).standard_normal(2 * cfg.npix)
+    out = []
+    for tma in (0, 1):
+        eng = Engine(cfg, sky)
+        eng.set_option(OPT_TMA, tma)
+        it, delta = eng.cg_solve(0, 0, "sample", eta=eta)
+        out.append((it, delta, eng.amplitude(0).copy(), eng.amplitude(1).copy()))
+    assert out[0][0] == out[1][0]
+    assert rel_err(out[1][2], out[0][2]) < 1e-13 and rel_err(out[1][3], out[0][3]) < 1e-13
+
+
 def test_cg_sample_vector_quirk_and_fix():
     """SURVEY Q1: with two diffuse components the reference's fluctuation lands in slot 1 only;
     DANG_OPT_FIX_SAMPLE_VECTOR switches to the per-component form.  Both match the oracle."""
