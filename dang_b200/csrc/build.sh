@@ -1,9 +1,36 @@
 #!/bin/bash
 # Builds dang_b200/libdang_gpu.so for sm_100a (cross-compiles without a GPU).
+# One object per translation unit, compiled in parallel, then one link.
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
 out="$here/../libdang_gpu.so"
+obj="$here/_obj"
+mkdir -p "$obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-"$NVCC" -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
-  -Xcompiler -fPIC,-O2,-Wall -shared -o "$out" "$here/dang_gpu.cu" -ldl "$@"
+FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2,-Wall "$@")
+units=(dang_gpu host_cg host_data host_mh_pp host_mh_fs)
+declare -A deps=(
+  [dang_gpu]="kernels_data.cuh"
+  [host_cg]="kernels_cg.cuh kernels_uni.cuh"
+  [host_data]="kernels_data.cuh kernels_uni.cuh"
+  [host_mh_pp]="kernels_mh.cuh"
+  [host_mh_fs]="kernels_mh.cuh kernels_uni.cuh"
+)
+pids=()
+for u in "${units[@]}"; do
+  # rebuild a unit when its source, one of its headers or this script is newer than its object
+  stale=0
+  [ -f "$obj/$u.o" ] || stale=1
+  for d in "$u.cu" host.cuh common.cuh build.sh ../../include/dang_gpu.h ${deps[$u]}; do
+    [ "$here/$d" -nt "$obj/$u.o" ] && stale=1
+  done
+  if [ "$stale" = 1 ]; then
+    "$NVCC" "${FLAGS[@]}" -c "$here/$u.cu" -o "$obj/$u.o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+objs=()
+for u in "${units[@]}"; do objs+=("$obj/$u.o"); done
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$out" "${objs[@]}" -ldl
 echo "built $out"

@@ -79,6 +79,46 @@ __device__ __forceinline__ double2 ldg_stream2(const double *p) {
   return v;
 }
 
+// ---------------------------------------------------------------- device-resident solver / sampler state
+// scalars of one solve, device resident (DESIGN.md "CG control")
+#define DG_CG_HIST 1024   // passes whose (alpha, beta) are kept for the recompute form
+#define DG_CG_MAXM 32     // largest checkpoint interval
+
+struct CgScalars {
+  double delta_new, delta_old, alpha, beta, dq;
+  double alpha_prev;  // alpha of the pass that ran last (deferred x update, see cg_fused_pass_kernel)
+  double converge;
+  int iter, i_max, done, pad;
+  int ckpt, m;        // recompute form: pass whose state is stored in (r, d); checkpoint interval
+  double trace[256];
+  double ah[DG_CG_HIST], bh[DG_CG_HIST];  // alpha_i, beta_i used IN pass i (1-based)
+};
+
+#define DG_MH_THREADS 128
+#define DG_SUFF_CHUNK 4   // bands per register-resident accumulator chunk
+
+struct MhView {
+  int ic;          // component being sampled
+  int nind;        // which of its indices
+  int S;           // planes map_inds(1)..map_inds(2)
+  int plane[2];    // 0-based
+  int nsample, ml_mode, lnl_type, prior_type;
+  int is_synch;    // label == 'synch' (eval_jeffreys_prior, src/dang_lnl_mod.f90:289)
+  double gauss[2], uni[2], step;
+  const double *z, *u;        // injected deviates (device copies) or nullptr -> Philox(seed)
+  uint64_t seed;
+  unsigned char *decisions;   // optional instrumentation
+  double *lnl_trace;
+};
+
+struct MhScalars {
+  double sample[DG_MAXIND], theta[DG_MAXIND];
+  double lnl_old, accept;
+  int l, phase, skip, pad;
+  double sed[DG_MAX_BANDS];  // SED of the proposal per band (streaming lnL kernel)
+  double s0[DG_MAX_BANDS];   // SED at the chain's starting point (sufficient statistics)
+};
+
 // ---------------------------------------------------------------- SEDs
 // eval_sed, src/dang_component_mod.f90:778-813; evaluate_powerlaw :886-918; evaluate_mbb :920-958.
 //
@@ -215,7 +255,9 @@ __device__ __forceinline__ double sed_eval(const ModelView &mv, int ic, int k, i
 // Stream definition shared with the test oracle (DESIGN.md "RNG"):
 // counter = {slot_lo, slot_hi, stream, 'DANG'}, key = {seed_lo, seed_hi}.
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
   for (int r = 0; r < 10; r++) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
@@ -319,7 +361,7 @@ __device__ __forceinline__ void peer_exchange(const PeerComm &pc, const double *
   __syncwarp();
 }
 
-__global__ void peer_exchange_kernel(PeerComm pc, const double *local, int cnt, double *gathered) {
+static __global__ void peer_exchange_kernel(PeerComm pc, const double *local, int cnt, double *gathered) {
   peer_exchange(pc, local, cnt, gathered);
 }
 

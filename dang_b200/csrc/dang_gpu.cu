@@ -4,69 +4,10 @@
 // handle's stream; cross-rank traffic is an NCCL all-gather of a few doubles followed by a
 // rank-ordered sum on every rank (deterministic, identical bits everywhere).
 // There is deliberately no CPU fallback: every error surfaces as a nonzero return code.
-#include "../../include/dang_gpu.h"
-
-#include <cuda_runtime.h>
-#include <dlfcn.h>
-
-#include <cstdarg>
-#include <cstddef>
-#include <cstdio>
-#include <cmath>
-#include <cstring>
-#include <stdexcept>
-#include <string>
-#include <vector>
-
-#include "common.cuh"
-#include "kernels_cg.cuh"
+#include "host.cuh"
 #include "kernels_data.cuh"
-#include "kernels_mh.cuh"
-#include "kernels_uni.cuh"
-
-// ---------------------------------------------------------------- errors
-namespace {
-
-struct DgError : std::runtime_error {
-  int code;
-  DgError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
-};
-
-std::string vfmt(const char *f, va_list ap) {
-  char buf[1024];
-  vsnprintf(buf, sizeof buf, f, ap);
-  return buf;
-}
-[[noreturn]] void fail(int code, const char *f, ...) {
-  va_list ap;
-  va_start(ap, f);
-  std::string m = vfmt(f, ap);
-  va_end(ap);
-  throw DgError(code, m);
-}
-
-#define CK(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess)                                                                    \
-      fail(DANG_GPU_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,               \
-           cudaGetErrorString(e_));                                                           \
-  } while (0)
 
 thread_local std::string g_create_error;
-
-// ---------------------------------------------------------------- NCCL (loaded lazily)
-// Only multi-rank runs touch NCCL; it is dlopen'ed so a single-GPU Fortran host needs no NCCL.
-typedef struct { char internal[128]; } nccl_uid_t;
-typedef void *nccl_comm_t;
-struct NcclApi {
-  void *lib = nullptr;
-  int (*GetUniqueId)(nccl_uid_t *) = nullptr;
-  int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
-  int (*CommDestroy)(nccl_comm_t) = nullptr;
-  int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
-  const char *(*GetErrorString)(int) = nullptr;
-};
 NcclApi g_nccl;
 
 void nccl_load() {
@@ -87,215 +28,6 @@ void nccl_load() {
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
 }
-#define NCK(call)                                                                       \
-  do {                                                                                  \
-    int r_ = (call);                                                                    \
-    if (r_ != 0) fail(DANG_GPU_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
-  } while (0)
-const int NCCL_DOUBLE = 8;  // ncclFloat64
-
-// ---------------------------------------------------------------- host-side objects
-struct BandHost {
-  bool set = false;
-  double nu_c = 0;
-  int n = 0;
-  std::vector<double> nu0, tau0;
-};
-
-struct IndexHost {
-  int sample_index = 0, index_mode = DANG_INDEX_PERPIXEL, lnl_type = 0, prior_type = 0;
-  double gauss[2] = {0, 1}, uni[2] = {-1e300, 1e300}, step = 0;
-  int sample_nside = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
-};
-
-struct CompHost {
-  bool set = false;
-  int type = 0, cg_group = 0, sample_amplitude = 0, nind = 0;
-  std::string label;
-  double nu_ref = 0;
-  double *amp = nullptr;               // [nmaps][Ppad]
-  double *idx[DG_MAXIND] = {nullptr, nullptr};
-  IndexHost index[DG_MAXIND];
-};
-
-struct CgGroupHost {
-  bool set = false;
-  int cg_group = 0, i_max = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
-  double converge = 0;
-  double *x[3] = {nullptr, nullptr, nullptr};  // Q10: persists across Gibbs iterations
-  size_t x_len[3] = {0, 0, 0};
-  int last_iter[3] = {0, 0, 0};  // iterations of the previous solve (sizes the first batch)
-};
-
-struct KStat {
-  int64_t launches = 0;
-  double ms = 0, bytes = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
-};
-
-const int GATHER_MAX = 128;  // doubles per rank in one scalar exchange
-
-}  // namespace
-
-struct dang_gpu {
-  int device = 0, nside = 0, nmaps = 0, nbands = 0, ncomp = 0, num_sms = 0;
-  int64_t npix = 0, lo = 0, hi = 0, P = 0, Ppad = 0;
-  cudaStream_t stream = nullptr, d2h_stream = nullptr, h2d_stream = nullptr;
-  cudaEvent_t ev_compute = nullptr, ev_amp_dl = nullptr, ev_idx_dl = nullptr, ev_eta = nullptr;
-  bool amp_dl_pending = false, idx_dl_pending = false, eta_staged = false;
-  double *eta_stage = nullptr; size_t eta_stage_len = 0; int eta_stage_planes = 0;
-  std::string err;
-
-  // options
-  int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
-  int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
-  int use_tma = 0;  // TMA-staged K1 (measured slower than the LDG form on B200: kept as an experiment)
-
-  // ddata
-  bool maps_set = false, maps_borrowed = false;  // borrowed: sig/rms/mask belong to another handle (ensembles)
-  double *sig = nullptr, *rms = nullptr;
-  unsigned char *mask = nullptr;
-  double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
-
-  BandHost band[DG_MAX_BANDS];
-  double *bp_nu0 = nullptr, *bp_tau0 = nullptr, *bp_lnr_hi = nullptr, *bp_lnr_lo = nullptr;
-  int nbp = 0;
-  bool bp_dirty = true;   // band / component constants changed: rebuild the static tables
-  bool tab_dirty = true;  // an index map changed: re-tabulate SEDs
-  unsigned long long check_mask = ~0ull;  // index maps whose uniformity must be re-scanned
-  SedTable *tab = nullptr;
-  int uni_host[DG_MAX_COMPS * 3] = {};  // host copy of SedTable::uni (refreshed with the tables)
-  int nonuni_host[DG_MAX_COMPS * 3][DG_MAXIND] = {};  // host mirror of SedTable::nonuni
-  CompHost comp[DG_MAX_COMPS];
-  std::vector<CgGroupHost> cg;
-
-  // scratch
-  double *M = nullptr, *r = nullptr, *d = nullptr, *eta = nullptr;
-  size_t M_len = 0, v_len = 0, eta_len = 0;
-  int cg_layout = -1;
-  double *D = nullptr;  size_t D_len = 0;       // streaming full-sky data
-  double *zbuf = nullptr, *ubuf = nullptr; size_t zu_len = 0;
-  unsigned char *decisions = nullptr; double *lnl_trace = nullptr; size_t dec_len = 0;
-  int dec_mode = 0, dec_nsample = 0;            // 1 full-sky, 2 per-pixel
-  double *stage = nullptr; size_t stage_len = 0; // device staging for strided host copies
-  double *partials = nullptr; unsigned int *tickets = nullptr;
-  int grid_cap = 0;
-  double *sums_local = nullptr, *gathered = nullptr, *gathered_buf = nullptr;
-  CgScalars *cg_scalars = nullptr;
-  MhScalars *mh_scalars = nullptr;
-  void *pinned = nullptr;  // small pinned buffer for scalar read-back
-  std::vector<double> last_trace;
-
-  // comm
-  int nranks = 1, rank = 0;
-  nccl_comm_t comm = nullptr;
-  // NVLink mailboxes (CUDA IPC); peer.nranks == 1 until dang_gpu_comm_open_peers succeeds
-  Mail *mailbox = nullptr;
-  void *peer_ptr[DG_MAX_RANKS] = {};
-  PeerComm peer{};
-  bool use_mail = false;
-
-  // instrumentation
-  int64_t launches = 0;
-  KStat kstat[DANG_K_COUNT];
-  cudaEvent_t ev[16] = {};
-};
-
-namespace {
-
-// ---------------------------------------------------------------- helpers
-void set_device(dang_gpu *h) { CK(cudaSetDevice(h->device)); }
-
-template <typename T>
-void dfree(T *&p) {
-  if (p) cudaFree(p);
-  p = nullptr;
-}
-
-void ensure(double *&buf, size_t &len, size_t need) {
-  if (len >= need) return;
-  if (buf) CK(cudaFree(buf));
-  buf = nullptr;
-  CK(cudaMalloc(&buf, need * sizeof(double)));
-  len = need;
-}
-
-// Persistent-style launch: exactly as many blocks as are resident at once (blocks/SM from the
-// occupancy calculator x SM count), or fewer when the work is small; grid-stride loops inside.
-template <typename K>
-int occ_grid(dang_gpu *h, K kernel, int64_t work, int threads, size_t smem = 0) {
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-  if (per_sm < 1) per_sm = 1;
-  int64_t need = (work + threads - 1) / threads;
-  int64_t cap = (int64_t)h->num_sms * per_sm;
-  if (cap > h->grid_cap) cap = h->grid_cap;
-  int64_t g = need < cap ? need : cap;
-  return (int)(g < 1 ? 1 : g);
-}
-
-int grid_for(dang_gpu *h, int64_t work, int threads, int blocks_per_sm) {
-  int64_t need = (work + threads - 1) / threads;
-  int64_t cap = (int64_t)h->num_sms * blocks_per_sm;
-  if (cap > h->grid_cap) cap = h->grid_cap;
-  int64_t g = need < cap ? need : cap;
-  return (int)(g < 1 ? 1 : g);
-}
-
-struct KTimer {
-  dang_gpu *h;
-  int kid;
-  cudaEvent_t a = nullptr, b = nullptr;
-  KTimer(dang_gpu *h_, int kid_, double bytes) : h(h_), kid(kid_) {
-    h->launches++;
-    h->kstat[kid].launches++;
-    h->kstat[kid].bytes += bytes;
-    if (h->profile) {
-      CK(cudaEventCreate(&a));
-      CK(cudaEventCreate(&b));
-      CK(cudaEventRecord(a, h->stream));
-    }
-  }
-  void done() {
-    CK(cudaGetLastError());
-    if (h->profile) {
-      CK(cudaEventRecord(b, h->stream));
-      h->kstat[kid].pending.emplace_back(a, b);
-    }
-  }
-};
-
-void resolve_stats(dang_gpu *h) {
-  CK(cudaStreamSynchronize(h->stream));
-  for (int k = 0; k < DANG_K_COUNT; k++) {
-    for (auto &pr : h->kstat[k].pending) {
-      float ms = 0;
-      CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
-      h->kstat[k].ms += ms;
-      cudaEventDestroy(pr.first);
-      cudaEventDestroy(pr.second);
-    }
-    h->kstat[k].pending.clear();
-  }
-}
-
-// host (npix-strided, full sky) <-> device (Ppad-strided slice) plane copies
-void h2d_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
-  CK(cudaMemcpy2DAsync(dst, h->Ppad * sizeof(double), src + h->lo, h->npix * sizeof(double),
-                       h->P * sizeof(double), nplanes, cudaMemcpyHostToDevice, h->stream));
-}
-void d2h_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
-  CK(cudaMemcpy2DAsync(dst + h->lo, h->npix * sizeof(double), src, h->Ppad * sizeof(double),
-                       h->P * sizeof(double), nplanes, cudaMemcpyDeviceToHost, h->stream));
-}
-
-// ln(a/b) as a double-double from an extended-precision logarithm
-void dd_log_ratio(double a, double b, double &hi, double &lo) {
-  const long double L = logl((long double)a / (long double)b);
-  hi = (double)L;
-  lo = (double)(L - (long double)hi);
-}
-
 // static tables: flattened bandpasses, ln(nu/nu_ref) per (component, band [, bandpass sample])
 void upload_bandpasses(dang_gpu *h) {
   if (!h->bp_dirty) return;
@@ -422,648 +154,6 @@ void gather(dang_gpu *h, int cnt) {
     NCK(g_nccl.AllGather(h->sums_local, h->gathered, cnt, NCCL_DOUBLE, h->comm, h->stream));
   }
 }
-
-int flag_planes(int flag, int plane[2]) {  // 0-based planes; returns S
-  if (flag & 8) {
-    plane[0] = 1;
-    plane[1] = 2;
-    return 2;
-  }
-  int k = 0;
-  if (flag & 1) k = 0;
-  else if (flag & 2) k = 1;
-  else if (flag & 4) k = 2;
-  else fail(DANG_GPU_EUNSUPPORTED, "pol flag %d (T+Q+U) is dead code in the reference (SURVEY Q2)", flag);
-  plane[0] = plane[1] = k;
-  return 1;
-}
-
-double bytes_w(double n) { return n * 8.0; }
-
-// record that index map (c, l) on plane k is known constant (val = 0) or varying (val = 1)
-void set_nonuni(dang_gpu *h, int c, int k, int l, int val) {
-  const int m = (c * 3 + k) * DG_MAXIND + l;
-  CK(cudaMemsetAsync((char *)h->tab + offsetof(SedTable, nonuni) + m * sizeof(int), val ? 1 : 0, sizeof(int), h->stream));
-  h->nonuni_host[c * 3 + k][l] = val ? 1 : 0;
-  h->check_mask &= ~(1ull << m);
-  h->tab_dirty = true;
-}
-
-bool comp_uniform(const dang_gpu *h, int c, int k) { return h->uni_host[c * 3 + k] != 0; }
-
-// ---------------------------------------------------------------- amplitude draw
-template <int C>
-void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const double *eta,
-                   uint64_t seed, const int *comps, const int *og, int nog, int *n_iter,
-                   double *delta_final) {
-  constexpr int T = C * (C + 1) / 2;
-  ModelView mv = model_view(h);
-  CgView<C> cv;
-  memset(&cv, 0, sizeof cv);
-  cv.S = flag_planes(g.pol_flag[flag_n], cv.plane);
-  for (int c = 0; c < C; c++) cv.comp[c] = comps[c];
-  cv.nog = nog;
-  for (int o = 0; o < nog; o++) cv.og[o] = og[o];
-  const int S = cv.S;
-  for (int s = 0; s < S; s++)
-    if (cv.plane[s] >= h->nmaps) fail(DANG_GPU_EINVAL, "pol flag needs plane %d, nmaps = %d", cv.plane[s] + 1, h->nmaps);
-  const size_t vs = (size_t)S * h->Ppad;  // doubles per component
-  const int64_t n2 = (int64_t)(vs / 2);
-
-  // self%x: allocate + seed from c%amplitude on first use only (cg_search :227-239, Q10)
-  if (!g.x[flag_n] || g.x_len[flag_n] != C * vs) {
-    if (g.x[flag_n]) CK(cudaFree(g.x[flag_n]));
-    CK(cudaMalloc(&g.x[flag_n], C * vs * sizeof(double)));
-    g.x_len[flag_n] = C * vs;
-    CK(cudaMemsetAsync(g.x[flag_n], 0, C * vs * sizeof(double), h->stream));
-    for (int c = 0; c < C; c++)
-      for (int s = 0; s < S; s++)  // initialize_x :1216-1224
-        CK(cudaMemcpyAsync(g.x[flag_n] + c * vs + (size_t)s * h->Ppad,
-                           h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
-                           h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  }
-  if (h->M_len < T * vs) {
-    ensure(h->M, h->M_len, T * vs);
-    h->cg_layout = -1;
-  }
-  if (h->v_len < C * vs) {
-    size_t l1 = h->v_len, l2 = h->v_len;
-    ensure(h->r, l1, C * vs);
-    ensure(h->d, l2, C * vs);
-    h->v_len = C * vs;
-    h->cg_layout = -1;
-  }
-  // padding lanes must hold zeros (they are swept by the vectorised passes and nothing ever
-  // writes a nonzero there), so clear only when the plane layout of the scratch changes
-  if (h->cg_layout != C * 16 + S) {
-    CK(cudaMemsetAsync(h->M, 0, T * vs * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->r, 0, C * vs * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->d, 0, C * vs * sizeof(double), h->stream));
-    h->cg_layout = C * 16 + S;
-  }
-  cv.M = h->M;
-  cv.r = h->r;
-  cv.d = h->d;
-  cv.x = g.x[flag_n];
-  cv.seed = seed;
-  cv.fluct = 0;
-  cv.eta = nullptr;
-  // recompute form needs the (alpha, beta) history: fall back to streaming for very long solves
-  const int ckpt_m = (!h->cg_two_pass && g.i_max < DG_CG_HIST) ? h->cg_ckpt : 0;
-  cv.store_d = ckpt_m ? 0 : 1;
-  if (ml_mode == DANG_ML_SAMPLE) {  // :254-264
-    cv.fluct = h->fix_q1 ? 2 : 1;
-    if (eta) {
-      ensure(h->eta, h->eta_len, vs);
-      h2d_planes(h, h->eta, eta, S);  // host eta is [stokes][npix]
-      cv.eta = h->eta;
-    } else if (h->eta_staged && h->eta_stage_planes == S) {
-      CK(cudaStreamWaitEvent(h->stream, h->ev_eta, 0));  // uploaded by dang_gpu_stage_eta
-      cv.eta = h->eta_stage;
-      h->eta_staged = false;
-    }
-  }
-
-  CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
-  {
-    const int grid = grid_for(h, h->P, DG_THREADS, 4);
-    const double n_el = (double)S * h->P;
-    KTimer kt(h, DANG_K_RHS_BLOCKS,
-              bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + (ckpt_m ? 1.0 : 2.0) * C)) + bytes_w((double)h->P * 3));
-    // streaming kernel: out-of-group components must have tabulated SEDs; group components with
-    // varying indices get their SEDs staged per thread in dynamic shared memory
-    bool og_uni = true;
-    unsigned nu_mask = 0;
-    for (int s = 0; s < S; s++) {
-      for (int c = 0; c < C; c++)
-        if (!comp_uniform(h, comps[c], cv.plane[s])) nu_mask |= 1u << c;
-      for (int o = 0; o < nog; o++) og_uni = og_uni && comp_uniform(h, og[o], cv.plane[s]);
-    }
-    const size_t dsm = (size_t)__builtin_popcount(nu_mask) * h->nbands * 2 * DG_THREADS * sizeof(double);
-    const size_t tma_smem = (size_t)DG_TMA_STAGES * DG_TMA_BANDS * 2 * 2 * DG_TMA_TILE * sizeof(double);
-    if (h->use_tma && nu_mask == 0 && nog == 0) {
-      // TMA-staged stream: one block per SM, 3-stage shared-memory ring filled by cp.async.bulk
-      CK(cudaFuncSetAttribute(rhs_blocks_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
-      const int64_t ntiles = (h->Ppad + DG_TMA_TILE - 1) / DG_TMA_TILE;
-      const int g3 = (int)(ntiles < h->num_sms ? ntiles : h->num_sms);
-      rhs_blocks_tma_kernel<C><<<g3, DG_TMA_THREADS, tma_smem, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
-    } else if (og_uni && dsm <= 160 * 1024) {
-      if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(rhs_blocks_uni_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-      const int g2 = occ_grid(h, rhs_blocks_uni_kernel<C>, h->Ppad / 2, DG_THREADS, dsm);
-      rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask);
-    } else {
-      const int g1 = occ_grid(h, rhs_blocks_kernel<C>, h->P, DG_THREADS);
-      rhs_blocks_kernel<C><<<g1, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
-    }
-    kt.done();
-  }
-  gather(h, 4);
-  {
-    KTimer kt(h, DANG_K_SCALAR, 0);
-    cg_init_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks, g.i_max, g.converge);
-    kt.done();
-  }
-  CK(cudaMemcpyAsync((char *)h->cg_scalars + offsetof(CgScalars, m), &ckpt_m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-
-  struct Snap { double delta_new; int iter, done; };
-  bool have_state = false;
-  auto read_state = [&]() -> Snap {  // scalars + residual trace in one small copy
-    CgScalars *hs = (CgScalars *)h->pinned;
-    CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    have_state = true;
-    return Snap{hs->delta_new, hs->iter, hs->done};
-  };
-
-  const int fold = (h->nranks == 1 || h->use_mail) ? 1 : 0;
-  const int grid = h->cg_two_pass ? occ_grid(h, cg_update_pass_kernel<C>, n2, DG_THREADS)
-                   : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C>, n2, DG_THREADS)
-                                : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
-  const double el = (double)vs;
-  auto enqueue_pass = [&](int pass_no) {
-    if (!h->cg_two_pass) {
-      if (ckpt_m) {
-        // compulsory traffic of this launch: M, r, d in; on checkpoint passes also x in, r, d, x out
-        const double per_el = (pass_no % ckpt_m == 0) ? (T + (pass_no == ckpt_m ? 5.0 : 6.0) * C)
-                                                      : (T + (pass_no < ckpt_m ? 1.0 : 2.0) * C);
-        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
-        cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0, h->peer, h->gathered);
-        kt.done();
-      } else {
-        // compulsory traffic of this launch: x is touched on even passes only
-        const double per_el = (pass_no & 1) ? (T + 4.0 * C) : (T + 6.0 * C);
-        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
-        cg_fused_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, h->peer, h->gathered);
-        kt.done();
-      }
-      if (!fold) {
-        gather(h, 4);
-        KTimer ks(h, DANG_K_SCALAR, 0);
-        cg_fused_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
-        ks.done();
-      }
-    } else {
-      {
-        KTimer kt(h, DANG_K_CG_DQ, bytes_w(el * (T + 3.0 * C)));
-        cg_dq_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, h->M, h->r, h->d, n2,
-                                                                  h->partials, h->tickets, h->sums_local);
-        kt.done();
-      }
-      gather(h, 4);
-      {
-        KTimer ks(h, DANG_K_SCALAR, 0);
-        cg_dq_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
-        ks.done();
-      }
-      {
-        KTimer kt(h, DANG_K_CG_UPDATE, bytes_w(el * (T + 5.0 * C)));
-        cg_update_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local);
-        kt.done();
-      }
-      gather(h, 4);
-      KTimer ks(h, DANG_K_SCALAR, 0);
-      cg_rr_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
-      ks.done();
-    }
-  };
-  // Passes are enqueued without waiting for the convergence flag: a pass launched after the
-  // solve is done returns at once (device-side early exit).  The first batch is sized from the
-  // previous solve of this (group, flag) -- successive Gibbs iterations converge in almost the
-  // same number of steps -- and further batches of cg_chunk follow until the flag is seen.
-  const int max_pass = g.i_max - 1;
-  int enq = 0;
-  int batch = g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : h->cg_chunk;
-  Snap sn{0.0, 1, max_pass < 1};
-  while (!sn.done && enq < max_pass) {
-    if (batch > max_pass - enq) batch = max_pass - enq;
-    for (int it = 0; it < batch; it++) enqueue_pass(enq + it + 1);
-    enq += batch;
-    sn = read_state();
-    batch = h->cg_chunk;
-  }
-  if (!h->cg_two_pass) {  // bring x up to date (pending term of the deferred / checkpointed update)
-    KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 4.0 * C : 3.0 * C)));
-    if (ckpt_m)
-      cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-          h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1, h->peer, h->gathered);
-    else
-      cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
-    kt.done();
-  }
-
-  // unpack_amplitudes :1327-1335: x -> c%amplitude planes (after any download still reading them)
-  if (h->amp_dl_pending) {
-    CK(cudaStreamWaitEvent(h->stream, h->ev_amp_dl, 0));
-    h->amp_dl_pending = false;
-  }
-  for (int c = 0; c < C; c++)
-    for (int s = 0; s < S; s++)
-      CK(cudaMemcpyAsync(h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
-                         g.x[flag_n] + c * vs + (size_t)s * h->Ppad, h->P * sizeof(double),
-                         cudaMemcpyDeviceToDevice, h->stream));
-  {
-    CgScalars *hs = (CgScalars *)h->pinned;  // filled by the last read_state (the solve was done then)
-    if (!sn.done || !have_state) {  // ran out of passes (i_max) without seeing the flag: read the final state
-      CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-    }
-    int n = hs->iter < 256 ? hs->iter : 256;
-    h->last_trace.assign(hs->trace, hs->trace + n);
-    g.last_iter[flag_n] = hs->iter;
-    if (n_iter) *n_iter = hs->iter;
-    if (delta_final) *delta_final = hs->delta_new;
-  }
-}
-
-void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *eta, uint64_t seed,
-              int *n_iter, double *delta_final) {
-  CgGroupHost *g = nullptr;
-  for (auto &gg : h->cg)
-    if (gg.set && gg.cg_group == cg_group) g = &gg;
-  if (!g) fail(DANG_GPU_ESTATE, "CG group %d has not been set", cg_group);
-  if (flag_n < 0 || flag_n >= g->nflag) fail(DANG_GPU_EINVAL, "flag_n %d out of range", flag_n);
-  int comps[DG_MAX_COMPS], og[DG_MAX_COMPS], C = 0, nog = 0;
-  for (int c = 0; c < h->ncomp; c++) {
-    const CompHost &cc = h->comp[c];
-    if (!cc.set) fail(DANG_GPU_ESTATE, "component %d has not been set", c);
-    if (cc.cg_group == cg_group && cc.sample_amplitude) comps[C++] = c;
-    else og[nog++] = c;  // :430
-  }
-  if (C == 0) fail(DANG_GPU_EINVAL, "Woah there, number of CG components = 0 for CG group %d", cg_group);
-  if (C > DG_MAX_CG) fail(DANG_GPU_EUNSUPPORTED, "%d diffuse components in one CG group (max %d)", C, DG_MAX_CG);
-  switch (C) {
-    case 1: cg_solve_impl<1>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
-    case 2: cg_solve_impl<2>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
-    case 3: cg_solve_impl<3>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
-    default: cg_solve_impl<4>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
-  }
-}
-
-// ---------------------------------------------------------------- chi-square
-template <int NC>
-void launch_chisq(dang_gpu *h, const ModelView &mv, const ChisqView &cv, int) {
-  const int grid = occ_grid(h, chisq_kernel<NC>, h->P, DG_THREADS);
-  chisq_kernel<NC><<<grid, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
-}
-
-void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, double *chi_map,
-               double out4[4]) {
-  if (pol_lo < 1 || pol_hi > h->nmaps || pol_lo > pol_hi) fail(DANG_GPU_EINVAL, "bad pol_type range %d..%d", pol_lo, pol_hi);
-  ModelView mv = model_view(h);
-  ChisqView cv;
-  cv.k_lo = pol_lo - 1;
-  cv.k_hi = pol_hi - 1;
-  cv.sky = sky;
-  cv.res = res;
-  cv.chi_map = chi_map;
-  const int grid = grid_for(h, h->P, DG_THREADS, 4);
-  const bool maps = sky || res;
-  const double nk = maps ? h->nmaps : (pol_hi - pol_lo + 1);
-  double bytes = bytes_w((double)h->P * nk * (2.0 * h->nbands + h->ncomp * 2.0));
-  if (maps) bytes += bytes_w((double)h->P * h->nmaps * h->nbands * ((sky ? 1 : 0) + (res ? 1 : 0)));
-  KTimer kt(h, maps ? DANG_K_SKYMODEL : DANG_K_CHISQ, bytes);
-  bool uni = !maps && !chi_map && h->ncomp <= 4;
-  unsigned nu_mask = 0;
-  for (int k = cv.k_lo; k <= cv.k_hi && uni; k++)
-    for (int c = 0; c < h->ncomp; c++)
-      if (!comp_uniform(h, c, k)) nu_mask |= 1u << c;
-  const size_t dsm = (size_t)__builtin_popcount(nu_mask) * h->nbands * 2 * DG_THREADS * sizeof(double);
-  if (dsm > 160 * 1024) uni = false;
-  if (uni) {
-#define LAUNCH_CHISQ_UNI(NC)                                                                                  \
-    {                                                                                                         \
-      if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(chisq_uni_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); \
-      const int g2 = occ_grid(h, chisq_uni_kernel<NC>, h->Ppad / 2, DG_THREADS, dsm);                         \
-      chisq_uni_kernel<NC><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask); \
-    }
-    if (h->ncomp <= 1) LAUNCH_CHISQ_UNI(1)
-    else if (h->ncomp == 2) LAUNCH_CHISQ_UNI(2)
-    else if (h->ncomp == 3) LAUNCH_CHISQ_UNI(3)
-    else LAUNCH_CHISQ_UNI(4)
-#undef LAUNCH_CHISQ_UNI
-  }
-  else if (h->ncomp <= 1) launch_chisq<1>(h, mv, cv, grid);
-  else if (h->ncomp == 2) launch_chisq<2>(h, mv, cv, grid);
-  else if (h->ncomp == 3) launch_chisq<3>(h, mv, cv, grid);
-  else if (h->ncomp == 4) launch_chisq<4>(h, mv, cv, grid);
-  else launch_chisq<DG_MAX_COMPS>(h, mv, cv, grid);
-  kt.done();
-  gather(h, 4);
-  double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  for (int i = 0; i < 4; i++) {
-    out4[i] = 0.0;
-    for (int g = 0; g < h->nranks; g++) out4[i] += hp[g * 4 + i];
-  }
-}
-
-// ---------------------------------------------------------------- spectral-parameter draw
-void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode, MhView &mh) {
-  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set) fail(DANG_GPU_EINVAL, "bad component %d", ic);
-  const CompHost &c = h->comp[ic];
-  if (nind < 0 || nind >= c.nind) fail(DANG_GPU_EINVAL, "component %d has no index %d", ic, nind);
-  const IndexHost &ix = c.index[nind];
-  if (ix.sample_nside != h->nside)
-    fail(DANG_GPU_EUNSUPPORTED, "sample_nside %d /= nside %d needs HEALPix udgrade_ring (DESIGN.md, out of scope)",
-         ix.sample_nside, h->nside);
-  memset(&mh, 0, sizeof mh);
-  mh.ic = ic;
-  mh.nind = nind;
-  if (map_n == -1) {  // :157-163
-    mh.S = 2;
-    mh.plane[0] = 1;
-    mh.plane[1] = 2;
-  } else if (map_n >= 1 && map_n <= 3) {
-    mh.S = 1;
-    mh.plane[0] = mh.plane[1] = map_n - 1;
-  } else {
-    fail(DANG_GPU_EUNSUPPORTED, "map_n = %d (T+Q+U) is unreachable in the reference (SURVEY Q2)", map_n);
-  }
-  for (int s = 0; s < mh.S; s++)
-    if (mh.plane[s] >= h->nmaps) fail(DANG_GPU_EINVAL, "map_n %d needs plane %d, nmaps = %d", map_n, mh.plane[s] + 1, h->nmaps);
-  mh.nsample = nsample;
-  mh.ml_mode = ml_mode;
-  mh.lnl_type = ix.lnl_type;
-  mh.prior_type = ix.prior_type;
-  mh.is_synch = c.label == "synch";
-  mh.gauss[0] = ix.gauss[0];
-  mh.gauss[1] = ix.gauss[1];
-  mh.uni[0] = ix.uni[0];
-  mh.uni[1] = ix.uni[1];
-  mh.step = ix.step;
-}
-
-void ensure_zu(dang_gpu *h, size_t n) {
-  if (h->zu_len >= n) return;
-  dfree(h->zbuf);
-  dfree(h->ubuf);
-  CK(cudaMalloc(&h->zbuf, n * sizeof(double)));
-  CK(cudaMalloc(&h->ubuf, n * sizeof(double)));
-  h->zu_len = n;
-}
-
-void ensure_decisions(dang_gpu *h, size_t n) {
-  if (h->dec_len >= n) return;
-  dfree(h->decisions);
-  dfree(h->lnl_trace);
-  CK(cudaMalloc(&h->decisions, n));
-  CK(cudaMalloc(&h->lnl_trace, n * sizeof(double)));
-  h->dec_len = n;
-}
-
-void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
-                     double *accept) {
-  ModelView mv = model_view(h);
-  const size_t n = (size_t)mh.nsample * h->P;
-  mh.seed = seed;
-  if (z) {
-    ensure_zu(h, n > 0 ? n : 1);
-    // host [l][npix] -> device [l][P]
-    CK(cudaMemcpy2DAsync(h->zbuf, h->P * sizeof(double), z + h->lo, h->npix * sizeof(double),
-                         h->P * sizeof(double), mh.nsample, cudaMemcpyHostToDevice, h->stream));
-    mh.z = h->zbuf;
-    if (u) {
-      CK(cudaMemcpy2DAsync(h->ubuf, h->P * sizeof(double), u + h->lo, h->npix * sizeof(double),
-                           h->P * sizeof(double), mh.nsample, cudaMemcpyHostToDevice, h->stream));
-      mh.u = h->ubuf;
-    } else if (mh.ml_mode == DANG_ML_SAMPLE) {
-      fail(DANG_GPU_EINVAL, "z injected without u");
-    }
-  }
-  h->dec_mode = 0;
-  if (h->record) {
-    ensure_decisions(h, n > 0 ? n : 1);
-    CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
-    CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));  // NaN pattern
-    mh.decisions = h->decisions;
-    mh.lnl_trace = h->lnl_trace;
-    h->dec_mode = 2;
-    h->dec_nsample = mh.nsample;
-  }
-  const double n_el = (double)mh.S * h->P;
-  const double kbytes = bytes_w(n_el * (2.0 * h->nbands + h->ncomp + 1) + (double)h->P * 4);
-  // the lane-cooperative kernel covers the chisq likelihood with uniform / Gaussian prior;
-  // marginal lnL, 'prior' draws and the Jeffreys prior run on the strict kernel
-  const bool strict = h->perpixel_serial || mh.lnl_type != DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS;
-  if (strict) {
-    const size_t smem = (size_t)(2 * h->nbands * mh.S + 2 * h->nbands) * DG_MH_THREADS * sizeof(double);
-    if (smem > 200 * 1024) fail(DANG_GPU_EUNSUPPORTED, "per-pixel chain needs %zu B of shared memory", smem);
-    CK(cudaFuncSetAttribute(mh_perpixel_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = occ_grid(h, mh_perpixel_serial_kernel, h->P, DG_MH_THREADS, smem);
-    KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
-    mh_perpixel_serial_kernel<<<grid, DG_MH_THREADS, smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local);
-    kt.done();
-  } else {
-    const size_t smem = (size_t)2 * (DG_MH_THREADS / DG_MH_LANES) * (mh.nsample > 0 ? mh.nsample : 1) * sizeof(double);
-    if (smem > 160 * 1024) fail(DANG_GPU_EUNSUPPORTED, "nsample = %d needs %zu B of shared memory", mh.nsample, smem);
-    const int bpl = (h->nbands + DG_MH_LANES - 1) / DG_MH_LANES;
-    const int64_t work = h->P * DG_MH_LANES;
-    bool any_bp = false;
-    for (int j = 0; j < h->nbands; j++) any_bp = any_bp || h->band[j].n != 0;
-    int mode = MH_SED_GENERIC;
-    if (!any_bp) {
-      if (h->comp[mh.ic].type == DANG_COMP_POWERLAW) mode = MH_SED_POWERLAW;
-      else if (h->comp[mh.ic].type == DANG_COMP_MBB) mode = mh.nind == 0 ? MH_SED_MBB_BETA : MH_SED_MBB_T;
-    }
-    KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
-#define LAUNCH_PP(BPL, MODE)                                                                               \
-    {                                                                                                      \
-      CK(cudaFuncSetAttribute(mh_perpixel_kernel<BPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      const int grid = occ_grid(h, mh_perpixel_kernel<BPL, MODE>, work, DG_MH_THREADS, smem);              \
-      mh_perpixel_kernel<BPL, MODE><<<grid, DG_MH_THREADS, smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local); \
-    }
-#define LAUNCH_PP_MODE(BPL)                                     \
-    {                                                           \
-      if (mode == MH_SED_POWERLAW) LAUNCH_PP(BPL, MH_SED_POWERLAW) \
-      else if (mode == MH_SED_MBB_BETA) LAUNCH_PP(BPL, MH_SED_MBB_BETA) \
-      else if (mode == MH_SED_MBB_T) LAUNCH_PP(BPL, MH_SED_MBB_T)  \
-      else LAUNCH_PP(BPL, MH_SED_GENERIC)                       \
-    }
-    if (bpl <= 2) LAUNCH_PP_MODE(2)
-    else if (bpl <= 3) LAUNCH_PP_MODE(3)
-    else if (bpl <= 5) LAUNCH_PP_MODE(5)
-    else LAUNCH_PP_MODE(8)
-#undef LAUNCH_PP_MODE
-#undef LAUNCH_PP
-    kt.done();
-  }
-  gather(h, 1);
-  double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  double a = 0;
-  for (int g = 0; g < h->nranks; g++) a += hp[g];
-  if (accept) *accept = a;
-}
-
-// chain start (sample <- indices at global pixel 0) + sufficient statistics, gathered over ranks
-int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
-  CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
-  {
-    KTimer kt(h, DANG_K_SCALAR, 0);
-    mh_first_pixel_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->sums_local);
-    kt.done();
-  }
-  gather(h, 2);
-  {
-    KTimer kt(h, DANG_K_SCALAR, 0);
-    mh_fullsky_init_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, 2);
-    kt.done();
-  }
-  if (h->fullsky_stream) return 0;
-  const double n_el = (double)mh.S * h->P;
-  const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
-  const int cnt = nchunk * 3 * DG_SUFF_CHUNK;
-  KTimer kt(h, DANG_K_MH_SUFFSTAT, bytes_w(n_el * (2.0 * h->nbands + h->ncomp)));
-  bool uni = h->ncomp <= 4;
-  for (int s = 0; s < mh.S && uni; s++)
-    for (int c = 0; c < h->ncomp; c++)
-      if (c != mh.ic) uni = uni && comp_uniform(h, c, mh.plane[s]);
-  if (uni) {
-    const int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
-    if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
-    else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
-  } else {
-    const int grid = occ_grid(h, mh_suffstat_kernel, h->P, DG_THREADS);
-    mh_suffstat_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
-  }
-  kt.done();
-  gather(h, cnt);
-  return cnt;
-}
-
-// the sufficient-statistics form covers the chisq likelihood with uniform / Gaussian prior; the
-// marginal likelihood, the Jeffreys prior and 'prior' draws stream the maps per proposal
-bool fullsky_needs_stream(const MhView &mh) {
-  return mh.lnl_type != DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS;
-}
-
-void upload_fullsky_deviates(dang_gpu *h, MhView &mh, const double *z, const double *u, size_t n) {
-  if (!z) return;
-  ensure_zu(h, n > 0 ? n : 1);
-  CK(cudaMemcpyAsync(h->zbuf, z, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  mh.z = h->zbuf;
-  if (u) {
-    CK(cudaMemcpyAsync(h->ubuf, u, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    mh.u = h->ubuf;
-  } else if (mh.ml_mode == DANG_ML_SAMPLE) {
-    fail(DANG_GPU_EINVAL, "z injected without u");
-  }
-}
-
-void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
-                    double *accept) {
-  const int saved_stream = h->fullsky_stream;
-  struct Restore {
-    dang_gpu *h; int v;
-    ~Restore() { h->fullsky_stream = v; }
-  } restore{h, saved_stream};
-  if (fullsky_needs_stream(mh)) h->fullsky_stream = 1;
-  ModelView mv = model_view(h);
-  mh.seed = seed;
-  const size_t n = (size_t)mh.nsample;
-  upload_fullsky_deviates(h, mh, z, u, n);
-  ensure_decisions(h, n > 0 ? n : 1);
-  CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
-  CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));
-  mh.decisions = h->decisions;
-  mh.lnl_trace = h->lnl_trace;
-  h->dec_mode = 1;
-  h->dec_nsample = mh.nsample;
-
-  const int cnt = fullsky_statistics(h, mv, mh);
-  const double n_el = (double)mh.S * h->P;
-  if (h->fullsky_stream) {
-    const size_t dl = (size_t)h->nbands * mh.S * h->Ppad;
-    ensure(h->D, h->D_len, dl);
-    const int grid = grid_for(h, h->P, DG_THREADS, 4);
-    {
-      KTimer kt(h, DANG_K_MH_DATA, bytes_w(n_el * (2.0 * h->nbands + h->ncomp * 2.0)));
-      mh_data_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->D);
-      kt.done();
-    }
-    const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
-    const int cnt = mh.lnl_type == DANG_LNL_MARGINAL ? 2 + 4 * DG_SUFF_CHUNK * nchunk : 2;
-    if (cnt > GATHER_MAX) fail(DANG_GPU_EUNSUPPORTED, "full-sky marginal lnL with %d bands", h->nbands);
-    if (mh.lnl_type == DANG_LNL_PRIOR) {  // :255-257: no chain, draw the index from its Gaussian prior
-      KTimer ks(h, DANG_K_SCALAR, 0);
-      mh_fullsky_prior_draw_kernel<<<1, 1, 0, h->stream>>>(mh, h->mh_scalars);
-      ks.done();
-    }
-    for (int l = 0; l <= mh.nsample && mh.lnl_type != DANG_LNL_PRIOR; l++) {  // starting point + proposals
-      CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
-      if (mh.lnl_type == DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS) {
-        KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
-        mh_fullsky_lnl_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials,
-                                                                 h->tickets, h->sums_local);
-        kt.done();
-      }
-      if (mh.lnl_type == DANG_LNL_MARGINAL) {
-        KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
-        mh_fullsky_marginal_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials,
-                                                                      h->tickets, h->sums_local);
-        kt.done();
-      }
-      gather(h, cnt);
-      KTimer ks(h, DANG_K_SCALAR, 0);
-      mh_fullsky_step_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
-      ks.done();
-    }
-  } else {
-    KTimer ks(h, DANG_K_SCALAR, 0);
-    mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
-    ks.done();
-  }
-  {
-    const int grid = grid_for(h, h->P, DG_THREADS, 4);
-    KTimer kt(h, DANG_K_SCALAR, 0);
-    mh_fullsky_store_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars);
-    kt.done();
-  }
-  MhScalars *hs = (MhScalars *)h->pinned;
-  CK(cudaMemcpyAsync(hs, h->mh_scalars, sizeof(MhScalars), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  if (accept) *accept = hs->accept;
-}
-
-void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
-                  int max_blocks, int *blocks_run, double *step_size) {
-  if (fullsky_needs_stream(mh))
-    fail(DANG_GPU_EUNSUPPORTED, "the step-size tuner is built for the chisq likelihood with uniform / Gaussian prior");
-  if (max_blocks < 0) fail(DANG_GPU_EINVAL, "max_blocks = %d", max_blocks);
-  ModelView mv = model_view(h);
-  mh.seed = seed;
-  upload_fullsky_deviates(h, mh, z, u, (size_t)mh.nsample * max_blocks);
-  const int saved_stream = h->fullsky_stream;
-  h->fullsky_stream = 0;  // the tuner always runs on the sufficient statistics
-  int cnt = 0;
-  try {
-    cnt = fullsky_statistics(h, mv, mh);
-  } catch (...) {
-    h->fullsky_stream = saved_stream;
-    throw;
-  }
-  h->fullsky_stream = saved_stream;
-  double *d_out = h->sums_local + 100;  // scratch beyond the statistics rows
-  {
-    KTimer ks(h, DANG_K_SCALAR, 0);
-    mh_suff_tune_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt, max_blocks, d_out);
-    ks.done();
-  }
-  double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  h->comp[ic].index[nind].step = hp[0];  // c%step_size(nind), :708-710
-  if (blocks_run) *blocks_run = (int)hp[1];
-  if (step_size) *step_size = hp[0];
-}
-
-}  // namespace
-
 // ---------------------------------------------------------------- C ABI
 #define API_BEGIN                                   \
   if (!h) return DANG_GPU_EINVAL;                   \

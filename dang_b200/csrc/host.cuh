@@ -1,0 +1,310 @@
+// host.cuh -- host-side state of one handle (struct dang_gpu) and the launch helpers shared by the
+// translation units of libdang_gpu.so: dang_gpu.cu (C ABI, tables, maps), host_cg.cu (amplitude
+// draw), host_mh_pp.cu / host_mh_fs.cu (spectral-parameter draw), host_data.cu (chi-square).
+#pragma once
+#include "../../include/dang_gpu.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------- errors
+
+struct DgError : std::runtime_error {
+  int code;
+  DgError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+inline std::string vfmt(const char *f, va_list ap) {
+  char buf[1024];
+  vsnprintf(buf, sizeof buf, f, ap);
+  return buf;
+}
+[[noreturn]] inline void fail(int code, const char *f, ...) {
+  va_list ap;
+  va_start(ap, f);
+  std::string m = vfmt(f, ap);
+  va_end(ap);
+  throw DgError(code, m);
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      fail(DANG_GPU_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,               \
+           cudaGetErrorString(e_));                                                           \
+  } while (0)
+
+extern thread_local std::string g_create_error;
+// ---------------------------------------------------------------- NCCL (loaded lazily)
+// Only multi-rank runs touch NCCL; it is dlopen'ed so a single-GPU Fortran host needs no NCCL.
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void *nccl_comm_t;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+  int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+extern NcclApi g_nccl;
+void nccl_load();
+#define NCK(call)                                                                       \
+  do {                                                                                  \
+    int r_ = (call);                                                                    \
+    if (r_ != 0) fail(DANG_GPU_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+const int NCCL_DOUBLE = 8;  // ncclFloat64
+// ---------------------------------------------------------------- host-side objects
+struct BandHost {
+  bool set = false;
+  double nu_c = 0;
+  int n = 0;
+  std::vector<double> nu0, tau0;
+};
+
+struct IndexHost {
+  int sample_index = 0, index_mode = DANG_INDEX_PERPIXEL, lnl_type = 0, prior_type = 0;
+  double gauss[2] = {0, 1}, uni[2] = {-1e300, 1e300}, step = 0;
+  int sample_nside = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
+};
+
+struct CompHost {
+  bool set = false;
+  int type = 0, cg_group = 0, sample_amplitude = 0, nind = 0;
+  std::string label;
+  double nu_ref = 0;
+  double *amp = nullptr;               // [nmaps][Ppad]
+  double *idx[DG_MAXIND] = {nullptr, nullptr};
+  IndexHost index[DG_MAXIND];
+};
+
+struct CgGroupHost {
+  bool set = false;
+  int cg_group = 0, i_max = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
+  double converge = 0;
+  double *x[3] = {nullptr, nullptr, nullptr};  // Q10: persists across Gibbs iterations
+  size_t x_len[3] = {0, 0, 0};
+  int last_iter[3] = {0, 0, 0};  // iterations of the previous solve (sizes the first batch)
+};
+
+struct KStat {
+  int64_t launches = 0;
+  double ms = 0, bytes = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+const int GATHER_MAX = 128;  // doubles per rank in one scalar exchange
+
+struct dang_gpu {
+  int device = 0, nside = 0, nmaps = 0, nbands = 0, ncomp = 0, num_sms = 0;
+  int64_t npix = 0, lo = 0, hi = 0, P = 0, Ppad = 0;
+  cudaStream_t stream = nullptr, d2h_stream = nullptr, h2d_stream = nullptr;
+  cudaEvent_t ev_compute = nullptr, ev_amp_dl = nullptr, ev_idx_dl = nullptr, ev_eta = nullptr;
+  bool amp_dl_pending = false, idx_dl_pending = false, eta_staged = false;
+  double *eta_stage = nullptr; size_t eta_stage_len = 0; int eta_stage_planes = 0;
+  std::string err;
+
+  // options
+  int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
+  int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int use_tma = 0;  // TMA-staged K1 (measured slower than the LDG form on B200: kept as an experiment)
+
+  // ddata
+  bool maps_set = false, maps_borrowed = false;  // borrowed: sig/rms/mask belong to another handle (ensembles)
+  double *sig = nullptr, *rms = nullptr;
+  unsigned char *mask = nullptr;
+  double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
+
+  BandHost band[DG_MAX_BANDS];
+  double *bp_nu0 = nullptr, *bp_tau0 = nullptr, *bp_lnr_hi = nullptr, *bp_lnr_lo = nullptr;
+  int nbp = 0;
+  bool bp_dirty = true;   // band / component constants changed: rebuild the static tables
+  bool tab_dirty = true;  // an index map changed: re-tabulate SEDs
+  unsigned long long check_mask = ~0ull;  // index maps whose uniformity must be re-scanned
+  SedTable *tab = nullptr;
+  int uni_host[DG_MAX_COMPS * 3] = {};  // host copy of SedTable::uni (refreshed with the tables)
+  int nonuni_host[DG_MAX_COMPS * 3][DG_MAXIND] = {};  // host mirror of SedTable::nonuni
+  CompHost comp[DG_MAX_COMPS];
+  std::vector<CgGroupHost> cg;
+
+  // scratch
+  double *M = nullptr, *r = nullptr, *d = nullptr, *eta = nullptr;
+  size_t M_len = 0, v_len = 0, eta_len = 0;
+  int cg_layout = -1;
+  double *D = nullptr;  size_t D_len = 0;       // streaming full-sky data
+  double *zbuf = nullptr, *ubuf = nullptr; size_t zu_len = 0;
+  unsigned char *decisions = nullptr; double *lnl_trace = nullptr; size_t dec_len = 0;
+  int dec_mode = 0, dec_nsample = 0;            // 1 full-sky, 2 per-pixel
+  double *stage = nullptr; size_t stage_len = 0; // device staging for strided host copies
+  double *partials = nullptr; unsigned int *tickets = nullptr;
+  int grid_cap = 0;
+  double *sums_local = nullptr, *gathered = nullptr, *gathered_buf = nullptr;
+  CgScalars *cg_scalars = nullptr;
+  MhScalars *mh_scalars = nullptr;
+  void *pinned = nullptr;  // small pinned buffer for scalar read-back
+  std::vector<double> last_trace;
+
+  // comm
+  int nranks = 1, rank = 0;
+  nccl_comm_t comm = nullptr;
+  // NVLink mailboxes (CUDA IPC); peer.nranks == 1 until dang_gpu_comm_open_peers succeeds
+  Mail *mailbox = nullptr;
+  void *peer_ptr[DG_MAX_RANKS] = {};
+  PeerComm peer{};
+  bool use_mail = false;
+
+  // instrumentation
+  int64_t launches = 0;
+  KStat kstat[DANG_K_COUNT];
+  cudaEvent_t ev[16] = {};
+};
+// ---------------------------------------------------------------- helpers
+inline void set_device(dang_gpu *h) { CK(cudaSetDevice(h->device)); }
+
+template <typename T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+inline void ensure(double *&buf, size_t &len, size_t need) {
+  if (len >= need) return;
+  if (buf) CK(cudaFree(buf));
+  buf = nullptr;
+  CK(cudaMalloc(&buf, need * sizeof(double)));
+  len = need;
+}
+
+// Persistent-style launch: exactly as many blocks as are resident at once (blocks/SM from the
+// occupancy calculator x SM count), or fewer when the work is small; grid-stride loops inside.
+template <typename K>
+int occ_grid(dang_gpu *h, K kernel, int64_t work, int threads, size_t smem = 0) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t need = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)h->num_sms * per_sm;
+  if (cap > h->grid_cap) cap = h->grid_cap;
+  int64_t g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+inline int grid_for(dang_gpu *h, int64_t work, int threads, int blocks_per_sm) {
+  int64_t need = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)h->num_sms * blocks_per_sm;
+  if (cap > h->grid_cap) cap = h->grid_cap;
+  int64_t g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+struct KTimer {
+  dang_gpu *h;
+  int kid;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KTimer(dang_gpu *h_, int kid_, double bytes) : h(h_), kid(kid_) {
+    h->launches++;
+    h->kstat[kid].launches++;
+    h->kstat[kid].bytes += bytes;
+    if (h->profile) {
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&b));
+      CK(cudaEventRecord(a, h->stream));
+    }
+  }
+  void done() {
+    CK(cudaGetLastError());
+    if (h->profile) {
+      CK(cudaEventRecord(b, h->stream));
+      h->kstat[kid].pending.emplace_back(a, b);
+    }
+  }
+};
+
+inline void resolve_stats(dang_gpu *h) {
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < DANG_K_COUNT; k++) {
+    for (auto &pr : h->kstat[k].pending) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+      h->kstat[k].ms += ms;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    h->kstat[k].pending.clear();
+  }
+}
+
+// host (npix-strided, full sky) <-> device (Ppad-strided slice) plane copies
+inline void h2d_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
+  CK(cudaMemcpy2DAsync(dst, h->Ppad * sizeof(double), src + h->lo, h->npix * sizeof(double),
+                       h->P * sizeof(double), nplanes, cudaMemcpyHostToDevice, h->stream));
+}
+inline void d2h_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
+  CK(cudaMemcpy2DAsync(dst + h->lo, h->npix * sizeof(double), src, h->Ppad * sizeof(double),
+                       h->P * sizeof(double), nplanes, cudaMemcpyDeviceToHost, h->stream));
+}
+
+// ln(a/b) as a double-double from an extended-precision logarithm
+inline void dd_log_ratio(double a, double b, double &hi, double &lo) {
+  const long double L = logl((long double)a / (long double)b);
+  hi = (double)L;
+  lo = (double)(L - (long double)hi);
+}
+// defined in dang_gpu.cu
+void upload_bandpasses(dang_gpu *h);
+ModelView model_view(dang_gpu *h);
+void gather(dang_gpu *h, int cnt);  // exchange `cnt` doubles of sums_local between ranks -> h->gathered [rank][cnt]
+
+inline int flag_planes(int flag, int plane[2]) {  // 0-based planes; returns S
+  if (flag & 8) {
+    plane[0] = 1;
+    plane[1] = 2;
+    return 2;
+  }
+  int k = 0;
+  if (flag & 1) k = 0;
+  else if (flag & 2) k = 1;
+  else if (flag & 4) k = 2;
+  else fail(DANG_GPU_EUNSUPPORTED, "pol flag %d (T+Q+U) is dead code in the reference (SURVEY Q2)", flag);
+  plane[0] = plane[1] = k;
+  return 1;
+}
+
+inline double bytes_w(double n) { return n * 8.0; }
+
+// record that index map (c, l) on plane k is known constant (val = 0) or varying (val = 1)
+inline void set_nonuni(dang_gpu *h, int c, int k, int l, int val) {
+  const int m = (c * 3 + k) * DG_MAXIND + l;
+  CK(cudaMemsetAsync((char *)h->tab + offsetof(SedTable, nonuni) + m * sizeof(int), val ? 1 : 0, sizeof(int), h->stream));
+  h->nonuni_host[c * 3 + k][l] = val ? 1 : 0;
+  h->check_mask &= ~(1ull << m);
+  h->tab_dirty = true;
+}
+
+inline bool comp_uniform(const dang_gpu *h, int c, int k) { return h->uni_host[c * 3 + k] != 0; }
+
+// ---------------------------------------------------------------- entry points of the other translation units
+void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *eta, uint64_t seed,
+              int *n_iter, double *delta_final);                                   // host_cg.cu
+void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, double *chi_map,
+               double out4[4]);                                                    // host_data.cu
+void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode, MhView &mh);  // host_mh_fs.cu
+void ensure_zu(dang_gpu *h, size_t n);
+void ensure_decisions(dang_gpu *h, size_t n);
+void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);  // host_mh_pp.cu
+void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);   // host_mh_fs.cu
+void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
+                  int max_blocks, int *blocks_run, double *step_size);             // host_mh_fs.cu

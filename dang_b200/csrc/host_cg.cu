@@ -1,0 +1,258 @@
+// host_cg.cu -- amplitude draw: compute_rhs + cg_search + unpack_amplitudes for one (group, flag),
+// src/dang_cg_mod.f90:167-169 (launch logic; kernels in kernels_cg.cuh / kernels_uni.cuh).
+#include "host.cuh"
+#include "kernels_cg.cuh"
+#include "kernels_uni.cuh"
+
+namespace {
+// ---------------------------------------------------------------- amplitude draw
+template <int C>
+void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const double *eta,
+                   uint64_t seed, const int *comps, const int *og, int nog, int *n_iter,
+                   double *delta_final) {
+  constexpr int T = C * (C + 1) / 2;
+  ModelView mv = model_view(h);
+  CgView<C> cv;
+  memset(&cv, 0, sizeof cv);
+  cv.S = flag_planes(g.pol_flag[flag_n], cv.plane);
+  for (int c = 0; c < C; c++) cv.comp[c] = comps[c];
+  cv.nog = nog;
+  for (int o = 0; o < nog; o++) cv.og[o] = og[o];
+  const int S = cv.S;
+  for (int s = 0; s < S; s++)
+    if (cv.plane[s] >= h->nmaps) fail(DANG_GPU_EINVAL, "pol flag needs plane %d, nmaps = %d", cv.plane[s] + 1, h->nmaps);
+  const size_t vs = (size_t)S * h->Ppad;  // doubles per component
+  const int64_t n2 = (int64_t)(vs / 2);
+
+  // self%x: allocate + seed from c%amplitude on first use only (cg_search :227-239, Q10)
+  if (!g.x[flag_n] || g.x_len[flag_n] != C * vs) {
+    if (g.x[flag_n]) CK(cudaFree(g.x[flag_n]));
+    CK(cudaMalloc(&g.x[flag_n], C * vs * sizeof(double)));
+    g.x_len[flag_n] = C * vs;
+    CK(cudaMemsetAsync(g.x[flag_n], 0, C * vs * sizeof(double), h->stream));
+    for (int c = 0; c < C; c++)
+      for (int s = 0; s < S; s++)  // initialize_x :1216-1224
+        CK(cudaMemcpyAsync(g.x[flag_n] + c * vs + (size_t)s * h->Ppad,
+                           h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
+                           h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (h->M_len < T * vs) {
+    ensure(h->M, h->M_len, T * vs);
+    h->cg_layout = -1;
+  }
+  if (h->v_len < C * vs) {
+    size_t l1 = h->v_len, l2 = h->v_len;
+    ensure(h->r, l1, C * vs);
+    ensure(h->d, l2, C * vs);
+    h->v_len = C * vs;
+    h->cg_layout = -1;
+  }
+  // padding lanes must hold zeros (they are swept by the vectorised passes and nothing ever
+  // writes a nonzero there), so clear only when the plane layout of the scratch changes
+  if (h->cg_layout != C * 16 + S) {
+    CK(cudaMemsetAsync(h->M, 0, T * vs * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->r, 0, C * vs * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d, 0, C * vs * sizeof(double), h->stream));
+    h->cg_layout = C * 16 + S;
+  }
+  cv.M = h->M;
+  cv.r = h->r;
+  cv.d = h->d;
+  cv.x = g.x[flag_n];
+  cv.seed = seed;
+  cv.fluct = 0;
+  cv.eta = nullptr;
+  // recompute form needs the (alpha, beta) history: fall back to streaming for very long solves
+  const int ckpt_m = (!h->cg_two_pass && g.i_max < DG_CG_HIST) ? h->cg_ckpt : 0;
+  cv.store_d = ckpt_m ? 0 : 1;
+  if (ml_mode == DANG_ML_SAMPLE) {  // :254-264
+    cv.fluct = h->fix_q1 ? 2 : 1;
+    if (eta) {
+      ensure(h->eta, h->eta_len, vs);
+      h2d_planes(h, h->eta, eta, S);  // host eta is [stokes][npix]
+      cv.eta = h->eta;
+    } else if (h->eta_staged && h->eta_stage_planes == S) {
+      CK(cudaStreamWaitEvent(h->stream, h->ev_eta, 0));  // uploaded by dang_gpu_stage_eta
+      cv.eta = h->eta_stage;
+      h->eta_staged = false;
+    }
+  }
+
+  CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+  {
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    const double n_el = (double)S * h->P;
+    KTimer kt(h, DANG_K_RHS_BLOCKS,
+              bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + (ckpt_m ? 1.0 : 2.0) * C)) + bytes_w((double)h->P * 3));
+    // streaming kernel: out-of-group components must have tabulated SEDs; group components with
+    // varying indices get their SEDs staged per thread in dynamic shared memory
+    bool og_uni = true;
+    unsigned nu_mask = 0;
+    for (int s = 0; s < S; s++) {
+      for (int c = 0; c < C; c++)
+        if (!comp_uniform(h, comps[c], cv.plane[s])) nu_mask |= 1u << c;
+      for (int o = 0; o < nog; o++) og_uni = og_uni && comp_uniform(h, og[o], cv.plane[s]);
+    }
+    const size_t dsm = (size_t)__builtin_popcount(nu_mask) * h->nbands * 2 * DG_THREADS * sizeof(double);
+    const size_t tma_smem = (size_t)DG_TMA_STAGES * DG_TMA_BANDS * 2 * 2 * DG_TMA_TILE * sizeof(double);
+    if (h->use_tma && nu_mask == 0 && nog == 0) {
+      // TMA-staged stream: one block per SM, 3-stage shared-memory ring filled by cp.async.bulk
+      CK(cudaFuncSetAttribute(rhs_blocks_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+      const int64_t ntiles = (h->Ppad + DG_TMA_TILE - 1) / DG_TMA_TILE;
+      const int g3 = (int)(ntiles < h->num_sms ? ntiles : h->num_sms);
+      rhs_blocks_tma_kernel<C><<<g3, DG_TMA_THREADS, tma_smem, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    } else if (og_uni && dsm <= 160 * 1024) {
+      if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(rhs_blocks_uni_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      const int g2 = occ_grid(h, rhs_blocks_uni_kernel<C>, h->Ppad / 2, DG_THREADS, dsm);
+      rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask);
+    } else {
+      const int g1 = occ_grid(h, rhs_blocks_kernel<C>, h->P, DG_THREADS);
+      rhs_blocks_kernel<C><<<g1, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+    }
+    kt.done();
+  }
+  gather(h, 4);
+  {
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    cg_init_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks, g.i_max, g.converge);
+    kt.done();
+  }
+  CK(cudaMemcpyAsync((char *)h->cg_scalars + offsetof(CgScalars, m), &ckpt_m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+
+  struct Snap { double delta_new; int iter, done; };
+  bool have_state = false;
+  auto read_state = [&]() -> Snap {  // scalars + residual trace in one small copy
+    CgScalars *hs = (CgScalars *)h->pinned;
+    CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    have_state = true;
+    return Snap{hs->delta_new, hs->iter, hs->done};
+  };
+
+  const int fold = (h->nranks == 1 || h->use_mail) ? 1 : 0;
+  const int grid = h->cg_two_pass ? occ_grid(h, cg_update_pass_kernel<C>, n2, DG_THREADS)
+                   : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C>, n2, DG_THREADS)
+                                : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
+  const double el = (double)vs;
+  auto enqueue_pass = [&](int pass_no) {
+    if (!h->cg_two_pass) {
+      if (ckpt_m) {
+        // compulsory traffic of this launch: M, r, d in; on checkpoint passes also x in, r, d, x out
+        const double per_el = (pass_no % ckpt_m == 0) ? (T + (pass_no == ckpt_m ? 5.0 : 6.0) * C)
+                                                      : (T + (pass_no < ckpt_m ? 1.0 : 2.0) * C);
+        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
+        cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0, h->peer, h->gathered);
+        kt.done();
+      } else {
+        // compulsory traffic of this launch: x is touched on even passes only
+        const double per_el = (pass_no & 1) ? (T + 4.0 * C) : (T + 6.0 * C);
+        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
+        cg_fused_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, h->peer, h->gathered);
+        kt.done();
+      }
+      if (!fold) {
+        gather(h, 4);
+        KTimer ks(h, DANG_K_SCALAR, 0);
+        cg_fused_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+        ks.done();
+      }
+    } else {
+      {
+        KTimer kt(h, DANG_K_CG_DQ, bytes_w(el * (T + 3.0 * C)));
+        cg_dq_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, h->M, h->r, h->d, n2,
+                                                                  h->partials, h->tickets, h->sums_local);
+        kt.done();
+      }
+      gather(h, 4);
+      {
+        KTimer ks(h, DANG_K_SCALAR, 0);
+        cg_dq_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+        ks.done();
+      }
+      {
+        KTimer kt(h, DANG_K_CG_UPDATE, bytes_w(el * (T + 5.0 * C)));
+        cg_update_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local);
+        kt.done();
+      }
+      gather(h, 4);
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      cg_rr_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks);
+      ks.done();
+    }
+  };
+  // Passes are enqueued without waiting for the convergence flag: a pass launched after the
+  // solve is done returns at once (device-side early exit).  The first batch is sized from the
+  // previous solve of this (group, flag) -- successive Gibbs iterations converge in almost the
+  // same number of steps -- and further batches of cg_chunk follow until the flag is seen.
+  const int max_pass = g.i_max - 1;
+  int enq = 0;
+  int batch = g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : h->cg_chunk;
+  Snap sn{0.0, 1, max_pass < 1};
+  while (!sn.done && enq < max_pass) {
+    if (batch > max_pass - enq) batch = max_pass - enq;
+    for (int it = 0; it < batch; it++) enqueue_pass(enq + it + 1);
+    enq += batch;
+    sn = read_state();
+    batch = h->cg_chunk;
+  }
+  if (!h->cg_two_pass) {  // bring x up to date (pending term of the deferred / checkpointed update)
+    KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 4.0 * C : 3.0 * C)));
+    if (ckpt_m)
+      cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
+          h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1, h->peer, h->gathered);
+    else
+      cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
+    kt.done();
+  }
+
+  // unpack_amplitudes :1327-1335: x -> c%amplitude planes (after any download still reading them)
+  if (h->amp_dl_pending) {
+    CK(cudaStreamWaitEvent(h->stream, h->ev_amp_dl, 0));
+    h->amp_dl_pending = false;
+  }
+  for (int c = 0; c < C; c++)
+    for (int s = 0; s < S; s++)
+      CK(cudaMemcpyAsync(h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
+                         g.x[flag_n] + c * vs + (size_t)s * h->Ppad, h->P * sizeof(double),
+                         cudaMemcpyDeviceToDevice, h->stream));
+  {
+    CgScalars *hs = (CgScalars *)h->pinned;  // filled by the last read_state (the solve was done then)
+    if (!sn.done || !have_state) {  // ran out of passes (i_max) without seeing the flag: read the final state
+      CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    int n = hs->iter < 256 ? hs->iter : 256;
+    h->last_trace.assign(hs->trace, hs->trace + n);
+    g.last_iter[flag_n] = hs->iter;
+    if (n_iter) *n_iter = hs->iter;
+    if (delta_final) *delta_final = hs->delta_new;
+  }
+}
+}  // namespace
+
+void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *eta, uint64_t seed,
+              int *n_iter, double *delta_final) {
+  CgGroupHost *g = nullptr;
+  for (auto &gg : h->cg)
+    if (gg.set && gg.cg_group == cg_group) g = &gg;
+  if (!g) fail(DANG_GPU_ESTATE, "CG group %d has not been set", cg_group);
+  if (flag_n < 0 || flag_n >= g->nflag) fail(DANG_GPU_EINVAL, "flag_n %d out of range", flag_n);
+  int comps[DG_MAX_COMPS], og[DG_MAX_COMPS], C = 0, nog = 0;
+  for (int c = 0; c < h->ncomp; c++) {
+    const CompHost &cc = h->comp[c];
+    if (!cc.set) fail(DANG_GPU_ESTATE, "component %d has not been set", c);
+    if (cc.cg_group == cg_group && cc.sample_amplitude) comps[C++] = c;
+    else og[nog++] = c;  // :430
+  }
+  if (C == 0) fail(DANG_GPU_EINVAL, "Woah there, number of CG components = 0 for CG group %d", cg_group);
+  if (C > DG_MAX_CG) fail(DANG_GPU_EUNSUPPORTED, "%d diffuse components in one CG group (max %d)", C, DG_MAX_CG);
+  switch (C) {
+    case 1: cg_solve_impl<1>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+    case 2: cg_solve_impl<2>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+    case 3: cg_solve_impl<3>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+    default: cg_solve_impl<4>(h, *g, flag_n, ml_mode, eta, seed, comps, og, nog, n_iter, delta_final); break;
+  }
+}

@@ -1,0 +1,222 @@
+// host_mh_fs.cu -- full-sky branch of sample_index_mh (src/dang_sample_mod.f90:229-329) and the
+// step-size tuner (:623-717).
+#include "host.cuh"
+#include "kernels_mh.cuh"
+#include "kernels_uni.cuh"
+
+void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode, MhView &mh) {
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  const CompHost &c = h->comp[ic];
+  if (nind < 0 || nind >= c.nind) fail(DANG_GPU_EINVAL, "component %d has no index %d", ic, nind);
+  const IndexHost &ix = c.index[nind];
+  if (ix.sample_nside != h->nside)
+    fail(DANG_GPU_EUNSUPPORTED, "sample_nside %d /= nside %d needs HEALPix udgrade_ring (DESIGN.md, out of scope)",
+         ix.sample_nside, h->nside);
+  memset(&mh, 0, sizeof mh);
+  mh.ic = ic;
+  mh.nind = nind;
+  if (map_n == -1) {  // :157-163
+    mh.S = 2;
+    mh.plane[0] = 1;
+    mh.plane[1] = 2;
+  } else if (map_n >= 1 && map_n <= 3) {
+    mh.S = 1;
+    mh.plane[0] = mh.plane[1] = map_n - 1;
+  } else {
+    fail(DANG_GPU_EUNSUPPORTED, "map_n = %d (T+Q+U) is unreachable in the reference (SURVEY Q2)", map_n);
+  }
+  for (int s = 0; s < mh.S; s++)
+    if (mh.plane[s] >= h->nmaps) fail(DANG_GPU_EINVAL, "map_n %d needs plane %d, nmaps = %d", map_n, mh.plane[s] + 1, h->nmaps);
+  mh.nsample = nsample;
+  mh.ml_mode = ml_mode;
+  mh.lnl_type = ix.lnl_type;
+  mh.prior_type = ix.prior_type;
+  mh.is_synch = c.label == "synch";
+  mh.gauss[0] = ix.gauss[0];
+  mh.gauss[1] = ix.gauss[1];
+  mh.uni[0] = ix.uni[0];
+  mh.uni[1] = ix.uni[1];
+  mh.step = ix.step;
+}
+
+void ensure_zu(dang_gpu *h, size_t n) {
+  if (h->zu_len >= n) return;
+  dfree(h->zbuf);
+  dfree(h->ubuf);
+  CK(cudaMalloc(&h->zbuf, n * sizeof(double)));
+  CK(cudaMalloc(&h->ubuf, n * sizeof(double)));
+  h->zu_len = n;
+}
+
+void ensure_decisions(dang_gpu *h, size_t n) {
+  if (h->dec_len >= n) return;
+  dfree(h->decisions);
+  dfree(h->lnl_trace);
+  CK(cudaMalloc(&h->decisions, n));
+  CK(cudaMalloc(&h->lnl_trace, n * sizeof(double)));
+  h->dec_len = n;
+}
+
+namespace {
+// chain start (sample <- indices at global pixel 0) + sufficient statistics, gathered over ranks
+int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
+  CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+  {
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    mh_first_pixel_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->sums_local);
+    kt.done();
+  }
+  gather(h, 2);
+  {
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    mh_fullsky_init_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, 2);
+    kt.done();
+  }
+  if (h->fullsky_stream) return 0;
+  const double n_el = (double)mh.S * h->P;
+  const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  const int cnt = nchunk * 3 * DG_SUFF_CHUNK;
+  KTimer kt(h, DANG_K_MH_SUFFSTAT, bytes_w(n_el * (2.0 * h->nbands + h->ncomp)));
+  bool uni = h->ncomp <= 4;
+  for (int s = 0; s < mh.S && uni; s++)
+    for (int c = 0; c < h->ncomp; c++)
+      if (c != mh.ic) uni = uni && comp_uniform(h, c, mh.plane[s]);
+  if (uni) {
+    const int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
+    if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+    else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+  } else {
+    const int grid = occ_grid(h, mh_suffstat_kernel, h->P, DG_THREADS);
+    mh_suffstat_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+  }
+  kt.done();
+  gather(h, cnt);
+  return cnt;
+}
+
+// the sufficient-statistics form covers the chisq likelihood with uniform / Gaussian prior; the
+// marginal likelihood, the Jeffreys prior and 'prior' draws stream the maps per proposal
+bool fullsky_needs_stream(const MhView &mh) {
+  return mh.lnl_type != DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS;
+}
+
+void upload_fullsky_deviates(dang_gpu *h, MhView &mh, const double *z, const double *u, size_t n) {
+  if (!z) return;
+  ensure_zu(h, n > 0 ? n : 1);
+  CK(cudaMemcpyAsync(h->zbuf, z, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  mh.z = h->zbuf;
+  if (u) {
+    CK(cudaMemcpyAsync(h->ubuf, u, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    mh.u = h->ubuf;
+  } else if (mh.ml_mode == DANG_ML_SAMPLE) {
+    fail(DANG_GPU_EINVAL, "z injected without u");
+  }
+}
+}  // namespace
+
+void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed,
+                    double *accept) {
+  const int saved_stream = h->fullsky_stream;
+  struct Restore {
+    dang_gpu *h; int v;
+    ~Restore() { h->fullsky_stream = v; }
+  } restore{h, saved_stream};
+  if (fullsky_needs_stream(mh)) h->fullsky_stream = 1;
+  ModelView mv = model_view(h);
+  mh.seed = seed;
+  const size_t n = (size_t)mh.nsample;
+  upload_fullsky_deviates(h, mh, z, u, n);
+  ensure_decisions(h, n > 0 ? n : 1);
+  CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
+  CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));
+  mh.decisions = h->decisions;
+  mh.lnl_trace = h->lnl_trace;
+  h->dec_mode = 1;
+  h->dec_nsample = mh.nsample;
+
+  const int cnt = fullsky_statistics(h, mv, mh);
+  const double n_el = (double)mh.S * h->P;
+  if (h->fullsky_stream) {
+    const size_t dl = (size_t)h->nbands * mh.S * h->Ppad;
+    ensure(h->D, h->D_len, dl);
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    {
+      KTimer kt(h, DANG_K_MH_DATA, bytes_w(n_el * (2.0 * h->nbands + h->ncomp * 2.0)));
+      mh_data_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->D);
+      kt.done();
+    }
+    const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+    const int cnt = mh.lnl_type == DANG_LNL_MARGINAL ? 2 + 4 * DG_SUFF_CHUNK * nchunk : 2;
+    if (cnt > GATHER_MAX) fail(DANG_GPU_EUNSUPPORTED, "full-sky marginal lnL with %d bands", h->nbands);
+    if (mh.lnl_type == DANG_LNL_PRIOR) {  // :255-257: no chain, draw the index from its Gaussian prior
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      mh_fullsky_prior_draw_kernel<<<1, 1, 0, h->stream>>>(mh, h->mh_scalars);
+      ks.done();
+    }
+    for (int l = 0; l <= mh.nsample && mh.lnl_type != DANG_LNL_PRIOR; l++) {  // starting point + proposals
+      CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+      if (mh.lnl_type == DANG_LNL_CHISQ || mh.prior_type == DANG_PRIOR_JEFFREYS) {
+        KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
+        mh_fullsky_lnl_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials,
+                                                                 h->tickets, h->sums_local);
+        kt.done();
+      }
+      if (mh.lnl_type == DANG_LNL_MARGINAL) {
+        KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
+        mh_fullsky_marginal_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials,
+                                                                      h->tickets, h->sums_local);
+        kt.done();
+      }
+      gather(h, cnt);
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      mh_fullsky_step_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
+      ks.done();
+    }
+  } else {
+    KTimer ks(h, DANG_K_SCALAR, 0);
+    mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
+    ks.done();
+  }
+  {
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    mh_fullsky_store_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars);
+    kt.done();
+  }
+  MhScalars *hs = (MhScalars *)h->pinned;
+  CK(cudaMemcpyAsync(hs, h->mh_scalars, sizeof(MhScalars), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (accept) *accept = hs->accept;
+}
+
+void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
+                  int max_blocks, int *blocks_run, double *step_size) {
+  if (fullsky_needs_stream(mh))
+    fail(DANG_GPU_EUNSUPPORTED, "the step-size tuner is built for the chisq likelihood with uniform / Gaussian prior");
+  if (max_blocks < 0) fail(DANG_GPU_EINVAL, "max_blocks = %d", max_blocks);
+  ModelView mv = model_view(h);
+  mh.seed = seed;
+  upload_fullsky_deviates(h, mh, z, u, (size_t)mh.nsample * max_blocks);
+  const int saved_stream = h->fullsky_stream;
+  h->fullsky_stream = 0;  // the tuner always runs on the sufficient statistics
+  int cnt = 0;
+  try {
+    cnt = fullsky_statistics(h, mv, mh);
+  } catch (...) {
+    h->fullsky_stream = saved_stream;
+    throw;
+  }
+  h->fullsky_stream = saved_stream;
+  double *d_out = h->sums_local + 100;  // scratch beyond the statistics rows
+  {
+    KTimer ks(h, DANG_K_SCALAR, 0);
+    mh_suff_tune_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt, max_blocks, d_out);
+    ks.done();
+  }
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->comp[ic].index[nind].step = hp[0];  // c%step_size(nind), :708-710
+  if (blocks_run) *blocks_run = (int)hp[1];
+  if (step_size) *step_size = hp[0];
+}

@@ -24,20 +24,6 @@ struct CgView {
   int store_d;               // 0: the recompute CG form never reads the initial d (= r)
 };
 
-// scalars of one solve, device resident (DESIGN.md "CG control")
-#define DG_CG_HIST 1024   // passes whose (alpha, beta) are kept for the recompute form
-#define DG_CG_MAXM 32     // largest checkpoint interval
-
-struct CgScalars {
-  double delta_new, delta_old, alpha, beta, dq;
-  double alpha_prev;  // alpha of the pass that ran last (deferred x update, see cg_fused_pass_kernel)
-  double converge;
-  int iter, i_max, done, pad;
-  int ckpt, m;        // recompute form: pass whose state is stored in (r, d); checkpoint interval
-  double trace[256];
-  double ah[DG_CG_HIST], bh[DG_CG_HIST];  // alpha_i, beta_i used IN pass i (1-based)
-};
-
 template <int C>
 __device__ __forceinline__ int tri(int a, int b) {  // a <= b
   return a * C - a * (a - 1) / 2 + (b - a);
@@ -248,17 +234,17 @@ __device__ __forceinline__ void cg_fused_update(CgScalars *st, const double *sum
   if (st->m > 0 && (it - 1) - st->ckpt == st->m) st->ckpt = it - 1;  // pass it-1 stored its state
 }
 
-__global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, int nranks,
+static __global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, int nranks,
                                        int i_max, double converge) {
   cg_init_update(st, gathered, nranks, i_max, converge);
 }
-__global__ void cg_fused_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
+static __global__ void cg_fused_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
   if (st->done) return;
   cg_fused_update(st, gathered, nranks);
 }
 
 // two-pass form: after the d.q pass
-__global__ void cg_dq_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
+static __global__ void cg_dq_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
   if (st->done) return;
   double dq = 0.0;
   for (int g = 0; g < nranks; g++) dq += gathered[g * 4 + 0];
@@ -266,7 +252,7 @@ __global__ void cg_dq_scalars_kernel(CgScalars *st, const double *gathered, int 
   st->alpha = st->delta_new / dq;  // :297
 }
 // two-pass form: after the update pass
-__global__ void cg_rr_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
+static __global__ void cg_rr_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
   if (st->done) return;
   double rr = 0.0;
   for (int g = 0; g < nranks; g++) rr += gathered[g * 4 + 0];
@@ -473,7 +459,7 @@ cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__
 }
 
 // pending x update when the solve stopped after an odd number of passes
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 cg_x_fixup_kernel(const CgScalars *st, double *__restrict__ x, const double *__restrict__ d, int64_t n) {
   if (((st->iter - 1) & 1) == 0) return;
   const double a = st->alpha_prev;
@@ -576,7 +562,7 @@ cg_update_pass_kernel(const CgScalars *st, const double *__restrict__ M, double 
 }
 
 // initialize_x / unpack_amplitudes, src/dang_cg_mod.f90:1173-1282, 1284-1396: plane copies
-__global__ void copy_planes_kernel(double *dst, const double *src, int64_t n) {
+static __global__ void copy_planes_kernel(double *dst, const double *src, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
 }

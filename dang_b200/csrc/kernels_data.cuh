@@ -91,7 +91,7 @@ chisq_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned 
 }
 
 // mask_avg, src/dang_util_mod.f90:186-206: out[0] = sum over unmasked of map, out[1] = count
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 masked_sum_kernel(const double *map, const unsigned char *mask, int64_t P, double *partials,
                   unsigned int *ticket, double *out) {
   __shared__ double smem[4 * 32];
@@ -105,13 +105,13 @@ masked_sum_kernel(const double *map, const unsigned char *mask, int64_t P, doubl
   grid_reduce<4>(acc, smem, partials, ticket, out);
 }
 
-__global__ void fill_kernel(double *dst, int64_t n, double v) {
+static __global__ void fill_kernel(double *dst, int64_t n, double v) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
 }
 
 // mask (double, 0 / missval = masked) -> bytes, src/dang_data_mod.f90:153-161
-__global__ void mask_to_bytes_kernel(const double *mask, unsigned char *out, int64_t P, int64_t Ppad) {
+static __global__ void mask_to_bytes_kernel(const double *mask, unsigned char *out, int64_t P, int64_t Ppad) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Ppad; i += stride)
     out[i] = (i < P && mask[i] != 0.0 && mask[i] != -1.6375e30) ? 1 : 0;
@@ -122,7 +122,7 @@ __global__ void mask_to_bytes_kernel(const double *mask, unsigned char *out, int
 // grid = (blocks, ncomp * 3 * DG_MAXIND); the nonuni flags of the maps selected by check_mask must
 // be zero on entry.  Maps written by the samplers are never re-scanned: a full-sky draw leaves a
 // constant plane, a per-pixel draw a varying one, and the host sets their flags directly.
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 uniform_check_kernel(const ModelView mv, SedTable *tab, unsigned long long check_mask) {
   const int m = blockIdx.y;
   const int l = m % DG_MAXIND, k = (m / DG_MAXIND) % 3, c = m / (DG_MAXIND * 3);
@@ -138,7 +138,7 @@ uniform_check_kernel(const ModelView mv, SedTable *tab, unsigned long long check
 }
 
 // sed_table_kernel<<<ncomp*3, 32>>>: tabulate the per-band SED of every uniform (component, plane)
-__global__ void sed_table_kernel(const ModelView mv, SedTable *tab) {
+static __global__ void sed_table_kernel(const ModelView mv, SedTable *tab) {
   const int ck = blockIdx.x, c = ck / 3, k = ck % 3;
   if (c >= mv.ncomp || k >= mv.nmaps) {
     if (threadIdx.x == 0) tab->uni[ck] = 0;
@@ -158,7 +158,7 @@ __global__ void sed_table_kernel(const ModelView mv, SedTable *tab) {
 // fit_band_gain, src/dang_sample_mod.f90:570-621: the two masked, noise-weighted dot products of
 // one band against the current sky model.  out[0] = sum(map2*N_inv*map1), out[1] = sum(map1*N_inv*map1)
 // with map1 = sky_model, map2 = res_map + sky_model (update_sky_model :384-387 fused in).
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 band_gain_kernel(const ModelView mv, int k, int band, double *partials, unsigned int *ticket, double *out) {
   __shared__ double smem[4 * 32];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};

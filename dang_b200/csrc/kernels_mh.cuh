@@ -11,31 +11,6 @@
 #pragma once
 #include "common.cuh"
 
-#define DG_MH_THREADS 128
-#define DG_SUFF_CHUNK 4   // bands per register-resident accumulator chunk
-
-struct MhView {
-  int ic;          // component being sampled
-  int nind;        // which of its indices
-  int S;           // planes map_inds(1)..map_inds(2)
-  int plane[2];    // 0-based
-  int nsample, ml_mode, lnl_type, prior_type;
-  int is_synch;    // label == 'synch' (eval_jeffreys_prior, src/dang_lnl_mod.f90:289)
-  double gauss[2], uni[2], step;
-  const double *z, *u;        // injected deviates (device copies) or nullptr -> Philox(seed)
-  uint64_t seed;
-  unsigned char *decisions;   // optional instrumentation
-  double *lnl_trace;
-};
-
-struct MhScalars {
-  double sample[DG_MAXIND], theta[DG_MAXIND];
-  double lnl_old, accept;
-  int l, phase, skip, pad;
-  double sed[DG_MAX_BANDS];  // SED of the proposal per band (streaming lnL kernel)
-  double s0[DG_MAX_BANDS];   // SED at the chain's starting point (sufficient statistics)
-};
-
 // log(eval_normal_prior(x, mean, std)), src/dang_util_mod.f90:112-121 + dang_sample_mod.f90:261
 __device__ __forceinline__ double log_normal_prior(double x, double mean, double sd) {
   const double var = sd * sd;
@@ -83,7 +58,7 @@ __device__ __forceinline__ double mh_fast_rcp(double x) {
   return y;
 }
 
-__global__ void __launch_bounds__(DG_MH_THREADS)
+static __global__ void __launch_bounds__(DG_MH_THREADS)
 mh_perpixel_serial_kernel(const ModelView mv, const MhView mh, double *partials, unsigned int *ticket,
                           double *out) {
   extern __shared__ double dyn[];
@@ -440,7 +415,7 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
 // ---------------------------------------------------------------- K4: full-sky chain
 // start of the chain: sample(:) = c%indices(0, map_inds(1), :) (:240-243), broadcast from the
 // rank that owns global pixel 0 (gathered[0..1] of rank 0)
-__global__ void mh_fullsky_init_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
+static __global__ void mh_fullsky_init_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
                                        const double *gathered, int cnt) {
   ms->sample[0] = gathered[0];
   ms->sample[1] = gathered[1];
@@ -460,7 +435,7 @@ __global__ void mh_fullsky_init_kernel(const ModelView mv, const MhView mh, MhSc
 }
 
 // local values of the index maps at this handle's first pixel (rank 0 owns global pixel 0)
-__global__ void mh_first_pixel_kernel(const ModelView mv, const MhView mh, double *out) {
+static __global__ void mh_first_pixel_kernel(const ModelView mv, const MhView mh, double *out) {
   const CompView &cv = mv.comp[mh.ic];
   const size_t kp0 = (size_t)mh.plane[0] * mv.Ppad;
   out[0] = cv.nind > 0 ? cv.idx[0][kp0] : 0.0;
@@ -512,7 +487,7 @@ __device__ __forceinline__ void mh_accept_step(const MhView &mh, MhScalars *ms, 
 
 // streaming mode: consume the sums just reduced (gathered over ranks), decide, propose next.
 // Row layout: [0] chi-square lnL, [1] Jeffreys sum, [2 + 4*j + 2*s + {0,1}] = TNd, TNT (marginal).
-__global__ void mh_fullsky_step_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
+static __global__ void mh_fullsky_step_kernel(const ModelView mv, const MhView mh, MhScalars *ms,
                                        const double *gathered, int nranks, int cnt) {
   if (ms->skip) return;
   double lnl = 0.0;
@@ -549,13 +524,13 @@ __global__ void mh_fullsky_step_kernel(const ModelView mv, const MhView mh, MhSc
 }
 
 // lnl_type 'prior' (:255-257): no chain, the index is drawn from its Gaussian prior
-__global__ void mh_fullsky_prior_draw_kernel(const MhView mh, MhScalars *ms) {
+static __global__ void mh_fullsky_prior_draw_kernel(const MhView mh, MhScalars *ms) {
   ms->sample[mh.nind] = mh.gauss[0] + mh.gauss[1] * mh_draw_z(mh, 0);
   ms->skip = 1;
 }
 
 // D[j][s][Ppad] = data_raw for the sampled planes (streaming mode only)
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 mh_data_kernel(const ModelView mv, const MhView mh, double *D) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride)
@@ -565,7 +540,7 @@ mh_data_kernel(const ModelView mv, const MhView mh, double *D) {
 }
 
 // evaluate_lnL full sky, src/dang_lnl_mod.f90:126-182, for model = amplitude * ms->sed[j]
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 mh_fullsky_lnl_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, const double *D,
                       double *partials, unsigned int *ticket, double *out) {
   if (ms->skip) return;
@@ -605,7 +580,7 @@ mh_fullsky_lnl_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, 
 // evaluate_marginal_lnL full sky (:113-122): per (band, Stokes) the sums over ALL pixels (the
 // source ignores the mask) of TN*data and TN*model, TN = model / rms^2, model = amplitude * sed.
 // out[2 + 4*j + 2*s + {0,1}]; bands in chunks of DG_SUFF_CHUNK.
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 mh_fullsky_marginal_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, const double *D,
                            double *partials, unsigned int *tickets, double *out) {
   if (ms->skip) return;
@@ -652,7 +627,7 @@ mh_fullsky_marginal_kernel(const ModelView mv, const MhView mh, const MhScalars 
 // so that for a proposal with SED s0 + delta:  sum ((data - a s)/sigma)^2 = X - 2 delta Y + delta^2 Z.
 // Expanding about s0 (not about 0) keeps X at the chi-square itself: no cancellation.
 // out[chunk*24 + 3*jj + {0,1,2}]
-__global__ void __launch_bounds__(DG_THREADS)
+static __global__ void __launch_bounds__(DG_THREADS)
 mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, double *partials,
                    unsigned int *tickets, double *out) {
   constexpr int NV = 3 * DG_SUFF_CHUNK;
@@ -698,7 +673,7 @@ mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, dou
 // The whole full-sky chain from the statistics (:282-324), no map traffic.  One warp: lane j owns
 // band j (its statistics, s0 and the proposal's SED), lnL is a fixed-order butterfly over lanes;
 // every lane carries the same chain state, lane 0 publishes it.
-__global__ void __launch_bounds__(32)
+static __global__ void __launch_bounds__(32)
 mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const double *gathered,
                      int nranks, int cnt) {
   const int B = mv.nbands, j = threadIdx.x;
@@ -762,7 +737,7 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
 // blocks of nsample proposals; halve the step if accept/(nsample+1) < 0.4, x1.5 if > 0.6
 // (single-precision literals as in the source), stop when it lands in between.
 // out[0] = tuned step, out[1] = blocks run, out[2] = tuned flag.  Deviate slots: blk*nsample + l.
-__global__ void __launch_bounds__(32)
+static __global__ void __launch_bounds__(32)
 mh_suff_tune_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, const double *gathered,
                     int nranks, int cnt, int max_blocks, double *out) {
   const int B = mv.nbands, j = threadIdx.x;
@@ -833,7 +808,7 @@ mh_suff_tune_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, co
 }
 
 // index_full_res(:, map_inds) = sample(nind) -> c%indices (:329, :483)
-__global__ void mh_fullsky_store_kernel(const ModelView mv, const MhView mh, const MhScalars *ms) {
+static __global__ void mh_fullsky_store_kernel(const ModelView mv, const MhView mh, const MhScalars *ms) {
   const CompView &cv = mv.comp[mh.ic];
   const double v = ms->sample[mh.nind];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
