@@ -203,6 +203,7 @@ def run_gpu(args):
     # chi-square scalars come back synchronously).  All results have landed when the clock stops.
     sampled = [(ic, j) for ic, c in enumerate(cfg.comps) for j, s in enumerate(c.indices) if s.sample]
     single_solve = len(cfg.cg_groups) == 1 and "," not in cfg.cg_groups[0].poltype
+    fs_val = {}
 
     def e2e_step(it):
         if single_solve:
@@ -214,7 +215,12 @@ def run_gpu(args):
             eng.amplitude_async(ic, amp_h[ic])
         eng.sample_spectral_parameters(z=z_h, u=u_h)
         for ic, j in sampled:
-            eng.indices_async(ic, j, idx_h[ic])
+            if cfg.comps[ic].indices[j].region == "fullsky":
+                # the whole plane holds the chain's final sample (dang_sample_mod.f90:329,483): 8 bytes per
+                # plane come back; the host-side assignment c%indices(:,k,nind) = value is the reference's own
+                fs_val[(ic, j)] = (eng.index_fullsky(ic, j, 2), eng.index_fullsky(ic, j, 3))
+            else:
+                eng.indices_async(ic, j, idx_h[ic])
 
     if single_solve:
         eng.stage_eta(eta_h)
@@ -231,8 +237,9 @@ def run_gpu(args):
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(eng.event_elapsed_ms(2, 3), wall_ms))
-    nplanes_out = 2 * len(cfg.comps) + 2 * len(sampled)
-    d2h = 8 * P * nplanes_out + 8 * 8
+    n_pp = sum(1 for ic, j in sampled if cfg.comps[ic].indices[j].region != "fullsky")
+    nplanes_out = 2 * len(cfg.comps) + 2 * n_pp
+    d2h = 8 * P * nplanes_out + 8 * 8 + 16 * (len(sampled) - n_pp)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -268,7 +275,7 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": round(1e3 * ke / e2e_ms, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "what": "per step: injected deviates (eta, z, u) pinned host -> device; changed Q/U planes of every amplitude map and of the sampled index maps + chi-square device -> pinned host; copies overlap compute on dedicated streams"},
+                    "what": "per step: injected deviates (eta, z, u) pinned host -> device; changed Q/U planes of every amplitude map and of the per-pixel-sampled index maps, the value of every full-sky-sampled index (one double per plane) + chi-square device -> pinned host; copies overlap compute on dedicated streams"},
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu:

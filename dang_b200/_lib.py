@@ -42,6 +42,7 @@ SIGNATURES = {
     "dang_gpu_set_indices": (C.c_int, [vp, C.c_int, c_dp]),
     "dang_gpu_get_amplitude": (C.c_int, [vp, C.c_int, c_dp]),
     "dang_gpu_get_indices": (C.c_int, [vp, C.c_int, c_dp]),
+    "dang_gpu_get_index_fullsky": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp]),
     "dang_gpu_get_step_size": (C.c_int, [vp, C.c_int, C.c_int, c_dp]),
     "dang_gpu_set_cg_group": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, c_ip, C.c_int]),
     "dang_gpu_cg_solve": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp, C.c_uint64, c_ip, c_dp]),

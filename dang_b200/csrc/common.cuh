@@ -117,6 +117,7 @@ struct MhScalars {
   int l, phase, skip, pad;
   double sed[DG_MAX_BANDS];  // SED of the proposal per band (streaming lnL kernel)
   double s0[DG_MAX_BANDS];   // SED at the chain's starting point (sufficient statistics)
+  double chisq[2];           // chi-square per sampled plane at the chain's final state (statistics form)
 };
 
 // ---------------------------------------------------------------- SEDs
@@ -306,7 +307,7 @@ enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3, DG_STREAM_TUNE
 // the collective costs one NVLink round trip instead of an NCCL launch.
 // All ranks execute the same sequence of exchanges (they take identical decisions from
 // identical sums), so sequence numbers stay aligned; a rank can lead by at most one exchange.
-#define DG_MAIL_VALS 128
+#define DG_MAIL_VALS 256
 #define DG_MAIL_SLOTS 4
 #define DG_MAX_RANKS 32
 

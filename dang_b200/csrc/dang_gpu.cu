@@ -154,6 +154,25 @@ void gather(dang_gpu *h, int cnt) {
     NCK(g_nccl.AllGather(h->sums_local, h->gathered, cnt, NCCL_DOUBLE, h->comm, h->stream));
   }
 }
+// unmasked pixels over all ranks (compute_chisq's count, src/dang_data_mod.f90:153-161); counted once per
+// upload, the chi-square kernels refresh it as a by-product
+int64_t unmasked_count(dang_gpu *h) {
+  if (h->n_unmasked >= 0) return h->n_unmasked;
+  if (!h->maps_set) fail(DANG_GPU_ESTATE, "dang_gpu_upload_maps has not been called");
+  const int grid = grid_for(h, h->P, DG_THREADS, 4);
+  KTimer kt(h, DANG_K_SCALAR, 0);
+  masked_sum_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->sig, h->mask, h->P, h->partials, h->tickets, h->sums_local);
+  kt.done();
+  gather(h, 4);
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double n = 0;
+  for (int g = 0; g < h->nranks; g++) n += hp[g * 4 + 1];
+  h->n_unmasked = (int64_t)(n + 0.5);
+  return h->n_unmasked;
+}
+
 // ---------------------------------------------------------------- C ABI
 #define API_BEGIN                                   \
   if (!h) return DANG_GPU_EINVAL;                   \
@@ -217,9 +236,9 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaEventCreateWithFlags(&h->ev_idx_dl, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_eta, cudaEventDisableTiming));
     h->grid_cap = h->num_sms * 8;
-    CK(cudaMalloc(&h->partials, (size_t)h->grid_cap * 32 * 4 * sizeof(double)));
-    CK(cudaMalloc(&h->tickets, 16 * sizeof(unsigned int)));
-    CK(cudaMemset(h->tickets, 0, 16 * sizeof(unsigned int)));
+    CK(cudaMalloc(&h->partials, (size_t)h->grid_cap * GATHER_MAX * sizeof(double)));
+    CK(cudaMalloc(&h->tickets, 32 * sizeof(unsigned int)));
+    CK(cudaMemset(h->tickets, 0, 32 * sizeof(unsigned int)));
     CK(cudaMalloc(&h->sums_local, GATHER_MAX * sizeof(double)));
     CK(cudaMalloc(&h->gathered_buf, (size_t)GATHER_MAX * 64 * sizeof(double)));
     h->gathered = h->sums_local;  // single rank: no exchange
@@ -257,7 +276,7 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
   dfree(h->decisions); dfree(h->lnl_trace); dfree(h->stage); dfree(h->partials); dfree(h->tickets);
   dfree(h->sums_local); dfree(h->gathered_buf); dfree(h->cg_scalars); dfree(h->mh_scalars); dfree(h->tab);
-  dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo);
+  dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo); dfree(h->stat_buf);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -283,6 +302,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
     case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
     case DANG_OPT_TMA: h->use_tma = value != 0; break;
+    case DANG_OPT_STAT_CACHE: h->stat_cache = value != 0; h->stat_valid = false; h->chisq_valid = false; break;
     case DANG_OPT_CG_CHECKPOINT:
       h->cg_ckpt = value < 0 ? 0 : (value > DG_CG_MAXM ? DG_CG_MAXM : (int)value);
       break;
@@ -315,6 +335,8 @@ int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]) 
   if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) fail(DANG_GPU_EINVAL, "bad rank %d of %d", rank, nranks);
   h->nranks = nranks;
   h->rank = rank;
+  h->n_unmasked = -1;
+  touch(h);
   h->gathered = nranks > 1 ? h->gathered_buf : h->sums_local;
   if (nranks > 1) {
     nccl_load();
@@ -397,6 +419,7 @@ int dang_gpu_set_gain_offset(dang_gpu_t *h, const double *gain, const double *of
     if (gain) h->gain[j] = gain[j];
     if (offset) h->offset[j] = offset[j];
   }
+  touch(h);
   API_END
 }
 
@@ -427,6 +450,8 @@ int dang_gpu_upload_maps(dang_gpu_t *h, const double *sig_map, const double *rms
   }
   CK(cudaStreamSynchronize(h->stream));
   h->maps_set = true;
+  h->n_unmasked = -1;
+  touch(h);
   API_END
 }
 
@@ -446,6 +471,8 @@ int dang_gpu_share_maps(dang_gpu_t *h, dang_gpu_t *src) {
   }
   h->maps_borrowed = true;
   h->maps_set = true;
+  h->n_unmasked = -1;
+  touch(h);
   API_END
 }
 
@@ -484,6 +511,7 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   CK(cudaStreamSynchronize(h->stream));
   h->bp_dirty = true;
   h->tab_dirty = true;
+  touch(h);
   for (int k = 0; k < 3; k++)
     for (int l = 0; l < DG_MAXIND; l++) h->check_mask |= 1ull << ((ic * 3 + k) * DG_MAXIND + l);
   API_END
@@ -510,6 +538,7 @@ int dang_gpu_set_index(dang_gpu_t *h, int ic, int nind, int sample_index, int in
   ix.sample_nside = sample_nside;
   ix.nflag = nflag;
   for (int k = 0; k < nflag; k++) ix.pol_flag[k] = pol_flags[k];
+  touch(h);
   API_END
 }
 
@@ -518,6 +547,7 @@ int dang_gpu_set_amplitude(dang_gpu_t *h, int ic, const double *amplitude) {
   if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !amplitude) fail(DANG_GPU_EINVAL, "bad component %d", ic);
   h2d_planes(h, h->comp[ic].amp, amplitude, h->nmaps);
   CK(cudaStreamSynchronize(h->stream));
+  touch(h);
   API_END
 }
 
@@ -528,6 +558,7 @@ int dang_gpu_set_indices(dang_gpu_t *h, int ic, const double *indices) {
     h2d_planes(h, h->comp[ic].idx[l], indices + (size_t)l * h->nmaps * h->npix, h->nmaps);
   CK(cudaStreamSynchronize(h->stream));
   h->tab_dirty = true;
+  touch(h);
   for (int k = 0; k < 3; k++)
     for (int l = 0; l < DG_MAXIND; l++) h->check_mask |= 1ull << ((ic * 3 + k) * DG_MAXIND + l);
   API_END
@@ -547,6 +578,21 @@ int dang_gpu_get_indices(dang_gpu_t *h, int ic, double *indices) {
   for (int l = 0; l < h->comp[ic].nind; l++)
     d2h_planes(h, indices + (size_t)l * h->nmaps * h->npix, h->comp[ic].idx[l], h->nmaps);
   CK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int dang_gpu_get_index_fullsky(dang_gpu_t *h, int ic, int nind, int map_n, double *value) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || nind < 0 || nind >= h->comp[ic].nind || map_n < 1 ||
+      map_n > h->nmaps || !value)
+    fail(DANG_GPU_EINVAL, "bad component/index/map %d/%d/%d", ic, nind, map_n);
+  model_view(h);  // refreshes the uniformity flags
+  if (h->nonuni_host[ic * 3 + (map_n - 1)][nind] != 0)
+    fail(DANG_GPU_ESTATE, "plane %d of index %d of component %d is not constant", map_n, nind, ic);
+  CK(cudaMemcpyAsync(h->pinned, h->comp[ic].idx[nind] + (size_t)(map_n - 1) * h->Ppad, sizeof(double),
+                     cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *value = *(double *)h->pinned;
   API_END
 }
 
@@ -581,6 +627,7 @@ int dang_gpu_set_cg_group(dang_gpu_t *h, int cg_group, int i_max, double converg
 int dang_gpu_cg_solve(dang_gpu_t *h, int cg_group, int flag_n, int ml_mode, const double *eta,
                       uint64_t seed, int *n_iter, double *delta_final) {
   API_BEGIN
+  touch(h, 1);  // also when the solve fails half way: the amplitudes may have changed
   cg_solve(h, cg_group, flag_n, ml_mode, eta, seed, n_iter, delta_final);
   API_END
 }
@@ -617,8 +664,12 @@ int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsampl
     CK(cudaStreamWaitEvent(h->stream, h->ev_idx_dl, 0));
     h->idx_dl_pending = false;
   }
-  if (perpix) sample_perpixel(h, mh, z, u, seed, accept);
-  else sample_fullsky(h, mh, z, u, seed, accept);
+  if (perpix) {
+    touch(h, 2);
+    sample_perpixel(h, mh, z, u, seed, accept);
+  } else {
+    sample_fullsky(h, mh, z, u, seed, accept);  // bumps the version itself (after using the cache)
+  }
   // the written planes are varying after a per-pixel draw (masked pixels are zeroed, so even a
   // chain that never moved leaves a non-constant plane unless nothing is masked -- treating it as
   // varying is always safe) and constant after a full-sky draw
@@ -788,6 +839,7 @@ int dang_gpu_fit_band_gain(dang_gpu_t *h, int map_n, int band, int ml_mode, cons
     g = mu + sigma * (0.0 + 1.0 * zz);  // rand_normal(0,1), :615
   }
   h->gain[band] = g;             // ddata%gain(band) = gain, :619
+  touch(h);
   if (gain) *gain = g;
   API_END
 }

@@ -79,6 +79,7 @@ struct IndexHost {
   int sample_index = 0, index_mode = DANG_INDEX_PERPIXEL, lnl_type = 0, prior_type = 0;
   double gauss[2] = {0, 1}, uni[2] = {-1e300, 1e300}, step = 0;
   int sample_nside = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
+  double last_value = 0;  // value left by the last full-sky draw (the whole plane holds it)
 };
 
 struct CompHost {
@@ -106,7 +107,7 @@ struct KStat {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
-const int GATHER_MAX = 128;  // doubles per rank in one scalar exchange
+const int GATHER_MAX = 256;  // doubles per rank in one scalar exchange
 
 struct dang_gpu {
   int device = 0, nside = 0, nmaps = 0, nbands = 0, ncomp = 0, num_sms = 0;
@@ -156,6 +157,23 @@ struct dang_gpu {
   MhScalars *mh_scalars = nullptr;
   void *pinned = nullptr;  // small pinned buffer for scalar read-back
   std::vector<double> last_trace;
+
+  // statistics cache (DESIGN.md "One statistics pass per Gibbs iteration"): `version` counts changes of
+  // the model state (amplitudes, indices, maps, gains).  The per-plane sufficient statistics of the
+  // next full-sky draw, gathered when compute_chisq is asked for right after an amplitude draw, serve
+  // that chi-square, the draw itself and the chi-square after it.
+  int stat_cache = 1;            // DANG_OPT_STAT_CACHE
+  uint64_t version = 1;
+  int last_mutation = 0;         // 1: amplitude draw, 2: spectral-parameter draw, 0: anything else
+  bool stat_valid = false;
+  int stat_ic = -1, stat_nind = -1, stat_S = 0, stat_plane[2] = {0, 0}, stat_cnt = 0;
+  uint64_t stat_version = 0;
+  double *stat_buf = nullptr;    // [nranks][stat_cnt] gathered statistics
+  bool chisq_valid = false;
+  uint64_t chisq_version = 0;
+  int chisq_lo = 0, chisq_hi = 0;
+  double chisq_vals[4] = {0, 0, 0, 0};
+  int64_t n_unmasked = -1;       // all ranks; -1: not counted yet
 
   // comm
   int nranks = 1, rank = 0;
@@ -299,6 +317,13 @@ inline bool comp_uniform(const dang_gpu *h, int c, int k) { return h->uni_host[c
 // ---------------------------------------------------------------- entry points of the other translation units
 void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *eta, uint64_t seed,
               int *n_iter, double *delta_final);                                   // host_cg.cu
+int64_t unmasked_count(dang_gpu *h);  // dang_gpu.cu: unmasked pixels over all ranks (cached)
+inline void touch(dang_gpu *h, int what = 0) {  // the model state changed
+  h->version++;
+  h->last_mutation = what;
+}
+// host_mh_fs.cu: serve compute_chisq from the sufficient statistics of the upcoming full-sky draw
+bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]);
 void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, double *chi_map,
                double out4[4]);                                                    // host_data.cu
 void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode, MhView &mh);  // host_mh_fs.cu

@@ -14,6 +14,15 @@ void launch_chisq(dang_gpu *h, const ModelView &mv, const ChisqView &cv, int) {
 void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, double *chi_map,
                double out4[4]) {
   if (pol_lo < 1 || pol_hi > h->nmaps || pol_lo > pol_hi) fail(DANG_GPU_EINVAL, "bad pol_type range %d..%d", pol_lo, pol_hi);
+  if (!sky && !res && !chi_map && h->stat_cache) {
+    if (h->chisq_valid && h->chisq_version == h->version && h->chisq_lo == pol_lo && h->chisq_hi == pol_hi) {
+      // the full-sky draw that produced the current state left its chi-square behind
+      for (int k = 0; k < 3; k++) out4[k] = h->chisq_vals[k];
+      out4[3] = (double)unmasked_count(h);
+      return;
+    }
+    if (chisq_from_statistics(h, pol_lo, pol_hi, out4)) return;
+  }
   ModelView mv = model_view(h);
   ChisqView cv;
   cv.k_lo = pol_lo - 1;
@@ -61,4 +70,5 @@ void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, do
     out4[i] = 0.0;
     for (int g = 0; g < h->nranks; g++) out4[i] += hp[g * 4 + i];
   }
+  h->n_unmasked = (int64_t)(out4[3] + 0.5);
 }

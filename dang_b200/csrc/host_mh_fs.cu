@@ -75,7 +75,8 @@ int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
   if (h->fullsky_stream) return 0;
   const double n_el = (double)mh.S * h->P;
   const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
-  const int cnt = nchunk * 3 * DG_SUFF_CHUNK;
+  const int cnt = mh.S * nchunk * 3 * DG_SUFF_CHUNK;  // per plane, per band chunk: X, Y, Z
+  if (cnt > GATHER_MAX) fail(DANG_GPU_EUNSUPPORTED, "sufficient statistics of %d bands x %d planes", h->nbands, mh.S);
   KTimer kt(h, DANG_K_MH_SUFFSTAT, bytes_w(n_el * (2.0 * h->nbands + h->ncomp)));
   bool uni = h->ncomp <= 4;
   for (int s = 0; s < mh.S && uni; s++)
@@ -91,7 +92,24 @@ int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
   }
   kt.done();
   gather(h, cnt);
+  // keep the gathered rows: they serve this draw, and the chi-square before and after it
+  if (!h->stat_buf) CK(cudaMalloc(&h->stat_buf, (size_t)GATHER_MAX * DG_MAX_RANKS * sizeof(double)));
+  CK(cudaMemcpyAsync(h->stat_buf, h->gathered, (size_t)h->nranks * cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->stat_valid = true;
+  h->stat_ic = mh.ic;
+  h->stat_nind = mh.nind;
+  h->stat_S = mh.S;
+  h->stat_plane[0] = mh.plane[0];
+  h->stat_plane[1] = mh.plane[1];
+  h->stat_cnt = cnt;
+  h->stat_version = h->version;
   return cnt;
+}
+
+bool stat_cache_hit(const dang_gpu *h, const MhView &mh) {
+  return h->stat_cache && h->stat_valid && h->stat_version == h->version && h->stat_ic == mh.ic &&
+         h->stat_nind == mh.nind && h->stat_S == mh.S && h->stat_plane[0] == mh.plane[0] &&
+         h->stat_plane[1] == mh.plane[1];
 }
 
 // the sufficient-statistics form covers the chisq likelihood with uniform / Gaussian prior; the
@@ -134,7 +152,10 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
   h->dec_mode = 1;
   h->dec_nsample = mh.nsample;
 
-  const int cnt = fullsky_statistics(h, mv, mh);
+  // statistics gathered by the chi-square call that preceded this draw are still valid when the
+  // model state has not changed since (same chain start, same data)
+  const bool reuse = !h->fullsky_stream && stat_cache_hit(h, mh);
+  const int cnt = reuse ? h->stat_cnt : fullsky_statistics(h, mv, mh);
   const double n_el = (double)mh.S * h->P;
   if (h->fullsky_stream) {
     const size_t dl = (size_t)h->nbands * mh.S * h->Ppad;
@@ -174,7 +195,7 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
     }
   } else {
     KTimer ks(h, DANG_K_SCALAR, 0);
-    mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
+    mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->stat_buf, h->nranks, cnt);
     ks.done();
   }
   {
@@ -187,6 +208,68 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
   CK(cudaMemcpyAsync(hs, h->mh_scalars, sizeof(MhScalars), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (accept) *accept = hs->accept;
+  h->comp[mh.ic].index[mh.nind].last_value = hs->sample[mh.nind];
+  touch(h, 2);
+  h->stat_valid = false;
+  if (!h->fullsky_stream && h->stat_cache) {  // chi-square of the new state, from the statistics
+    h->chisq_valid = true;
+    h->chisq_version = h->version;
+    h->chisq_lo = mh.plane[0] + 1;
+    h->chisq_hi = mh.plane[mh.S - 1] + 1;
+    for (int k = 0; k < 4; k++) h->chisq_vals[k] = 0.0;
+    for (int sI = 0; sI < mh.S; sI++) h->chisq_vals[mh.plane[sI]] = hs->chisq[sI];
+  }
+}
+
+// compute_chisq right after an amplitude draw, when the next call in sample_spectral_parameters'
+// order (components -> indices -> pol flags, src/dang_sample_mod.f90:39-74) is a full-sky draw with
+// the chisq likelihood over the same planes: gather that draw's per-plane statistics now.  X_j is
+// the chi-square term of band j about the current state, so chisq_planes = sum_j X_j / nbands, and
+// the draw that follows (and the chi-square after it) need no further pass over the maps.
+bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]) {
+  if (!h->stat_cache || h->fullsky_stream || h->last_mutation != 1) return false;
+  int ic = -1, nind = -1;
+  for (int c = 0; c < h->ncomp && ic < 0; c++)
+    for (int l = 0; l < h->comp[c].nind && ic < 0; l++)
+      if (h->comp[c].set && h->comp[c].index[l].sample_index && h->comp[c].index[l].nflag > 0) {
+        ic = c;
+        nind = l;
+      }
+  if (ic < 0) return false;
+  const IndexHost &ix = h->comp[ic].index[nind];
+  if (ix.index_mode != DANG_INDEX_FULLSKY || ix.sample_nside != h->nside) return false;
+  const int flag = ix.pol_flag[0];
+  const int map_n = (flag & 8) ? -1 : (flag & 1) ? 1 : (flag & 2) ? 2 : (flag & 4) ? 3 : 0;
+  if (map_n == 0) return false;
+  MhView mh;
+  try {
+    mh_view(h, ic, nind, map_n, 0, DANG_ML_SAMPLE, mh);
+  } catch (const DgError &) {
+    return false;  // the draw itself will report what is wrong with it
+  }
+  if (fullsky_needs_stream(mh)) return false;
+  if (mh.plane[0] != pol_lo - 1 || mh.plane[mh.S - 1] != pol_hi - 1 || pol_hi - pol_lo + 1 != mh.S) return false;
+  ModelView mv = model_view(h);
+  const int64_t n_unmasked = unmasked_count(h);
+  int cnt = h->stat_cnt;
+  if (!stat_cache_hit(h, mh)) cnt = fullsky_statistics(h, mv, mh);
+  double *hp = (double *)h->pinned;
+  CK(cudaMemcpyAsync(hp, h->stat_buf, (size_t)h->nranks * cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int B = h->nbands, nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  for (int k = 0; k < 4; k++) out4[k] = 0.0;
+  for (int s = 0; s < mh.S; s++) {
+    double tot = 0.0;
+    for (int j = 0; j < B; j++) {
+      const int o = (s * nchunk + j / DG_SUFF_CHUNK) * 3 * DG_SUFF_CHUNK + 3 * (j % DG_SUFF_CHUNK);
+      double X = 0.0;
+      for (int g = 0; g < h->nranks; g++) X += hp[(size_t)g * cnt + o];  // rank order: same bits on every rank
+      tot += X / (double)B;
+    }
+    out4[mh.plane[s]] = tot;
+  }
+  out4[3] = (double)n_unmasked;
+  return true;
 }
 
 void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
@@ -207,10 +290,10 @@ void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, co
     throw;
   }
   h->fullsky_stream = saved_stream;
-  double *d_out = h->sums_local + 100;  // scratch beyond the statistics rows
+  double *d_out = h->sums_local + GATHER_MAX - 4;  // scratch beyond the statistics rows
   {
     KTimer ks(h, DANG_K_SCALAR, 0);
-    mh_suff_tune_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt, max_blocks, d_out);
+    mh_suff_tune_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->stat_buf, h->nranks, cnt, max_blocks, d_out);
     ks.done();
   }
   double *hp = (double *)h->pinned;

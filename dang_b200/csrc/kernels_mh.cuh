@@ -626,7 +626,7 @@ mh_fullsky_marginal_kernel(const ModelView mv, const MhView mh, const MhScalars 
 //   X_j = sum t^2,  Y_j = sum t u,  Z_j = sum u^2      (unmasked pixels, sampled planes)
 // so that for a proposal with SED s0 + delta:  sum ((data - a s)/sigma)^2 = X - 2 delta Y + delta^2 Z.
 // Expanding about s0 (not about 0) keeps X at the chi-square itself: no cancellation.
-// out[chunk*24 + 3*jj + {0,1,2}]
+// out[(s*nchunk + chunk)*12 + 3*jj + {0,1,2}]: per plane s, bands in chunks of DG_SUFF_CHUNK
 static __global__ void __launch_bounds__(DG_THREADS)
 mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, double *partials,
                    unsigned int *tickets, double *out) {
@@ -635,6 +635,7 @@ mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, dou
   const CompView &cv = mv.comp[mh.ic];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int nchunk = (mv.nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  for (int s = 0; s < mh.S; s++)
   for (int ch = 0; ch < nchunk; ch++) {
     double acc[NV];
 #pragma unroll
@@ -645,27 +646,26 @@ mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, dou
       const int j = ch * DG_SUFF_CHUNK + jj;
       s0[jj] = j < mv.nbands ? ms->s0[j] : 0.0;
     }
+    const int k = mh.plane[s];
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
       if (!mv.mask[p]) continue;
-      for (int s = 0; s < mh.S; s++) {
-        const int k = mh.plane[s];
-        const double a = cv.amp[(size_t)k * mv.Ppad + p];
+      const double a = cv.amp[(size_t)k * mv.Ppad + p];
 #pragma unroll
-        for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
-          const int j = ch * DG_SUFF_CHUNK + jj;
-          if (j < mv.nbands) {
-            const double d = mh_data_value(mv, mh.ic, j, k, p);
-            const double rms = ldg_stream(mv.rms + plane_off(mv, j, k) + p);
-            const double t = (d - a * s0[jj]) / rms;
-            const double u = a / rms;
-            acc[3 * jj + 0] += t * t;
-            acc[3 * jj + 1] += t * u;
-            acc[3 * jj + 2] += u * u;
-          }
+      for (int jj = 0; jj < DG_SUFF_CHUNK; jj++) {
+        const int j = ch * DG_SUFF_CHUNK + jj;
+        if (j < mv.nbands) {
+          const double d = mh_data_value(mv, mh.ic, j, k, p);
+          const double rms = ldg_stream(mv.rms + plane_off(mv, j, k) + p);
+          const double t = (d - a * s0[jj]) / rms;
+          const double u = a / rms;
+          acc[3 * jj + 0] += t * t;
+          acc[3 * jj + 1] += t * u;
+          acc[3 * jj + 2] += u * u;
         }
       }
     }
-    grid_reduce<NV>(acc, smem, partials + (size_t)ch * NV * gridDim.x, tickets + ch, out + ch * NV);
+    const int sc = s * nchunk + ch;
+    grid_reduce<NV>(acc, smem, partials + (size_t)sc * NV * gridDim.x, tickets + sc, out + sc * NV);
     __syncthreads();
   }
 }
@@ -678,11 +678,20 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
                      int nranks, int cnt) {
   const int B = mv.nbands, j = threadIdx.x;
   double X = 0.0, Y = 0.0, Z = 0.0, s0 = 0.0;
+  double Xk[2] = {0.0, 0.0}, Yk[2] = {0.0, 0.0}, Zk[2] = {0.0, 0.0};  // per plane, summed over ranks in rank order
   if (j < B) {
-    for (int g = 0; g < nranks; g++) {
-      X += gathered[g * cnt + 3 * j + 0];
-      Y += gathered[g * cnt + 3 * j + 1];
-      Z += gathered[g * cnt + 3 * j + 2];
+    const int nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+    const int o = (j / DG_SUFF_CHUNK) * 3 * DG_SUFF_CHUNK + 3 * (j % DG_SUFF_CHUNK);
+    for (int s = 0; s < mh.S; s++) {
+      for (int g = 0; g < nranks; g++) {
+        const double *row = gathered + (size_t)g * cnt + (size_t)s * nchunk * 3 * DG_SUFF_CHUNK + o;
+        Xk[s] += row[0];
+        Yk[s] += row[1];
+        Zk[s] += row[2];
+      }
+      X += Xk[s];
+      Y += Yk[s];
+      Z += Zk[s];
     }
     s0 = ms->s0[j];
   }
@@ -722,6 +731,20 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
       if (mh.decisions) mh.decisions[l] = acc ? 1 : 0;
     }
   }
+  // chi-square of the final state per plane, from the same statistics (what compute_chisq would
+  // sum after the draw: sum_j sum_pix ((d - sky)/sigma)^2 / nbands, src/dang_data_mod.f90:514-523)
+  double chi[2] = {0.0, 0.0};
+  {
+    const double sed = (j < B) ? sed_theta(mv, mh.ic, j, sample[0], sample[1]) : 0.0;
+    const double dl = sed - s0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      double v = (j < B && s < mh.S) ? (Xk[s] - 2.0 * dl * Yk[s] + dl * dl * Zk[s]) / (double)B : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      chi[s] = v;
+    }
+  }
   if (j == 0) {
     ms->sample[0] = sample[0];
     ms->sample[1] = sample[1];
@@ -730,6 +753,8 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
     ms->l = mh.nsample;
     ms->phase = 1;
     ms->skip = 1;
+    ms->chisq[0] = chi[0];
+    ms->chisq[1] = chi[1];
   }
 }
 
@@ -742,11 +767,20 @@ mh_suff_tune_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, co
                     int nranks, int cnt, int max_blocks, double *out) {
   const int B = mv.nbands, j = threadIdx.x;
   double X = 0.0, Y = 0.0, Z = 0.0, s0 = 0.0;
+  double Xk[2] = {0.0, 0.0}, Yk[2] = {0.0, 0.0}, Zk[2] = {0.0, 0.0};  // per plane, summed over ranks in rank order
   if (j < B) {
-    for (int g = 0; g < nranks; g++) {
-      X += gathered[g * cnt + 3 * j + 0];
-      Y += gathered[g * cnt + 3 * j + 1];
-      Z += gathered[g * cnt + 3 * j + 2];
+    const int nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+    const int o = (j / DG_SUFF_CHUNK) * 3 * DG_SUFF_CHUNK + 3 * (j % DG_SUFF_CHUNK);
+    for (int s = 0; s < mh.S; s++) {
+      for (int g = 0; g < nranks; g++) {
+        const double *row = gathered + (size_t)g * cnt + (size_t)s * nchunk * 3 * DG_SUFF_CHUNK + o;
+        Xk[s] += row[0];
+        Yk[s] += row[1];
+        Zk[s] += row[2];
+      }
+      X += Xk[s];
+      Y += Yk[s];
+      Z += Zk[s];
     }
     s0 = ms->s0[j];
   }

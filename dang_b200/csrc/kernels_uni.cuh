@@ -378,17 +378,20 @@ mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms,
   const int64_t n2 = mv.Ppad / 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  // one sweep per (plane, band chunk): the statistics are kept per plane so that the chi-square of
+  // compute_chisq (per plane) can be formed from them as well (DESIGN.md "statistics cache")
+  for (int s = 0; s < mh.S; s++)
   for (int ch = 0; ch < nchunk; ch++) {
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    const int k = mh.plane[s];
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
       const int64_t p = 2 * e;
       const uchar2 mk = *reinterpret_cast<const uchar2 *>(mv.mask + p);
       const bool use0 = mk.x != 0, use1 = mk.y != 0;
       if (!use0 && !use1) continue;
-      for (int s = 0; s < mh.S; s++) {
-        const int k = mh.plane[s];
+      {
         double2 a[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++)
@@ -430,7 +433,8 @@ mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms,
         }
       }
     }
-    grid_reduce<NV>(acc, smem, partials + (size_t)ch * NV * gridDim.x, tickets + ch, out + ch * NV);
+    const int sc = s * nchunk + ch;
+    grid_reduce<NV>(acc, smem, partials + (size_t)sc * NV * gridDim.x, tickets + sc, out + sc * NV);
     __syncthreads();
   }
 }

@@ -28,6 +28,7 @@ OPT_FIX_SAMPLE_VECTOR, OPT_CG_TWO_PASS, OPT_FULLSKY_STREAM, OPT_PROFILE, OPT_CG_
 OPT_PERPIXEL_SERIAL = 7
 OPT_CG_CHECKPOINT = 8
 OPT_TMA = 9
+OPT_STAT_CACHE = 10
 KERNEL_COUNT = 12
 
 
@@ -172,6 +173,12 @@ class Engine:
     def stage_eta(self, eta: np.ndarray, nplanes: int = 2):
         """Upload the next cg_solve's normals in the background; call that solve with eta=None."""
         self._ck(self.lib.dang_gpu_stage_eta(self.h, _dp(eta), nplanes))
+
+    def index_fullsky(self, ic: int, nind: int, map_n: int) -> float:
+        """The value the whole plane holds after a full-sky draw (8 bytes instead of a map download)."""
+        v = C.c_double()
+        self._ck(self.lib.dang_gpu_get_index_fullsky(self.h, ic, nind, map_n, C.byref(v)))
+        return v.value
 
     def set_amplitude(self, ic: int, amp: np.ndarray):
         self._ck(self.lib.dang_gpu_set_amplitude(self.h, ic, _dp(np.ascontiguousarray(amp, dtype=np.float64))))

@@ -150,6 +150,13 @@ module dang_gpu_mod
        integer(c_int), value :: ic, nind, map_n
        real(c_double) :: mean
      end function dang_gpu_index_mean
+     integer(c_int) function dang_gpu_get_index_fullsky(h, ic, nind, map_n, value) &
+          bind(C, name='dang_gpu_get_index_fullsky')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic, nind, map_n
+       real(c_double) :: value
+     end function dang_gpu_get_index_fullsky
   end interface
 
 contains
@@ -396,6 +403,26 @@ contains
        if (c%nindices > 0) call gpu_check(dang_gpu_get_indices(handle, int(i-1,c_int), c%indices), 'get_indices')
     end do
   end subroutine dang_gpu_download_components
+
+  subroutine dang_gpu_download_fullsky_index(c, ic, nind, map_n)
+    ! After a full-sky draw the whole plane holds one value (dang_sample_mod.f90:329,483): fetch the
+    ! 8 bytes and do the reference's own assignment on the host instead of downloading the map.
+    type(dang_comps), pointer, intent(inout) :: c
+    integer(i4b),              intent(in)    :: ic, nind, map_n
+    real(c_double) :: value
+    integer(i4b)   :: k
+    if (map_n == -1) then
+       do k = 2, 3
+          call gpu_check(dang_gpu_get_index_fullsky(handle, int(ic-1,c_int), int(nind-1,c_int), int(k,c_int), value), &
+               'get_index_fullsky')
+          c%indices(:,k,nind) = value
+       end do
+    else
+       call gpu_check(dang_gpu_get_index_fullsky(handle, int(ic-1,c_int), int(nind-1,c_int), int(map_n,c_int), value), &
+            'get_index_fullsky')
+       c%indices(:,map_n,nind) = value
+    end if
+  end subroutine dang_gpu_download_fullsky_index
 
   subroutine dang_gpu_download_sky_model(ddata)
     ! sky_model / res_map / chi_map <- device, only when write_maps is due (dang.f90:119-121)

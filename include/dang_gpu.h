@@ -85,7 +85,12 @@ enum {
   /* 1: K1 streams sig/rms through a shared-memory ring filled by the TMA bulk-copy engine
    * (cp.async.bulk + mbarrier) when all SEDs are tabulated; 0 (default): 16-byte LDG loads, which
    * measured faster (285 vs 313 us at nside 512: K1 is issue-bound, not load-bound). */
-  DANG_OPT_TMA = 9
+  DANG_OPT_TMA = 9,
+  /* 1 (default): dang_gpu_chisq called right after an amplitude draw gathers the per-plane sufficient
+   * statistics of the full-sky draw that follows (when the next index in sample_spectral_parameters'
+   * order is a full-sky chisq draw over the same planes); that chi-square, the draw, and the chi-square
+   * after the draw are then all served by ONE pass over the maps.  0: every call streams the maps. */
+  DANG_OPT_STAT_CACHE = 10
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
@@ -138,6 +143,10 @@ int dang_gpu_set_amplitude(dang_gpu_t *h, int ic, const double *amplitude);
 int dang_gpu_set_indices(dang_gpu_t *h, int ic, const double *indices);
 int dang_gpu_get_amplitude(dang_gpu_t *h, int ic, double *amplitude); /* -> c%amplitude */
 int dang_gpu_get_indices(dang_gpu_t *h, int ic, double *indices);     /* -> c%indices   */
+/* The value every pixel of plane map_n of c%indices(:,:,nind) holds after a full-sky draw (the reference
+ * assigns the chain's final sample to the whole plane, src/dang_sample_mod.f90:329,483): 8 bytes instead of
+ * a map download; the shim fills c%indices(:,map_n,nind) with it.  DANG_GPU_ESTATE if the plane varies. */
+int dang_gpu_get_index_fullsky(dang_gpu_t *h, int ic, int nind, int map_n, double *value);
 int dang_gpu_get_step_size(dang_gpu_t *h, int ic, int nind, double *step_size);
 
 /* ---- cg_groups(i): constructor_cg, src/dang_cg_mod.f90:57-120 ---- */

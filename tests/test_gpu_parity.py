@@ -426,6 +426,86 @@ def test_full_gibbs_chain_c1():
             assert rel_err(eng.amplitude(ic), ora.amplitude(ic)) < TOL
             assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-13
 
+@pytest.mark.parametrize("nside,name", [(16, "c2"), (8, "c2")])
+def test_full_gibbs_chain_c2_one_statistics_pass(nside, name):
+    """Gibbs iterations of the headline config (CG amplitudes + full-sky beta_d): the chi-square after
+    the amplitude draw, the full-sky draw and the chi-square after it are served by ONE pass over the
+    maps (statistics cache); everything still follows the oracle, and the uncached path agrees."""
+    from dang_b200.engine import OPT_STAT_CACHE, Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case(name, nside, perturb=False)
+    ora, eng, plain = Oracle(cfg, sky), Engine(cfg, sky), Engine(cfg, sky)
+    plain.set_option(OPT_STAT_CACHE, 0)
+    rng = np.random.default_rng(5)
+    nsample = cfg.nsample
+    ic = [i for i, c in enumerate(cfg.comps) if any(s.sample for s in c.indices)][0]
+    for it in range(1, 5):
+        eta = rng.standard_normal(2 * cfg.npix)
+        its_o, _ = ora.sample_cg_group(0, 1, eta)
+        chisq_o, planes_o = ora.compute_chisq()
+        n0 = eng.launch_count(reset=True)
+        r = eng.sample_cg_groups(eta=eta)
+        rp = plain.sample_cg_groups(eta=eta)
+        assert r[0][0] == its_o[0] == rp[0][0]
+        assert abs(r[1] - chisq_o) <= TOL * chisq_o
+        assert abs(rp[1] - chisq_o) <= TOL * chisq_o
+        assert abs(r[1] - rp[1]) <= 1e-13 * chisq_o
+        if it > 1:
+            z, u = rng.standard_normal(nsample * cfg.npix), rng.random(nsample * cfg.npix)
+            acc_o = ora.sample_spectral_parameters(nsample, 1, z, u)
+            eng.kernel_stats(reset=True)
+            acc, chisq_g = eng.sample_spectral_parameters(nsample=nsample, z=z, u=u)
+            st = eng.kernel_stats()
+            # no pass over the maps at all in this block: the statistics were gathered by the chi-square call
+            assert st["mh_suffstat_kernel"]["launches"] == 0 and st["chisq_kernel"]["launches"] == 0, st
+            accp, chisq_p = plain.sample_spectral_parameters(nsample=nsample, z=z, u=u)
+            chisq_o, _ = ora.compute_chisq()
+            assert acc == accp
+            assert abs(chisq_g - chisq_o) <= TOL * chisq_o
+            assert abs(chisq_p - chisq_o) <= TOL * chisq_o
+            dec_g, lnl_g = eng.decisions(nsample, fullsky=True)
+            dec_p, lnl_p = plain.decisions(nsample, fullsky=True)
+            assert np.array_equal(dec_g, dec_p)
+            assert eng.index_fullsky(ic, 0, 2) == ora.indices(ic)[0, 1, 0] == eng.index_fullsky(ic, 0, 3)
+        for i2 in range(2):
+            assert rel_err(eng.amplitude(i2), ora.amplitude(i2)) < TOL
+            assert rel_err(eng.indices(i2), ora.indices(i2)) < 1e-13
+
+
+def test_statistics_cache_is_invalidated_by_state_changes():
+    """A chi-square served from cached statistics must never survive a change of the model state."""
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c2", 8, perturb=False)
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    rng = np.random.default_rng(6)
+    eta = rng.standard_normal(2 * cfg.npix)
+    ora.sample_cg_group(0, 1, eta)
+    eng.sample_cg_groups(eta=eta, stats=False)
+    c1 = eng.compute_chisq()          # gathers the statistics of the coming beta_d draw
+    assert abs(c1 - ora.compute_chisq()[0]) <= TOL * c1
+    assert eng.compute_chisq() == c1  # served again (cache or kernel), same state
+    amp = eng.amplitude(0)
+    amp[1] *= 1.5
+    eng.set_amplitude(0, amp)
+    ora.amplitude(0)[:] = amp
+    ora.update_sky_model()
+    c2 = eng.compute_chisq()
+    assert abs(c2 - ora.compute_chisq()[0]) <= TOL * c2 and abs(c2 - c1) > 1e-3 * c1
+    # a draw after the change uses fresh statistics
+    nsample = 12
+    z, u = rng.standard_normal(nsample * cfg.npix), rng.random(nsample * cfg.npix)
+    ora.sample_spectral_parameters(nsample, 1, z, u)
+    acc, c3 = eng.sample_spectral_parameters(nsample=nsample, z=z, u=u)
+    assert abs(c3 - ora.compute_chisq()[0]) <= TOL * c3
+    idx = eng.indices(1)
+    idx[0] += 0.01
+    eng.set_indices(1, idx)
+    ora.indices(1)[:] = idx
+    ora.update_sky_model()
+    c4 = eng.compute_chisq()
+    assert abs(c4 - ora.compute_chisq()[0]) <= TOL * c4
+
 
 def test_freefree_lognormal_cmb_components():
     """The remaining diffuse SED types (evaluate_freefree :1001-1040, evaluate_lognormal :960-999,
