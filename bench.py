@@ -207,8 +207,8 @@ def run_gpu(args):
 
     def e2e_step(it):
         if single_solve:
-            eng.sample_cg_groups(eta=None)          # uses the staged eta
-            eng.stage_eta(eta_h)                    # next step's deviates
+            eng.stage_eta(eta_h)                    # next step's deviates: upload overlaps this step's solve
+            eng.sample_cg_groups(eta=None)          # consumes the deviates staged one step earlier
         else:
             eng.sample_cg_groups(eta=eta_h)
         for ic in range(len(cfg.comps)):

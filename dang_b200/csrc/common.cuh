@@ -366,6 +366,14 @@ static __global__ void peer_exchange_kernel(PeerComm pc, const double *local, in
   peer_exchange(pc, local, cnt, gathered);
 }
 
+// Small results go back to the host through stores into mapped pinned memory, not through the
+// copy engine: a cudaMemcpyAsync of a few bytes queues behind whatever bulk download (amplitude
+// maps on the d2h stream) the device-to-host engine is busy with and would stall the compute stream.
+static __global__ void readback_kernel(unsigned int *dst_host, const unsigned int *src, int nwords) {
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst_host[i] = src[i];
+  __threadfence_system();
+}
+
 // ---------------------------------------------------------------- deterministic reductions
 // Two-stage tree: per-thread serial partial -> warp shuffle -> shared-memory tree over warps
 // -> one partial per block in global memory -> fixed-order final sum by the block that

@@ -127,7 +127,7 @@ ModelView model_view(dang_gpu *h) {
     // back only after a scan, otherwise the host mirror (kept by set_nonuni) already has them
     if (scanned) {
       int *hu = (int *)((char *)h->pinned + 32 * 1024);
-      CK(cudaMemcpyAsync(hu, (char *)h->tab + offsetof(SedTable, nonuni), sizeof(h->nonuni_host), cudaMemcpyDeviceToHost, h->stream));
+      readback(h, hu, (char *)h->tab + offsetof(SedTable, nonuni), sizeof(h->nonuni_host));
       CK(cudaStreamSynchronize(h->stream));
       memcpy(h->nonuni_host, hu, sizeof(h->nonuni_host));
     }
@@ -165,7 +165,7 @@ int64_t unmasked_count(dang_gpu *h) {
   kt.done();
   gather(h, 4);
   double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   double n = 0;
   for (int g = 0; g < h->nranks; g++) n += hp[g * 4 + 1];
@@ -215,6 +215,9 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+
     h->nside = nside;
     h->npix = npix;
     h->nmaps = nmaps;
@@ -232,9 +235,11 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_amp_dl, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_idx_dl, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_eta, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaEventCreateWithFlags(&h->ev_eta[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_eta_used[i], cudaEventDisableTiming));
+    }
     h->grid_cap = h->num_sms * 8;
     CK(cudaMalloc(&h->partials, (size_t)h->grid_cap * GATHER_MAX * sizeof(double)));
     CK(cudaMalloc(&h->tickets, 32 * sizeof(unsigned int)));
@@ -271,7 +276,11 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   if (h->mailbox) cudaFree(h->mailbox);
   if (!h->maps_borrowed) { dfree(h->sig); dfree(h->rms); dfree(h->mask); }
   dfree(h->bp_nu0); dfree(h->bp_tau0);
-  for (auto &c : h->comp) { dfree(c.amp); dfree(c.idx[0]); dfree(c.idx[1]); }
+  for (auto &c : h->comp) {
+    dfree(c.amp); dfree(c.amp_alt); dfree(c.idx[0]); dfree(c.idx[1]);
+    if (c.ev_read) cudaEventDestroy(c.ev_read);
+    if (c.ev_read_alt) cudaEventDestroy(c.ev_read_alt);
+  }
   for (auto &g : h->cg) for (auto &x : g.x) dfree(x);
   dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
   dfree(h->decisions); dfree(h->lnl_trace); dfree(h->stage); dfree(h->partials); dfree(h->tickets);
@@ -282,8 +291,8 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   cudaStreamSynchronize(h->d2h_stream);
   cudaStreamSynchronize(h->h2d_stream);
-  dfree(h->eta_stage);
-  for (cudaEvent_t e : {h->ev_compute, h->ev_amp_dl, h->ev_idx_dl, h->ev_eta}) if (e) cudaEventDestroy(e);
+  dfree(h->eta_stage[0]); dfree(h->eta_stage[1]);
+  for (cudaEvent_t e : {h->ev_compute, h->ev_idx_dl, h->ev_eta[0], h->ev_eta[1], h->ev_eta_used[0], h->ev_eta_used[1]}) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->d2h_stream);
   cudaStreamDestroy(h->h2d_stream);
   cudaStreamDestroy(h->stream);
@@ -302,6 +311,17 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
     case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
     case DANG_OPT_TMA: h->use_tma = value != 0; break;
+    case DANG_OPT_L2_PERSIST_MB: {
+      // the set-aside shrinks the L2 every other kernel sees, so it exists only while the option is on
+      h->l2_persist_mb = value < 0 ? 0 : (int)value;
+      size_t want = (size_t)h->l2_persist_mb << 20;
+      if (want > h->l2_persist_max) want = h->l2_persist_max;
+      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      if (getenv("DANG_GPU_VERBOSE"))
+        fprintf(stderr, "dang_gpu: persisting L2 %zu MB (max %zu MB, window max %zu MB)\n", want >> 20,
+                h->l2_persist_max >> 20, h->l2_window_max >> 20);
+      break;
+    }
     case DANG_OPT_STAT_CACHE: h->stat_cache = value != 0; h->stat_valid = false; h->chisq_valid = false; break;
     case DANG_OPT_CG_CHECKPOINT:
       h->cg_ckpt = value < 0 ? 0 : (value > DG_CG_MAXM ? DG_CG_MAXM : (int)value);
@@ -495,6 +515,7 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   c.nind = (type == DANG_COMP_MBB || type == DANG_COMP_LOGNORMAL) ? 2 : (type == DANG_COMP_CMB ? 0 : 1);
   const size_t n2 = (size_t)h->nmaps * h->Ppad;
   if (!c.amp) CK(cudaMalloc(&c.amp, n2 * sizeof(double)));
+  amp_write_barrier(h, c);
   CK(cudaMemsetAsync(c.amp, 0, n2 * sizeof(double), h->stream));
   if (amplitude) h2d_planes(h, c.amp, amplitude, h->nmaps);
   for (int l = 0; l < c.nind; l++) {
@@ -545,6 +566,7 @@ int dang_gpu_set_index(dang_gpu_t *h, int ic, int nind, int sample_index, int in
 int dang_gpu_set_amplitude(dang_gpu_t *h, int ic, const double *amplitude) {
   API_BEGIN
   if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !amplitude) fail(DANG_GPU_EINVAL, "bad component %d", ic);
+  amp_write_barrier(h, h->comp[ic]);
   h2d_planes(h, h->comp[ic].amp, amplitude, h->nmaps);
   CK(cudaStreamSynchronize(h->stream));
   touch(h);
@@ -589,8 +611,7 @@ int dang_gpu_get_index_fullsky(dang_gpu_t *h, int ic, int nind, int map_n, doubl
   model_view(h);  // refreshes the uniformity flags
   if (h->nonuni_host[ic * 3 + (map_n - 1)][nind] != 0)
     fail(DANG_GPU_ESTATE, "plane %d of index %d of component %d is not constant", map_n, nind, ic);
-  CK(cudaMemcpyAsync(h->pinned, h->comp[ic].idx[nind] + (size_t)(map_n - 1) * h->Ppad, sizeof(double),
-                     cudaMemcpyDeviceToHost, h->stream));
+  readback(h, h->pinned, h->comp[ic].idx[nind] + (size_t)(map_n - 1) * h->Ppad, sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   *value = *(double *)h->pinned;
   API_END
@@ -751,7 +772,7 @@ int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean
   kt.done();
   gather(h, 4);
   double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   double s = 0, n = 0;
   for (int g = 0; g < h->nranks; g++) { s += hp[g * 4]; n += hp[g * 4 + 1]; }
@@ -769,8 +790,13 @@ int dang_gpu_get_amplitude_async(dang_gpu_t *h, int ic, int k_lo, int k_hi, doub
   CK(cudaMemcpy2DAsync(amplitude + o * h->npix + h->lo, h->npix * sizeof(double), h->comp[ic].amp + o * h->Ppad,
                        h->Ppad * sizeof(double), h->P * sizeof(double), k_hi - k_lo + 1, cudaMemcpyDeviceToHost,
                        h->d2h_stream));
-  CK(cudaEventRecord(h->ev_amp_dl, h->d2h_stream));
-  h->amp_dl_pending = true;
+  CompHost &cc = h->comp[ic];
+  if (!cc.ev_read) {
+    CK(cudaEventCreateWithFlags(&cc.ev_read, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&cc.ev_read_alt, cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(cc.ev_read, h->d2h_stream));
+  cc.read_pending = true;
   API_END
 }
 
@@ -793,7 +819,7 @@ int dang_gpu_get_indices_async(dang_gpu_t *h, int ic, int nind, int k_lo, int k_
 int dang_gpu_download_wait(dang_gpu_t *h) {
   API_BEGIN
   CK(cudaStreamSynchronize(h->d2h_stream));
-  h->amp_dl_pending = false;
+  for (auto &c : h->comp) c.read_pending = c.read_pending_alt = false;
   h->idx_dl_pending = false;
   API_END
 }
@@ -801,13 +827,16 @@ int dang_gpu_download_wait(dang_gpu_t *h) {
 int dang_gpu_stage_eta(dang_gpu_t *h, const double *eta, int nplanes) {
   API_BEGIN
   if (!eta || nplanes < 1 || nplanes > 2) fail(DANG_GPU_EINVAL, "stage_eta: nplanes = %d", nplanes);
-  ensure(h->eta_stage, h->eta_stage_len, (size_t)nplanes * h->Ppad);
-  // the previous consumer (K1 of the last solve) has finished: every solve ends with a sync
-  CK(cudaMemcpy2DAsync(h->eta_stage, h->Ppad * sizeof(double), eta + h->lo, h->npix * sizeof(double),
+  if (h->eta_count == 2) fail(DANG_GPU_ESTATE, "the deviates of two solves are already staged");
+  const int slot = (h->eta_head + h->eta_count) % 2;
+  ensure(h->eta_stage[slot], h->eta_stage_len[slot], (size_t)nplanes * h->Ppad);
+  // the slot's previous consumer (K1 of an earlier solve) must have read it
+  if (h->eta_used_recorded[slot]) CK(cudaStreamWaitEvent(h->h2d_stream, h->ev_eta_used[slot], 0));
+  CK(cudaMemcpy2DAsync(h->eta_stage[slot], h->Ppad * sizeof(double), eta + h->lo, h->npix * sizeof(double),
                        h->P * sizeof(double), nplanes, cudaMemcpyHostToDevice, h->h2d_stream));
-  CK(cudaEventRecord(h->ev_eta, h->h2d_stream));
-  h->eta_staged = true;
-  h->eta_stage_planes = nplanes;
+  CK(cudaEventRecord(h->ev_eta[slot], h->h2d_stream));
+  h->eta_stage_planes[slot] = nplanes;
+  h->eta_count++;
   API_END
 }
 
@@ -824,7 +853,7 @@ int dang_gpu_fit_band_gain(dang_gpu_t *h, int map_n, int band, int ml_mode, cons
   }
   gather(h, 4);
   double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   double mu = 0.0, sigma = 0.0;
   for (int g = 0; g < h->nranks; g++) {

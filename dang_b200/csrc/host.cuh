@@ -88,6 +88,11 @@ struct CompHost {
   std::string label;
   double nu_ref = 0;
   double *amp = nullptr;               // [nmaps][Ppad]
+  // Second amplitude buffer: while an asynchronous download still reads `amp`, the next solve unpacks
+  // into `amp_alt` and the two swap roles, so a download never stalls the solve that follows it.
+  double *amp_alt = nullptr;
+  cudaEvent_t ev_read = nullptr, ev_read_alt = nullptr;  // last download that read amp / amp_alt
+  bool read_pending = false, read_pending_alt = false;
   double *idx[DG_MAXIND] = {nullptr, nullptr};
   IndexHost index[DG_MAXIND];
 };
@@ -113,14 +118,21 @@ struct dang_gpu {
   int device = 0, nside = 0, nmaps = 0, nbands = 0, ncomp = 0, num_sms = 0;
   int64_t npix = 0, lo = 0, hi = 0, P = 0, Ppad = 0;
   cudaStream_t stream = nullptr, d2h_stream = nullptr, h2d_stream = nullptr;
-  cudaEvent_t ev_compute = nullptr, ev_amp_dl = nullptr, ev_idx_dl = nullptr, ev_eta = nullptr;
-  bool amp_dl_pending = false, idx_dl_pending = false, eta_staged = false;
-  double *eta_stage = nullptr; size_t eta_stage_len = 0; int eta_stage_planes = 0;
+  cudaEvent_t ev_compute = nullptr, ev_idx_dl = nullptr;
+  bool idx_dl_pending = false;
+  // staged deviates of the next solves: a two-slot FIFO, so the upload for solve k+1 runs while solve k
+  // (which consumes the other slot) is still computing
+  double *eta_stage[2] = {nullptr, nullptr}; size_t eta_stage_len[2] = {0, 0}; int eta_stage_planes[2] = {0, 0};
+  cudaEvent_t ev_eta[2] = {nullptr, nullptr}, ev_eta_used[2] = {nullptr, nullptr};
+  bool eta_used_recorded[2] = {false, false};
+  int eta_head = 0, eta_count = 0;
   std::string err;
 
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int l2_persist_mb = 0;  // MB of the CG block matrices kept persisting in L2 during a solve (0: off)
+  size_t l2_persist_max = 0, l2_window_max = 0;
   int use_tma = 0;  // TMA-staged K1 (measured slower than the LDG form on B200: kept as an experiment)
 
   // ddata
@@ -281,6 +293,21 @@ inline void dd_log_ratio(double a, double b, double &hi, double &lo) {
   hi = (double)L;
   lo = (double)(L - (long double)hi);
 }
+// device -> pinned host (h->pinned) for small results, stream ordered, bypassing the copy engine
+inline void readback(dang_gpu *h, void *dst_pinned, const void *src_dev, size_t bytes) {
+  if (bytes % 4 != 0) fail(DANG_GPU_EINVAL, "readback of %zu bytes", bytes);
+  readback_kernel<<<1, 128, 0, h->stream>>>((unsigned int *)dst_pinned, (const unsigned int *)src_dev, (int)(bytes / 4));
+  CK(cudaGetLastError());
+}
+
+// anything that overwrites c.amp in place waits for a download that may still be reading it
+inline void amp_write_barrier(dang_gpu *h, CompHost &c) {
+  if (c.read_pending) {
+    CK(cudaStreamWaitEvent(h->stream, c.ev_read, 0));
+    c.read_pending = false;
+  }
+}
+
 // defined in dang_gpu.cu
 void upload_bandpasses(dang_gpu *h);
 ModelView model_view(dang_gpu *h);

@@ -1,5 +1,7 @@
 // host_cg.cu -- amplitude draw: compute_rhs + cg_search + unpack_amplitudes for one (group, flag),
 // src/dang_cg_mod.f90:167-169 (launch logic; kernels in kernels_cg.cuh / kernels_uni.cuh).
+#include <utility>
+
 #include "host.cuh"
 #include "kernels_cg.cuh"
 #include "kernels_uni.cuh"
@@ -62,6 +64,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   cv.seed = seed;
   cv.fluct = 0;
   cv.eta = nullptr;
+  int staged_slot = -1;
   // recompute form needs the (alpha, beta) history: fall back to streaming for very long solves
   const int ckpt_m = (!h->cg_two_pass && g.i_max < DG_CG_HIST) ? h->cg_ckpt : 0;
   cv.store_d = ckpt_m ? 0 : 1;
@@ -71,10 +74,12 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       ensure(h->eta, h->eta_len, vs);
       h2d_planes(h, h->eta, eta, S);  // host eta is [stokes][npix]
       cv.eta = h->eta;
-    } else if (h->eta_staged && h->eta_stage_planes == S) {
-      CK(cudaStreamWaitEvent(h->stream, h->ev_eta, 0));  // uploaded by dang_gpu_stage_eta
-      cv.eta = h->eta_stage;
-      h->eta_staged = false;
+    } else if (h->eta_count > 0 && h->eta_stage_planes[h->eta_head] == S) {
+      CK(cudaStreamWaitEvent(h->stream, h->ev_eta[h->eta_head], 0));  // uploaded by dang_gpu_stage_eta
+      cv.eta = h->eta_stage[h->eta_head];
+      staged_slot = h->eta_head;
+      h->eta_head = (h->eta_head + 1) % 2;
+      h->eta_count--;
     }
   }
 
@@ -110,6 +115,10 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       rhs_blocks_kernel<C><<<g1, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
     }
     kt.done();
+    if (staged_slot >= 0) {  // the slot may be refilled once K1 has read it
+      CK(cudaEventRecord(h->ev_eta_used[staged_slot], h->stream));
+      h->eta_used_recorded[staged_slot] = true;
+    }
   }
   gather(h, 4);
   {
@@ -123,7 +132,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   bool have_state = false;
   auto read_state = [&]() -> Snap {  // scalars + residual trace in one small copy
     CgScalars *hs = (CgScalars *)h->pinned;
-    CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
+    readback(h, hs, h->cg_scalars, offsetof(CgScalars, ah));
     CK(cudaStreamSynchronize(h->stream));
     have_state = true;
     return Snap{hs->delta_new, hs->iter, hs->done};
@@ -187,6 +196,25 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   // solve is done returns at once (device-side early exit).  The first batch is sized from the
   // previous solve of this (group, flag) -- successive Gibbs iterations converge in almost the
   // same number of steps -- and further batches of cg_chunk follow until the flag is seen.
+  // L2 residency for the block matrices: every pass re-reads M (and r); the working set (250 MB at
+  // nside 512) exceeds the 126 MB L2 and a cyclic stream gets no hits from LRU, so a slice of M is
+  // marked persisting for the passes of this solve (DANG_OPT_L2_PERSIST_MB) and the rest streams.
+  bool l2_window = false;
+  if (h->l2_persist_mb > 0 && h->l2_persist_max > 0) {
+    size_t want = (size_t)h->l2_persist_mb << 20;
+    if (want > h->l2_persist_max) want = h->l2_persist_max;
+    size_t win = (size_t)T * vs * sizeof(double);
+    if (win > h->l2_window_max) win = h->l2_window_max;
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.base_ptr = h->M;
+    av.accessPolicyWindow.num_bytes = win;
+    av.accessPolicyWindow.hitRatio = want >= win ? 1.0f : (float)((double)want / (double)win);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    l2_window = true;
+  }
   const int max_pass = g.i_max - 1;
   int enq = 0;
   int batch = g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : h->cg_chunk;
@@ -208,20 +236,47 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     kt.done();
   }
 
-  // unpack_amplitudes :1327-1335: x -> c%amplitude planes (after any download still reading them)
-  if (h->amp_dl_pending) {
-    CK(cudaStreamWaitEvent(h->stream, h->ev_amp_dl, 0));
-    h->amp_dl_pending = false;
+  if (l2_window) {  // later kernels stream: drop the window and release the persisting lines
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.num_bytes = 0;
+    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    CK(cudaCtxResetPersistingL2Cache());
   }
-  for (int c = 0; c < C; c++)
+  // unpack_amplitudes :1327-1335: x -> c%amplitude planes.  If an asynchronous download is still
+  // reading a component's planes the new state goes into its second buffer (solved planes from x, the
+  // others carried over) and the buffers swap roles; the download is never waited for.
+  for (int c = 0; c < C; c++) {
+    CompHost &cc = h->comp[comps[c]];
+    if (cc.read_pending) {
+      const size_t n2a = (size_t)h->nmaps * h->Ppad;
+      if (!cc.amp_alt) {
+        CK(cudaMalloc(&cc.amp_alt, n2a * sizeof(double)));
+        CK(cudaMemsetAsync(cc.amp_alt, 0, n2a * sizeof(double), h->stream));
+      }
+      if (cc.read_pending_alt) {  // the download before the pending one read the buffer we are about to write
+        CK(cudaStreamWaitEvent(h->stream, cc.ev_read_alt, 0));
+        cc.read_pending_alt = false;
+      }
+      for (int k = 0; k < h->nmaps; k++) {
+        bool solved = false;
+        for (int s = 0; s < S; s++) solved = solved || cv.plane[s] == k;
+        if (!solved)
+          CK(cudaMemcpyAsync(cc.amp_alt + (size_t)k * h->Ppad, cc.amp + (size_t)k * h->Ppad, h->P * sizeof(double),
+                             cudaMemcpyDeviceToDevice, h->stream));
+      }
+      std::swap(cc.amp, cc.amp_alt);
+      std::swap(cc.ev_read, cc.ev_read_alt);
+      std::swap(cc.read_pending, cc.read_pending_alt);
+    }
     for (int s = 0; s < S; s++)
-      CK(cudaMemcpyAsync(h->comp[comps[c]].amp + (size_t)cv.plane[s] * h->Ppad,
-                         g.x[flag_n] + c * vs + (size_t)s * h->Ppad, h->P * sizeof(double),
-                         cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaMemcpyAsync(cc.amp + (size_t)cv.plane[s] * h->Ppad, g.x[flag_n] + c * vs + (size_t)s * h->Ppad,
+                         h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
   {
     CgScalars *hs = (CgScalars *)h->pinned;  // filled by the last read_state (the solve was done then)
     if (!sn.done || !have_state) {  // ran out of passes (i_max) without seeing the flag: read the final state
-      CK(cudaMemcpyAsync(hs, h->cg_scalars, offsetof(CgScalars, ah), cudaMemcpyDeviceToHost, h->stream));
+      readback(h, hs, h->cg_scalars, offsetof(CgScalars, ah));
       CK(cudaStreamSynchronize(h->stream));
     }
     int n = hs->iter < 256 ? hs->iter : 256;

@@ -64,7 +64,7 @@ void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, do
   kt.done();
   gather(h, 4);
   double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < 4; i++) {
     out4[i] = 0.0;

@@ -205,7 +205,7 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
     kt.done();
   }
   MhScalars *hs = (MhScalars *)h->pinned;
-  CK(cudaMemcpyAsync(hs, h->mh_scalars, sizeof(MhScalars), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hs, h->mh_scalars, sizeof(MhScalars));
   CK(cudaStreamSynchronize(h->stream));
   if (accept) *accept = hs->accept;
   h->comp[mh.ic].index[mh.nind].last_value = hs->sample[mh.nind];
@@ -254,7 +254,7 @@ bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]) 
   int cnt = h->stat_cnt;
   if (!stat_cache_hit(h, mh)) cnt = fullsky_statistics(h, mv, mh);
   double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->stat_buf, (size_t)h->nranks * cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hp, h->stat_buf, (size_t)h->nranks * cnt * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   const int B = h->nbands, nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
   for (int k = 0; k < 4; k++) out4[k] = 0.0;
@@ -297,7 +297,7 @@ void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, co
     ks.done();
   }
   double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hp, d_out, 3 * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   h->comp[ic].index[nind].step = hp[0];  // c%step_size(nind), :708-710
   if (blocks_run) *blocks_run = (int)hp[1];

@@ -80,7 +80,7 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
   }
   gather(h, 1);
   double *hp = (double *)h->pinned;
-  CK(cudaMemcpyAsync(hp, h->gathered, (size_t)h->nranks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  readback(h, hp, h->gathered, (size_t)h->nranks * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   double a = 0;
   for (int g = 0; g < h->nranks; g++) a += hp[g];

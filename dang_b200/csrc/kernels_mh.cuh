@@ -710,8 +710,14 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
   };
   double lnl_old = lnl_of(s0) + prior_of(sample[mh.nind]);  // :250, :261, :268
   double accept = 0.0;
+  double zl = 0.0, ul = 0.0;  // deviates of 32 consecutive proposals, one per lane (off the serial path)
   for (int l = 0; l < mh.nsample; l++) {
-    theta[mh.nind] = sample[mh.nind] + (0.0 + mh.step * mh_draw_z(mh, l));  // :286
+    if ((l & 31) == 0 && l + j < mh.nsample) {
+      zl = mh_draw_z(mh, l + j);
+      ul = mh_draw_u(mh, l + j);
+    }
+    const double z_l = __shfl_sync(0xffffffffu, zl, l & 31), u_l = __shfl_sync(0xffffffffu, ul, l & 31);
+    theta[mh.nind] = sample[mh.nind] + (0.0 + mh.step * z_l);  // :286
     if (theta[mh.nind] < mh.uni[0] || theta[mh.nind] > mh.uni[1]) {          // :287, Q5
       if (mh.decisions && j == 0) mh.decisions[l] = 2;
       continue;
@@ -720,7 +726,7 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
     const double lnl_new = lnl_of(sed) + prior_of(theta[mh.nind]);  // :306
     const double diff = lnl_new - lnl_old;
     const double ratio = exp(diff);  // :310, Q4
-    const bool acc = (mh.ml_mode == 0) ? (ratio > 1.0) : (ratio > mh_draw_u(mh, l));
+    const bool acc = (mh.ml_mode == 0) ? (ratio > 1.0) : (ratio > u_l);
     if (acc) {
       sample[mh.nind] = theta[mh.nind];
       lnl_old = lnl_new;

@@ -90,7 +90,10 @@ enum {
    * statistics of the full-sky draw that follows (when the next index in sample_spectral_parameters'
    * order is a full-sky chisq draw over the same planes); that chi-square, the draw, and the chi-square
    * after the draw are then all served by ONE pass over the maps.  0: every call streams the maps. */
-  DANG_OPT_STAT_CACHE = 10
+  DANG_OPT_STAT_CACHE = 10,
+  /* MB of the CG block matrices M marked persisting in L2 (cudaAccessPolicyWindow) for the passes of a
+   * solve; the rest of the CG state streams.  0: off. */
+  DANG_OPT_L2_PERSIST_MB = 11
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
@@ -211,8 +214,9 @@ int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean
  * return at once; the library orders them against its own later writes (a solve's unpack waits
  * for a pending amplitude download, a sampler for a pending index download).
  * dang_gpu_download_wait blocks until every pending download has landed.
- * dang_gpu_stage_eta uploads the S*npix normals of the NEXT dang_gpu_cg_solve while other work
- * runs; that solve is then called with eta == NULL and uses the staged deviates (once).
+ * dang_gpu_stage_eta uploads the S*npix normals of a coming dang_gpu_cg_solve while other work runs;
+ * that solve is then called with eta == NULL and uses the staged deviates (once).  Up to two solves'
+ * deviates can be staged (first in, first out), so the upload for solve k+1 overlaps solve k.
  * Host buffers should be pinned (dang_gpu_host_alloc) or the copies serialise. */
 int dang_gpu_get_amplitude_async(dang_gpu_t *h, int ic, int k_lo, int k_hi, double *amplitude);
 int dang_gpu_get_indices_async(dang_gpu_t *h, int ic, int nind, int k_lo, int k_hi, double *indices);

@@ -377,6 +377,48 @@ def test_async_staging_matches_synchronous_calls():
         assert np.array_equal(a.indices(ic), b.indices(ic))
 
 
+def test_async_pipeline_two_deep():
+    """The bench's end-to-end pattern: the deviates of solve k+1 are staged BEFORE solve k runs (two-slot
+    FIFO), every step's amplitudes are downloaded into their own host arrays without ever waiting
+    (the next solve unpacks into the second amplitude buffer), and every download holds exactly the
+    state of its step."""
+    from dang_b200.engine import DangGpuError, Engine
+    cfg, sky = small_case("c2", 16)
+    rng = np.random.default_rng(43)
+    nstep = 5
+    etas = [rng.standard_normal(2 * cfg.npix) for _ in range(nstep + 1)]
+    a, b = Engine(cfg, sky), Engine(cfg, sky)
+    out = [[np.zeros((3, cfg.npix)) for _ in cfg.comps] for _ in range(nstep)]
+    ref = []
+    b.stage_eta(etas[0])
+    for it in range(nstep):
+        a.sample_cg_groups(eta=etas[it], stats=False)
+        ref.append([a.amplitude(ic).copy() for ic in range(2)])
+        b.stage_eta(etas[it + 1])          # queued behind the deviates this solve consumes
+        if it == 0:
+            with pytest.raises(DangGpuError):
+                b.stage_eta(etas[it + 1])  # a third set does not fit
+        b.sample_cg_groups(eta=None, stats=False)
+        for ic in range(2):
+            b.amplitude_async(ic, out[it][ic])
+        a.sample_spectral_parameters(stats=True)
+        b.sample_spectral_parameters(stats=True)
+    b.download_wait()
+    for it in range(nstep):
+        for ic in range(2):
+            assert np.array_equal(out[it][ic][1:3], ref[it][ic][1:3]), (it, ic)
+    for ic in range(2):
+        assert np.array_equal(a.amplitude(ic), b.amplitude(ic))
+        assert np.array_equal(a.indices(ic), b.indices(ic))
+    # in-place writers respect a pending download too
+    b.amplitude_async(0, out[0][0])
+    amp = ref[0][0] * 2.0
+    b.set_amplitude(0, amp)
+    b.download_wait()
+    assert np.array_equal(out[0][0][1:3], a.amplitude(0)[1:3])
+    assert np.array_equal(b.amplitude(0), amp)
+
+
 def test_golden_vectors_through_the_c_abi():
     """The committed fixture tests/golden/c1_nside4.npz (oracle output, made by
     tests/golden/make_golden.py) reproduced on the GPU with the same injected deviates."""
