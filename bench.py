@@ -111,7 +111,8 @@ def run_gpu(args):
 
     from dang_b200.engine import OPT_PROFILE, Engine, setup_torch_comm
     from dang_b200.healpix import ring_partition
-    from dang_b200.synth import make_config, make_sky
+    from dang_b200.synth import make_config, make_sky, make_sky_slice
+    from dang_b200.healpix import pix2z_ring
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -122,9 +123,23 @@ def run_gpu(args):
     assert world == args.gpus or world == 1, (world, args.gpus)
 
     cfg = make_config(args.config, nside=args.nside)
-    sky = make_sky(cfg)
-    bounds = ring_partition(cfg.nside, world, weights=(sky.mask != 0).astype(np.float64))
+    # big configs (nside >= 1024): every rank builds only its own pixel slice of the synthetic sky
+    big = cfg.nside >= 1024
+    if big:
+        z_all = pix2z_ring(cfg.nside, np.arange(cfg.npix))
+        mask_all = np.where(np.abs(z_all) < np.sin(np.deg2rad(5.0)), 0.0, 1.0)
+        del z_all
+    else:
+        sky = make_sky(cfg)
+        mask_all = sky.mask
+    # streaming kernels cost the same for masked and unmasked pixels; per-pixel Metropolis chains run
+    # only on unmasked ones: balance total pixels, or unmasked pixels when a per-pixel index is sampled
+    per_pixel = any(s.sample and s.region != "fullsky" for c in cfg.comps for s in c.indices)
+    bounds = ring_partition(cfg.nside, world, weights=(mask_all != 0).astype(np.float64) if per_pixel else None)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    if big:
+        del mask_all
+        sky = make_sky_slice(cfg, lo, hi)
     eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
     for kv in args.opt:
         k, v = kv.split("=")
@@ -184,17 +199,23 @@ def run_gpu(args):
     # one (z, u) pair per sample_index_mh call: nsample slots for a full-sky index,
     # nsample*npix for a per-pixel one
     calls = [s for c in cfg.comps for s in c.indices if s.sample for _ in s.poltype.split(",")]
-    z_h = [pinned_array(eng.lib, (cfg.nsample * (1 if s.region == "fullsky" else npix),)) for s in calls]
-    u_h = [pinned_array(eng.lib, (cfg.nsample * (1 if s.region == "fullsky" else npix),)) for s in calls]
+    # injected per-pixel Metropolis deviates are nsample*npix doubles per call (16 GB per step at nside 2048):
+    # big configs draw them on the device in the end-to-end leg too and say so
+    host_zu = not (big and per_pixel)
+    if host_zu:
+        z_h = [pinned_array(eng.lib, (cfg.nsample * (1 if s.region == "fullsky" else npix),)) for s in calls]
+        u_h = [pinned_array(eng.lib, (cfg.nsample * (1 if s.region == "fullsky" else npix),)) for s in calls]
+    else:
+        z_h = u_h = None
     amp_h = [pinned_array(eng.lib, (cfg.nmaps, npix)) for _ in cfg.comps]
     idx_h = [pinned_array(eng.lib, (len(c.indices), cfg.nmaps, npix)) for c in cfg.comps]
     rng = np.random.default_rng(20260103 + rank * 0)
     eta_h[:] = rng.standard_normal(2 * npix)
-    for zz, uu in zip(z_h, u_h):
+    for zz, uu in zip(z_h or [], u_h or []):
         zz[:] = rng.standard_normal(zz.size)
         uu[:] = rng.random(uu.size)
     P = hi - lo
-    h2d = 8 * (2 * P + sum(2 * cfg.nsample * (1 if s.region == "fullsky" else P) for s in calls))
+    h2d = 8 * (2 * P + (sum(2 * cfg.nsample * (1 if s.region == "fullsky" else P) for s in calls) if host_zu else 0))
 
     # Every step: this step's deviates host -> device (eta staged on a copy stream while the
     # previous step computes; z/u inside the sampler call), this step's results device -> host
@@ -213,7 +234,7 @@ def run_gpu(args):
             eng.sample_cg_groups(eta=eta_h)
         for ic in range(len(cfg.comps)):
             eng.amplitude_async(ic, amp_h[ic])
-        eng.sample_spectral_parameters(z=z_h, u=u_h)
+        eng.sample_spectral_parameters(z=z_h, u=u_h, seed=7 + 2 * it)
         for ic, j in sampled:
             if cfg.comps[ic].indices[j].region == "fullsky":
                 # the whole plane holds the chain's final sample (dang_sample_mod.f90:329,483): 8 bytes per
@@ -236,7 +257,8 @@ def run_gpu(args):
     eng.event_record(3)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max_over_ranks(max(eng.event_elapsed_ms(2, 3), wall_ms))
+    e2e_dev_ms = eng.event_elapsed_ms(2, 3)
+    e2e_ms = max_over_ranks(max(e2e_dev_ms, wall_ms))
     n_pp = sum(1 for ic, j in sampled if cfg.comps[ic].indices[j].region != "fullsky")
     nplanes_out = 2 * len(cfg.comps) + 2 * n_pp
     d2h = 8 * P * nplanes_out + 8 * 8 + 16 * (len(sampled) - n_pp)
@@ -259,23 +281,27 @@ def run_gpu(args):
                                        "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
                                    for k, v in stats.items() if v["launches"]}}
         line = {
-            "metric": METRIC, "value": round(1e3 / ms_per_step, 3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC if (cfg.name == "c2" and cfg.nside == 512) else f"Gibbs iterations/sec (nside={cfg.nside}, Q+U, synch+dust)",
+            "value": round(1e3 / ms_per_step, 3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{cfg.name}: nside={cfg.nside}, {cfg.nbands} delta bands, Q+U, synch+dust, "
-                                   f"CG amplitudes + full-sky beta_d, NUMSAMPLE={cfg.nsample}",
+            "config": {"workload": f"{cfg.name}: nside={cfg.nside}, {cfg.nbands} bands, Q+U, synch+dust, CG amplitudes + "
+                                   + " + ".join(f"{s.region} {c.label} {s.label}" for c in cfg.comps for s in c.indices if s.sample)
+                                   + f", NUMSAMPLE={cfg.nsample}",
                        "npix": cfg.npix,
                        "n_cg_iterations": {"min": int(min(n_cg)), "max": int(max(n_cg)), "mean": round(float(np.mean(n_cg)), 2)},
                        "parallelism": f"ring-range pixel shards x{world}" + ("" if world == 1 else (", scalar exchange over NVLink mailboxes" if mailboxes else ", scalar exchange by NCCL all-gather")),
-                       "l2": "working set (sig+rms 1.2 GB, CG state 0.7 GB) >> 126 MB L2, no flush needed",
+                       "l2": f"working set per GPU (sig+rms {16e-9 * cfg.nbands * 2 * P:.2f} GB + CG state) >> 126 MB L2, no flush needed",
                        "rng": "device Philox4x32-10"},
             "pixel_band_updates_per_s": round(2 * cfg.npix * cfg.nbands * 1e3 / ms_per_step, 1),
             "gpu_launches": launches,
             "clocks": clocks,
             "e2e": {"value": round(1e3 * ke / e2e_ms, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h,
-                    "what": "per step: injected deviates (eta, z, u) pinned host -> device; changed Q/U planes of every amplitude map and of the per-pixel-sampled index maps, the value of every full-sky-sampled index (one double per plane) + chi-square device -> pinned host; copies overlap compute on dedicated streams"},
+                    "d2h_bytes_per_step": d2h, "steps": ke,
+                    "ms_per_step_device_rank0": round(e2e_dev_ms / ke, 4), "ms_per_step_wall_rank0": round(wall_ms / ke, 4),
+                    "what": "per step: injected deviates (eta, z, u) pinned host -> device; changed Q/U planes of every amplitude map and of the per-pixel-sampled index maps, the value of every full-sky-sampled index (one double per plane) + chi-square device -> pinned host; copies overlap compute on dedicated streams"
+                            + ("" if host_zu else "; per-pixel Metropolis deviates drawn on the device (16 GB per step otherwise)")},
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu:

@@ -116,6 +116,45 @@ TRUE_THETA = {"synch": (-3.1,), "dust": (1.55, 19.6)}
 TRUE_AMP_SIGMA = {"synch": 10.0, "dust": 50.0}
 
 
+def make_sky_slice(cfg: RunConfig, lo: int, hi: int, seed: int = SEED_SKY, noise_seed: int = SEED_NOISE) -> Sky:
+    """The same sky model for ONE rank of a large sharded run: full-sky-shaped arrays (the C ABI takes
+    the reference's full-size allocatables) of which only pixels [lo, hi) are ever written, so the
+    untouched pages of the calloc'ed arrays never become resident (nside 2048 x 20 bands is 48 GB of
+    maps; eight ranks each building the full sky would not fit the host).  Draws are seeded per
+    (array, band, plane, lo), so the slices of different ranks are independent; they are NOT the
+    numbers make_sky() draws -- parity tests use make_sky(), benches of big configs use this."""
+    npix, nb, nm = cfg.npix, cfg.nbands, cfg.nmaps
+    n = hi - lo
+    truth, amp0, idx0 = {}, {}, {}
+    sig = np.zeros((nb, nm, npix))
+    rms = np.zeros((nb, nm, npix))
+    for ic, c in enumerate(cfg.comps):
+        amp0[c.label] = np.zeros((nm, npix))
+        idx0[c.label] = np.zeros((len(c.indices), nm, npix))
+        for k, s in enumerate(c.indices):
+            idx0[c.label][k][:, lo:hi] = s.init
+        if c.label in TRUE_THETA:
+            rng = np.random.default_rng([seed, 1, ic, lo])
+            a = rng.normal(0.0, TRUE_AMP_SIGMA[c.label], size=(2, n))
+            for j, b in enumerate(cfg.bands):
+                sig[j, 1:3, lo:hi] += a * band_sed(b, c, *TRUE_THETA[c.label])
+        truth[c.label] = None
+    # one noise realisation per plane, rolled by a band-dependent lag (cheap on the host, and every
+    # (pixel, band) still sees an independent-looking draw)
+    nrng = np.random.default_rng([noise_seed, 2, lo])
+    q0, g0 = nrng.random(size=(2, n)), nrng.standard_normal(size=(2, n))
+    for j, b in enumerate(cfg.bands):
+        r = band_sigma(b.nu_ghz) * (1.0 + 0.3 * np.roll(q0, 7919 * (j + 1), axis=1))
+        rms[j, :, lo:hi] = 1.0
+        rms[j, 1:3, lo:hi] = r
+        sig[j, 1:3, lo:hi] += r * np.roll(g0, 104729 * (j + 1), axis=1)
+    mask = np.zeros(npix)
+    z = pix2z_ring(cfg.nside, np.arange(lo, hi))
+    mask[lo:hi] = np.where(np.abs(z) < np.sin(np.deg2rad(5.0)), 0.0, 1.0)
+    return Sky(sig=sig, rms=rms, mask=mask, gain=np.ones(nb), offset=np.zeros(nb),
+               amplitude=amp0, indices=idx0, truth=truth)
+
+
 def make_sky(cfg: RunConfig, seed: int = SEED_SKY, noise_seed: int = SEED_NOISE) -> Sky:
     npix, nb, nm = cfg.npix, cfg.nbands, cfg.nmaps
     rng = np.random.default_rng(seed)
