@@ -140,6 +140,7 @@ def run_gpu(args):
     if big:
         del mask_all
         sky = make_sky_slice(cfg, lo, hi)
+    mask_slice = sky.mask[lo:hi]
     eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
     for kv in args.opt:
         k, v = kv.split("=")
@@ -192,6 +193,7 @@ def run_gpu(args):
         step(2 + args.warmup + args.steps + k)
     stats = eng.kernel_stats(reset=True)
     eng.set_option(OPT_PROFILE, 0)
+    k5_fallbacks = eng.perpixel_stats()[0] if per_pixel else None
 
     # --- end to end through the C ABI with host buffers: deviates in, maps out, every step
     npix = cfg.npix
@@ -293,7 +295,9 @@ def run_gpu(args):
                        "n_cg_iterations": {"min": int(min(n_cg)), "max": int(max(n_cg)), "mean": round(float(np.mean(n_cg)), 2)},
                        "parallelism": f"ring-range pixel shards x{world}" + ("" if world == 1 else (", scalar exchange over NVLink mailboxes" if mailboxes else ", scalar exchange by NCCL all-gather")),
                        "l2": f"working set per GPU (sig+rms {16e-9 * cfg.nbands * 2 * P:.2f} GB + CG state) >> 126 MB L2, no flush needed",
-                       "rng": "device Philox4x32-10"},
+                       "rng": "device Philox4x32-10",
+                       **({"k5_fp64_fallbacks_per_proposal": round(k5_fallbacks / (cfg.nsample * float((mask_slice != 0).sum()) * world), 6)}
+                          if k5_fallbacks is not None else {})},
             "pixel_band_updates_per_s": round(2 * cfg.npix * cfg.nbands * 1e3 / ms_per_step, 1),
             "gpu_launches": launches,
             "clocks": clocks,

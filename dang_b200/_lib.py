@@ -51,6 +51,7 @@ SIGNATURES = {
     "dang_gpu_sample_index": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp,
                                         C.c_uint64, c_dp]),
     "dang_gpu_get_decisions": (C.c_int, [vp, C.POINTER(C.c_ubyte), c_dp]),
+    "dang_gpu_perpixel_stats": (C.c_int, [vp, c_dp, c_dp]),
     "dang_gpu_tune_index": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp,
                                       C.c_uint64, C.c_int, c_ip, c_dp]),
     "dang_gpu_chisq": (C.c_int, [vp, C.c_int, C.c_int, c_dp, c_i64p]),

@@ -131,6 +131,8 @@ struct dang_gpu {
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int pp_fast = 1;        // certified fp32 screening in the per-pixel Metropolis kernel (DANG_OPT_PERPIXEL_FAST)
+  double pp_fallbacks = 0, pp_violations = 0;  // of the last per-pixel draw (all ranks)
   int l2_persist_mb = 0;  // MB of the CG block matrices kept persisting in L2 during a solve (0: off)
   size_t l2_persist_max = 0, l2_window_max = 0;
   int use_tma = 0;  // TMA-staged K1 (measured slower than the LDG form on B200: kept as an experiment)
@@ -357,6 +359,8 @@ void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode,
 void ensure_zu(dang_gpu *h, size_t n);
 void ensure_decisions(dang_gpu *h, size_t n);
 void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);  // host_mh_pp.cu
+void launch_perpixel_fast(dang_gpu *h, const ModelView &mv, const MhView &mh, int bpl, int mode, int64_t work,
+                          size_t smem);                                            // host_mh_ppf.cu
 void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);   // host_mh_fs.cu
 void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
                   int max_blocks, int *blocks_run, double *step_size);             // host_mh_fs.cu

@@ -21,6 +21,7 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
       fail(DANG_GPU_EINVAL, "z injected without u");
     }
   }
+  bool pp_fast_ran = false;
   h->dec_mode = 0;
   if (h->record) {
     ensure_decisions(h, n > 0 ? n : 1);
@@ -56,6 +57,9 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
       if (h->comp[mh.ic].type == DANG_COMP_POWERLAW) mode = MH_SED_POWERLAW;
       else if (h->comp[mh.ic].type == DANG_COMP_MBB) mode = mh.nind == 0 ? MH_SED_MBB_BETA : MH_SED_MBB_T;
     }
+    // certified fp32 screening (kernels_mh_fast.cuh) for delta-band power-law / mbb draws; everything
+    // else (tabulated bandpasses, other SED types) evaluates every proposal in fp64
+    const bool fast = h->pp_fast && mode != MH_SED_GENERIC;
     KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
 #define LAUNCH_PP(BPL, MODE)                                                                               \
     {                                                                                                      \
@@ -70,19 +74,32 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
       else if (mode == MH_SED_MBB_T) LAUNCH_PP(BPL, MH_SED_MBB_T)  \
       else LAUNCH_PP(BPL, MH_SED_GENERIC)                       \
     }
-    if (bpl <= 2) LAUNCH_PP_MODE(2)
+    if (fast) {
+      const int bplr = bpl <= 2 ? 2 : bpl <= 3 ? 3 : bpl <= 5 ? 5 : 8;
+      launch_perpixel_fast(h, mv, mh, bpl, mode, work, smem + (size_t)4 * bplr * DG_MH_THREADS * sizeof(double));
+    }
+    else if (bpl <= 2) LAUNCH_PP_MODE(2)
     else if (bpl <= 3) LAUNCH_PP_MODE(3)
     else if (bpl <= 5) LAUNCH_PP_MODE(5)
     else LAUNCH_PP_MODE(8)
 #undef LAUNCH_PP_MODE
 #undef LAUNCH_PP
     kt.done();
+    pp_fast_ran = fast;
   }
-  gather(h, 1);
+  const int cnt = pp_fast_ran ? 4 : 1;
+  gather(h, cnt);
   double *hp = (double *)h->pinned;
-  readback(h, hp, h->gathered, (size_t)h->nranks * sizeof(double));
+  readback(h, hp, h->gathered, (size_t)h->nranks * cnt * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
   double a = 0;
-  for (int g = 0; g < h->nranks; g++) a += hp[g];
+  h->pp_fallbacks = h->pp_violations = 0.0;
+  for (int g = 0; g < h->nranks; g++) {
+    a += hp[g * cnt];
+    if (pp_fast_ran) {
+      h->pp_fallbacks += hp[g * cnt + 1];
+      h->pp_violations += hp[g * cnt + 2];
+    }
+  }
   if (accept) *accept = a;
 }

@@ -29,6 +29,8 @@ OPT_PERPIXEL_SERIAL = 7
 OPT_CG_CHECKPOINT = 8
 OPT_TMA = 9
 OPT_STAT_CACHE = 10
+OPT_L2_PERSIST_MB = 11
+OPT_PERPIXEL_FAST = 12
 KERNEL_COUNT = 12
 
 
@@ -242,6 +244,12 @@ class Engine:
         self._ck(self.lib.dang_gpu_sample_index(self.h, ic, nind, map_n, nsample, ML_MODES[ml_mode],
                                                 _dp(zz), _dp(uu), seed, C.byref(acc)))
         return acc.value
+
+    def perpixel_stats(self) -> Tuple[float, float]:
+        """(fp64 fallbacks, bound violations) of the last per-pixel draw's fp32 screening."""
+        f, v = C.c_double(), C.c_double()
+        self._ck(self.lib.dang_gpu_perpixel_stats(self.h, C.byref(f), C.byref(v)))
+        return f.value, v.value
 
     def tune_index(self, ic: int, nind: int, map_n: int, nsample: Optional[int] = None,
                    ml_mode: Optional[str] = None, z: Optional[np.ndarray] = None,

@@ -93,7 +93,13 @@ enum {
   DANG_OPT_STAT_CACHE = 10,
   /* MB of the CG block matrices M marked persisting in L2 (cudaAccessPolicyWindow) for the passes of a
    * solve; the rest of the CG state streams.  0: off. */
-  DANG_OPT_L2_PERSIST_MB = 11
+  DANG_OPT_L2_PERSIST_MB = 11,
+  /* Per-pixel Metropolis, delta bands, power-law / mbb indices.  1 (default): every proposal is screened
+   * in single precision from the chi-square DIFFERENCE about the chain's starting point (the data term
+   * cancels analytically) with a running error bound; a proposal whose |diff - ln u| is inside the bound
+   * is re-evaluated in fp64 with the arithmetic of the fp64 kernel, so the decisions are the fp64
+   * kernel's (dang_gpu_perpixel_stats counts the fallbacks).  0: every proposal in fp64. */
+  DANG_OPT_PERPIXEL_FAST = 12
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
@@ -182,6 +188,10 @@ int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsampl
  * per-pixel: [l*npix + pix] for this handle's pixels (other entries untouched).
  * lnl: lnl_new of every evaluated proposal, same indexing (may be NULL). */
 int dang_gpu_get_decisions(dang_gpu_t *h, unsigned char *decisions, double *lnl);
+/* screening statistics of the last per-pixel dang_gpu_sample_index (all ranks): proposals decided by the
+ * fp64 fallback; in record mode (option 6) also the proposals whose screened difference broke its error
+ * bound or whose certain decision differed from the fp64 one (must be 0). */
+int dang_gpu_perpixel_stats(dang_gpu_t *h, double *fallbacks, double *violations);
 /* tune_spectral_parameter_length, src/dang_sample_mod.f90:623-717 (full-sky chain).
  * z, u hold max_blocks*nsample slots, [block*nsample + l]. */
 int dang_gpu_tune_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsample, int ml_mode,

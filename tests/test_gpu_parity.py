@@ -197,12 +197,13 @@ def test_device_rng_eta_matches_philox_definition():
 
 
 # ------------------------------------------------------------------ spectral-parameter draw
-def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11, serial=0):
-    from dang_b200.engine import OPT_PERPIXEL_SERIAL, OPT_RECORD, Engine
+def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11, serial=0, fast=1):
+    from dang_b200.engine import OPT_PERPIXEL_FAST, OPT_PERPIXEL_SERIAL, OPT_RECORD, Engine
     from oracle.binding import Oracle
     ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
     eng.set_option(OPT_RECORD, 1)
     eng.set_option(OPT_PERPIXEL_SERIAL, serial)
+    eng.set_option(OPT_PERPIXEL_FAST, fast)
     z, u = deviates(cfg, nsample, seed=seed)
     acc_o, dec_o, lnl_o = ora.sample_index_mh(ic, nind, -1, nsample, 1 if ml_mode == "sample" else 0, z, u,
                                               want_trace=True)
@@ -211,17 +212,23 @@ def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11, serial=
     return ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g)
 
 
-@pytest.mark.parametrize("serial", [0, 1])  # lane-cooperative (default) and strict-order kernels
+# kernels: fp32-screened lane-cooperative (default), fp64 lane-cooperative, strict reference order
+@pytest.mark.parametrize("kernel", ["screened", "fp64", "serial"])
 @pytest.mark.parametrize("name,ic,nind,nside", [("c1", 0, 0, 16), ("c3", 1, 0, 4), ("c3", 0, 0, 4), ("c4", 1, 0, 8),
-                                                ("c4", 1, 1, 8), ("c2", 1, 1, 8)])
-def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside, serial):
+                                                ("c4", 1, 1, 8), ("c2", 1, 1, 8), ("c4", 0, 0, 8)])
+def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside, kernel):
     cfg, sky = small_case(name, nside)
     cfg.comps[ic].indices[nind].sample = True
     cfg.comps[ic].indices[nind].region = "per-pixel"
     nsample = 12
-    ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(cfg, sky, ic, nind, nsample, serial=serial)
+    ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(
+        cfg, sky, ic, nind, nsample, serial=int(kernel == "serial"), fast=int(kernel == "screened"))
     assert np.array_equal(dec_g, dec_o), f"{(dec_g != dec_o).sum()} decisions differ"
     assert acc_g == acc_o
+    if kernel == "screened":  # record mode checks every screened difference against its error bound
+        fallbacks, violations = eng.perpixel_stats()
+        assert violations == 0, (fallbacks, violations)
+        assert fallbacks <= 0.02 * (dec_o < 2).sum(), (fallbacks, (dec_o < 2).sum())
     ev = dec_o < 2
     assert rel_err(lnl_g[ev], lnl_o[ev]) < TOL
     # accepted proposals are stored verbatim => index maps agree to the last bit up to the
@@ -230,6 +237,34 @@ def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside, serial):
     assert rel_err(idx_g, idx_o) < 1e-14
     assert np.all(idx_g[nind][1:3][:, sky.mask == 0] == 0.0)
     assert np.array_equal(idx_g[nind][0], idx_o[nind][0])  # I plane untouched
+
+
+@pytest.mark.parametrize("name,ic,nind", [("c4", 1, 0), ("c4", 1, 1), ("c1", 0, 0)])
+def test_perpixel_screened_kernel_takes_the_fp64_decisions(name, ic, nind):
+    """Production mode (no recording): the fp32-screened kernel and the fp64 kernel leave identical index
+    maps and acceptance counts after long chains with big steps, at a size where ~1e6 proposals are
+    decided; the fallback rate stays small."""
+    from dang_b200.engine import OPT_PERPIXEL_FAST, Engine
+    cfg, sky = small_case(name, 64)
+    spec = cfg.comps[ic].indices[nind]
+    spec.sample, spec.region = True, "per-pixel"
+    spec.step *= 3.0
+    nsample = 40
+    z, u = deviates(cfg, nsample, seed=5)
+    a, b = Engine(cfg, sky), Engine(cfg, sky)
+    b.set_option(OPT_PERPIXEL_FAST, 0)
+    acc_a = a.sample_index_mh(ic, nind, -1, nsample, "sample", z, u)
+    acc_b = b.sample_index_mh(ic, nind, -1, nsample, "sample", z, u)
+    fallbacks, _ = a.perpixel_stats()
+    assert acc_a == acc_b and acc_a > 0
+    assert np.array_equal(a.indices(ic), b.indices(ic))
+    n_unmasked = int((sky.mask != 0).sum())
+    assert fallbacks < 0.005 * nsample * n_unmasked, (fallbacks, nsample * n_unmasked)
+    # and with the device RNG
+    acc_a = a.sample_index_mh(ic, nind, -1, nsample, "sample", seed=99)
+    acc_b = b.sample_index_mh(ic, nind, -1, nsample, "sample", seed=99)
+    assert acc_a == acc_b
+    assert np.array_equal(a.indices(ic), b.indices(ic))
 
 
 def test_perpixel_optimize_mode_and_uniform_prior():
