@@ -298,23 +298,23 @@ __host__ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t
 enum { DG_STREAM_ETA = 1, DG_STREAM_MH_Z = 2, DG_STREAM_MH_U = 3, DG_STREAM_TUNE_Z = 4, DG_STREAM_TUNE_U = 5, DG_STREAM_GAIN = 6 };
 
 // ---------------------------------------------------------------- cross-rank scalar exchange
-// Every rank owns a mailbox in its own HBM, mapped into all peers with CUDA IPC.  An exchange
-// is: write my row of <= DG_MAIL_VALS doubles into slot (seq mod DG_MAIL_SLOTS) of EVERY rank's
-// mailbox over NVLink, publish it with a release store of the sequence number, then wait for
-// every rank's row in my own mailbox and copy the rows out in rank order (=> the sums formed
-// from them are bit-identical everywhere).  One warp does it, lane = peer rank; it runs inside
-// the kernel that produced the partial sums, so a CG iteration on N GPUs is still ONE launch and
-// the collective costs one NVLink round trip instead of an NCCL launch.
-// All ranks execute the same sequence of exchanges (they take identical decisions from
-// identical sums), so sequence numbers stay aligned; a rank can lead by at most one exchange.
+// Every rank owns a mailbox in its own HBM, mapped into all peers with CUDA IPC.  An exchange is: write
+// my row of <= DG_MAIL_VALS doubles into slot (seq mod DG_MAIL_SLOTS) of EVERY rank's mailbox over
+// NVLink, then wait for every rank's row in my own mailbox and copy the rows out in rank order (=> the
+// sums formed from them are bit-identical everywhere).  The rows travel in the low-latency form NCCL's
+// LL protocol uses: every 8-byte store carries 4 bytes of payload and the 4-byte sequence number of the
+// exchange, so a word is valid exactly when its flag matches -- no fence, no separate "ready" store,
+// one NVLink write latency.  One warp does it inside the kernel that produced the partial sums, so a CG
+// iteration on N GPUs is still ONE launch.
+// All ranks execute the same sequence of exchanges (they take identical decisions from identical
+// sums), so sequence numbers stay aligned; a rank can lead by at most one exchange, and a slot is
+// reused only DG_MAIL_SLOTS exchanges later.
 #define DG_MAIL_VALS 256
 #define DG_MAIL_SLOTS 4
 #define DG_MAX_RANKS 32
 
 struct Mail {
-  double vals[DG_MAIL_VALS];
-  unsigned long long seq;
-  unsigned long long pad[15];
+  unsigned long long w[2 * DG_MAIL_VALS];  // {payload half (low 32 bits), flag (high 32 bits)} x 2 per double
 };
 
 struct PeerComm {
@@ -324,13 +324,11 @@ struct PeerComm {
   Mail *box[DG_MAX_RANKS];       // box[g]: rank g's mailbox [DG_MAIL_SLOTS][nranks] (peer-mapped)
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_ll(unsigned long long *p, unsigned int data, unsigned int flag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(flag) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void ld_ll(const unsigned long long *p, unsigned int &data, unsigned int &flag) {
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(data), "=r"(flag) : "l"(p) : "memory");
 }
 
 // Called by ONE full warp.  local[cnt] -> gathered[nranks][cnt] (rank order).
@@ -339,24 +337,46 @@ __device__ __forceinline__ void peer_exchange(const PeerComm &pc, const double *
   const int lane = threadIdx.x & 31;
   __syncwarp();  // `local` was written by one lane of this warp
   const unsigned long long seq = *pc.seq + 1;
+  const unsigned int flag = (unsigned int)seq;  // never 0 in practice; a stale slot holds seq - DG_MAIL_SLOTS
   const int slot = (int)(seq % DG_MAIL_SLOTS);
-  if (lane < pc.nranks) {
-    Mail *dst = pc.box[lane] + (size_t)slot * pc.nranks + pc.rank;  // my row in rank `lane`'s box
-    for (int i = 0; i < cnt; i++) dst->vals[i] = local[i];
-    __threadfence_system();
-    st_release_sys(&dst->seq, seq);
-    const Mail *src = pc.box[pc.rank] + (size_t)slot * pc.nranks + lane;  // rank `lane`'s row in my box
-    const long long t0 = clock64();
-    bool ok = true;
-    while (ld_acquire_sys(&src->seq) != seq) {
-      if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; fail loudly instead of hanging
-        ok = false;
-        break;
+  const int nw = 2 * cnt, total = pc.nranks * nw;
+  // send: word k of my row to every rank (item = peer * nw + k, strided over the warp)
+  for (int it = lane; it < total; it += 32) {
+    const int g = it / nw, k = it - g * nw;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(local[k >> 1]);
+    const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
+    Mail *dst = pc.box[g] + (size_t)slot * pc.nranks + pc.rank;  // my row in rank g's box
+    st_ll(&dst->w[k], half, flag);
+  }
+  // receive: every rank's row from my own box (all 32 lanes stay in step for the shuffle)
+  bool ok = true;
+  const long long t0 = clock64();
+  for (int base = 0; base < total; base += 32) {
+    const int it = base + lane;
+    const bool active = it < total;
+    const int g = active ? it / nw : 0, k = active ? it - g * nw : 0;
+    unsigned int half = 0, f = flag;
+    if (active) {
+      const Mail *src = pc.box[pc.rank] + (size_t)slot * pc.nranks + g;
+      ld_ll(&src->w[k], half, f);
+      while (f != flag) {
+        if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; fail loudly instead of hanging
+          ok = false;
+          half = 0;
+          break;
+        }
+        ld_ll(&src->w[k], half, f);
       }
     }
-    if (!ok) atomicExch(pc.error, 1);
-    for (int i = 0; i < cnt; i++) gathered[lane * cnt + i] = ok ? src->vals[i] : 0.0;
+    __syncwarp();
+    // the two halves of a double sit in neighbouring lanes (nw is even, so lane parity == k parity)
+    const unsigned int other = __shfl_xor_sync(0xffffffffu, half, 1);
+    if (active && !(k & 1)) {
+      const unsigned long long bits = ((unsigned long long)other << 32) | half;
+      gathered[g * cnt + (k >> 1)] = __longlong_as_double((long long)bits);
+    }
   }
+  if (!ok) atomicExch(pc.error, 1);
   __syncwarp();
   if (lane == 0) *pc.seq = seq;
   __syncwarp();
