@@ -36,6 +36,8 @@ SIGNATURES = {
     "dang_gpu_set_gain_offset": (C.c_int, [vp, c_dp, c_dp]),
     "dang_gpu_set_component": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.c_double, C.c_int, C.c_int,
                                          c_dp, c_dp]),
+    "dang_gpu_set_template": (C.c_int, [vp, C.c_int, c_dp, c_dp, c_ip, C.c_int]),
+    "dang_gpu_get_template_amplitudes": (C.c_int, [vp, C.c_int, c_dp]),
     "dang_gpu_set_index": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp,
                                      C.c_double, C.c_int, c_ip, C.c_int]),
     "dang_gpu_set_amplitude": (C.c_int, [vp, C.c_int, c_dp]),

@@ -39,8 +39,9 @@ struct CompView {
   int type;     // DANG_COMP_*
   int nind;
   double nu_ref;
-  double *amp;             // [nmaps][Ppad]
+  double *amp;             // [nmaps][Ppad]; type 'template': the (normalised) template map
   double *idx[DG_MAXIND];  // each [nmaps][Ppad]
+  const double *tamp;      // type 'template': template_amplitudes [3][DG_MAX_BANDS] (its "SED" table), else null
 };
 
 // Model description handed to kernels by value (lives in the constant bank: every thread reads
@@ -235,6 +236,7 @@ __device__ __forceinline__ double sed_theta(const ModelView &mv, int ic, int ban
     case 2: return sed_mbb(mv, ic, band, t0, t1);
     case 3: return sed_freefree(mv, ic, band, t0);
     case 4: return sed_lognormal(mv, ic, band, t0, t1);
+    case 6: return 0.0;  // 'template': always tabulated (sed_table_kernel copies template_amplitudes)
     default: return sed_cmb(mv, band);
   }
 }

@@ -95,6 +95,7 @@ ModelView model_view(dang_gpu *h) {
     mv.comp[c].nu_ref = h->comp[c].nu_ref;
     mv.comp[c].amp = h->comp[c].amp;
     for (int l = 0; l < DG_MAXIND; l++) mv.comp[c].idx[l] = h->comp[c].idx[l];
+    mv.comp[c].tamp = h->comp[c].is_template ? h->comp[c].tamp : nullptr;
   }
   mv.bp_nu0 = h->bp_nu0;
   mv.bp_tau0 = h->bp_tau0;
@@ -154,6 +155,14 @@ void gather(dang_gpu *h, int cnt) {
     NCK(g_nccl.AllGather(h->sums_local, h->gathered, cnt, NCCL_DOUBLE, h->comm, h->stream));
   }
 }
+// template_amplitudes host mirror -> device table; the tabulated "SEDs" must be rebuilt
+void upload_tamp(dang_gpu *h, CompHost &c) {
+  if (!c.tamp) CK(cudaMalloc(&c.tamp, sizeof c.tamp_host));
+  // pageable source: the copy is staged before the call returns, so the mirror may change right after
+  CK(cudaMemcpyAsync(c.tamp, c.tamp_host, sizeof c.tamp_host, cudaMemcpyHostToDevice, h->stream));
+  h->tab_dirty = true;
+}
+
 // unmasked pixels over all ranks (compute_chisq's count, src/dang_data_mod.f90:153-161); counted once per
 // upload, the chi-square kernels refresh it as a by-product
 int64_t unmasked_count(dang_gpu *h) {
@@ -277,7 +286,7 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   if (!h->maps_borrowed) { dfree(h->sig); dfree(h->rms); dfree(h->mask); }
   dfree(h->bp_nu0); dfree(h->bp_tau0);
   for (auto &c : h->comp) {
-    dfree(c.amp); dfree(c.amp_alt); dfree(c.idx[0]); dfree(c.idx[1]);
+    dfree(c.amp); dfree(c.amp_alt); dfree(c.idx[0]); dfree(c.idx[1]); dfree(c.tamp);
     if (c.ev_read) cudaEventDestroy(c.ev_read);
     if (c.ev_read_alt) cudaEventDestroy(c.ev_read_alt);
   }
@@ -285,7 +294,7 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
   dfree(h->decisions); dfree(h->lnl_trace); dfree(h->stage); dfree(h->partials); dfree(h->tickets);
   dfree(h->sums_local); dfree(h->gathered_buf); dfree(h->cg_scalars); dfree(h->mh_scalars); dfree(h->tab);
-  dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo); dfree(h->stat_buf);
+  dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo); dfree(h->stat_buf); dfree(h->tb); dfree(h->tq); dfree(h->tmpl_scalars);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -502,9 +511,9 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
                            const double *indices) {
   API_BEGIN
   if (ic < 0 || ic >= h->ncomp) fail(DANG_GPU_EINVAL, "component %d of %d", ic, h->ncomp);
-  if (type < DANG_COMP_POWERLAW || type > DANG_COMP_CMB)
+  if (type < DANG_COMP_POWERLAW || type > DANG_COMP_TEMPLATE)
     fail(DANG_GPU_EUNSUPPORTED,
-         "component type %d: power-law, mbb, freefree, lognormal and cmb are built; template / monopole / hi_fit / T_cmb "
+         "component type %d: power-law, mbb, freefree, lognormal, cmb and template are built; monopole / hi_fit / T_cmb "
          "are not (DESIGN.md)", type);
   CompHost &c = h->comp[ic];
   c.set = true;
@@ -513,7 +522,14 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   c.nu_ref = nu_ref_hz;
   c.cg_group = cg_group;
   c.sample_amplitude = sample_amplitude != 0;
-  c.nind = (type == DANG_COMP_MBB || type == DANG_COMP_LOGNORMAL) ? 2 : (type == DANG_COMP_CMB ? 0 : 1);
+  c.nind = (type == DANG_COMP_MBB || type == DANG_COMP_LOGNORMAL) ? 2 : ((type == DANG_COMP_CMB || type == DANG_COMP_TEMPLATE) ? 0 : 1);
+  c.is_template = type == DANG_COMP_TEMPLATE;
+  if (c.is_template) {  // until dang_gpu_set_template: empty template, zero amplitudes, no fitted band
+    memset(c.tamp_host, 0, sizeof c.tamp_host);
+    memset(c.corr, 0, sizeof c.corr);
+    c.nfit = 0;
+    upload_tamp(h, c);
+  }
   const size_t n2 = (size_t)h->nmaps * h->Ppad;
   if (!c.amp) CK(cudaMalloc(&c.amp, n2 * sizeof(double)));
   amp_write_barrier(h, c);
@@ -536,6 +552,43 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   touch(h);
   for (int k = 0; k < 3; k++)
     for (int l = 0; l < DG_MAXIND; l++) h->check_mask |= 1ull << ((ic * 3 + k) * DG_MAXIND + l);
+  API_END
+}
+
+int dang_gpu_set_template(dang_gpu_t *h, int ic, const double *template_map, const double *template_amplitudes,
+                          const int *corr, int nfit) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !h->comp[ic].is_template)
+    fail(DANG_GPU_EINVAL, "component %d is not a template component", ic);
+  if (!template_map || !corr) fail(DANG_GPU_EINVAL, "null template / corr pointer");
+  CompHost &c = h->comp[ic];
+  int count = 0;
+  for (int j = 0; j < h->nbands; j++) {
+    c.corr[j] = corr[j] != 0;
+    count += c.corr[j];
+  }
+  if (count != nfit) fail(DANG_GPU_EINVAL, "nfit = %d but corr selects %d bands", nfit, count);
+  c.nfit = nfit;
+  amp_write_barrier(h, c);
+  h2d_planes(h, c.amp, template_map, h->nmaps);  // c%template, already divided by temp_norm (:574-577)
+  memset(c.tamp_host, 0, sizeof c.tamp_host);
+  if (template_amplitudes)  // Fortran template_amplitudes(nbands, nmaps) == C [plane][band]
+    for (int k = 0; k < h->nmaps; k++)
+      for (int j = 0; j < h->nbands; j++) c.tamp_host[k][j] = template_amplitudes[(size_t)k * h->nbands + j];
+  upload_tamp(h, c);
+  for (auto &g : h->cg)
+    for (int f = 0; f < 3; f++) g.xt_set[f] = false;
+  CK(cudaStreamSynchronize(h->stream));
+  touch(h);
+  API_END
+}
+
+int dang_gpu_get_template_amplitudes(dang_gpu_t *h, int ic, double *template_amplitudes) {
+  API_BEGIN
+  if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !h->comp[ic].is_template || !template_amplitudes)
+    fail(DANG_GPU_EINVAL, "component %d is not a template component", ic);
+  for (int k = 0; k < h->nmaps; k++)
+    for (int j = 0; j < h->nbands; j++) template_amplitudes[(size_t)k * h->nbands + j] = h->comp[ic].tamp_host[k][j];
   API_END
 }
 

@@ -91,6 +91,12 @@ struct CompHost {
   // Second amplitude buffer: while an asynchronous download still reads `amp`, the next solve unpacks
   // into `amp_alt` and the two swap roles, so a download never stalls the solve that follows it.
   double *amp_alt = nullptr;
+  // type 'template' (src/dang_component_mod.f90:536-577): amp holds the template map
+  bool is_template = false;
+  double *tamp = nullptr;                       // device [3][DG_MAX_BANDS] template_amplitudes
+  double tamp_host[3][DG_MAX_BANDS] = {};
+  int corr[DG_MAX_BANDS] = {};
+  int nfit = 0;
   cudaEvent_t ev_read = nullptr, ev_read_alt = nullptr;  // last download that read amp / amp_alt
   bool read_pending = false, read_pending_alt = false;
   double *idx[DG_MAXIND] = {nullptr, nullptr};
@@ -102,6 +108,8 @@ struct CgGroupHost {
   int cg_group = 0, i_max = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
   double converge = 0;
   double *x[3] = {nullptr, nullptr, nullptr};  // Q10: persists across Gibbs iterations
+  double xt[3][16] = {};                       // ... and so do the template amplitudes in the tail of x
+  bool xt_set[3] = {false, false, false};
   size_t x_len[3] = {0, 0, 0};
   int last_iter[3] = {0, 0, 0};  // iterations of the previous solve (sizes the first batch)
 };
@@ -156,6 +164,8 @@ struct dang_gpu {
   std::vector<CgGroupHost> cg;
 
   // scratch
+  double *tb = nullptr, *tq = nullptr; size_t t_len = 0;  // template CG: b and q planes
+  struct TmplScalars *tmpl_scalars = nullptr;
   double *M = nullptr, *r = nullptr, *d = nullptr, *eta = nullptr;
   size_t M_len = 0, v_len = 0, eta_len = 0;
   int cg_layout = -1;
@@ -353,6 +363,10 @@ inline void touch(dang_gpu *h, int what = 0) {  // the model state changed
 }
 // host_mh_fs.cu: serve compute_chisq from the sufficient statistics of the upcoming full-sky draw
 bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]);
+void cg_solve_template(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const double *eta, uint64_t seed,
+                       const int *comps, int C, int tcomp, const int *og, int nog, int *n_iter,
+                       double *delta_final);                                       // host_tmpl.cu
+void upload_tamp(dang_gpu *h, CompHost &c);                                        // dang_gpu.cu
 void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, double *chi_map,
                double out4[4]);                                                    // host_data.cu
 void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode, MhView &mh);  // host_mh_fs.cu

@@ -147,7 +147,9 @@ static __global__ void sed_table_kernel(const ModelView mv, SedTable *tab) {
   const CompView &cv = mv.comp[c];
   bool uni = true;
   for (int l = 0; l < cv.nind; l++) uni = uni && tab->nonuni[ck][l] == 0;
-  if (uni) {
+  if (cv.tamp) {  // 'template': eval_signal = template_amplitudes(band, plane) * template(pix, plane)
+    for (int j = threadIdx.x; j < mv.nbands; j += blockDim.x) tab->sed[ck][j] = cv.tamp[k * DG_MAX_BANDS + j];
+  } else if (uni) {
     const double t0 = cv.nind > 0 ? cv.idx[0][(size_t)k * mv.Ppad] : 0.0;
     const double t1 = cv.nind > 1 ? cv.idx[1][(size_t)k * mv.Ppad] : 0.0;
     for (int j = threadIdx.x; j < mv.nbands; j += blockDim.x) tab->sed[ck][j] = sed_theta(mv, c, j, t0, t1);

@@ -46,7 +46,8 @@ enum {
 };
 
 /* c%type, src/dang_component_mod.f90:791-809 */
-enum { DANG_COMP_POWERLAW = 1, DANG_COMP_MBB = 2, DANG_COMP_FREEFREE = 3, DANG_COMP_LOGNORMAL = 4, DANG_COMP_CMB = 5 };
+enum { DANG_COMP_POWERLAW = 1, DANG_COMP_MBB = 2, DANG_COMP_FREEFREE = 3, DANG_COMP_LOGNORMAL = 4, DANG_COMP_CMB = 5,
+       DANG_COMP_TEMPLATE = 6 };
 /* c%lnl_type, src/dang_sample_mod.f90:249-258 */
 enum { DANG_LNL_CHISQ = 0, DANG_LNL_MARGINAL = 1, DANG_LNL_PRIOR = 2 };
 /* c%prior_type, src/dang_sample_mod.f90:260-266 */
@@ -144,6 +145,16 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label,
                            double nu_ref_hz, int cg_group, int sample_amplitude,
                            const double *amplitude /* (npix,nmaps) */,
                            const double *indices /* (npix,nmaps,nindices) */);
+/* type 'template' (src/dang_component_mod.f90:536-577), after dang_gpu_set_component(type = DANG_COMP_TEMPLATE,
+ * amplitude = indices = NULL): template_map = c%template (npix,nmaps), already divided by temp_norm (:574-577);
+ * template_amplitudes = c%template_amplitudes (nbands,nmaps) or NULL for zeros; corr[nbands] = c%corr; nfit = c%nfit.
+ * eval_signal of such a component is template_amplitudes(band,plane) * template(pix,plane) everywhere (chi-square,
+ * sky model, the data of the Metropolis draws); in a CG group it adds `nfit` scalar unknowns, one per fitted band
+ * (compute_rhs :560-587, compute_Ax :745-768,:867-893, compute_sample_vector :1077-1096, unpack :1374-1392).
+ * Built for CG_POLTYPE = Q+U with one template per group placed after the group's diffuse components. */
+int dang_gpu_set_template(dang_gpu_t *h, int ic, const double *template_map, const double *template_amplitudes,
+                          const int *corr, int nfit);
+int dang_gpu_get_template_amplitudes(dang_gpu_t *h, int ic, double *template_amplitudes); /* -> (nbands,nmaps) */
 int dang_gpu_set_index(dang_gpu_t *h, int ic, int nind, int sample_index, int index_mode,
                        int lnl_type, int prior_type, const double gauss_prior[2],
                        const double uni_prior[2], double step_size, int sample_nside,

@@ -57,6 +57,12 @@ typedef struct {
   int sample_nside[ORA_MAXIND];
   int nflag[ORA_MAXIND];
   int pol_flag[ORA_MAXIND][3];
+  /* type 'template' (src/dang_component_mod.f90:536-577): template map (already divided by its
+   * maximum, :574-577), one amplitude per (band, plane), which bands are fitted, how many */
+  double *template_map;        /* [nmaps][npix] */
+  double *template_amplitudes; /* [nmaps][nbands] */
+  int *corr;                   /* [nbands] */
+  int nfit;
 } ora_comp;
 
 struct ora_state {
@@ -135,6 +141,9 @@ void ora_destroy(ora_state *st) {
   for (int i = 0; i < st->ncomp; i++) {
     free(st->comp[i].amplitude);
     free(st->comp[i].indices);
+    free(st->comp[i].template_map);
+    free(st->comp[i].template_amplitudes);
+    free(st->comp[i].corr);
   }
   free(st->bp);
   free(st->comp);
@@ -216,6 +225,7 @@ int ora_set_component(ora_state *st, int ic, int type, const char *label, double
     case ORA_FREEFREE: c->nindices = 1; break;
     case ORA_LOGNORMAL: c->nindices = 2; break;
     case ORA_CMB: c->nindices = 0; break;
+    case ORA_TEMPLATE: c->nindices = 0; break; /* :537 */
     default: return 2;
   }
   size_t n2 = (size_t)st->npix * st->nmaps;
@@ -234,6 +244,39 @@ int ora_set_component(ora_state *st, int ic, int type, const char *label, double
   }
   return 0;
 }
+
+/* type 'template', src/dang_component_mod.f90:536-577: template map normalised by its maximum per
+ * plane (:574-577, done here as the constructor does), template_amplitudes(nbands,nmaps), corr, nfit */
+int ora_set_template(ora_state *st, int ic, const double *template_map, const double *template_amplitudes,
+                     const int *corr, int nfit) {
+  if (ic < 0 || ic >= st->ncomp || st->comp[ic].type != ORA_TEMPLATE) return 1;
+  ora_comp *c = &st->comp[ic];
+  const size_t n2 = (size_t)st->npix * st->nmaps;
+  free(c->template_map);
+  free(c->template_amplitudes);
+  free(c->corr);
+  c->template_map = xcalloc(n2, sizeof(double));
+  c->template_amplitudes = xcalloc((size_t)st->nmaps * st->nbands, sizeof(double));
+  c->corr = xcalloc(st->nbands, sizeof(int));
+  memcpy(c->template_map, template_map, n2 * sizeof(double));
+  for (int k = 0; k < st->nmaps; k++) { /* :574-577 */
+    double mx = c->template_map[IDX2(st, 0, k)];
+    for (int i = 1; i < st->npix; i++)
+      if (c->template_map[IDX2(st, i, k)] > mx) mx = c->template_map[IDX2(st, i, k)];
+    for (int i = 0; i < st->npix; i++) c->template_map[IDX2(st, i, k)] = c->template_map[IDX2(st, i, k)] / mx;
+  }
+  if (template_amplitudes)
+    memcpy(c->template_amplitudes, template_amplitudes, (size_t)st->nmaps * st->nbands * sizeof(double));
+  int count = 0;
+  for (int j = 0; j < st->nbands; j++) {
+    c->corr[j] = corr[j] != 0;
+    count += c->corr[j];
+  }
+  c->nfit = nfit;
+  return count == nfit ? 0 : 2;
+}
+double *ora_template_map(ora_state *st, int ic) { return st->comp[ic].template_map; }
+double *ora_template_amplitudes(ora_state *st, int ic) { return st->comp[ic].template_amplitudes; }
 
 int ora_set_index(ora_state *st, int ic, int nind, int sample_index, int index_mode, int lnl_type,
                   int prior_type, const double gauss[2], const double uni[2], double step_size,
@@ -395,13 +438,17 @@ static double eval_sed_c(const ora_state *st, const ora_comp *c, int band, int p
     case ORA_FREEFREE: return eval_freefree(st, c, band, pix, k, theta);
     case ORA_LOGNORMAL: return eval_lognormal(st, c, band, pix, k, theta);
     case ORA_CMB: return (double)(1.0f) / ora_a2t(&st->bp[band]);
+    case ORA_TEMPLATE: return c->template_map[IDX2(st, pix, map_n - 1)]; /* :803-804 */
     default: return 0.0;
   }
 }
 
-/* eval_signal, src/dang_component_mod.f90:754-776 (diffuse branch :773) */
+/* eval_signal, src/dang_component_mod.f90:754-776 (template :766-767, diffuse branch :773) */
 static double eval_signal_c(const ora_state *st, const ora_comp *c, int band, int pix, int map_n,
                             const double *theta) {
+  if (c->type == ORA_TEMPLATE)
+    return c->template_amplitudes[(size_t)(map_n - 1) * st->nbands + band] *
+           c->template_map[IDX2(st, pix, map_n - 1)];
   return c->amplitude[IDX2(st, pix, map_n - 1)] * eval_sed_c(st, c, band, pix, map_n, theta);
 }
 
@@ -466,12 +513,24 @@ long ora_cg_n(const ora_cg *g, int flag_n) {
   for (int ic = 0; ic < g->st->ncomp; ic++) {
     const ora_comp *c = &g->st->comp[ic];
     if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-    n += m;
+    if (c->type == ORA_TEMPLATE) n += c->nfit; /* :409-414 (only the Q+U branch sizes b correctly) */
+    else n += m;
   }
   return n;
 }
 
 double *ora_cg_x(ora_cg *g, int flag_n) { return g->x[flag_n]; }
+
+/* 0-based slot of band j among the fitted bands of a template component (the counter l(l_ind) of
+ * compute_Ax, :655,886-887), or -1 when the band is not fitted */
+static int template_slot(const ora_state *st, const ora_comp *c, int j) {
+  if (!c->corr[j]) return -1;
+  int l = 0;
+  for (int jj = 0; jj < j; jj++)
+    if (c->corr[jj]) l++;
+  (void)st;
+  return l;
+}
 
 /* compute_rhs, src/dang_cg_mod.f90:326-596 */
 void ora_compute_rhs(ora_cg *g, int flag_n, double *b) {
@@ -502,6 +561,17 @@ void ora_compute_rhs(ora_cg *g, int flag_n, double *b) {
                 data[IDX3(st, i, k - 1, j)] - eval_signal_c(st, c, j, i, k, NULL);
       }
     }
+    if (c->type == ORA_TEMPLATE) { /* :444-460: templates are also removed from the bands they are not fitted to */
+      for (int j = 0; j < nbands; j++) {
+        if (c->corr[j]) continue;
+        for (int i = 0; i < npix; i++) {
+          if (masked(st, i)) continue;
+          for (int k = 1; k <= nmaps; k++)
+            data[IDX3(st, i, k - 1, j)] =
+                data[IDX3(st, i, k - 1, j)] - eval_signal_c(st, c, j, i, k, NULL);
+        }
+      }
+    }
   }
 
   long offset = 0;
@@ -509,6 +579,29 @@ void ora_compute_rhs(ora_cg *g, int flag_n, double *b) {
     const ora_comp *c = &st->comp[ic];
     if (c->cg_group != g->cg_group) continue;
     if (!c->sample_amplitude) continue;
+    if (c->type == ORA_TEMPLATE) { /* :560-587: one masked, noise-weighted sum per fitted band */
+      int l = 0;
+      double *val_array = xcalloc((size_t)S * npix, sizeof(double));
+      for (int j = 0; j < nbands; j++) {
+        if (!c->corr[j]) continue;
+        for (long i = 0; i < (long)S * npix; i++) val_array[i] = 0.0;
+        for (int i = 0; i < npix; i++) {
+          if (masked(st, i)) continue;
+          for (int s = 0; s < S; s++) { /* :568-569: both planes accumulate into val_array(i) */
+            const double rms = st->rms_map[IDX3(st, i, planes[s] - 1, j)];
+            val_array[i] = val_array[i] + data[IDX3(st, i, planes[s] - 1, j)] / (rms * rms) *
+                                              eval_sed_c(st, c, j, i, planes[s], NULL);
+          }
+        }
+        double sum = 0.0;
+        for (long i = 0; i < (long)S * npix; i++) sum += val_array[i];
+        b[offset + l] = b[offset + l] + sum;
+        l++;
+      }
+      free(val_array);
+      offset += c->nfit;
+      continue;
+    }
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < npix; i++) {
       for (int j = 0; j < nbands; j++) {
@@ -530,7 +623,7 @@ void ora_compute_rhs(ora_cg *g, int flag_n, double *b) {
   free(data);
 }
 
-/* compute_Ax, src/dang_cg_mod.f90:598-911 (diffuse components) */
+/* compute_Ax, src/dang_cg_mod.f90:598-911 (diffuse and template components) */
 void ora_compute_Ax(ora_cg *g, const double *x, int flag_n, double *res) {
   ora_state *st = g->st;
   const int npix = st->npix, nbands = st->nbands;
@@ -548,6 +641,18 @@ void ora_compute_Ax(ora_cg *g, const double *x, int flag_n, double *res) {
     for (int ic = 0; ic < st->ncomp; ic++) { /* temp1 = T_nu x, :685-769 */
       const ora_comp *c = &st->comp[ic];
       if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
+      if (c->type == ORA_TEMPLATE) { /* :745-768 */
+        const int l = template_slot(st, c, j);
+        if (l >= 0)
+          for (int i = 0; i < npix; i++) {
+            if (masked(st, i)) continue;
+            for (int s = 0; s < S; s++)
+              temp1[(long)s * npix + i] =
+                  temp1[(long)s * npix + i] + x[offset + l] * eval_sed_c(st, c, j, i, planes[s], NULL);
+          }
+        offset += c->nfit;
+        continue;
+      }
 #pragma omp parallel for schedule(static)
       for (int i = 0; i < npix; i++) {
         if (masked(st, i)) continue;
@@ -570,6 +675,20 @@ void ora_compute_Ax(ora_cg *g, const double *x, int flag_n, double *res) {
     for (int ic = 0; ic < st->ncomp; ic++) { /* temp3 = T_nu^t temp1, :801-894 */
       const ora_comp *c = &st->comp[ic];
       if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
+      if (c->type == ORA_TEMPLATE) { /* :867-893: val_array over both planes, then sum() */
+        const int l = template_slot(st, c, j);
+        if (l >= 0) {
+          double sum = 0.0;
+          for (int s = 0; s < S; s++)
+            for (int i = 0; i < npix; i++) {
+              if (masked(st, i)) continue;
+              sum += temp1[(long)s * npix + i] * eval_sed_c(st, c, j, i, planes[s], NULL);
+            }
+          temp3[offset + l] = temp3[offset + l] + sum;
+        }
+        offset += c->nfit;
+        continue;
+      }
 #pragma omp parallel for schedule(static)
       for (int i = 0; i < npix; i++) {
         if (masked(st, i)) continue;
@@ -610,9 +729,28 @@ void ora_compute_sample_vector(ora_cg *g, const double *eta, int flag_n, double 
             eta[(long)s * npix + i] / st->rms_map[IDX3(st, i, planes[s] - 1, j)];
     }
     long offset = 0;
+    long diffuse_len = 0; /* :950-964: templates sit after ALL diffuse entries, counter l never reset (Q8) */
+    for (int ic = 0; ic < st->ncomp; ic++) {
+      const ora_comp *c = &st->comp[ic];
+      if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
+      if (c->type != ORA_TEMPLATE) diffuse_len += n;
+    }
     for (int ic = 0; ic < st->ncomp; ic++) { /* temp2 = T^t temp1, :1021-1097 */
       const ora_comp *c = &st->comp[ic];
       if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
+      if (c->type == ORA_TEMPLATE) { /* :1077-1096 (one template component per group: Q8 not modelled) */
+        const int l = template_slot(st, c, j);
+        if (l >= 0) {
+          double sum = 0.0;
+          for (int s = 0; s < S; s++)
+            for (int i = 0; i < npix; i++) {
+              if (masked(st, i)) continue;
+              sum += temp1[(long)s * npix + i] * eval_sed_c(st, c, j, i, planes[s], NULL);
+            }
+          temp2[diffuse_len + l] = temp2[diffuse_len + l] + sum;
+        }
+        continue;
+      }
       const long off = fix_q1 ? offset : 0;
 #pragma omp parallel for schedule(static)
       for (int i = 0; i < npix; i++) {
@@ -638,6 +776,18 @@ static void initialize_x(ora_cg *g, int flag_n) {
   for (int ic = 0; ic < st->ncomp; ic++) {
     const ora_comp *c = &st->comp[ic];
     if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
+    if (c->type == ORA_TEMPLATE) { /* :1264-1279: Q+U takes plane 2's amplitudes */
+      int l = 0;
+      for (int j = 0; j < st->nbands; j++) {
+        if (c->corr[j]) {
+          g->x[flag_n][offset + l] = c->template_amplitudes[(size_t)(planes[0] - 1) * st->nbands + j];
+          l++;
+        }
+        if (l >= c->nfit) break;
+      }
+      offset += l;
+      continue;
+    }
     for (int s = 0; s < S; s++) {
       for (int i = 0; i < st->npix; i++)
         g->x[flag_n][offset + i] = c->amplitude[IDX2(st, i, planes[s] - 1)];
@@ -655,6 +805,19 @@ void ora_unpack_amplitudes(ora_cg *g, int flag_n) {
   for (int ic = 0; ic < st->ncomp; ic++) {
     ora_comp *c = &st->comp[ic];
     if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
+    if (c->type == ORA_TEMPLATE) { /* :1374-1392: Q+U writes the fitted value to planes 2 and 3 */
+      int l = 0;
+      for (int j = 0; j < st->nbands; j++) {
+        if (c->corr[j]) {
+          for (int s = 0; s < S; s++)
+            c->template_amplitudes[(size_t)(planes[s] - 1) * st->nbands + j] = g->x[flag_n][offset + l];
+          l++;
+        }
+        if (l >= c->nfit) break;
+      }
+      offset += l;
+      continue;
+    }
     for (int s = 0; s < S; s++) {
       for (int i = 0; i < st->npix; i++)
         c->amplitude[IDX2(st, i, planes[s] - 1)] = g->x[flag_n][offset + i];

@@ -34,7 +34,7 @@ extern "C" {
 #define ORA_MAXIND 2
 
 /* component types, src/dang_component_mod.f90:791-809 */
-enum { ORA_POWERLAW = 1, ORA_MBB = 2, ORA_FREEFREE = 3, ORA_LOGNORMAL = 4, ORA_CMB = 5 };
+enum { ORA_POWERLAW = 1, ORA_MBB = 2, ORA_FREEFREE = 3, ORA_LOGNORMAL = 4, ORA_CMB = 5, ORA_TEMPLATE = 6 };
 /* *_LNL_TYPE, src/dang_sample_mod.f90:249-258 */
 enum { ORA_LNL_CHISQ = 0, ORA_LNL_MARGINAL = 1, ORA_LNL_PRIOR = 2 };
 /* *_PRIOR, src/dang_sample_mod.f90:260-266 */
@@ -64,6 +64,12 @@ void ora_set_pol_type(ora_state *st, int lo, int hi); /* ddata%pol_type(1), (siz
 int ora_set_component(ora_state *st, int ic, int type, const char *label, double nu_ref,
                       int cg_group, int sample_amplitude, const double *amplitude /*npix*nmaps*/,
                       const double *indices /*npix*nmaps*nindices*/);
+/* type 'template' (src/dang_component_mod.f90:536-577); template_map [nmaps][npix] is normalised by its
+ * maximum per plane inside, as the constructor does; template_amplitudes [nmaps][nbands] */
+int ora_set_template(ora_state *st, int ic, const double *template_map, const double *template_amplitudes,
+                     const int *corr, int nfit);
+double *ora_template_map(ora_state *st, int ic);        /* [nmaps][npix], normalised */
+double *ora_template_amplitudes(ora_state *st, int ic); /* [nmaps][nbands] */
 int ora_set_index(ora_state *st, int ic, int nind /*0-based*/, int sample_index, int index_mode,
                   int lnl_type, int prior_type, const double gauss[2], const double uni[2],
                   double step_size, int tuned, int sample_nside, const int *pol_flags, int nflag);
