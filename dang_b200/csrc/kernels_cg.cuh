@@ -87,8 +87,9 @@ rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsi
 #pragma unroll
       for (int c = 0; c < C; c++)
         same = same && sed_uniform(mv, cg.comp[c], cg.plane[0]) == sed_uniform(mv, cg.comp[c], cg.plane[1]);
-      for (int o = 0; o < cg.nog; o++)
-        same = same && sed_uniform(mv, cg.og[o], cg.plane[0]) == sed_uniform(mv, cg.og[o], cg.plane[1]);
+      for (int o = 0; o < cg.nog; o++)  // (a template's "SED" is template_amplitudes(band, plane): per plane)
+        same = same && mv.comp[cg.og[o]].tamp == nullptr &&
+               sed_uniform(mv, cg.og[o], cg.plane[0]) == sed_uniform(mv, cg.og[o], cg.plane[1]);
 #pragma unroll
       for (int c = 0; c < C; c++)
         same = same && th[0][c][0] == th[1][c][0] && th[0][c][1] == th[1][c][1];

@@ -54,7 +54,7 @@ chisq_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned 
 #pragma unroll
         for (int c = 0; c < NC; c++) {
           if (c < mv.ncomp) {
-            if (k > ka && sed_uniform(mv, c, k) == sed_uniform(mv, c, k > 0 ? k - 1 : 0) && th[k][c][0] == th[k > 0 ? k - 1 : 0][c][0] && th[k][c][1] == th[k > 0 ? k - 1 : 0][c][1])
+            if (k > ka && mv.comp[c].tamp == nullptr && sed_uniform(mv, c, k) == sed_uniform(mv, c, k > 0 ? k - 1 : 0) && th[k][c][0] == th[k > 0 ? k - 1 : 0][c][0] && th[k][c][1] == th[k > 0 ? k - 1 : 0][c][1])
               sed[k][c] = sed[k > 0 ? k - 1 : 0][c];
             else
               sed[k][c] = sed_eval(mv, c, k, j, th[k][c][0], th[k][c][1]);

@@ -91,6 +91,15 @@ class Engine:
         # initialize_components
         for ic, c in enumerate(cfg.comps):
             nu_ref = c.nu_ref_ghz * 1e9 if c.nu_ref_ghz < 1e7 else c.nu_ref_ghz  # dang_param_mod.f90:571-573
+            if c.type == "template":
+                # c%template (already divided by temp_norm), c%template_amplitudes(nbands,nmaps), c%corr, c%nfit
+                self._ck(self.lib.dang_gpu_set_component(self.h, ic, COMP_TYPES[c.type], c.label.encode(), nu_ref,
+                                                         c.cg_group, int(c.amp_sample), None, None))
+                corr = (C.c_int * cfg.nbands)(*[int(bool(v)) for v in c.corr])
+                tmap = np.ascontiguousarray(sky.template[c.label], dtype=np.float64)
+                tamp = np.ascontiguousarray(sky.template_amplitudes[c.label], dtype=np.float64)
+                self._ck(self.lib.dang_gpu_set_template(self.h, ic, _dp(tmap), _dp(tamp), corr, int(sum(map(bool, c.corr)))))
+                continue
             amp = np.ascontiguousarray(sky.amplitude[c.label], dtype=np.float64)
             idx = np.ascontiguousarray(sky.indices[c.label], dtype=np.float64)
             self._ck(self.lib.dang_gpu_set_component(self.h, ic, COMP_TYPES[c.type], c.label.encode(), nu_ref,
@@ -175,6 +184,12 @@ class Engine:
     def stage_eta(self, eta: np.ndarray, nplanes: int = 2):
         """Upload the next cg_solve's normals in the background; call that solve with eta=None."""
         self._ck(self.lib.dang_gpu_stage_eta(self.h, _dp(eta), nplanes))
+
+    def template_amplitudes(self, ic: int) -> np.ndarray:
+        """c%template_amplitudes as [plane][band] (Fortran (nbands, nmaps))."""
+        out = np.zeros((self.nmaps, self.nbands))
+        self._ck(self.lib.dang_gpu_get_template_amplitudes(self.h, ic, _dp(out)))
+        return out
 
     def index_fullsky(self, ic: int, nind: int, map_n: int) -> float:
         """The value the whole plane holds after a full-sky draw (8 bytes instead of a map download)."""

@@ -110,6 +110,8 @@ class Sky:
     amplitude: Dict[str, np.ndarray]   # initial component amplitudes [nmaps][npix]
     indices: Dict[str, np.ndarray]     # initial index maps [nindices][nmaps][npix]
     truth: Dict[str, np.ndarray]       # true amplitudes used to build the sky
+    template: Dict[str, np.ndarray] = None             # type 'template': c%template [nmaps][npix] (max = 1 per plane)
+    template_amplitudes: Dict[str, np.ndarray] = None  # c%template_amplitudes [nmaps][nbands]
 
 
 TRUE_THETA = {"synch": (-3.1,), "dust": (1.55, 19.6)}

@@ -35,7 +35,8 @@ module dang_gpu_mod
   integer(i8b), save :: gpu_seed = 20260101_i8b   ! device Philox seed, advanced every draw
 
   ! enums of include/dang_gpu.h
-  integer(c_int), parameter :: COMP_POWERLAW = 1, COMP_MBB = 2, COMP_FREEFREE = 3, COMP_LOGNORMAL = 4, COMP_CMB = 5
+  integer(c_int), parameter :: COMP_POWERLAW = 1, COMP_MBB = 2, COMP_FREEFREE = 3, COMP_LOGNORMAL = 4, COMP_CMB = 5, &
+       COMP_TEMPLATE = 6
   integer(c_int), parameter :: LNL_CHISQ = 0, LNL_MARGINAL = 1, LNL_PRIOR = 2
   integer(c_int), parameter :: PRIOR_UNIFORM = 0, PRIOR_GAUSSIAN = 1, PRIOR_JEFFREYS = 2
   integer(c_int), parameter :: ML_OPTIMIZE = 0, ML_SAMPLE = 1
@@ -150,6 +151,21 @@ module dang_gpu_mod
        integer(c_int), value :: ic, nind, map_n
        real(c_double) :: mean
      end function dang_gpu_index_mean
+     integer(c_int) function dang_gpu_set_template(h, ic, template, template_amplitudes, corr, nfit) &
+          bind(C, name='dang_gpu_set_template')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic, nfit
+       real(c_double) :: template(*), template_amplitudes(*)   ! (0:npix-1,nmaps), (nbands,nmaps)
+       integer(c_int) :: corr(*)
+     end function dang_gpu_set_template
+     integer(c_int) function dang_gpu_get_template_amplitudes(h, ic, template_amplitudes) &
+          bind(C, name='dang_gpu_get_template_amplitudes')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic
+       real(c_double) :: template_amplitudes(*)
+     end function dang_gpu_get_template_amplitudes
      integer(c_int) function dang_gpu_get_index_fullsky(h, ic, nind, map_n, value) &
           bind(C, name='dang_gpu_get_index_fullsky')
        import :: c_int, c_double, c_ptr
@@ -189,6 +205,8 @@ contains
        comp_type_enum = COMP_LOGNORMAL
     else if (trim(ctype) == 'cmb') then
        comp_type_enum = COMP_CMB
+    else if (trim(ctype) == 'template') then
+       comp_type_enum = COMP_TEMPLATE
     else
        write(*,*) 'dang_gpu: component type '//trim(ctype)//' is not on the GPU path yet'
        stop
@@ -222,6 +240,14 @@ contains
 
     do i = 1, ncomp                          ! component_list (dang_component_mod.f90:12-65)
        c => component_list(i)%p
+       if (trim(c%type) == 'template') then   ! dang_component_mod.f90:536-577: c%template is already / temp_norm
+          call gpu_check(dang_gpu_set_component(handle, int(i-1,c_int), COMP_TEMPLATE, &
+               trim(c%label)//c_null_char, c%nu_ref, int(c%cg_group,c_int), merge(1_c_int,0_c_int,c%sample_amplitude), &
+               dummy, dummy), 'set_component')   ! (amplitude / indices are ignored for this type)
+          call gpu_check(dang_gpu_set_template(handle, int(i-1,c_int), c%template, c%template_amplitudes, &
+               merge(1_c_int,0_c_int,c%corr), int(c%nfit,c_int)), 'set_template')
+          cycle
+       end if
        call gpu_check(dang_gpu_set_component(handle, int(i-1,c_int), comp_type_enum(c%type), &
             trim(c%label)//c_null_char, c%nu_ref, int(c%cg_group,c_int), merge(1_c_int,0_c_int,c%sample_amplitude), &
             c%amplitude, c%indices), 'set_component')
@@ -399,6 +425,11 @@ contains
     integer(i4b) :: i
     do i = 1, ncomp
        c => component_list(i)%p
+       if (trim(c%type) == 'template') then   ! unpack_amplitudes :1374-1392 left them in the handle
+          call gpu_check(dang_gpu_get_template_amplitudes(handle, int(i-1,c_int), c%template_amplitudes), &
+               'get_template_amplitudes')
+          cycle
+       end if
        call gpu_check(dang_gpu_get_amplitude(handle, int(i-1,c_int), c%amplitude), 'get_amplitude')
        if (c%nindices > 0) call gpu_check(dang_gpu_get_indices(handle, int(i-1,c_int), c%indices), 'get_indices')
     end do

@@ -58,6 +58,9 @@ def load(omp: bool = False) -> C.CDLL:
         "ora_chi_map": (c_dp, [vp]),
         "ora_step_size": (d, [vp, i, i]),
         "ora_nindices": (i, [vp, i]),
+        "ora_set_template": (i, [vp, i, c_dp, c_dp, ip, i]),
+        "ora_template_map": (c_dp, [vp, i]),
+        "ora_template_amplitudes": (c_dp, [vp, i]),
         "ora_set_gain": (None, [vp, i, d]),
         "ora_eval_sed": (d, [vp, i, i, i, i, c_dp]),
         "ora_eval_signal": (d, [vp, i, i, i, i, c_dp]),
@@ -116,6 +119,18 @@ class Oracle:
                          _dp(sky.offset))
         lib.ora_set_pol_type(self.st, *cfg.pol_type)
         for ic, c in enumerate(cfg.comps):
+            if c.type == "template":
+                rc = lib.ora_set_component(self.st, ic, COMP_TYPES[c.type], c.label.encode(),
+                                           c.nu_ref_ghz, c.cg_group, int(c.amp_sample), None, None)
+                assert rc == 0
+                corr = (C.c_int * cfg.nbands)(*[int(bool(v)) for v in c.corr])
+                # the oracle divides by the per-plane maximum itself (the constructor's :574-577); the
+                # map handed over here is already normalised, so that division is by 1
+                rc = lib.ora_set_template(self.st, ic, _dp(np.ascontiguousarray(sky.template[c.label])),
+                                          _dp(np.ascontiguousarray(sky.template_amplitudes[c.label])), corr,
+                                          int(sum(map(bool, c.corr))))
+                assert rc == 0, rc
+                continue
             rc = lib.ora_set_component(self.st, ic, COMP_TYPES[c.type], c.label.encode(),
                                        c.nu_ref_ghz, c.cg_group, int(c.amp_sample),
                                        _dp(sky.amplitude[c.label]), _dp(sky.indices[c.label]))
@@ -160,6 +175,9 @@ class Oracle:
     def indices(self, ic):
         nind = self.lib.ora_nindices(self.st, ic)
         return self._view(self.lib.ora_indices(self.st, ic), (nind, self.nmaps, self.npix))
+
+    def template_amplitudes(self, ic):
+        return self._view(self.lib.ora_template_amplitudes(self.st, ic), (self.nmaps, self.nbands))
 
     def sky_model(self):
         return self._view(self.lib.ora_sky_model(self.st), (self.nbands, self.nmaps, self.npix))

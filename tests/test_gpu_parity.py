@@ -628,6 +628,78 @@ def test_freefree_lognormal_cmb_components():
     assert rel_err(eng.indices(2), ora.indices(2)) < 1e-14
 
 
+def test_template_cg_operator_matches_oracle():
+    """Right-hand side and matrix-free apply with the template's border rows: the residual norms of the first
+    CG iterations agree with the oracle to rounding.  (Later iterations do not, in ANY two implementations:
+    the bordered system is ill-conditioned and the CG trajectory amplifies 1e-16 differences by ~1e3 per
+    iteration -- the oracle itself changes trajectory with its summation order -- so for this path parity is
+    asserted on the operator here and on the converged solution below, not on the iteration count.)"""
+    from dang_b200.engine import Engine
+    from helpers import template_case
+    from oracle.binding import Oracle
+    cfg, sky, _ = template_case(16)
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    eta = np.random.default_rng(1).standard_normal(2 * cfg.npix)
+    it_o, delta_o, tr_o = ora.cg_search_trace(0, 0, 1, eta)
+    it_g, delta_g = eng.cg_solve(0, 0, "sample", eta)
+    tr_g = eng.cg_trace()
+    assert np.max(np.abs(tr_g[:5] - tr_o[:5]) / tr_o[:5]) < 1e-12
+    assert delta_g <= cfg.cg_groups[0].converge and delta_o <= cfg.cg_groups[0].converge
+    assert abs(it_g - it_o) <= 6
+
+
+@pytest.mark.parametrize("ml_mode", ["optimize", "sample"])
+def test_template_component_cg_and_draws(ml_mode):
+    """a dust TEMPLATE fitted per band next to diffuse synchrotron (the arXiv:2201.03530 set-up).
+    The bordered CG (template rows / columns), its warm start, the chi-square / sky model and a full-sky
+    beta_s draw whose data have the template removed follow the oracle.  Both sides iterate to a tight
+    threshold so that what is compared is the solution of the linear system, not where the CG stopped."""
+    from dang_b200.engine import Engine
+    from helpers import template_case
+    from oracle.binding import Oracle
+    cfg, sky, tamp_true = template_case(16)
+    cfg.ml_mode = ml_mode
+    cfg.cg_groups[0].converge, cfg.cg_groups[0].max_iter = 1e-20, 300
+    spec = cfg.comps[0].indices[0]
+    spec.sample, spec.region, spec.step = True, "fullsky", 0.002
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    rng = np.random.default_rng(3)
+    ml = 1 if ml_mode == "sample" else 0
+    tol = 1e-8
+    for it in range(1, 4):
+        eta = rng.standard_normal(2 * cfg.npix)
+        its_o, _ = ora.sample_cg_group(0, ml, eta)
+        r = eng.sample_cg_groups(ml_mode=ml_mode, eta=eta)
+        assert abs(r[0][0] - its_o[0]) <= 10, (r[0], its_o)
+        chisq_o, _ = ora.compute_chisq()
+        assert abs(r[1] - chisq_o) <= tol * chisq_o
+        assert rel_err(eng.amplitude(0), ora.amplitude(0)) < tol
+        ta_g, ta_o = eng.template_amplitudes(1), ora.template_amplitudes(1)
+        assert rel_err(ta_g, ta_o) < tol
+        assert np.array_equal(ta_g[1], ta_g[2]) and np.all(ta_g[0] == 0.0)
+        if it == 1 and ml_mode == "optimize":  # the fit sees the true amplitudes through the noise
+            assert np.allclose(ta_g[1], tamp_true, rtol=0.1, atol=2.0)
+        nsample = 12
+        z, u = rng.standard_normal(nsample * cfg.npix), rng.random(nsample * cfg.npix)
+        ora.sample_spectral_parameters(nsample, ml, z, u)
+        acc, chisq_g = eng.sample_spectral_parameters(nsample=nsample, ml_mode=ml_mode, z=z, u=u)
+        chisq_o, _ = ora.compute_chisq()
+        assert abs(chisq_g - chisq_o) <= tol * chisq_o
+        assert rel_err(eng.indices(0), ora.indices(0)) < 1e-14
+    sky_g, res_g, chi_g = eng.update_sky_model()
+    assert rel_err(sky_g, ora.sky_model()) < tol and rel_err(res_g, ora.res_map()) < tol
+
+
+def test_template_unsupported_layouts_are_loud():
+    from dang_b200.engine import DangGpuError, Engine
+    from helpers import template_case
+    cfg, sky, _ = template_case(4)
+    cfg.cg_groups[0].poltype = "Q"   # the reference sizes b for template rows only in the Q+U branch
+    eng = Engine(cfg, sky)
+    with pytest.raises(DangGpuError, match="Q\\+U"):
+        eng.sample_cg_groups(eta=np.zeros(cfg.npix))
+
+
 def test_band_gain_fit_intensity():
     """fit_band_gain on a Stokes-I run (TQU = T): gains and offsets enter the data, the fitted
     gain matches the oracle and feeds the next chi-square."""
@@ -709,8 +781,8 @@ def test_errors_are_loud_and_specific():
     with pytest.raises(DangGpuError, match="CG group"):
         eng.cg_solve(ig=5)
     lib = _lib.load()
-    # unsupported component type (template / monopole / hi_fit have no enum value in the ABI)
-    rc = lib.dang_gpu_set_component(eng.h, 0, 6, b"tmpl", 30e9, 1, 1, None, None)
+    # unsupported component type (monopole / hi_fit / T_cmb have no enum value in the ABI)
+    rc = lib.dang_gpu_set_component(eng.h, 0, 7, b"mono", 30e9, 1, 1, None, None)
     assert rc == 3 and b"power-law" in lib.dang_gpu_last_error(eng.h)
     # bad geometry at creation
     h = _lib.vp()

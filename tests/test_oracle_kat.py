@@ -212,3 +212,21 @@ def test_golden_vectors():
     now = run_case()
     for k in gold.files:
         assert np.array_equal(gold[k], now[k]) or rel_err(now[k], gold[k]) < 1e-13, k
+
+
+def test_template_fit_recovers_a_noiseless_sky():
+    """Template branches of compute_rhs / compute_Ax / unpack_amplitudes (src/dang_cg_mod.f90:560-587,
+    :745-768, :867-893, :1374-1392): on a noiseless sky = synchrotron + per-band template amplitudes the CG
+    returns the input template amplitudes and synchrotron map, and the chi-square of the result vanishes."""
+    from helpers import template_case
+    from oracle.binding import Oracle
+    cfg, sky, tamp_true = template_case(8, noise=False)
+    ora = Oracle(cfg, sky)
+    its, delta = ora.sample_cg_group(0, 0, np.zeros(2 * cfg.npix))  # optimize mode: no fluctuation
+    assert 2 < its[0] < cfg.cg_groups[0].max_iter and delta[0] <= cfg.cg_groups[0].converge
+    ta = ora.template_amplitudes(1)
+    assert np.allclose(ta[1], tamp_true, rtol=1e-7, atol=1e-9) and np.array_equal(ta[1], ta[2])
+    assert np.all(ta[0] == 0.0)  # the I plane is never written by a Q+U solve (:1379-1381)
+    m = sky.mask != 0
+    assert np.max(np.abs(ora.amplitude(0)[1:3][:, m] - sky.truth["synch"][1:3][:, m])) < 1e-5
+    assert ora.compute_chisq()[0] < 1e-12
