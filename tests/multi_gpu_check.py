@@ -62,6 +62,29 @@ def main():
         eng.comm_check()
         eng.close()
         dist.barrier()
+    # a CG group with a template component: border-row sums cross ranks like the CG dot products
+    from helpers import template_case
+    cfg, sky, _ = template_case(16)
+    cfg.cg_groups[0].converge, cfg.cg_groups[0].max_iter = 1e-20, 300
+    bounds = ring_partition(cfg.nside, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
+    setup_torch_comm(eng, mailboxes=os.environ.get("DANG_GPU_MAILBOX", "1") != "0")
+    ora = Oracle(cfg, sky)
+    rng = np.random.default_rng(78)
+    for it in (1, 2):
+        eta = rng.standard_normal(2 * cfg.npix)
+        ora.sample_cg_group(0, 1, eta)
+        r = eng.sample_cg_groups(eta=eta)
+        chisq_o, _ = ora.compute_chisq()
+        assert abs(r[1] - chisq_o) <= 1e-8 * chisq_o, (rank, r[1], chisq_o)
+        ta_g, ta_o = eng.template_amplitudes(1), ora.template_amplitudes(1)
+        assert np.max(np.abs(ta_g - ta_o)) <= 1e-8 * np.max(np.abs(ta_o)), (rank, ta_g, ta_o)
+        a, b = eng.amplitude(0)[:, lo:hi], ora.amplitude(0)[:, lo:hi]
+        assert np.max(np.abs(a - b)) <= 1e-8 * np.max(np.abs(ora.amplitude(0))), (rank, "template group amplitudes")
+    eng.comm_check()
+    eng.close()
+    dist.barrier()
     print(f"rank {rank}/{world}: multi-GPU parity ok (pixels [{lo},{hi}), worst amplitude error {worst:.2e})", flush=True)
     dist.destroy_process_group()
 
