@@ -294,7 +294,7 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   dfree(h->M); dfree(h->r); dfree(h->d); dfree(h->eta); dfree(h->D); dfree(h->zbuf); dfree(h->ubuf);
   dfree(h->decisions); dfree(h->lnl_trace); dfree(h->stage); dfree(h->partials); dfree(h->tickets);
   dfree(h->sums_local); dfree(h->gathered_buf); dfree(h->cg_scalars); dfree(h->mh_scalars); dfree(h->tab);
-  dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo); dfree(h->stat_buf); dfree(h->tb); dfree(h->tq); dfree(h->tmpl_scalars);
+  dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo); dfree(h->stat_buf); dfree(h->k5_kj); if (h->k5_st4) cudaFree(h->k5_st4); dfree(h->tb); dfree(h->tq); dfree(h->tmpl_scalars);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -319,7 +319,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_CG_CHUNK: h->cg_chunk = value < 1 ? 1 : (int)value; break;
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
     case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
-    case DANG_OPT_PERPIXEL_FAST: h->pp_fast = value != 0; break;
+    case DANG_OPT_PERPIXEL_FAST: h->pp_fast = value != 0; h->pp_split = value == 2; break;
     case DANG_OPT_TMA: h->use_tma = value != 0; break;
     case DANG_OPT_L2_PERSIST_MB: {
       // the set-aside shrinks the L2 every other kernel sees, so it exists only while the option is on

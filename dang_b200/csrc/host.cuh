@@ -139,6 +139,8 @@ struct dang_gpu {
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int pp_split = 0;       // 1: split form of the screened kernel (rng / state / chain kernels), measured slower
+  void *k5_st4 = nullptr; float *k5_kj = nullptr; size_t k5_len = 0;  // its fp32 state scratch
   int pp_fast = 1;        // certified fp32 screening in the per-pixel Metropolis kernel (DANG_OPT_PERPIXEL_FAST)
   double pp_fallbacks = 0, pp_violations = 0;  // of the last per-pixel draw (all ranks)
   int l2_persist_mb = 0;  // MB of the CG block matrices kept persisting in L2 during a solve (0: off)
@@ -375,6 +377,7 @@ void ensure_decisions(dang_gpu *h, size_t n);
 void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);  // host_mh_pp.cu
 void launch_perpixel_fast(dang_gpu *h, const ModelView &mv, const MhView &mh, int bpl, int mode, int64_t work,
                           size_t smem);                                            // host_mh_ppf.cu
+void launch_perpixel_split(dang_gpu *h, const ModelView &mv, MhView &mh, int bpl, int mode, int64_t work);  // host_mh_ppf.cu
 void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);   // host_mh_fs.cu
 void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
                   int max_blocks, int *blocks_run, double *step_size);             // host_mh_fs.cu

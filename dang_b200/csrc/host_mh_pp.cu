@@ -74,7 +74,9 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
       else if (mode == MH_SED_MBB_T) LAUNCH_PP(BPL, MH_SED_MBB_T)  \
       else LAUNCH_PP(BPL, MH_SED_GENERIC)                       \
     }
-    if (fast) {
+    if (fast && h->pp_split && !h->record) {
+      launch_perpixel_split(h, mv, mh, bpl, mode, work);
+    } else if (fast) {
       const int bplr = bpl <= 2 ? 2 : bpl <= 3 ? 3 : bpl <= 5 ? 5 : 8;
       launch_perpixel_fast(h, mv, mh, bpl, mode, work, smem + (size_t)4 * bplr * DG_MH_THREADS * sizeof(double));
     }

@@ -99,7 +99,10 @@ enum {
    * in single precision from the chi-square DIFFERENCE about the chain's starting point (the data term
    * cancels analytically) with a running error bound; a proposal whose |diff - ln u| is inside the bound
    * is re-evaluated in fp64 with the arithmetic of the fp64 kernel, so the decisions are the fp64
-   * kernel's (dang_gpu_perpixel_stats counts the fallbacks).  0: every proposal in fp64. */
+   * kernel's (dang_gpu_perpixel_stats counts the fallbacks).  2: the same in split form (deviates and the fp64
+   * state in their own kernels, then an fp32-only chain kernel) -- a measured experiment, slower (10.1 against
+   * 7.9 ms per index at nside 512 x 20 bands: the chain loop needs > 128 registers either way).
+   * 0: every proposal in fp64. */
   DANG_OPT_PERPIXEL_FAST = 12
 };
 

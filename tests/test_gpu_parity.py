@@ -267,6 +267,24 @@ def test_perpixel_screened_kernel_takes_the_fp64_decisions(name, ic, nind):
     assert np.array_equal(a.indices(ic), b.indices(ic))
 
 
+def test_perpixel_split_form_matches():
+    """The split form of the screened kernel (option 12 = 2: rng / state / chain kernels) leaves the same
+    index maps and acceptance counts as the default monolithic kernel, with injected and device deviates."""
+    from dang_b200.engine import OPT_PERPIXEL_FAST, Engine
+    cfg, sky = small_case("c4", 32)
+    for ic, nind in ((1, 0), (1, 1)):
+        spec = cfg.comps[ic].indices[nind]
+        spec.sample, spec.region = True, "per-pixel"
+    nsample = 20
+    z, u = deviates(cfg, nsample, seed=9)
+    a, b = Engine(cfg, sky), Engine(cfg, sky)
+    b.set_option(OPT_PERPIXEL_FAST, 2)
+    for ic, nind in ((1, 0), (1, 1)):
+        assert a.sample_index_mh(ic, nind, -1, nsample, "sample", z, u) == b.sample_index_mh(ic, nind, -1, nsample, "sample", z, u)
+        assert a.sample_index_mh(ic, nind, -1, nsample, "sample", seed=5) == b.sample_index_mh(ic, nind, -1, nsample, "sample", seed=5)
+        assert np.array_equal(a.indices(ic), b.indices(ic))
+
+
 def test_perpixel_optimize_mode_and_uniform_prior():
     cfg, sky = small_case("c1", 8)
     cfg.comps[0].indices[0].prior = "uniform"
