@@ -387,7 +387,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--nside", type=int, default=None, help="override the map size (tests only)")
-    ap.add_argument("--cpu-nside", type=int, default=128, help="map size of the bounded CPU sample")
+    ap.add_argument("--cpu-nside", type=int, default=256, help="map size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (experiments), e.g. --opt 8=16")
     args = ap.parse_args()
