@@ -129,3 +129,51 @@ def test_chisq_is_sharding_invariant(case):
         e.close()
     assert parts[0][1] + parts[1][1] == n
     assert rel_err(parts[0][0] + parts[1][0], planes) < 1e-13
+
+
+def test_one_statistics_pass_serves_both_chisquares(case):
+    """Headline iteration at full size: chi-square from the cached sufficient statistics (before and after the
+    full-sky draw) against the streaming chi-square kernel, and the draw itself against the uncached path."""
+    from dang_b200.engine import OPT_STAT_CACHE
+    cfg, sky, _ = case
+    rng = np.random.default_rng(8)
+    z, u = rng.standard_normal(cfg.nsample), rng.random(cfg.nsample)
+    out = {}
+    for cache in (1, 0):
+        eng = engine(cfg, sky, {OPT_STAT_CACHE: cache})
+        for it in (1, 2):
+            eng.cg_solve(0, 0, "sample", seed=40 + it)
+            c_before = eng.compute_chisq()
+            eng.kernel_stats(reset=True)
+            acc = eng.sample_index_mh(1, 0, -1, cfg.nsample, "sample", z, u)
+            c_after = eng.compute_chisq()
+            st = eng.kernel_stats()
+        out[cache] = (c_before, acc, c_after, eng.index_fullsky(1, 0, 2), st["mh_suffstat_kernel"]["launches"], st["chisq_kernel"]["launches"])
+        eng.close()
+    assert out[1][4] == 0 and out[1][5] == 0      # cached: no pass over the maps in the draw or after it
+    assert out[0][4] == 1 and out[0][5] == 1      # uncached: one statistics pass + one chi-square pass
+    assert abs(out[1][0] - out[0][0]) <= 1e-12 * out[0][0]
+    assert out[1][1] == out[0][1] and out[1][3] == out[0][3]
+    assert abs(out[1][2] - out[0][2]) <= 1e-12 * out[0][2]
+
+
+def test_screened_perpixel_chains_equal_fp64_chains_at_full_size():
+    """Config c4's per-pixel beta_d and T_d draws at nside 512 (3.1 M chains x 20 proposals x 20 bands): the
+    fp32-screened kernel leaves bit-identical index maps and acceptance counts, with a tiny fallback rate."""
+    from dang_b200.engine import OPT_PERPIXEL_FAST
+    from dang_b200.synth import make_config, make_sky
+    cfg = make_config("c4", nside=NSIDE)
+    sky = make_sky(cfg)
+    a, b = engine(cfg, sky), engine(cfg, sky, {OPT_PERPIXEL_FAST: 0})
+    n_unmasked = int((sky.mask != 0).sum())
+    for eng in (a, b):
+        eng.cg_solve(0, 0, "sample", seed=3)
+    for nind in (0, 1):
+        acc_a = a.sample_index_mh(1, nind, -1, cfg.nsample, "sample", seed=11 + nind)
+        acc_b = b.sample_index_mh(1, nind, -1, cfg.nsample, "sample", seed=11 + nind)
+        fallbacks, _ = a.perpixel_stats()
+        assert acc_a == acc_b and 0 < acc_a < cfg.nsample * n_unmasked
+        assert fallbacks < 2e-3 * cfg.nsample * n_unmasked, fallbacks
+        ia, ib = a.indices(1)[nind], b.indices(1)[nind]
+        assert np.array_equal(ia, ib)
+        assert np.all(ia[1:3][:, sky.mask == 0] == 0.0)
