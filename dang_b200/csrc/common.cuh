@@ -460,3 +460,46 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *smem, doubl
   }
   return threadIdx.x < 32;
 }
+
+// Grouped variant: block b belongs to group (b % ngroup) and the partials of each group are summed
+// separately (in block order) by the last block: out[g * NV + i].  gridDim.x must be a multiple of
+// ngroup.  Lets one launch run several independent reductions side by side instead of one after the
+// other (each with its own grid-wide tail).
+template <int NV>
+__device__ __forceinline__ bool grid_reduce_grouped(double (&v)[NV], double *smem, double *partials,
+                                                    unsigned int *ticket, double *out, int ngroup) {
+  __shared__ bool is_last_g;
+  block_reduce<NV>(v, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) partials[(size_t)i * gridDim.x + blockIdx.x] = v[i];
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last_g = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last_g) return false;
+  __threadfence();
+  const unsigned int nsub = gridDim.x / ngroup;
+  for (int g = 0; g < ngroup; g++) {
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double a = 0.0;
+      for (unsigned int k = threadIdx.x; k < nsub; k += blockDim.x)
+        a += __ldcg(&partials[(size_t)i * gridDim.x + (size_t)k * ngroup + g]);
+      acc[i] = a;
+    }
+    __syncthreads();  // smem reuse
+    block_reduce<NV>(acc, smem);
+    if (threadIdx.x == 0)
+#pragma unroll
+      for (int i = 0; i < NV; i++) out[g * NV + i] = acc[i];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *ticket = 0;
+    __threadfence();
+  }
+  return threadIdx.x < 32;
+}

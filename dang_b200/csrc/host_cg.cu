@@ -140,7 +140,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
 
   const int fold = (h->nranks == 1 || h->use_mail) ? 1 : 0;
   const int grid = h->cg_two_pass ? occ_grid(h, cg_update_pass_kernel<C>, n2, DG_THREADS)
-                   : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C>, n2, DG_THREADS)
+                   : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C, false>, n2, DG_THREADS)
                                 : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
   const double el = (double)vs;
   auto enqueue_pass = [&](int pass_no) {
@@ -150,8 +150,9 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
         const double per_el = (pass_no % ckpt_m == 0) ? (T + (pass_no == ckpt_m ? 5.0 : 6.0) * C)
                                                       : (T + (pass_no < ckpt_m ? 1.0 : 2.0) * C);
         KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
-        cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0, h->peer, h->gathered);
+        cg_recompute_pass_kernel<C, false><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0, h->peer, h->gathered,
+            CgAmpOut<C>{});
         kt.done();
       } else {
         // compulsory traffic of this launch: x is touched on even passes only
@@ -226,26 +227,9 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     sn = read_state();
     batch = h->cg_chunk;
   }
-  if (!h->cg_two_pass) {  // bring x up to date (pending term of the deferred / checkpointed update)
-    KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 4.0 * C : 3.0 * C)));
-    if (ckpt_m)
-      cg_recompute_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
-          h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1, h->peer, h->gathered);
-    else
-      cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
-    kt.done();
-  }
-
-  if (l2_window) {  // later kernels stream: drop the window and release the persisting lines
-    cudaStreamAttrValue av;
-    memset(&av, 0, sizeof av);
-    av.accessPolicyWindow.num_bytes = 0;
-    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
-    CK(cudaCtxResetPersistingL2Cache());
-  }
-  // unpack_amplitudes :1327-1335: x -> c%amplitude planes.  If an asynchronous download is still
-  // reading a component's planes the new state goes into its second buffer (solved planes from x, the
-  // others carried over) and the buffers swap roles; the download is never waited for.
+  // unpack_amplitudes :1327-1335: x -> c%amplitude planes.  If an asynchronous download is still reading a
+  // component's planes the new state goes into its second buffer (solved planes from x, the others carried
+  // over) and the buffers swap roles; the download is never waited for.
   for (int c = 0; c < C; c++) {
     CompHost &cc = h->comp[comps[c]];
     if (cc.read_pending) {
@@ -269,10 +253,46 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       std::swap(cc.ev_read, cc.ev_read_alt);
       std::swap(cc.read_pending, cc.read_pending_alt);
     }
-    for (int s = 0; s < S; s++)
-      CK(cudaMemcpyAsync(cc.amp + (size_t)cv.plane[s] * h->Ppad, g.x[flag_n] + c * vs + (size_t)s * h->Ppad,
-                         h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
+  // The last pass of the recompute form brings x up to date and writes the amplitude planes in the same
+  // sweep -- when it has anything to do (a solve that stopped exactly on a checkpoint needs no pass).
+  bool unpacked = false;
+  if (!h->cg_two_pass) {  // bring x up to date (pending term of the deferred / checkpointed update)
+    KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 5.0 * C : 3.0 * C)));
+    if (ckpt_m) {
+      CgAmpOut<C> ao{};
+      const CgScalars *hs0 = (const CgScalars *)h->pinned;
+      const bool planes_contiguous = S == 1 || cv.plane[1] == cv.plane[0] + 1;
+      if (sn.done && have_state && planes_contiguous && (hs0->iter - 1) - hs0->ckpt > 0) {
+        for (int c = 0; c < C; c++) ao.p[c] = h->comp[comps[c]].amp + (size_t)cv.plane[0] * h->Ppad;
+        unpacked = true;
+      }
+      if (unpacked)
+        cg_recompute_pass_kernel<C, true><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1, h->peer, h->gathered, ao);
+      else
+        cg_recompute_pass_kernel<C, false><<<grid, DG_THREADS, 0, h->stream>>>(
+            h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, 0, 1, h->peer, h->gathered, ao);
+    } else {
+      cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
+    }
+    kt.done();
+  }
+
+  if (l2_window) {  // later kernels stream: drop the window and release the persisting lines
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.num_bytes = 0;
+    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    CK(cudaCtxResetPersistingL2Cache());
+  }
+  if (!unpacked)
+    for (int c = 0; c < C; c++) {
+      CompHost &cc = h->comp[comps[c]];
+      for (int s = 0; s < S; s++)
+        CK(cudaMemcpyAsync(cc.amp + (size_t)cv.plane[s] * h->Ppad, g.x[flag_n] + c * vs + (size_t)s * h->Ppad,
+                           h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
   {
     CgScalars *hs = (CgScalars *)h->pinned;  // filled by the last read_state (the solve was done then)
     if (!sn.done || !have_state) {  // ran out of passes (i_max) without seeing the flag: read the final state

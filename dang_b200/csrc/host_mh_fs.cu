@@ -83,7 +83,11 @@ int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
     for (int c = 0; c < h->ncomp; c++)
       if (c != mh.ic) uni = uni && comp_uniform(h, c, mh.plane[s]);
   if (uni) {
-    const int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2, DG_THREADS);
+    // one (plane, band chunk) combination per block: the grid is a multiple of the number of combinations
+    const int ncombo = mh.S * nchunk;
+    int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2 * ncombo, DG_THREADS);
+    g2 = g2 / ncombo * ncombo;
+    if (g2 < ncombo) g2 = ncombo;
     if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
     else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
   } else {

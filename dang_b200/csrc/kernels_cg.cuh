@@ -24,6 +24,13 @@ struct CgView {
   int store_d;               // 0: the recompute CG form never reads the initial d (= r)
 };
 
+// destination of the amplitude planes when unpack_amplitudes is folded into the final CG pass
+// (per component: c%amplitude + plane[0] * Ppad, S contiguous planes), or nulls
+template <int C>
+struct CgAmpOut {
+  double *p[C];
+};
+
 template <int C>
 __device__ __forceinline__ int tri(int a, int b) {  // a <= b
   return a * C - a * (a - 1) / 2 + (b - a);
@@ -362,12 +369,12 @@ cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__rest
 //   stored (r, d) = (r_{c+1}, d_c);   pass i:  d_i = r_i + beta_i d_{i-1};  q = M d_i;
 //   x += alpha_i d_i;  r_{i+1} = r_i - alpha_i q          (cg_search :296-305)
 // final = 1: the solve is over; bring x up to date from the last checkpoint (no reduction).
-template <int C>
+template <int C, bool UNPACK>
 __global__ void __launch_bounds__(DG_THREADS)
 cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
                          double *__restrict__ r, double *__restrict__ d, int64_t n2,
                          double *partials, unsigned int *ticket, double *out, int fold, int final,
-                         PeerComm pc, double *gathered) {
+                         PeerComm pc, double *gathered, CgAmpOut<C> ao) {
   constexpr int T = C * (C + 1) / 2;
   if (st->done && !final) return;
   const int c0 = st->ckpt;
@@ -449,6 +456,8 @@ cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__
         *reinterpret_cast<double2 *>(d + c * vs + 2 * e) = dv[c];
       }
       if (with_x) *reinterpret_cast<double2 *>(x + c * vs + 2 * e) = xv[c];
+      // unpack_amplitudes (:1327-1335) folded into the last pass: x -> c%amplitude planes
+      if (UNPACK && final && ao.p[c]) *reinterpret_cast<double2 *>(ao.p[c] + 2 * e) = xv[c];
     }
   }
   if (final) return;

@@ -376,17 +376,21 @@ mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms,
   if (threadIdx.x < B) s0s[threadIdx.x] = ms->s0[threadIdx.x];
   __syncthreads();
   const int64_t n2 = mv.Ppad / 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
-  // one sweep per (plane, band chunk): the statistics are kept per plane so that the chi-square of
-  // compute_chisq (per plane) can be formed from them as well (DESIGN.md "statistics cache")
-  for (int s = 0; s < mh.S; s++)
-  for (int ch = 0; ch < nchunk; ch++) {
+  // One (plane, band chunk) combination per block: the statistics are kept per plane so that the chi-square
+  // of compute_chisq (per plane) can be formed from them as well (DESIGN.md "statistics cache"), and the
+  // S * nchunk sweeps run side by side in ONE grid phase (blocks b, b + ncombo, ... share a combination)
+  // instead of one after the other, each with its own reduction tail.  gridDim.x is a multiple of ncombo.
+  const int ncombo = mh.S * nchunk;
+  const int combo = blockIdx.x % ncombo, sub = blockIdx.x / ncombo, nsub = gridDim.x / ncombo;
+  const int64_t stride = (int64_t)nsub * blockDim.x;
+  {
+    const int s = combo / nchunk, ch = combo % nchunk;
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) acc[i] = 0.0;
     const int k = mh.plane[s];
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    for (int64_t e = (int64_t)sub * blockDim.x + threadIdx.x; e < n2; e += stride) {
       const int64_t p = 2 * e;
       const uchar2 mk = *reinterpret_cast<const uchar2 *>(mv.mask + p);
       const bool use0 = mk.x != 0, use1 = mk.y != 0;
@@ -433,9 +437,7 @@ mh_suffstat_uni_kernel(const ModelView mv, const MhView mh, const MhScalars *ms,
         }
       }
     }
-    const int sc = s * nchunk + ch;
-    grid_reduce<NV>(acc, smem, partials + (size_t)sc * NV * gridDim.x, tickets + sc, out + sc * NV);
-    __syncthreads();
+    grid_reduce_grouped<NV>(acc, smem, partials, tickets, out, ncombo);  // out[(s * nchunk + ch) * NV + ...]
   }
 }
 
