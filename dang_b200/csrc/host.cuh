@@ -312,6 +312,7 @@ inline void readback(dang_gpu *h, void *dst_pinned, const void *src_dev, size_t 
   if (bytes % 4 != 0) fail(DANG_GPU_EINVAL, "readback of %zu bytes", bytes);
   readback_kernel<<<1, 128, 0, h->stream>>>((unsigned int *)dst_pinned, (const unsigned int *)src_dev, (int)(bytes / 4));
   CK(cudaGetLastError());
+  h->launches++;  // (dang_gpu_launch_count: every kernel of this library counts)
 }
 
 // anything that overwrites c.amp in place waits for a download that may still be reading it
