@@ -332,6 +332,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
                 h->l2_persist_max >> 20, h->l2_window_max >> 20);
       break;
     }
+    case DANG_OPT_PERPIXEL_BP_SERIES: h->pp_bp_series = value != 0; break;
     case DANG_OPT_STAT_CACHE: h->stat_cache = value != 0; h->stat_valid = false; h->chisq_valid = false; break;
     case DANG_OPT_CG_CHECKPOINT:
       h->cg_ckpt = value < 0 ? 0 : (value > DG_CG_MAXM ? DG_CG_MAXM : (int)value);

@@ -139,6 +139,7 @@ struct dang_gpu {
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int pp_bp_series = 1;   // tabulated bandpasses: moment series in the per-pixel chains (DANG_OPT_PERPIXEL_BP_SERIES)
   int pp_split = 0;       // 1: split form of the screened kernel (rng / state / chain kernels), measured slower
   void *k5_st4 = nullptr; float *k5_kj = nullptr; size_t k5_len = 0;  // its fp32 state scratch
   int pp_fast = 1;        // certified fp32 screening in the per-pixel Metropolis kernel (DANG_OPT_PERPIXEL_FAST)

@@ -53,25 +53,35 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
     bool any_bp = false;
     for (int j = 0; j < h->nbands; j++) any_bp = any_bp || h->band[j].n != 0;
     int mode = MH_SED_GENERIC;
+    size_t bp_smem = 0;
     if (!any_bp) {
       if (h->comp[mh.ic].type == DANG_COMP_POWERLAW) mode = MH_SED_POWERLAW;
       else if (h->comp[mh.ic].type == DANG_COMP_MBB) mode = mh.nind == 0 ? MH_SED_MBB_BETA : MH_SED_MBB_T;
+    } else if (h->pp_bp_series) {  // tabulated bandpasses: moment series about the chain's first point (kernels_mh.cuh)
+      if (h->comp[mh.ic].type == DANG_COMP_POWERLAW) mode = MH_SED_BP_POWERLAW;
+      else if (h->comp[mh.ic].type == DANG_COMP_MBB && mh.nind == 0) mode = MH_SED_BP_MBB_BETA;
+      if (mode != MH_SED_GENERIC) {
+        const int bplr = bpl <= 2 ? 2 : bpl <= 3 ? 3 : bpl <= 5 ? 5 : 8;
+        bp_smem = (size_t)bplr * (DG_MH_KM + 2) * DG_MH_THREADS * sizeof(double);
+      }
     }
     // certified fp32 screening (kernels_mh_fast.cuh) for delta-band power-law / mbb draws; everything
     // else (tabulated bandpasses, other SED types) evaluates every proposal in fp64
-    const bool fast = h->pp_fast && mode != MH_SED_GENERIC;
+    const bool fast = h->pp_fast && mode != MH_SED_GENERIC && mode < MH_SED_BP_POWERLAW;
     KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
 #define LAUNCH_PP(BPL, MODE)                                                                               \
     {                                                                                                      \
-      CK(cudaFuncSetAttribute(mh_perpixel_kernel<BPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      const int grid = occ_grid(h, mh_perpixel_kernel<BPL, MODE>, work, DG_MH_THREADS, smem);              \
-      mh_perpixel_kernel<BPL, MODE><<<grid, DG_MH_THREADS, smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local); \
+      CK(cudaFuncSetAttribute(mh_perpixel_kernel<BPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + bp_smem))); \
+      const int grid = occ_grid(h, mh_perpixel_kernel<BPL, MODE>, work, DG_MH_THREADS, smem + bp_smem);    \
+      mh_perpixel_kernel<BPL, MODE><<<grid, DG_MH_THREADS, smem + bp_smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local); \
     }
 #define LAUNCH_PP_MODE(BPL)                                     \
     {                                                           \
       if (mode == MH_SED_POWERLAW) LAUNCH_PP(BPL, MH_SED_POWERLAW) \
       else if (mode == MH_SED_MBB_BETA) LAUNCH_PP(BPL, MH_SED_MBB_BETA) \
       else if (mode == MH_SED_MBB_T) LAUNCH_PP(BPL, MH_SED_MBB_T)  \
+      else if (mode == MH_SED_BP_POWERLAW) LAUNCH_PP(BPL, MH_SED_BP_POWERLAW) \
+      else if (mode == MH_SED_BP_MBB_BETA) LAUNCH_PP(BPL, MH_SED_BP_MBB_BETA) \
       else LAUNCH_PP(BPL, MH_SED_GENERIC)                       \
     }
     if (fast && h->pp_split && !h->record) {

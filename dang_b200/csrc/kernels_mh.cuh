@@ -242,7 +242,20 @@ mh_perpixel_serial_kernel(const ModelView mv, const MhView mh, double *partials,
 // -(x-mu)^2/(2 sigma^2) - ln(sigma sqrt(2 pi)): lnL agrees to ~1e-16 relative, so a decision can
 // differ from the reference's only when |diff - ln u| < ~1e-14.
 #define DG_MH_LANES 4
-enum { MH_SED_POWERLAW = 0, MH_SED_MBB_BETA = 1, MH_SED_MBB_T = 2, MH_SED_GENERIC = 3 };
+enum { MH_SED_POWERLAW = 0, MH_SED_MBB_BETA = 1, MH_SED_MBB_T = 2, MH_SED_GENERIC = 3,
+       MH_SED_BP_POWERLAW = 4, MH_SED_BP_MBB_BETA = 5 };
+
+// Tabulated bandpasses (MH_SED_BP_*): the bandpass-integrated SED of a proposal beta = beta_0 + delta is
+//     sum_i w_i exp(delta L_i),  w_i = tau_i [Planck ratio_i] exp((beta_0 [+1]) L_i),  L_i = ln(nu_i / nu_ref),
+// and across one band L_i stays within ~0.15 of the band centre's L_c, so
+//     = exp(delta L_c) sum_k (delta^k / k!) m_k,   m_k = sum_i w_i (L_i - L_c)^k.
+// The moments m_0..m_8 are formed ONCE per pixel and band at the chain's first point (n_bp exp, the summand
+// of evaluate_powerlaw / evaluate_mbb, src/dang_component_mod.f90:909-914,949-955, in its order, so m_0 is
+// the reference's SED there bit for bit); a proposal then costs one exp and 8 FMAs per band instead of
+// n_bp exp -- 128x fewer transcendentals at config c3's n_bp = 128.  The series is cut at
+// |delta| max|L_i - L_c| <= 0.1 (remainder < 3e-15 relative, below the rounding of the n_bp-term sum it
+// replaces); beyond that the proposal is summed directly.
+#define DG_MH_KM 8
 
 template <int BPL, int MODE>
 __global__ void __launch_bounds__(DG_MH_THREADS)
@@ -259,6 +272,10 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
   double *zs = dyn + (size_t)g * nsample, *lus = dyn + (size_t)(PB + g) * nsample;
   double *wzs = dyn + (size_t)(g - lane / L) * nsample;  // first pixel of this warp
   double *wlus = wzs + (size_t)PB * nsample;
+  constexpr bool BPM = MODE == MH_SED_BP_POWERLAW || MODE == MH_SED_BP_MBB_BETA;
+  constexpr bool PLAW = MODE == MH_SED_POWERLAW || MODE == MH_SED_BP_POWERLAW;
+  constexpr bool MBBB = MODE == MH_SED_MBB_BETA || MODE == MH_SED_BP_MBB_BETA;
+  double *mks = dyn + (size_t)2 * PB * nsample + tid;  // BPM: m_k / k! and max|L_i - L_c| per band, [.][threads]
   double acc[1] = {0.0};
   const CompView &cv = mv.comp[mh.ic];
   const SedTable &tab = *mv.tab;
@@ -313,14 +330,46 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
           D1[i] = mh_data_value(mv, mh.ic, j, mh.plane[1], pp);
           W1[i] = 1.0 / ldg_stream(mv.rms + plane_off(mv, j, mh.plane[1]) + pp);
         }
-        if (MODE == MH_SED_MBB_BETA) {
+        if (MBBB) {
           const double z = DG_H / (DG_KB * idx1);
           F[i] = (exp(z * nu_ref) - 1.0) / (exp(z * nuc[i]) - 1.0);
         } else if (MODE == MH_SED_MBB_T) {
           F[i] = exp_scaled(idx0 + 1.0, Lh[i], Ll[i]);
         }
+        if (BPM && bp[i]) {  // moments of the bandpass-integrated SED about the chain's first point
+          const BandView &bv = mv.band[j];
+          const double *lh = mv.bp_lnr_hi + (size_t)mh.ic * mv.nbp + bv.off, *ll = mv.bp_lnr_lo + (size_t)mh.ic * mv.nbp + bv.off;
+          const double *nu0 = mv.bp_nu0 + bv.off, *tau = mv.bp_tau0 + bv.off;
+          const double z = MBBB ? DG_H / (DG_KB * idx1) : 0.0;
+          const double eref = MBBB ? exp(z * nu_ref) - 1.0 : 0.0;
+          double m[DG_MH_KM + 1], dlmax = 0.0;
+#pragma unroll
+          for (int k = 0; k <= DG_MH_KM; k++) m[k] = 0.0;
+          for (int q = 0; q < bv.n; q++) {
+            if (nu0[q] == 0.0) continue;  // :911, :951
+            double w;
+            if (PLAW) w = tau[q] * exp_scaled(cur, lh[q], ll[q]);
+            else w = tau[q] * eref / (exp(z * nu0[q]) - 1.0) * exp_scaled(cur + 1.0, lh[q], ll[q]);
+            const double dl = (lh[q] - Lh[i]) + (ll[q] - Ll[i]);
+            dlmax = fmax(dlmax, fabs(dl));
+            double pw = w;
+#pragma unroll
+            for (int k = 0; k <= DG_MH_KM; k++) {
+              m[k] = m[k] + pw;   // m[0] accumulates in the reference's order: the reference's SED at `cur`
+              pw *= dl;
+            }
+          }
+          double fact = 1.0;
+#pragma unroll
+          for (int k = 0; k <= DG_MH_KM; k++) {
+            if (k > 1) fact *= (double)k;
+            mks[((size_t)i * (DG_MH_KM + 2) + k) * DG_MH_THREADS] = m[k] / fact;
+          }
+          mks[((size_t)i * (DG_MH_KM + 2) + DG_MH_KM + 1) * DG_MH_THREADS] = dlmax;
+        }
       }
     }
+    const double theta_ref = cur;
     // deviates of this warp's PW chains, slot-indexed (Q5), generated by all 32 lanes
     __syncwarp();
     {
@@ -363,8 +412,19 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
         const int j = r + i * L;
         if (j < B) {
           double sed;
-          if (MODE == MH_SED_POWERLAW) sed = exp_scaled(xe, Lh[i], Ll[i]);
-          else if (MODE == MH_SED_MBB_BETA) sed = F[i] * exp_scaled(xe + 1.0, Lh[i], Ll[i]);
+          if (BPM && bp[i]) {
+            const double *mk = mks + (size_t)i * (DG_MH_KM + 2) * DG_MH_THREADS;
+            const double dlt = xe - theta_ref;
+            if (fabs(dlt) * mk[(DG_MH_KM + 1) * DG_MH_THREADS] <= 0.1) {
+              double poly = mk[DG_MH_KM * DG_MH_THREADS];
+#pragma unroll
+              for (int k = DG_MH_KM - 1; k >= 0; k--) poly = fma(poly, dlt, mk[k * DG_MH_THREADS]);
+              sed = exp_scaled(dlt, Lh[i], Ll[i]) * poly;
+            } else {
+              sed = sed_theta(mv, mh.ic, j, xe, idx1);  // far from the first point: sum the bandpass directly
+            }
+          } else if (PLAW) sed = exp_scaled(xe, Lh[i], Ll[i]);
+          else if (MBBB) sed = F[i] * exp_scaled(xe + 1.0, Lh[i], Ll[i]);
           else if (MODE == MH_SED_MBB_T) sed = eref * mh_fast_rcp(exp(zT * nuc[i]) - 1.0) * F[i];
           else sed = sed_theta(mv, mh.ic, j, mh.nind == 0 ? xe : idx0, mh.nind == 0 ? idx1 : xe);
           const double t0 = (D0[i] - amp0 * sed) * W0[i];

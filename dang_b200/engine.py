@@ -31,6 +31,7 @@ OPT_TMA = 9
 OPT_STAT_CACHE = 10
 OPT_L2_PERSIST_MB = 11
 OPT_PERPIXEL_FAST = 12
+OPT_PERPIXEL_BP_SERIES = 13
 KERNEL_COUNT = 12
 
 

@@ -103,7 +103,12 @@ enum {
    * state in their own kernels, then an fp32-only chain kernel) -- a measured experiment, slower (10.1 against
    * 7.9 ms per index at nside 512 x 20 bands: the chain loop needs > 128 registers either way).
    * 0: every proposal in fp64. */
-  DANG_OPT_PERPIXEL_FAST = 12
+  DANG_OPT_PERPIXEL_FAST = 12,
+  /* Per-pixel Metropolis with tabulated bandpasses, power-law beta / mbb beta.  1 (default): the bandpass-
+   * integrated SED of a proposal comes from a 9-term moment series about the chain's first point (the n_bp
+   * exponentials are evaluated once per pixel and band instead of once per proposal; remainder < 3e-15);
+   * 0: every proposal sums the bandpass (evaluate_powerlaw / evaluate_mbb as written). */
+  DANG_OPT_PERPIXEL_BP_SERIES = 13
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */

@@ -267,6 +267,39 @@ def test_perpixel_screened_kernel_takes_the_fp64_decisions(name, ic, nind):
     assert np.array_equal(a.indices(ic), b.indices(ic))
 
 
+@pytest.mark.parametrize("ic,nind", [(0, 0), (1, 0)])
+def test_perpixel_bandpass_moment_series(ic, nind):
+    """Config c3 (tabulated bandpasses, n_bp = 128): the moment series about the chain's first point gives the
+    oracle's decisions and lnL, and the same chains as summing the bandpass for every proposal -- also with
+    steps large enough to push proposals beyond the series' range (direct-sum fallback)."""
+    from dang_b200.engine import OPT_PERPIXEL_BP_SERIES, OPT_RECORD, Engine
+    from oracle.binding import Oracle
+    for step_scale in (1.0, 12.0):
+        cfg, sky = small_case("c3", 8)
+        spec = cfg.comps[ic].indices[nind]
+        spec.sample, spec.region = True, "per-pixel"
+        spec.step *= step_scale
+        nsample = 16
+        z, u = deviates(cfg, nsample, seed=21)
+        ora = Oracle(cfg, sky)
+        acc_o, dec_o, lnl_o = ora.sample_index_mh(ic, nind, -1, nsample, 1, z, u, want_trace=True)
+        res = {}
+        for series in (1, 0):
+            eng = Engine(cfg, sky)
+            eng.set_option(OPT_RECORD, 1)
+            eng.set_option(OPT_PERPIXEL_BP_SERIES, series)
+            acc = eng.sample_index_mh(ic, nind, -1, nsample, "sample", z, u)
+            dec, lnl = eng.decisions(nsample, fullsky=False)
+            res[series] = (acc, dec, lnl, eng.indices(ic).copy())
+            assert np.array_equal(dec, dec_o) and acc == acc_o, (series, step_scale)
+            ev = dec_o < 2
+            assert rel_err(lnl[ev], lnl_o[ev]) < TOL
+            assert rel_err(eng.indices(ic), ora.indices(ic)) < 1e-14
+        assert np.array_equal(res[1][3], res[0][3])
+        ev = dec_o < 2
+        assert rel_err(res[1][2][ev], res[0][2][ev]) < 1e-12
+
+
 def test_perpixel_split_form_matches():
     """The split form of the screened kernel (option 12 = 2: rng / state / chain kernels) leaves the same
     index maps and acceptance counts as the default monolithic kernel, with injected and device deviates."""
