@@ -73,6 +73,9 @@ struct BandHost {
   double nu_c = 0;
   int n = 0;
   std::vector<double> nu0, tau0;
+  // what the device sees: the table itself, or its Gauss-quadrature compression (upload_bandpasses)
+  int n_dev = 0;
+  std::vector<double> nu0_dev, tau0_dev;
 };
 
 struct IndexHost {
@@ -139,6 +142,7 @@ struct dang_gpu {
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int bp_quad = 8;        // nodes of the Gauss-quadrature compression of tabulated bandpasses (0: off)
   int pp_bp_series = 1;   // tabulated bandpasses: moment series in the per-pixel chains (DANG_OPT_PERPIXEL_BP_SERIES)
   int pp_split = 0;       // 1: split form of the screened kernel (rng / state / chain kernels), measured slower
   void *k5_st4 = nullptr; float *k5_kj = nullptr; size_t k5_len = 0;  // its fp32 state scratch

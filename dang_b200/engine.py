@@ -32,6 +32,7 @@ OPT_STAT_CACHE = 10
 OPT_L2_PERSIST_MB = 11
 OPT_PERPIXEL_FAST = 12
 OPT_PERPIXEL_BP_SERIES = 13
+OPT_BP_QUADRATURE = 14
 KERNEL_COUNT = 12
 
 

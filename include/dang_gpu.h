@@ -108,7 +108,13 @@ enum {
    * integrated SED of a proposal comes from a 9-term moment series about the chain's first point (the n_bp
    * exponentials are evaluated once per pixel and band instead of once per proposal; remainder < 3e-15);
    * 0: every proposal sums the bandpass (evaluate_powerlaw / evaluate_mbb as written). */
-  DANG_OPT_PERPIXEL_BP_SERIES = 13
+  DANG_OPT_PERPIXEL_BP_SERIES = 13,
+  /* Tabulated bandpasses are handed to the device as the n-point Gauss quadrature of the discrete measure
+   * {ln(nu0_i / nu_c), tau0_i} (default n = 8; 0: the table itself).  The rule reproduces the table's sum for
+   * every polynomial in ln nu up to degree 2n-1, so bandpass-integrated SEDs agree with the n_bp-term sums of
+   * evaluate_powerlaw / evaluate_mbb / ... to < 1e-15 relative while costing n instead of n_bp
+   * transcendentals per band.  Bands with n_bp <= 2n or negative weights keep their table. */
+  DANG_OPT_BP_QUADRATURE = 14
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */

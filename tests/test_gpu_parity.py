@@ -300,6 +300,32 @@ def test_perpixel_bandpass_moment_series(ic, nind):
         assert rel_err(res[1][2][ev], res[0][2][ev]) < 1e-12
 
 
+def test_bandpass_gauss_quadrature_matches_the_full_table():
+    """Tabulated bandpasses reach the device as their 8-point Gauss quadrature (DANG_OPT_BP_QUADRATURE): chi-square,
+    sky model and CG amplitudes agree with the full 128-sample tables (option 0) to rounding, and with the oracle."""
+    from dang_b200.engine import OPT_BP_QUADRATURE, Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c3", 8)
+    ora = Oracle(cfg, sky)
+    ora.update_sky_model()
+    chisq_o, _ = ora.compute_chisq()
+    eta = np.random.default_rng(2).standard_normal(2 * cfg.npix)
+    its_o, _ = ora.sample_cg_group(0, 1, eta)
+    out = {}
+    for nq in (8, 0):
+        eng = Engine(cfg, sky)
+        eng.set_option(OPT_BP_QUADRATURE, nq)
+        c0 = eng.compute_chisq()
+        sky_g, _, _ = eng.update_sky_model()
+        it, _ = eng.cg_solve(0, 0, "sample", eta)
+        out[nq] = (c0, sky_g, it, eng.amplitude(0), eng.amplitude(1))
+        assert abs(c0 - chisq_o) <= TOL * chisq_o and it == its_o[0]
+        assert rel_err(eng.amplitude(0), ora.amplitude(0)) < TOL and rel_err(eng.amplitude(1), ora.amplitude(1)) < TOL
+    assert abs(out[8][0] - out[0][0]) <= 1e-13 * out[0][0]
+    assert rel_err(out[8][1], out[0][1]) < 1e-13
+    assert rel_err(out[8][3], out[0][3]) < 1e-11 and rel_err(out[8][4], out[0][4]) < 1e-11
+
+
 def test_perpixel_split_form_matches():
     """The split form of the screened kernel (option 12 = 2: rng / state / chain kernels) leaves the same
     index maps and acceptance counts as the default monolithic kernel, with injected and device deviates."""
