@@ -151,6 +151,12 @@ module dang_gpu_mod
        integer(c_int), value :: ic, nind, map_n
        real(c_double) :: mean
      end function dang_gpu_index_mean
+     integer(c_int) function dang_gpu_set_option(h, option, value) bind(C, name='dang_gpu_set_option')
+       import :: c_int, c_double, c_ptr          ! option ids: the DANG_OPT_* enum of include/dang_gpu.h
+       type(c_ptr), value :: h
+       integer(c_int), value :: option
+       real(c_double), value :: value
+     end function dang_gpu_set_option
      integer(c_int) function dang_gpu_set_template(h, ic, template, template_amplitudes, corr, nfit) &
           bind(C, name='dang_gpu_set_template')
        import :: c_int, c_double, c_ptr
