@@ -147,14 +147,16 @@ mh_perpixel_fast_kernel(const __grid_constant__ ModelView mv, const __grid_const
   const bool record = mh.decisions != nullptr;
   const float kappa = MODE == MH_SED_MBB_T ? DG_K5_KAPPA_T : DG_K5_KAPPA_BETA;
 
-  // per-lane band constants in single precision: ln(nu/nu_ref) (beta modes) or h nu / k (T mode)
-  float cf[BPL];
-#pragma unroll
-  for (int i = 0; i < BPL; i++) {
-    const int j = r + i * L;
-    if (MODE == MH_SED_MBB_T) cf[i] = j < B ? (float)(DG_H / DG_KB * mv.band[j].nu_c) : 0.0f;
-    else cf[i] = j < B ? (float)tab.lnr_hi[mh.ic][j] : 0.0f;
+  // band constants in single precision: ln(nu/nu_ref) (beta modes) or h nu / k (T mode); in shared memory
+  // (indexed by band) rather than BPL registers per lane: the chain loop is register-bound
+  __shared__ float scf[BPL * L];
+  if (tid < BPL * L) {
+    const int j = tid;
+    if (MODE == MH_SED_MBB_T) scf[j] = j < B ? (float)(DG_H / DG_KB * mv.band[j].nu_c) : 0.0f;
+    else scf[j] = j < B ? (float)tab.lnr_hi[mh.ic][j] : 0.0f;
   }
+  __syncthreads();
+  const float *cf = scf + r;  // band r + i L -> cf[i * L]
   const float cref = (float)(DG_H / DG_KB * nu_ref);
 
   const int64_t ngroups = (int64_t)gridDim.x * PB;
@@ -180,7 +182,7 @@ mh_perpixel_fast_kernel(const __grid_constant__ ModelView mv, const __grid_const
 
     // ---- state at the chain's first point, evaluated in fp64, kept in fp32: t, g per (band, Stokes),
     //      gs = |g0| + |g1|; T mode: K_j = 1 + 1/em1(h nu_j / k T) per band and for the reference frequency
-    float tr0[BPL], tr1[BPL], g0[BPL], g1[BPL], gs[BPL], kj[BPL];
+    float tr0[BPL], tr1[BPL], g0[BPL], g1[BPL], kj[BPL];
     float kref = 1.0f;
     {
       double zF = 0.0, erefF = 0.0;
@@ -192,7 +194,7 @@ mh_perpixel_fast_kernel(const __grid_constant__ ModelView mv, const __grid_const
 #pragma unroll
       for (int i = 0; i < BPL; i++) {
         const int j = r + i * L;
-        tr0[i] = tr1[i] = g0[i] = g1[i] = gs[i] = 0.0f;
+        tr0[i] = tr1[i] = g0[i] = g1[i] = 0.0f;
         kj[i] = 1.0f;
         if (j < B) {
           const double Lh = tab.lnr_hi[mh.ic][j], Ll = tab.lnr_lo[mh.ic][j];
@@ -221,7 +223,6 @@ mh_perpixel_fast_kernel(const __grid_constant__ ModelView mv, const __grid_const
             tr1[i] = (float)((D1 - m1) * W1);
             g1[i] = (float)(m1 * W1);
           }
-          gs[i] = fabsf(g0[i]) + fabsf(g1[i]);
         }
       }
     }
@@ -291,19 +292,19 @@ mh_perpixel_fast_kernel(const __grid_constant__ ModelView mv, const __grid_const
         for (int i = 0; i < BPL; i++) {
           float b, w2;
           if (MODE == MH_SED_MBB_T) {
-            const float n2 = kj[i] * k5_em1f(cf[i] * d, w2);
+            const float n2 = kj[i] * k5_em1f(cf[i * L] * d, w2);
             const float inv = __frcp_rn(1.0f + n2);
             rho[i] = (n1 - n2) * inv;
             b = fmaf(fabsf(n1), w1, fabsf(n2) * w2) * inv;
           } else {
-            const float xx = d * cf[i];
+            const float xx = d * cf[i * L];
             rho[i] = k5_em1f(xx, w2);
             b = fabsf(rho[i]) * w2 * (1.0f + fabsf(xx));
           }
           const float a0 = g0[i] * rho[i], a1 = g1[i] * rho[i];
           lam = fmaf(a0, fmaf(2.0f, tr0[i], -a0), lam);
           lam = fmaf(a1, fmaf(2.0f, tr1[i], -a1), lam);
-          A1 = fmaf(gs[i], b, A1);
+          A1 = fmaf(fabsf(g0[i]) + fabsf(g1[i]), b, A1);
           A2 += fabsf(a0) + fabsf(a1);
         }
       }
@@ -370,8 +371,7 @@ mh_perpixel_fast_kernel(const __grid_constant__ ModelView mv, const __grid_const
           tr1[i] -= a1;
           g0[i] += a0;
           g1[i] += a1;
-          gs[i] = fabsf(g0[i]) + fabsf(g1[i]);
-          if (MODE == MH_SED_MBB_T) kj[i] = 1.0f + __frcp_rn(k5_em1f(cf[i] * iT));
+          if (MODE == MH_SED_MBB_T) kj[i] = 1.0f + __frcp_rn(k5_em1f(cf[i * L] * iT));
         }
         dT += kap * A1 + 1.2e-7f * (tmax + A2);       // error of a (b-scaled) + rounding of t - a
         kap += 1.5e-7f;                               // g picks up ~1 ulp per update
