@@ -4,8 +4,8 @@
  * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (no reference fixtures exist, reference
  * cannot be built here).  Every function cites the reference file:line it follows.
  * Loop nests, operation order and quirks are kept; the
- * dead "T+Q+U" branches (iand(flag,0), Q2) and template/monopole/hi_fit components
- * are not restated.
+ * dead "T+Q+U" branches (iand(flag,0), Q2) and the monopole / hi_fit / T_cmb components
+ * are not restated; the `template` type is (Q+U fits, one template per CG group).
  *
  * OpenMP pragmas sit on the same pixel loops as the reference's !$OMP PARALLEL DO and
  * are only active when built with -fopenmp (the bench CPU baseline); tests build
