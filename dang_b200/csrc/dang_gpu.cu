@@ -52,6 +52,10 @@ static bool gauss_compress(const BandHost &b, int nq, std::vector<double> &nu_q,
   }
   const int m = (int)x.size();
   if (m <= 2 * nq || W <= 0.0) return false;
+  // the error estimate assumes g varies on scales >~ 0.25 in ln(nu) across a band of half-width <= 0.25
+  // (a 16th-order remainder ~ (4 x 0.25)^16 / 16! = 5e-14 for an SED as steep as nu^4); wider bands keep their table
+  for (int i = 0; i < m; i++)
+    if (fabs(x[i]) > 0.25) return false;
   // Lanczos with full re-orthogonalisation: J = tridiag(beta_k, alpha_k, beta_{k+1})
   std::vector<std::vector<long double>> q(nq, std::vector<long double>(m));
   std::vector<long double> alpha(nq), beta(nq, 0.0L);

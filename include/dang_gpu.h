@@ -113,7 +113,8 @@ enum {
    * {ln(nu0_i / nu_c), tau0_i} (default n = 8; 0: the table itself).  The rule reproduces the table's sum for
    * every polynomial in ln nu up to degree 2n-1, so bandpass-integrated SEDs agree with the n_bp-term sums of
    * evaluate_powerlaw / evaluate_mbb / ... to < 1e-15 relative while costing n instead of n_bp
-   * transcendentals per band.  Bands with n_bp <= 2n or negative weights keep their table. */
+   * transcendentals per band.  Bands with n_bp <= 2n, negative weights or a half-width above 0.25 in
+   * ln(nu) keep their table. */
   DANG_OPT_BP_QUADRATURE = 14
 };
 
