@@ -1054,6 +1054,24 @@ int dang_gpu_fit_band_gain(dang_gpu_t *h, int map_n, int band, int ml_mode, cons
   API_END
 }
 
+int dang_gpu_bandpass_quadrature(double nu_c_hz, int n_bp, const double *nu0_hz, const double *tau0, int nq,
+                                 double *nu_q_hz, double *w_q) {
+  if (n_bp < 1 || !nu0_hz || !tau0 || nq < 1 || nq > 32 || !nu_q_hz || !w_q) return DANG_GPU_EINVAL;
+  BandHost b;
+  b.set = true;
+  b.nu_c = nu_c_hz;
+  b.n = n_bp;
+  b.nu0.assign(nu0_hz, nu0_hz + n_bp);
+  b.tau0.assign(tau0, tau0 + n_bp);
+  std::vector<double> nu, w;
+  if (!gauss_compress(b, nq, nu, w)) return DANG_GPU_EUNSUPPORTED;  // the table would be kept
+  for (int k = 0; k < nq; k++) {
+    nu_q_hz[k] = nu[k];
+    w_q[k] = w[k];
+  }
+  return DANG_GPU_OK;
+}
+
 int dang_gpu_host_alloc(void **ptr, uint64_t bytes) {
   return cudaMallocHost(ptr, bytes) == cudaSuccess ? DANG_GPU_OK : DANG_GPU_ECUDA;
 }

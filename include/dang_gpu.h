@@ -259,6 +259,13 @@ int dang_gpu_get_indices_async(dang_gpu_t *h, int ic, int nind, int k_lo, int k_
 int dang_gpu_download_wait(dang_gpu_t *h);
 int dang_gpu_stage_eta(dang_gpu_t *h, const double *eta, int nplanes);
 
+/* The n-point Gauss quadrature the library substitutes for a tabulated bandpass (DANG_OPT_BP_QUADRATURE):
+ * nodes nu_q [Hz] and weights w_q with sum_q w_q g(nu_q) == sum_i tau0_i g(nu0_i) for every g polynomial in
+ * ln(nu) up to degree 2 nq - 1.  Host-only (no device needed); DANG_GPU_EUNSUPPORTED when the library would keep
+ * the table (n_bp <= 2 nq, negative weights, half-width above 0.25 in ln nu). */
+int dang_gpu_bandpass_quadrature(double nu_c_hz, int n_bp, const double *nu0_hz, const double *tau0, int nq,
+                                 double *nu_q_hz, double *w_q);
+
 /* ---- instrumentation (bench.py) ---- */
 int dang_gpu_host_alloc(void **ptr, uint64_t bytes); /* pinned host memory */
 int dang_gpu_host_free(void *ptr);

@@ -54,3 +54,49 @@ def test_fails_loudly_without_a_gpu():
     with pytest.raises(DangGpuError) as ei:
         Engine(cfg, sky)
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_bandpass_gauss_quadrature_reproduces_the_table_sums():
+    """Host-only: the 8-point Gauss rule the library hands to the device instead of a 128-sample bandpass
+    (DANG_OPT_BP_QUADRATURE) reproduces the bandpass-integrated power-law and modified-blackbody SEDs of
+    evaluate_powerlaw / evaluate_mbb (src/dang_component_mod.f90:909-914, 949-955) to rounding, for every c3 band
+    and the extremes of the priors; short, wide or negative-weight tables are refused (the table is kept)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from dang_b200 import _lib
+    from dang_b200.synth import H_PLANCK, K_B, make_config
+    lib = _lib.load()
+    dp = lambda a: a.ctypes.data_as(_lib.c_dp)
+    cfg = make_config("c3", nside=4)
+    worst = 0.0
+    for band in cfg.bands:
+        nu = np.ascontiguousarray(band.bp_nu_ghz, dtype=np.float64) * 1e9
+        tau = np.ascontiguousarray(band.bp_tau, dtype=np.float64)
+        tau = tau / tau.sum()
+        nq, wq = np.zeros(8), np.zeros(8)
+        assert lib.dang_gpu_bandpass_quadrature(band.nu_ghz * 1e9, len(nu), dp(nu), dp(tau), 8, dp(nq), dp(wq)) == 0
+        assert abs(wq.sum() - 1.0) < 1e-13 and np.all(wq > 0) and nu.min() < nq.min() and nq.max() < nu.max()
+        for beta, T, nu_ref in [(-3.1, None, 30e9), (-2.0, None, 30e9), (-4.0, None, 30e9), (1.55, 19.6, 353e9),
+                                (2.2, 10.0, 353e9), (1.0, 35.0, 353e9)]:
+            if T is None:
+                g = lambda v: (v / nu_ref) ** beta
+            else:
+                z = H_PLANCK / (K_B * T)
+                g = lambda v: (np.exp(z * nu_ref) - 1.0) / (np.exp(z * v) - 1.0) * (v / nu_ref) ** (beta + 1.0)
+            full, quad = np.sum(tau * g(nu)), np.sum(wq * g(nq))
+            worst = max(worst, abs(full - quad) / abs(full))
+    assert worst < 5e-15, worst
+    # refused: too few samples for the rule, a negative weight, a band wider than +-0.25 in ln(nu)
+    nu = np.linspace(90e9, 110e9, 12)
+    tau = np.full(12, 1.0 / 12)
+    out = np.zeros(8)
+    assert lib.dang_gpu_bandpass_quadrature(100e9, 12, dp(nu), dp(tau), 8, dp(out), dp(out.copy())) == 3
+    nu = np.linspace(90e9, 110e9, 64)
+    tau = np.full(64, 1.0 / 64)
+    tau[5] = -1e-3
+    assert lib.dang_gpu_bandpass_quadrature(100e9, 64, dp(nu), dp(tau), 8, dp(out), dp(out.copy())) == 3
+    nu = np.linspace(50e9, 150e9, 64)
+    tau = np.full(64, 1.0 / 64)
+    assert lib.dang_gpu_bandpass_quadrature(100e9, 64, dp(nu), dp(tau), 8, dp(out), dp(out.copy())) == 3
