@@ -757,6 +757,21 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
   }
   double sample[DG_MAXIND] = {ms->sample[0], ms->sample[1]};
   double theta[DG_MAXIND] = {sample[0], sample[1]};
+  // mbb beta chain on a delta band: the Planck factor eref / (exp(z nu_c) - 1) does not move (T is fixed),
+  // so it is formed once; sed_mbb multiplies exactly this quotient by the power law: same bits, 1 exp per
+  // proposal on the chain's serial path instead of 3
+  const bool planck_fixed = j < B && mv.comp[mh.ic].type == 2 && mh.nind == 0 && mv.band[j].n == 0;
+  double Fj = 0.0, lh = 0.0, ll = 0.0;
+  if (planck_fixed) {
+    const double z = DG_H / (DG_KB * sample[1]);
+    Fj = (exp(z * mv.comp[mh.ic].nu_ref) - 1.0) / (exp(z * mv.band[j].nu_c) - 1.0);
+    lh = mv.tab->lnr_hi[mh.ic][j];
+    ll = mv.tab->lnr_lo[mh.ic][j];
+  }
+  auto sed_of = [&](double t0, double t1) -> double {
+    if (j >= B) return 0.0;
+    return planck_fixed ? Fj * exp_scaled(t0 + 1.0, lh, ll) : sed_theta(mv, mh.ic, j, t0, t1);
+  };
   // lnL(theta) = -1/2 sum_j (X_j - 2 delta_j Y_j + delta_j^2 Z_j), delta_j = sed_j(theta) - s0_j
   auto lnl_of = [&](double sed) -> double {
     const double dl = sed - s0;
@@ -782,7 +797,7 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
       if (mh.decisions && j == 0) mh.decisions[l] = 2;
       continue;
     }
-    const double sed = (j < B) ? sed_theta(mv, mh.ic, j, theta[0], theta[1]) : 0.0;
+    const double sed = sed_of(theta[0], theta[1]);
     const double lnl_new = lnl_of(sed) + prior_of(theta[mh.nind]);  // :306
     const double diff = lnl_new - lnl_old;
     const double ratio = exp(diff);  // :310, Q4
@@ -801,7 +816,7 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
   // sum after the draw: sum_j sum_pix ((d - sky)/sigma)^2 / nbands, src/dang_data_mod.f90:514-523)
   double chi[2] = {0.0, 0.0};
   {
-    const double sed = (j < B) ? sed_theta(mv, mh.ic, j, sample[0], sample[1]) : 0.0;
+    const double sed = sed_of(sample[0], sample[1]);
     const double dl = sed - s0;
 #pragma unroll
     for (int s = 0; s < 2; s++) {
