@@ -179,6 +179,103 @@ module dang_gpu_mod
        integer(c_int), value :: ic, nind, map_n
        real(c_double) :: value
      end function dang_gpu_get_index_fullsky
+     ! ---- multi-GPU (INTEGRATION.md section 3): one MPI rank per GPU
+     integer(c_int) function dang_gpu_comm_unique_id(id) bind(C, name='dang_gpu_comm_unique_id')
+       import :: c_int, c_char
+       character(kind=c_char) :: id(128)
+     end function dang_gpu_comm_unique_id
+     integer(c_int) function dang_gpu_comm_init(h, nranks, rank, id) bind(C, name='dang_gpu_comm_init')
+       import :: c_int, c_char, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: nranks, rank
+       character(kind=c_char), intent(in) :: id(128)
+     end function dang_gpu_comm_init
+     integer(c_int) function dang_gpu_comm_ipc_handle(h, handle) bind(C, name='dang_gpu_comm_ipc_handle')
+       import :: c_int, c_char, c_ptr
+       type(c_ptr), value :: h
+       character(kind=c_char) :: handle(64)
+     end function dang_gpu_comm_ipc_handle
+     integer(c_int) function dang_gpu_comm_open_peers(h, handles) bind(C, name='dang_gpu_comm_open_peers')
+       import :: c_int, c_char, c_ptr
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: handles(*)       ! nranks * 64 bytes, rank-major
+     end function dang_gpu_comm_open_peers
+     integer(c_int) function dang_gpu_comm_check(h) bind(C, name='dang_gpu_comm_check')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: h
+     end function dang_gpu_comm_check
+     ! ---- staging (INTEGRATION.md section 4): copies on dedicated streams, host arrays page-locked
+     integer(c_int) function dang_gpu_stage_eta(h, eta, nplanes) bind(C, name='dang_gpu_stage_eta')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: eta(*)
+       integer(c_int), value :: nplanes
+     end function dang_gpu_stage_eta
+     integer(c_int) function dang_gpu_get_amplitude_async(h, ic, k_lo, k_hi, amplitude) &
+          bind(C, name='dang_gpu_get_amplitude_async')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic, k_lo, k_hi
+       real(c_double) :: amplitude(*)
+     end function dang_gpu_get_amplitude_async
+     integer(c_int) function dang_gpu_get_indices_async(h, ic, nind, k_lo, k_hi, indices) &
+          bind(C, name='dang_gpu_get_indices_async')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic, nind, k_lo, k_hi
+       real(c_double) :: indices(*)
+     end function dang_gpu_get_indices_async
+     integer(c_int) function dang_gpu_download_wait(h) bind(C, name='dang_gpu_download_wait')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: h
+     end function dang_gpu_download_wait
+     integer(c_int) function dang_gpu_host_alloc(ptr, bytes) bind(C, name='dang_gpu_host_alloc')
+       import :: c_int, c_int64_t, c_ptr
+       type(c_ptr) :: ptr                                     ! c_f_pointer it onto the allocatable's shape
+       integer(c_int64_t), value :: bytes
+     end function dang_gpu_host_alloc
+     integer(c_int) function dang_gpu_host_free(ptr) bind(C, name='dang_gpu_host_free')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ptr
+     end function dang_gpu_host_free
+     integer(c_int) function dang_gpu_sync(h) bind(C, name='dang_gpu_sync')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: h
+     end function dang_gpu_sync
+     ! ---- state pushed again by the host (swap_cg_maps, offsets / gains read from file, warm starts)
+     integer(c_int) function dang_gpu_set_gain_offset(h, gain, offset) bind(C, name='dang_gpu_set_gain_offset')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: gain(*), offset(*)
+     end function dang_gpu_set_gain_offset
+     integer(c_int) function dang_gpu_set_amplitude(h, ic, amplitude) bind(C, name='dang_gpu_set_amplitude')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic
+       real(c_double), intent(in) :: amplitude(*)
+     end function dang_gpu_set_amplitude
+     integer(c_int) function dang_gpu_set_indices(h, ic, indices) bind(C, name='dang_gpu_set_indices')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic
+       real(c_double), intent(in) :: indices(*)
+     end function dang_gpu_set_indices
+     ! ---- tune_spectral_parameter_length (dang_sample_mod.f90:623-717)
+     integer(c_int) function dang_gpu_tune_index(h, ic, nind, map_n, nsample, ml_mode, z, u, seed, max_blocks, &
+          blocks_run, step_size) bind(C, name='dang_gpu_tune_index')
+       import :: c_int, c_double, c_ptr, c_int64_t
+       type(c_ptr), value :: h, z, u                          ! z = u = c_null_ptr: device RNG
+       integer(c_int), value :: ic, nind, map_n, nsample, ml_mode, max_blocks
+       integer(c_int64_t), value :: seed
+       integer(c_int) :: blocks_run
+       real(c_double) :: step_size
+     end function dang_gpu_tune_index
+     integer(c_int) function dang_gpu_get_step_size(h, ic, nind, step_size) bind(C, name='dang_gpu_get_step_size')
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int), value :: ic, nind
+       real(c_double) :: step_size
+     end function dang_gpu_get_step_size
   end interface
 
 contains

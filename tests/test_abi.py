@@ -100,3 +100,22 @@ def test_bandpass_gauss_quadrature_reproduces_the_table_sums():
     nu = np.linspace(50e9, 150e9, 64)
     tau = np.full(64, 1.0 / 64)
     assert lib.dang_gpu_bandpass_quadrature(100e9, 64, dp(nu), dp(tau), 8, dp(out), dp(out.copy())) == 3
+
+
+def test_fortran_shim_binds_the_declared_abi():
+    """fortran/dang_gpu_mod.f90 cannot be compiled in this image (no Fortran compiler), so at least keep it
+    consistent with the header: every name it binds is declared in include/dang_gpu.h, and everything a host
+    needs (all but the test / bench instrumentation) is bound."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "dang_gpu.h")).read()
+    shim = open(os.path.join(root, "fortran", "dang_gpu_mod.f90")).read()
+    declared = set(re.findall(r"\b(dang_gpu_[a-z_0-9]+)\s*\(", header))
+    bound = set(re.findall(r"name='(dang_gpu_[a-z_0-9]+)'", shim))
+    assert bound <= declared, bound - declared
+    instrumentation = {"dang_gpu_cg_trace", "dang_gpu_get_cg_x", "dang_gpu_get_decisions", "dang_gpu_event_record",
+                       "dang_gpu_event_elapsed_ms", "dang_gpu_launch_count", "dang_gpu_kernel_stats",
+                       "dang_gpu_kernel_name", "dang_gpu_perpixel_stats", "dang_gpu_share_maps",
+                       "dang_gpu_bandpass_quadrature"}
+    assert declared - bound <= instrumentation, (declared - bound) - instrumentation
