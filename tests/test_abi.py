@@ -119,3 +119,29 @@ def test_fortran_shim_binds_the_declared_abi():
                        "dang_gpu_kernel_name", "dang_gpu_perpixel_stats", "dang_gpu_share_maps",
                        "dang_gpu_bandpass_quadrature"}
     assert declared - bound <= instrumentation, (declared - bound) - instrumentation
+
+
+def test_python_constants_match_the_header_enums():
+    """dang_b200/engine.py and config.py mirror the header's enums by value: keep them in step."""
+    import os
+    import re
+
+    from dang_b200 import config, engine
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "dang_gpu.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(DANG_[A-Z0-9_]+)\s*=\s*(\d+)", header)}
+    for name, value in vars(engine).items():
+        if name.startswith("OPT_"):
+            key = "DANG_" + name
+            alias = {"DANG_OPT_RECORD": "DANG_OPT_RECORD_DECISIONS"}
+            assert enums[alias.get(key, key)] == value, name
+    assert engine.KERNEL_COUNT == enums["DANG_K_COUNT"]
+    assert config.COMP_TYPES == {"power-law": enums["DANG_COMP_POWERLAW"], "mbb": enums["DANG_COMP_MBB"],
+                                 "freefree": enums["DANG_COMP_FREEFREE"], "lognormal": enums["DANG_COMP_LOGNORMAL"],
+                                 "cmb": enums["DANG_COMP_CMB"], "template": enums["DANG_COMP_TEMPLATE"]}
+    assert config.LNL_TYPES == {"chisq": enums["DANG_LNL_CHISQ"], "marginal": enums["DANG_LNL_MARGINAL"],
+                                "prior": enums["DANG_LNL_PRIOR"]}
+    assert config.PRIOR_TYPES == {"uniform": enums["DANG_PRIOR_UNIFORM"], "gaussian": enums["DANG_PRIOR_GAUSSIAN"],
+                                  "jeffreys": enums["DANG_PRIOR_JEFFREYS"]}
+    assert config.ML_MODES == {"optimize": enums["DANG_ML_OPTIMIZE"], "sample": enums["DANG_ML_SAMPLE"]}
+    assert config.INDEX_MODES == {"fullsky": enums["DANG_INDEX_FULLSKY"], "per-pixel": enums["DANG_INDEX_PERPIXEL"]}
