@@ -322,7 +322,9 @@ struct Mail {
 struct PeerComm {
   int nranks, rank;
   unsigned long long *seq;       // device counter of exchanges done by this rank
-  int *error;                    // set on timeout
+  int *error;                    // set on timeout; lives in mapped pinned host memory, the host checks it at
+                                 // the end of every API call (a timed-out exchange is fatal: DANG_GPU_ENCCL)
+  long long timeout_cycles;      // DANG_GPU_PEER_TIMEOUT_S (default 30 s) in SM clocks
   Mail *box[DG_MAX_RANKS];       // box[g]: rank g's mailbox [DG_MAIL_SLOTS][nranks] (peer-mapped)
 };
 
@@ -362,10 +364,10 @@ __device__ __forceinline__ void peer_exchange(const PeerComm &pc, const double *
       const Mail *src = pc.box[pc.rank] + (size_t)slot * pc.nranks + g;
       ld_ll(&src->w[k], half, f);
       while (f != flag) {
-        if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; fail loudly instead of hanging
-          ok = false;
-          half = 0;
-          break;
+        if (clock64() - t0 > pc.timeout_cycles) {  // a peer died: fail loudly instead of hanging.  The missing
+          ok = false;                              // words become a NaN, so every sum formed from this exchange
+          half = 0xfff80000u;                      // is poisoned (a CG solve stops at once: NaN > converge is
+          break;                                   // false) and the host turns the flag into DANG_GPU_ENCCL
         }
         ld_ll(&src->w[k], half, f);
       }
@@ -378,7 +380,10 @@ __device__ __forceinline__ void peer_exchange(const PeerComm &pc, const double *
       gathered[g * cnt + (k >> 1)] = __longlong_as_double((long long)bits);
     }
   }
-  if (!ok) atomicExch(pc.error, 1);
+  if (!ok) {
+    *(volatile int *)pc.error = 1;
+    __threadfence_system();
+  }
   __syncwarp();
   if (lane == 0) *pc.seq = seq;
   __syncwarp();

@@ -302,6 +302,8 @@ int64_t unmasked_count(dang_gpu *h) {
   try {                                             \
     set_device(h);
 #define API_END                                     \
+    if (h->peer_error_host && *h->peer_error_host)  \
+      fail(DANG_GPU_ENCCL, "a peer rank did not answer a scalar exchange within the timeout; results of this handle are poisoned"); \
     return DANG_GPU_OK;                             \
   } catch (const DgError &e) {                      \
     h->err = e.what();                              \
@@ -374,7 +376,7 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaMalloc(&h->mh_scalars, sizeof(MhScalars)));
     CK(cudaMalloc(&h->tab, sizeof(SedTable)));
     CK(cudaMemset(h->tab, 0, sizeof(SedTable)));
-    CK(cudaMallocHost(&h->pinned, 64 * 1024));
+    CK(cudaMallocHost(&h->pinned, 256 * 1024));
     h->peer.nranks = 1;
     h->peer.rank = 0;
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&h->ev[i]));
@@ -382,20 +384,24 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     return DANG_GPU_OK;
   } catch (const DgError &e) {
     g_create_error = e.what();
-    delete h;
+    if (h) dang_gpu_destroy(h);  // releases whatever streams, events and buffers were created so far
     return e.code;
+  } catch (const std::exception &e) {
+    g_create_error = e.what();
+    if (h) dang_gpu_destroy(h);
+    return DANG_GPU_ECUDA;
   }
 }
 
 int dang_gpu_destroy(dang_gpu_t *h) {
   if (!h) return DANG_GPU_EINVAL;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) g_nccl.CommDestroy(h->comm);
   for (int g = 0; g < DG_MAX_RANKS; g++)
     if (h->peer_ptr[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_ptr[g]);
   if (h->peer.seq) cudaFree(h->peer.seq);
-  if (h->peer.error) cudaFree(h->peer.error);
+  if (h->peer_error_host) cudaFreeHost((void *)h->peer_error_host);
   if (h->mailbox) cudaFree(h->mailbox);
   if (!h->maps_borrowed) { dfree(h->sig); dfree(h->rms); dfree(h->mask); }
   dfree(h->bp_nu0); dfree(h->bp_tau0);
@@ -412,13 +418,11 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
-  cudaStreamSynchronize(h->d2h_stream);
-  cudaStreamSynchronize(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
+  if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
   dfree(h->eta_stage[0]); dfree(h->eta_stage[1]);
   for (cudaEvent_t e : {h->ev_compute, h->ev_idx_dl, h->ev_eta[0], h->ev_eta[1], h->ev_eta_used[0], h->ev_eta_used[1]}) if (e) cudaEventDestroy(e);
-  cudaStreamDestroy(h->d2h_stream);
-  cudaStreamDestroy(h->h2d_stream);
-  cudaStreamDestroy(h->stream);
+  for (cudaStream_t st : {h->d2h_stream, h->h2d_stream, h->stream}) if (st) cudaStreamDestroy(st);
   delete h;
   return DANG_GPU_OK;
 }
@@ -482,7 +486,9 @@ int dang_gpu_comm_unique_id(char id[128]) {
 
 int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]) {
   API_BEGIN
-  if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) fail(DANG_GPU_EINVAL, "bad rank %d of %d", rank, nranks);
+  // every gather buffer (gathered_buf, stat_buf, the pinned read-back area) is sized for DG_MAX_RANKS rows
+  if (nranks < 1 || nranks > DG_MAX_RANKS || rank < 0 || rank >= nranks)
+    fail(DANG_GPU_EINVAL, "bad rank %d of %d (at most %d ranks)", rank, nranks, DG_MAX_RANKS);
   h->nranks = nranks;
   h->rank = rank;
   h->n_unmasked = -1;
@@ -507,8 +513,20 @@ int dang_gpu_comm_ipc_handle(dang_gpu_t *h, char handle[64]) {
     CK(cudaMemset(h->mailbox, 0, n));
     CK(cudaMalloc(&h->peer.seq, sizeof(unsigned long long)));
     CK(cudaMemset(h->peer.seq, 0, sizeof(unsigned long long)));
-    CK(cudaMalloc(&h->peer.error, sizeof(int)));
-    CK(cudaMemset(h->peer.error, 0, sizeof(int)));
+    // the timeout flag lives in mapped pinned host memory: the kernels set it, every API call checks it
+    int *eh = nullptr;
+    CK(cudaHostAlloc((void **)&eh, sizeof(int), cudaHostAllocMapped));
+    *eh = 0;
+    h->peer_error_host = eh;
+    CK(cudaHostGetDevicePointer((void **)&h->peer.error, eh, 0));
+    {
+      int khz = 0;
+      CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+      const char *ts = getenv("DANG_GPU_PEER_TIMEOUT_S");
+      double secs = ts ? atof(ts) : 30.0;
+      if (!(secs > 0)) secs = 30.0;
+      h->peer.timeout_cycles = (long long)(secs * 1e3 * (double)khz);
+    }
     CK(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t ih;
@@ -539,12 +557,7 @@ int dang_gpu_comm_open_peers(dang_gpu_t *h, const char *handles) {
 
 int dang_gpu_comm_check(dang_gpu_t *h) {
   API_BEGIN
-  if (h->use_mail) {
-    int err = 0;
-    CK(cudaMemcpyAsync(&err, h->peer.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (err) fail(DANG_GPU_ENCCL, "a peer rank did not answer a scalar exchange within the timeout");
-  }
+  if (h->use_mail) CK(cudaStreamSynchronize(h->stream));  // API_END reads the (host-mapped) timeout flag
   API_END
 }
 
@@ -560,6 +573,7 @@ int dang_gpu_set_band(dang_gpu_t *h, int band, double nu_c_hz, int n_bp, const d
   b.nu0.assign(nu0_hz, nu0_hz + n_bp);
   b.tau0.assign(tau0, tau0 + n_bp);
   h->bp_dirty = true;
+  touch(h);  // every SED changes: cached statistics / chi-squares are stale
   API_END
 }
 
@@ -1116,7 +1130,7 @@ const char *dang_gpu_kernel_name(int kernel) {
   static const char *names[DANG_K_COUNT] = {
       "rhs_blocks_kernel", "cg_pass_kernel", "cg_dq_pass_kernel", "cg_update_pass_kernel",
       "chisq_kernel", "chisq_kernel(maps)", "mh_data_kernel", "mh_fullsky_lnl_kernel",
-      "mh_suffstat_kernel", "mh_perpixel_kernel", "scalar kernels", "cg_x_fixup"};
+      "mh_suffstat_kernel", "mh_perpixel_kernel", "scalar kernels", "cg_final_pass(x,unpack)"};
   return (kernel >= 0 && kernel < DANG_K_COUNT) ? names[kernel] : "?";
 }
 

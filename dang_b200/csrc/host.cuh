@@ -213,6 +213,7 @@ struct dang_gpu {
   Mail *mailbox = nullptr;
   void *peer_ptr[DG_MAX_RANKS] = {};
   PeerComm peer{};
+  volatile int *peer_error_host = nullptr;  // host view of peer.error (mapped pinned memory)
   bool use_mail = false;
 
   // instrumentation
@@ -262,11 +263,17 @@ inline int grid_for(dang_gpu *h, int64_t work, int threads, int blocks_per_sm) {
 struct KTimer {
   dang_gpu *h;
   int kid;
+  double bytes;
+  bool deferred;
   cudaEvent_t a = nullptr, b = nullptr;
-  KTimer(dang_gpu *h_, int kid_, double bytes) : h(h_), kid(kid_) {
+  // deferred: the launch is booked later with commit(), once the host knows whether the kernel did any work
+  // (a CG pass enqueued after convergence returns at once: it must not be credited with a pass's bytes)
+  KTimer(dang_gpu *h_, int kid_, double bytes_, bool deferred_ = false) : h(h_), kid(kid_), bytes(bytes_), deferred(deferred_) {
     h->launches++;
-    h->kstat[kid].launches++;
-    h->kstat[kid].bytes += bytes;
+    if (!deferred) {
+      h->kstat[kid].launches++;
+      h->kstat[kid].bytes += bytes;
+    }
     if (h->profile) {
       CK(cudaEventCreate(&a));
       CK(cudaEventCreate(&b));
@@ -277,8 +284,15 @@ struct KTimer {
     CK(cudaGetLastError());
     if (h->profile) {
       CK(cudaEventRecord(b, h->stream));
-      h->kstat[kid].pending.emplace_back(a, b);
+      if (!deferred) h->kstat[kid].pending.emplace_back(a, b);
     }
+  }
+  // book a deferred launch: under `kid` with its bytes if it worked, else as a scalar (early-exit) launch
+  void commit(bool worked) {
+    const int k = worked ? kid : DANG_K_SCALAR;
+    h->kstat[k].launches++;
+    if (worked) h->kstat[k].bytes += bytes;
+    if (a) h->kstat[k].pending.emplace_back(a, b);
   }
 };
 

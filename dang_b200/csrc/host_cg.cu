@@ -143,24 +143,27 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
                    : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C, false>, n2, DG_THREADS)
                                 : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
   const double el = (double)vs;
+  std::vector<std::pair<int, KTimer>> pass_recs;  // (pass number, launch) booked once the iteration count is known
   auto enqueue_pass = [&](int pass_no) {
     if (!h->cg_two_pass) {
       if (ckpt_m) {
         // compulsory traffic of this launch: M, r, d in; on checkpoint passes also x in, r, d, x out
         const double per_el = (pass_no % ckpt_m == 0) ? (T + (pass_no == ckpt_m ? 5.0 : 6.0) * C)
                                                       : (T + (pass_no < ckpt_m ? 1.0 : 2.0) * C);
-        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
+        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el), true);
         cg_recompute_pass_kernel<C, false><<<grid, DG_THREADS, 0, h->stream>>>(
             h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, 0, h->peer, h->gathered,
             CgAmpOut<C>{});
         kt.done();
+        pass_recs.emplace_back(pass_no, kt);
       } else {
         // compulsory traffic of this launch: x is touched on even passes only
         const double per_el = (pass_no & 1) ? (T + 4.0 * C) : (T + 6.0 * C);
-        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el));
+        KTimer kt(h, DANG_K_CG_PASS, bytes_w(el * per_el), true);
         cg_fused_pass_kernel<C><<<grid, DG_THREADS, 0, h->stream>>>(
             h->cg_scalars, h->M, g.x[flag_n], h->r, h->d, n2, h->partials, h->tickets, h->sums_local, fold, h->peer, h->gathered);
         kt.done();
+        pass_recs.emplace_back(pass_no, kt);
       }
       if (!fold) {
         gather(h, 4);
@@ -258,10 +261,13 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   // sweep -- when it has anything to do (a solve that stopped exactly on a checkpoint needs no pass).
   bool unpacked = false;
   if (!h->cg_two_pass) {  // bring x up to date (pending term of the deferred / checkpointed update)
-    KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 5.0 * C : 3.0 * C)));
+    const CgScalars *hs0 = (const CgScalars *)h->pinned;
+    // the final pass works only if passes ran since the last checkpoint (recompute form) / an odd number of
+    // passes ran (streaming form); when the host does not know (no state read yet) it is booked as working
+    const bool final_works = !(sn.done && have_state) || (ckpt_m ? (hs0->iter - 1) - hs0->ckpt > 0 : ((hs0->iter - 1) & 1) != 0);
+    KTimer kt(h, DANG_K_CG_FIXUP, bytes_w(el * (ckpt_m ? T + 5.0 * C : 3.0 * C)), true);
     if (ckpt_m) {
       CgAmpOut<C> ao{};
-      const CgScalars *hs0 = (const CgScalars *)h->pinned;
       const bool planes_contiguous = S == 1 || cv.plane[1] == cv.plane[0] + 1;
       if (sn.done && have_state && planes_contiguous && (hs0->iter - 1) - hs0->ckpt > 0) {
         for (int c = 0; c < C; c++) ao.p[c] = h->comp[comps[c]].amp + (size_t)cv.plane[0] * h->Ppad;
@@ -277,6 +283,7 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       cg_x_fixup_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->cg_scalars, g.x[flag_n], h->d, (int64_t)(C * vs));
     }
     kt.done();
+    kt.commit(final_works);
   }
 
   if (l2_window) {  // later kernels stream: drop the window and release the persisting lines
@@ -304,6 +311,8 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     g.last_iter[flag_n] = hs->iter;
     if (n_iter) *n_iter = hs->iter;
     if (delta_final) *delta_final = hs->delta_new;
+    // passes enqueued after convergence returned at once: they are booked as scalar launches, without bytes
+    for (auto &pr : pass_recs) pr.second.commit(pr.first <= hs->iter - 1);
   }
 }
 }  // namespace

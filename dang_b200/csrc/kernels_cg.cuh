@@ -354,7 +354,10 @@ cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__rest
     }
   }
   const bool last = grid_reduce<4>(acc, smem, partials, ticket, out);
-  if (fold && last && threadIdx.x == 0) cg_fused_update(st, out, 1);
+  if (fold && last) {  // warp 0 of the last block: exchange over NVLink (if any), advance the scalars
+    if (pc.nranks > 1) peer_exchange(pc, out, 4, gathered);
+    if (threadIdx.x == 0) cg_fused_update(st, pc.nranks > 1 ? gathered : out, pc.nranks);
+  }
 }
 
 // ---------------------------------------------------------------- K2r: recompute form

@@ -89,6 +89,7 @@ def load(omp: bool = False) -> C.CDLL:
         "ora_philox_uniforms": (None, [C.c_ulonglong, C.c_uint, C.c_ulonglong, ll, c_dp]),
         "ora_philox_raw": (None, [C.POINTER(C.c_uint), C.c_uint, C.c_uint]),
         "ora_num_threads": (i, []),
+        "ora_set_num_threads": (None, [i]),
     }
     for name_, (res, args) in sigs.items():
         fn = getattr(lib, name_)

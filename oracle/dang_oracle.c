@@ -106,6 +106,16 @@ int ora_num_threads(void) {
 #endif
 }
 
+/* Thread count of the OpenMP build (bench.py sets it explicitly: torch.distributed.run exports
+ * OMP_NUM_THREADS=1 to its workers, which would silently turn the CPU baseline into a 1-core run). */
+void ora_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ construction */
 
 ora_state *ora_create(int nside, int npix, int nmaps, int nbands, int ncomp) {

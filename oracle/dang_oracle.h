@@ -160,6 +160,7 @@ void ora_philox_uniforms(unsigned long long seed, unsigned int stream, unsigned 
                          long n, double *u);
 
 int ora_num_threads(void);
+void ora_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -30,11 +30,20 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     worst = 0.0
-    for name, nside in (("c1", 16), ("c2", 16)):
+    ns = int(os.environ.get("DANG_MGC_NSIDE", "16"))
+    from dang_b200.engine import OPT_CG_CHECKPOINT
+    # (config, nside, CG form): the default checkpointed-recompute form, the streaming form (checkpoint 0) and a
+    # solve with i_max >= DG_CG_HIST (1024), which also takes the streaming form -- all exchange the CG sums
+    # inside the pass kernel when the NVLink mailboxes are on, and must follow the single-rank oracle
+    for name, nside, form in (("c1", ns, "recompute"), ("c2", ns, "recompute"), ("c2", 16, "streaming"), ("c1", 16, "imax2000")):
         cfg, sky = small_case(name, nside, perturb=(name == "c1"))
+        if form == "imax2000":
+            cfg.cg_groups[0].max_iter = 2000
         bounds = ring_partition(cfg.nside, world, weights=(sky.mask != 0).astype(np.float64))
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
+        if form == "streaming":
+            eng.set_option(OPT_CG_CHECKPOINT, 0)
         setup_torch_comm(eng, mailboxes=os.environ.get("DANG_GPU_MAILBOX", "1") != "0")
         ora = Oracle(cfg, sky)
         rng = np.random.default_rng(77)
@@ -43,7 +52,12 @@ def main():
             eta = rng.standard_normal(2 * cfg.npix)
             its_o, _ = ora.sample_cg_group(0, 1, eta)
             r = eng.sample_cg_groups(eta=eta)
-            assert r[0][0] == its_o[0], (rank, r[0], its_o)
+            assert r[0][0] == its_o[0], (rank, name, form, r[0], its_o)
+            # every rank took the same decisions from the same sums: identical final residual everywhere
+            dl = torch.tensor([r[0][1]], dtype=torch.float64, device="cuda")
+            dall = [torch.zeros_like(dl) for _ in range(world)]
+            dist.all_gather(dall, dl)
+            assert all(float(t.item()) == r[0][1] for t in dall), (rank, name, form, [float(t.item()) for t in dall])
             chisq_o, _ = ora.compute_chisq()
             assert abs(r[1] - chisq_o) <= 1e-10 * chisq_o, (rank, r[1], chisq_o)
             if it > 1:
