@@ -19,7 +19,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -49,47 +48,66 @@ def ncu_traffic(kernel: str):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region.  The region is short (20 steps x 1.5 ms), so
+    an `nvidia-smi -lms` child process never gets a sample in (its start-up alone is longer); this is an NVML
+    polling thread (pynvml) started before the region and stopped right after it, ~1 ms per sample.  Falls
+    back to one nvidia-smi query if NVML is not importable."""
 
-    def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+
+    def __init__(self, cuda_index: int):
+        import threading
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._t = None
+        self.src = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:  # NVML ignores CUDA_VISIBLE_DEVICES: address the device by UUID
+                uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+                hdl = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                hdl = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(hdl, pynvml.NVML_CLOCK_SM))
+            self.src = "nvml"
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(hdl, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hdl)
+                        for bit, name in self.REASONS.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(hdl) / 1e3)
+                    except Exception:
+                        break
+                    time.sleep(0.0005)
+            self._t = threading.Thread(target=loop, daemon=True)
+            self._t.start()
         except Exception:
-            self.p = None
+            self._t = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        for r in rows:
-            if len(r) < 9:
-                continue
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": self.src}
+        if self._t is not None:
+            self._stop.set()
+            self._t.join(timeout=2)
+        if not self.samples:  # last resort: one query (after the region; says so)
             try:
-                sm.append(float(r[1]))
-                out["sm_max_mhz"] = float(r[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower() == "active":
-                    reasons.add(name)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+                r = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0].split(", ")
+                out.update(sm_mhz=float(r[0]), sm_max_mhz=float(r[1]), samples=1, source="nvidia-smi after the region")
+            except Exception:
+                pass
+            return out
+        out["sm_mhz"] = float(np.median(self.samples))
+        out["sm_mhz_min"] = float(np.min(self.samples))
+        out["power_w_max"] = round(float(np.max(self.power)), 1) if self.power else None
+        out["reasons"] = sorted(self.reasons)
+        out["samples"] = len(self.samples)
         return out
 
 
@@ -265,6 +283,7 @@ def run_gpu(args):
     nplanes_out = 2 * len(cfg.comps) + 2 * n_pp
     d2h = 8 * P * nplanes_out + 8 * 8 + 16 * (len(sampled) - n_pp)
 
+    eng.comm_check()  # a timed-out scalar exchange would have poisoned the sums: fail instead of printing
     if rank == 0:
         peak, peak_src = peaks()
         ms_per_step = ms / args.steps
@@ -280,7 +299,7 @@ def run_gpu(args):
                     "avg_launch_us": round(1e3 * s["ms"] / max(s["launches"], 1), 2),
                     "share_of_kernel_time": round(s["ms"] / tot, 3),
                     "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
-                                       "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+                                       "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if (v["ms"] > 0 and v["bytes"] > 0) else None}
                                    for k, v in stats.items() if v["launches"]}}
         line = {
             "metric": METRIC if (cfg.name == "c2" and cfg.nside == 512) else f"Gibbs iterations/sec (nside={cfg.nside}, Q+U, synch+dust)",
@@ -288,9 +307,7 @@ def run_gpu(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{cfg.name}: nside={cfg.nside}, {cfg.nbands} bands, Q+U, synch+dust, CG amplitudes + "
-                                   + " + ".join(f"{s.region} {c.label} {s.label}" for c in cfg.comps for s in c.indices if s.sample)
-                                   + f", NUMSAMPLE={cfg.nsample}",
+            "config": {"workload": workload_name(cfg),
                        "npix": cfg.npix,
                        "n_cg_iterations": {"min": int(min(n_cg)), "max": int(max(n_cg)), "mean": round(float(np.mean(n_cg)), 2)},
                        "parallelism": f"ring-range pixel shards x{world}" + ("" if world == 1 else (", scalar exchange over NVLink mailboxes" if mailboxes else ", scalar exchange by NCCL all-gather")),
@@ -309,74 +326,96 @@ def run_gpu(args):
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(args, sample_seconds=True)
+            line["cpu_baseline"] = cpu_baseline(args, sky=None if big else sky)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------ CPU arm (oracle, all host cores)
-def cpu_gibbs_time(nside: int, nsteps: int, config: str, budget_s: float = 1e9):
-    """Seconds per Gibbs iteration of the OpenMP oracle at `nside` (reference cost structure:
-    three-sweep compute_Ax with SED re-evaluation, full-map data copies, per-proposal sweeps).
-    Runs at most `nsteps` timed iterations and stops early once `budget_s` is spent."""
+def host_threads() -> int:
+    """Cores this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, so the
+    thread count is set explicitly (ora_set_num_threads) instead of inherited from the environment."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_gibbs_time(nside, nsteps: int, config: str, budget_s: float = 1e9, sky=None):
+    """Seconds per Gibbs iteration of the OpenMP oracle on the SAME config and map size as the GPU arm
+    (reference cost structure: three-sweep compute_Ax with SED re-evaluation, full-map data copies,
+    per-proposal sweeps).  One untimed cold iteration (iter == 1: no spectral draw, cold-start CG), then at most
+    `nsteps` timed iterations, stopping early once `budget_s` seconds of timed work are spent."""
     from dang_b200.synth import make_config, make_sky
-    from oracle.binding import Oracle
+    from oracle.binding import Oracle, load
     cfg = make_config(config, nside=nside)
-    sky = make_sky(cfg)
+    if sky is None:
+        sky = make_sky(cfg)
+    threads = host_threads()
+    load(omp=True).ora_set_num_threads(threads)
     ora = Oracle(cfg, sky, omp=True)
     rng = np.random.default_rng(3)
+    calls = [s for c in cfg.comps for s in c.indices if s.sample for _ in s.poltype.split(",")]
+    # a full-sky chain reads nsample deviates; a per-pixel one nsample * npix (slot-indexed)
+    nz = cfg.nsample if (len(calls) == 1 and calls[0].region == "fullsky") else cfg.nsample * cfg.npix * max(1, len(calls))
     times, n_cg = [], []
-    t_start = time.perf_counter()
-    for it in range(nsteps + 1):  # first iteration is the cold start (iter == 1): untimed
+    for it in range(nsteps + 1):
         eta = rng.standard_normal(2 * cfg.npix)
-        z, u = rng.standard_normal(cfg.nsample * cfg.npix), rng.random(cfg.nsample * cfg.npix)
+        z, u = rng.standard_normal(nz), rng.random(nz)
         t0 = time.perf_counter()
         its, _ = ora.sample_cg_group(0, 1, eta)
         ora.compute_chisq()
-        ora.sample_spectral_parameters(cfg.nsample, 1, z, u)
-        ora.compute_chisq()
+        if it > 0:
+            ora.sample_spectral_parameters(cfg.nsample, 1, z, u)
+            ora.compute_chisq()
         dt = time.perf_counter() - t0
         if it > 0:
             times.append(dt)
             n_cg.append(its[0])
-            if time.perf_counter() - t_start > budget_s:
+            if sum(times) > budget_s:
                 break
-    return float(np.mean(times)), n_cg, ora.lib.ora_num_threads()
+    return cfg, float(np.mean(times)), n_cg, ora.lib.ora_num_threads()
 
 
-def cpu_baseline(args, sample_seconds=False):
-    full = args.nside or 512
-    ns = args.cpu_nside
-    sec, n_cg, threads = cpu_gibbs_time(ns, 1, args.config)
-    scale = (full / ns) ** 2
-    return {"value": round(1.0 / (sec * scale), 5), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"1 Gibbs iteration of the OpenMP oracle at nside={ns} ({1.0 / scale:.4g} of the pixels, "
-                      f"{sec:.2f} s), time scaled x{scale:g} to nside={full}; n_cg={n_cg[0]}"}
+def cpu_baseline(args, sky=None):
+    """rank 0, N = 1 only: a bounded sample (one timed Gibbs iteration after the cold one, 10-30 s of CPU work)
+    of the same workload at the same size."""
+    cfg, sec, n_cg, threads = cpu_gibbs_time(args.nside, 1, args.config, sky=sky)
+    return {"value": round(1.0 / sec, 5), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"1 timed Gibbs iteration (after the cold first one) of the OpenMP oracle -- the CPU restatement of "
+                      f"the reference -- on the same config at the same size (nside={cfg.nside}): {sec:.2f} s, n_cg={n_cg[0]}"}
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path (its C restatement: the Fortran cannot
+    be built) on all host cores, on THIS config at THIS size.  Steps are whole Gibbs
+    iterations; the run stops after --steps of them or ~150 s of timed work, whichever comes first, and reports
+    the steps actually timed.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    full = args.nside or 512
-    ns = args.cpu_nside
-    scale = (full / ns) ** 2
-    # each step is a bounded sample of the workload (nside=cpu-nside); the run stops after
-    # --steps samples or ~60 s, whichever comes first, and reports the steps actually timed
-    sec, n_cg, threads = cpu_gibbs_time(ns, max(1, args.steps), args.config, budget_s=60.0)
-    v = round(1.0 / (sec * scale), 5)
-    sample = (f"Gibbs iterations of the OpenMP oracle (CPU restatement of the reference; the Fortran reference "
-              f"cannot be built here) at nside={ns}, time per iteration scaled x{scale:g} to nside={full}")
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(n_cg), "warmup": 1, "ms_per_step": round(sec * scale * 1e3, 2),
+    cfg, sec, n_cg, threads = cpu_gibbs_time(args.nside, max(1, args.steps), args.config, budget_s=150.0)
+    v = round(1.0 / sec, 5)
+    sample = (f"{len(n_cg)} Gibbs iterations of the OpenMP oracle (CPU restatement of the reference; no Fortran compiler "
+              f"exists here or on the GPU box) on {threads} threads, config {cfg.name} at nside={cfg.nside}, same workload as the GPU arm")
+    line = {"impl": "reference", "metric": METRIC if (cfg.name == "c2" and cfg.nside == 512) else f"Gibbs iterations/sec (nside={cfg.nside}, Q+U, synch+dust)",
+            "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(n_cg), "warmup": 1, "ms_per_step": round(sec * 1e3, 2),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{args.config}: nside={full}, Q+U, synch+dust, CG amplitudes + full-sky beta_d",
-                       "n_cg_iterations": {"min": int(min(n_cg)), "max": int(max(n_cg))}},
+            "config": {"workload": workload_name(cfg), "npix": cfg.npix,
+                       "n_cg_iterations": {"min": int(min(n_cg)), "max": int(max(n_cg)), "mean": round(float(np.mean(n_cg)), 2)},
+                       "steps_requested": args.steps},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg) -> str:
+    return (f"{cfg.name}: nside={cfg.nside}, {cfg.nbands} bands, Q+U, synch+dust, CG amplitudes + "
+            + " + ".join(f"{s.region} {c.label} {s.label}" for c in cfg.comps for s in c.indices if s.sample)
+            + f", NUMSAMPLE={cfg.nsample}")
 
 
 def main():
@@ -387,7 +426,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--nside", type=int, default=None, help="override the map size (tests only)")
-    ap.add_argument("--cpu-nside", type=int, default=256, help="map size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (experiments), e.g. --opt 8=16")
     args = ap.parse_args()

@@ -91,6 +91,8 @@ struct CgScalars {
   double converge;
   int iter, i_max, done, pad;
   int ckpt, m;        // recompute form: pass whose state is stored in (r, d); checkpoint interval
+  int x_at;           // persistent solve kernel: x (and the amplitude planes) hold the state after pass x_at
+  unsigned int gen;   // ... and its grid barrier: passes completed in the running launch
   double trace[256];
   double ah[DG_CG_HIST], bh[DG_CG_HIST];  // alpha_i, beta_i used IN pass i (1-based)
 };

@@ -451,6 +451,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
       break;
     }
     case DANG_OPT_PERPIXEL_BP_SERIES: h->pp_bp_series = value != 0; break;
+    case DANG_OPT_CG_PERSISTENT: h->cg_persistent = value != 0; break;
     case DANG_OPT_BP_QUADRATURE:
       h->bp_quad = value < 0 ? 0 : (value > 32 ? 32 : (int)value);
       h->bp_dirty = true;

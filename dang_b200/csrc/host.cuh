@@ -142,6 +142,7 @@ struct dang_gpu {
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int cg_persistent = 1;  // whole solve in one persistent cooperative kernel (DANG_OPT_CG_PERSISTENT)
   int bp_quad = 8;        // nodes of the Gauss-quadrature compression of tabulated bandpasses (0: off)
   int pp_bp_series = 1;   // tabulated bandpasses: moment series in the per-pixel chains (DANG_OPT_PERPIXEL_BP_SERIES)
   int pp_split = 0;       // 1: split form of the screened kernel (rng / state / chain kernels), measured slower

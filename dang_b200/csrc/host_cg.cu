@@ -4,6 +4,7 @@
 
 #include "host.cuh"
 #include "kernels_cg.cuh"
+#include "kernels_cg_solve.cuh"
 #include "kernels_uni.cuh"
 
 namespace {
@@ -84,8 +85,10 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   }
 
   CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+  // one rank, or NVLink mailboxes: the last block of K1 sees every rank's sums and starts the scalar state itself
+  const bool fold_all = h->nranks == 1 || h->use_mail;
+  const CgInit ci{fold_all ? h->cg_scalars : nullptr, g.i_max, ckpt_m, g.converge, h->gathered};
   {
-    const int grid = grid_for(h, h->P, DG_THREADS, 4);
     const double n_el = (double)S * h->P;
     KTimer kt(h, DANG_K_RHS_BLOCKS,
               bytes_w(n_el * (2.0 * h->nbands + 1 + C + T + (ckpt_m ? 1.0 : 2.0) * C)) + bytes_w((double)h->P * 3));
@@ -105,14 +108,14 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       CK(cudaFuncSetAttribute(rhs_blocks_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
       const int64_t ntiles = (h->Ppad + DG_TMA_TILE - 1) / DG_TMA_TILE;
       const int g3 = (int)(ntiles < h->num_sms ? ntiles : h->num_sms);
-      rhs_blocks_tma_kernel<C><<<g3, DG_TMA_THREADS, tma_smem, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+      rhs_blocks_tma_kernel<C><<<g3, DG_TMA_THREADS, tma_smem, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, ci, h->peer);
     } else if (og_uni && dsm <= 160 * 1024) {
       if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(rhs_blocks_uni_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       const int g2 = occ_grid(h, rhs_blocks_uni_kernel<C>, h->Ppad / 2, DG_THREADS, dsm);
-      rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask);
+      rhs_blocks_uni_kernel<C><<<g2, DG_THREADS, dsm, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, nu_mask, ci, h->peer);
     } else {
       const int g1 = occ_grid(h, rhs_blocks_kernel<C>, h->P, DG_THREADS);
-      rhs_blocks_kernel<C><<<g1, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local);
+      rhs_blocks_kernel<C><<<g1, DG_THREADS, 0, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, ci, h->peer);
     }
     kt.done();
     if (staged_slot >= 0) {  // the slot may be refilled once K1 has read it
@@ -120,13 +123,12 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
       h->eta_used_recorded[staged_slot] = true;
     }
   }
-  gather(h, 4);
-  {
+  if (!fold_all) {  // NCCL transport: gather on the stream, then a 1-thread kernel
+    gather(h, 4);
     KTimer kt(h, DANG_K_SCALAR, 0);
-    cg_init_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks, g.i_max, g.converge);
+    cg_init_scalars_kernel<<<1, 1, 0, h->stream>>>(h->cg_scalars, h->gathered, h->nranks, g.i_max, g.converge, ckpt_m);
     kt.done();
   }
-  CK(cudaMemcpyAsync((char *)h->cg_scalars + offsetof(CgScalars, m), &ckpt_m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
 
   struct Snap { double delta_new; int iter, done; };
   bool have_state = false;
@@ -138,10 +140,79 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     return Snap{hs->delta_new, hs->iter, hs->done};
   };
 
+  // unpack_amplitudes :1327-1335: x -> c%amplitude planes.  If an asynchronous download is still reading a
+  // component's planes the new state goes into its second buffer (solved planes from x, the others carried
+  // over) and the buffers swap roles; the download is never waited for.
+  for (int c = 0; c < C; c++) {
+    CompHost &cc = h->comp[comps[c]];
+    if (cc.read_pending) {
+      const size_t n2a = (size_t)h->nmaps * h->Ppad;
+      if (!cc.amp_alt) {
+        CK(cudaMalloc(&cc.amp_alt, n2a * sizeof(double)));
+        CK(cudaMemsetAsync(cc.amp_alt, 0, n2a * sizeof(double), h->stream));
+      }
+      if (cc.read_pending_alt) {  // the download before the pending one read the buffer we are about to write
+        CK(cudaStreamWaitEvent(h->stream, cc.ev_read_alt, 0));
+        cc.read_pending_alt = false;
+      }
+      for (int k = 0; k < h->nmaps; k++) {
+        bool solved = false;
+        for (int s = 0; s < S; s++) solved = solved || cv.plane[s] == k;
+        if (!solved)
+          CK(cudaMemcpyAsync(cc.amp_alt + (size_t)k * h->Ppad, cc.amp + (size_t)k * h->Ppad, h->P * sizeof(double),
+                             cudaMemcpyDeviceToDevice, h->stream));
+      }
+      std::swap(cc.amp, cc.amp_alt);
+      std::swap(cc.ev_read, cc.ev_read_alt);
+      std::swap(cc.read_pending, cc.read_pending_alt);
+    }
+  }
+  // ---- default form: the whole loop of cg_search in one persistent cooperative kernel (kernels_cg_solve.cuh)
+  const bool persistent = h->cg_persistent && ckpt_m > 0 && fold_all;
+  if (persistent) {
+    CgAmpOut<C> ao{};
+    for (int c = 0; c < C; c++) ao.p[c] = h->comp[comps[c]].amp + (size_t)cv.plane[0] * h->Ppad;  // S contiguous planes
+    int k_pred = g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : 0x7fffffff;  // pass the previous solve ended on
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_solve_kernel<C>, DG_THREADS, 0));
+    if (per_sm < DG_CG_BLOCKS_PER_SM) fail(DANG_GPU_ECUDA, "cg_solve_kernel: %d resident blocks per SM, %d needed", per_sm, DG_CG_BLOCKS_PER_SM);
+    const int64_t cgrid = grid_for(h, n2, DG_THREADS, DG_CG_BLOCKS_PER_SM);  // every block resident: the kernel has a grid barrier
+    CgScalars *st = h->cg_scalars;
+    const double *Mp = h->M;
+    double *xp = g.x[flag_n], *rp = h->r, *dp = h->d, *part = h->partials, *outp = h->sums_local, *gath = h->gathered;
+    unsigned int *tick = h->tickets;
+    int64_t n2v = n2;
+    PeerComm pcv = h->peer;
+    void *args[] = {&st, &Mp, &xp, &rp, &dp, &n2v, &part, &tick, &outp, &pcv, &gath, &ao, &k_pred};
+    KTimer kt(h, DANG_K_CG_PASS, 0, true);
+    CK(cudaLaunchCooperativeKernel((void *)cg_solve_kernel<C>, dim3((unsigned)cgrid), dim3(DG_THREADS), args, 0, h->stream));
+    kt.done();
+    CgScalars *hs = (CgScalars *)h->pinned;
+    readback(h, hs, h->cg_scalars, offsetof(CgScalars, ah));
+    CK(cudaStreamSynchronize(h->stream));
+    // compulsory traffic of the sweeps that ran: M, r (and d after the first checkpoint) in; checkpoint passes
+    // write r, d; sweeps that carry x read it and write x + the amplitude planes
+    const int n_pass = hs->iter - 1;
+    double per_el = 0.0;
+    int x_at = 0;
+    for (int pn = 1; pn <= n_pass; pn++) {
+      const bool store = pn % ckpt_m == 0, with_x = store || pn >= k_pred;
+      per_el += T + C + (pn > ckpt_m ? C : 0) + (store ? 2.0 * C : 0.0) + (with_x ? 3.0 * C : 0.0);
+      if (with_x) x_at = pn;
+    }
+    if (n_pass > x_at) per_el += T + C + (n_pass > ckpt_m ? C : 0) + 3.0 * C;  // closing sweep
+    kt.bytes = bytes_w((double)vs * per_el);
+    kt.commit(true);
+    int n = hs->iter < 256 ? hs->iter : 256;
+    h->last_trace.assign(hs->trace, hs->trace + n);
+    g.last_iter[flag_n] = hs->iter;
+    if (n_iter) *n_iter = hs->iter;
+    if (delta_final) *delta_final = hs->delta_new;
+    return;
+  }
+
   const int fold = (h->nranks == 1 || h->use_mail) ? 1 : 0;
-  const int grid = h->cg_two_pass ? occ_grid(h, cg_update_pass_kernel<C>, n2, DG_THREADS)
-                   : ckpt_m     ? occ_grid(h, cg_recompute_pass_kernel<C, false>, n2, DG_THREADS)
-                                : occ_grid(h, cg_fused_pass_kernel<C>, n2, DG_THREADS);
+  const int grid = grid_for(h, n2, DG_THREADS, DG_CG_BLOCKS_PER_SM);  // the same grid for every form (bit-equal sums)
   const double el = (double)vs;
   std::vector<std::pair<int, KTimer>> pass_recs;  // (pass number, launch) booked once the iteration count is known
   auto enqueue_pass = [&](int pass_no) {
@@ -229,33 +300,6 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     enq += batch;
     sn = read_state();
     batch = h->cg_chunk;
-  }
-  // unpack_amplitudes :1327-1335: x -> c%amplitude planes.  If an asynchronous download is still reading a
-  // component's planes the new state goes into its second buffer (solved planes from x, the others carried
-  // over) and the buffers swap roles; the download is never waited for.
-  for (int c = 0; c < C; c++) {
-    CompHost &cc = h->comp[comps[c]];
-    if (cc.read_pending) {
-      const size_t n2a = (size_t)h->nmaps * h->Ppad;
-      if (!cc.amp_alt) {
-        CK(cudaMalloc(&cc.amp_alt, n2a * sizeof(double)));
-        CK(cudaMemsetAsync(cc.amp_alt, 0, n2a * sizeof(double), h->stream));
-      }
-      if (cc.read_pending_alt) {  // the download before the pending one read the buffer we are about to write
-        CK(cudaStreamWaitEvent(h->stream, cc.ev_read_alt, 0));
-        cc.read_pending_alt = false;
-      }
-      for (int k = 0; k < h->nmaps; k++) {
-        bool solved = false;
-        for (int s = 0; s < S; s++) solved = solved || cv.plane[s] == k;
-        if (!solved)
-          CK(cudaMemcpyAsync(cc.amp_alt + (size_t)k * h->Ppad, cc.amp + (size_t)k * h->Ppad, h->P * sizeof(double),
-                             cudaMemcpyDeviceToDevice, h->stream));
-      }
-      std::swap(cc.amp, cc.amp_alt);
-      std::swap(cc.ev_read, cc.ev_read_alt);
-      std::swap(cc.read_pending, cc.read_pending_alt);
-    }
   }
   // The last pass of the recompute form brings x up to date and writes the amplitude planes in the same
   // sweep -- when it has anything to do (a solve that stopped exactly on a checkpoint needs no pass).

@@ -9,6 +9,11 @@
 #pragma once
 #include "common.cuh"
 
+// Every CG pass form runs on the same grid (DG_CG_BLOCKS_PER_SM resident blocks per SM x SM count, or fewer when the
+// sky slice is small): the deterministic grid reduction depends on the grid size, and the forms must agree to
+// the last bit; the persistent solve kernel additionally needs every block resident.
+#define DG_CG_BLOCKS_PER_SM 3
+
 template <int C>
 struct CgView {
   int comp[C];               // indices into ModelView::comp, in component_list order
@@ -36,13 +41,82 @@ __device__ __forceinline__ int tri(int a, int b) {  // a <= b
   return a * C - a * (a - 1) / 2 + (b - a);
 }
 
+// One block-local CG step on a pair of elements, shared by every CG form (streaming, checkpointed
+// recompute, persistent solve) with the roundings written out -- explicit FMAs, fixed order -- so that the
+// forms agree to the last bit whatever the compiler would have contracted in each kernel:
+//   d <- r + beta d (:305);  q = M d (:296);  r <- r - alpha q (:300)
+template <int C>
+__device__ __forceinline__ void cg_block_step(const double2 (&m)[C * (C + 1) / 2], double2 (&dv)[C], double2 (&rv)[C],
+                                              double2 (&q)[C], double alpha, double beta) {
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    dv[c].x = fma(beta, dv[c].x, rv[c].x);
+    dv[c].y = fma(beta, dv[c].y, rv[c].y);
+  }
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    double qx = 0.0, qy = 0.0;
+#pragma unroll
+    for (int c2 = 0; c2 < C; c2++) {
+      const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+      qx = fma(mm.x, dv[c2].x, qx);
+      qy = fma(mm.y, dv[c2].y, qy);
+    }
+    q[c].x = qx;
+    q[c].y = qy;
+  }
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    rv[c].x = fma(-alpha, q[c].x, rv[c].x);
+    rv[c].y = fma(-alpha, q[c].y, rv[c].y);
+  }
+}
+// x <- x + alpha d (:298)
+template <int C>
+__device__ __forceinline__ void cg_block_x(double2 (&xv)[C], const double2 (&dv)[C], double alpha) {
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    xv[c].x = fma(alpha, dv[c].x, xv[c].x);
+    xv[c].y = fma(alpha, dv[c].y, xv[c].y);
+  }
+}
+// the four sums of a pass: acc += {r.r, r.Mr, r.q, d.q}
+template <int C>
+__device__ __forceinline__ void cg_block_sums(const double2 (&m)[C * (C + 1) / 2], const double2 (&dv)[C],
+                                              const double2 (&rv)[C], const double2 (&q)[C], double (&acc)[4]) {
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    double mx = 0.0, my = 0.0;
+#pragma unroll
+    for (int c2 = 0; c2 < C; c2++) {
+      const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
+      mx = fma(mm.x, rv[c2].x, mx);
+      my = fma(mm.y, rv[c2].y, my);
+    }
+    acc[0] = fma(rv[c].y, rv[c].y, fma(rv[c].x, rv[c].x, acc[0]));
+    acc[1] = fma(rv[c].y, my, fma(rv[c].x, mx, acc[1]));
+    acc[2] = fma(rv[c].y, q[c].y, fma(rv[c].x, q[c].x, acc[2]));
+    acc[3] = fma(dv[c].y, q[c].y, fma(dv[c].x, q[c].x, acc[3]));
+  }
+}
+
+// K1 epilogue: when the last block of K1 can see every rank's sums (one rank, or NVLink mailboxes) it starts
+// the solve's scalar state itself -- no gather kernel, no 1-thread init launch.
+struct CgInit {
+  CgScalars *st;      // nullptr: the host launches cg_init_scalars_kernel after its own gather
+  int i_max, m;
+  double converge;
+  double *gathered;
+};
+__device__ __forceinline__ void cg_init_fold(const CgInit &ci, const PeerComm &pc, double *out, bool last);
+
 // K1: one pass over sig/rms builds b2 = b + fluctuation, the blocks M, and the initial
 // residual r = b2 - M x (warm start x, Q10), d = r; reduces {r.r, r.M r}.
 // out[0] = sum r^2, out[1] = sum r.Mr
 template <int C>
 __global__ void __launch_bounds__(DG_THREADS)
 rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsigned int *ticket,
-                  double *out) {
+                  double *out, const CgInit ci, const PeerComm pc) {
   constexpr int T = C * (C + 1) / 2;
   __shared__ double smem[2 * 32];
   double acc[2] = {0.0, 0.0};
@@ -186,7 +260,7 @@ rhs_blocks_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsi
       }
     }
   }
-  grid_reduce<2>(acc, smem, partials, ticket, out);
+  cg_init_fold(ci, pc, out, grid_reduce<2>(acc, smem, partials, ticket, out));
 }
 
 // ---------------------------------------------------------------- scalar control
@@ -211,8 +285,19 @@ __device__ __forceinline__ void cg_init_update(CgScalars *st, const double *sums
   st->done = !(1 < i_max && rr > converge);
   st->trace[0] = rr;
   st->ckpt = 0;
+  st->x_at = 0;
+  st->gen = 0u;
   st->ah[1] = st->alpha;
   st->bh[1] = 0.0;
+}
+
+__device__ __forceinline__ void cg_init_fold(const CgInit &ci, const PeerComm &pc, double *out, bool last) {
+  if (!ci.st || !last) return;  // `last`: warp 0 of the block that finished the grid reduction
+  if (pc.nranks > 1) peer_exchange(pc, out, 4, ci.gathered);
+  if (threadIdx.x == 0) {
+    cg_init_update(ci.st, pc.nranks > 1 ? ci.gathered : out, pc.nranks, ci.i_max, ci.converge);
+    ci.st->m = ci.m;
+  }
 }
 
 // After a fused pass: {r'.r', r'.Mr', r'.q, d.q} with q = M d.
@@ -224,7 +309,8 @@ __device__ __forceinline__ void cg_fused_update(CgScalars *st, const double *sum
   const double delta_old = st->delta_new;
   const double delta_new = s[0];
   const double beta = delta_new / delta_old;
-  const double dq = s[1] + 2.0 * beta * s[2] + beta * beta * s[3];
+  // explicit roundings: every CG form (and every kernel this is inlined into) must produce the same bits
+  const double dq = __dadd_rn(__dadd_rn(s[1], __dmul_rn(__dmul_rn(2.0, beta), s[2])), __dmul_rn(__dmul_rn(beta, beta), s[3]));
   st->delta_old = delta_old;
   st->delta_new = delta_new;
   st->beta = beta;
@@ -243,8 +329,9 @@ __device__ __forceinline__ void cg_fused_update(CgScalars *st, const double *sum
 }
 
 static __global__ void cg_init_scalars_kernel(CgScalars *st, const double *gathered, int nranks,
-                                       int i_max, double converge) {
+                                       int i_max, double converge, int m) {
   cg_init_update(st, gathered, nranks, i_max, converge);
+  st->m = m;
 }
 static __global__ void cg_fused_scalars_kernel(CgScalars *st, const double *gathered, int nranks) {
   if (st->done) return;
@@ -285,7 +372,7 @@ static __global__ void cg_rr_scalars_kernel(CgScalars *st, const double *gathere
 // (11 / 15 doubles for C = 2) against the 15 of SURVEY 8d's bytes_cg_it.
 // fold = 1 (single rank): the last block also advances the scalars, saving a launch.
 template <int C>
-__global__ void __launch_bounds__(DG_THREADS)
+__global__ void __launch_bounds__(DG_THREADS, DG_CG_BLOCKS_PER_SM)
 cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
                      double *__restrict__ r, double *__restrict__ d, int64_t n2 /* vec2 elements */,
                      double *partials, unsigned int *ticket, double *out, int fold, PeerComm pc,
@@ -309,45 +396,16 @@ cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__rest
       if (with_x) xv[c] = *reinterpret_cast<const double2 *>(x + c * vs + 2 * e);
     }
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-      dv[c].x = rv[c].x + beta * dp[c].x;  // :305 (of the previous iteration)
-      dv[c].y = rv[c].y + beta * dp[c].y;
-    }
+    for (int c = 0; c < C; c++) dv[c] = dp[c];
     double2 q[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-      double qx = 0.0, qy = 0.0;
-#pragma unroll
-      for (int c2 = 0; c2 < C; c2++) {
-        const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
-        qx += mm.x * dv[c2].x;
-        qy += mm.y * dv[c2].y;
-      }
-      q[c].x = qx;
-      q[c].y = qy;
+    cg_block_step<C>(m, dv, rv, q, alpha, beta);  // :305 (of the previous iteration), :296, :300
+    if (with_x) {                                 // :298, twice
+      cg_block_x<C>(xv, dp, alpha_prev);
+      cg_block_x<C>(xv, dv, alpha);
     }
+    cg_block_sums<C>(m, dv, rv, q, acc);
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      if (with_x) {
-        xv[c].x = (xv[c].x + alpha_prev * dp[c].x) + alpha * dv[c].x;  // :298, twice
-        xv[c].y = (xv[c].y + alpha_prev * dp[c].y) + alpha * dv[c].y;
-      }
-      rv[c].x = rv[c].x - alpha * q[c].x;   // :300
-      rv[c].y = rv[c].y - alpha * q[c].y;
-      acc[3] += dv[c].x * q[c].x + dv[c].y * q[c].y;
-    }
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-      double mx = 0.0, my = 0.0;
-#pragma unroll
-      for (int c2 = 0; c2 < C; c2++) {
-        const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
-        mx += mm.x * rv[c2].x;
-        my += mm.y * rv[c2].y;
-      }
-      acc[0] += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
-      acc[1] += rv[c].x * mx + rv[c].y * my;
-      acc[2] += rv[c].x * q[c].x + rv[c].y * q[c].y;
       *reinterpret_cast<double2 *>(d + c * vs + 2 * e) = dv[c];
       if (with_x) *reinterpret_cast<double2 *>(x + c * vs + 2 * e) = xv[c];
       *reinterpret_cast<double2 *>(r + c * vs + 2 * e) = rv[c];
@@ -373,7 +431,7 @@ cg_fused_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__rest
 //   x += alpha_i d_i;  r_{i+1} = r_i - alpha_i q          (cg_search :296-305)
 // final = 1: the solve is over; bring x up to date from the last checkpoint (no reduction).
 template <int C, bool UNPACK>
-__global__ void __launch_bounds__(DG_THREADS)
+__global__ void __launch_bounds__(DG_THREADS, DG_CG_BLOCKS_PER_SM)
 cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
                          double *__restrict__ r, double *__restrict__ d, int64_t n2,
                          double *partials, unsigned int *ticket, double *out, int fold, int final,
@@ -409,49 +467,10 @@ cg_recompute_pass_kernel(CgScalars *st, const double *__restrict__ M, double *__
     }
     for (int i = 0; i < nstep; i++) {
       const double alpha = sa[i], beta = sb[i];
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        dv[c].x = rv[c].x + beta * dv[c].x;  // :305
-        dv[c].y = rv[c].y + beta * dv[c].y;
-      }
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        double qx = 0.0, qy = 0.0;
-#pragma unroll
-        for (int c2 = 0; c2 < C; c2++) {
-          const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
-          qx += mm.x * dv[c2].x;
-          qy += mm.y * dv[c2].y;
-        }
-        q[c].x = qx;
-        q[c].y = qy;
-      }
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        if (with_x) {
-          xv[c].x = xv[c].x + alpha * dv[c].x;  // :298
-          xv[c].y = xv[c].y + alpha * dv[c].y;
-        }
-        rv[c].x = rv[c].x - alpha * q[c].x;     // :300
-        rv[c].y = rv[c].y - alpha * q[c].y;
-      }
+      cg_block_step<C>(m, dv, rv, q, alpha, beta);  // :305, :296, :300
+      if (with_x) cg_block_x<C>(xv, dv, alpha);     // :298
     }
-    if (!final) {
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        double mx = 0.0, my = 0.0;
-#pragma unroll
-        for (int c2 = 0; c2 < C; c2++) {
-          const double2 mm = m[c <= c2 ? tri<C>(c, c2) : tri<C>(c2, c)];
-          mx += mm.x * rv[c2].x;
-          my += mm.y * rv[c2].y;
-        }
-        acc[0] += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
-        acc[1] += rv[c].x * mx + rv[c].y * my;
-        acc[2] += rv[c].x * q[c].x + rv[c].y * q[c].y;
-        acc[3] += dv[c].x * q[c].x + dv[c].y * q[c].y;
-      }
-    }
+    if (!final) cg_block_sums<C>(m, dv, rv, q, acc);
 #pragma unroll
     for (int c = 0; c < C; c++) {
       if (store) {
@@ -480,8 +499,8 @@ cg_x_fixup_kernel(const CgScalars *st, double *__restrict__ x, const double *__r
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n / 2; e += stride) {
     double2 xv = *reinterpret_cast<const double2 *>(x + 2 * e);
     const double2 dv = *reinterpret_cast<const double2 *>(d + 2 * e);
-    xv.x = xv.x + a * dv.x;
-    xv.y = xv.y + a * dv.y;
+    xv.x = fma(a, dv.x, xv.x);
+    xv.y = fma(a, dv.y, xv.y);
     *reinterpret_cast<double2 *>(x + 2 * e) = xv;
   }
 }
@@ -489,7 +508,7 @@ cg_x_fixup_kernel(const CgScalars *st, double *__restrict__ x, const double *__r
 // ---------------------------------------------------------------- classic two-pass form
 // pass A: d <- r + beta d (skipped on the first iteration), sum d.(M d)      (:296-297)
 template <int C>
-__global__ void __launch_bounds__(DG_THREADS)
+__global__ void __launch_bounds__(DG_THREADS, DG_CG_BLOCKS_PER_SM)
 cg_dq_pass_kernel(const CgScalars *st, const double *__restrict__ M, const double *__restrict__ r,
                   double *__restrict__ d, int64_t n2, double *partials, unsigned int *ticket,
                   double *out) {
@@ -532,7 +551,7 @@ cg_dq_pass_kernel(const CgScalars *st, const double *__restrict__ M, const doubl
 
 // pass B: x += alpha d; r -= alpha (M d); sum r.r                            (:298-303)
 template <int C>
-__global__ void __launch_bounds__(DG_THREADS)
+__global__ void __launch_bounds__(DG_THREADS, DG_CG_BLOCKS_PER_SM)
 cg_update_pass_kernel(const CgScalars *st, const double *__restrict__ M, double *__restrict__ x,
                       double *__restrict__ r, const double *__restrict__ d, int64_t n2,
                       double *partials, unsigned int *ticket, double *out) {

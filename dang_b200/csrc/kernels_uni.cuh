@@ -94,7 +94,7 @@ __device__ __forceinline__ bool same_indices(const ModelView &mv, int ic, int k,
 template <int C>
 __global__ void __launch_bounds__(DG_THREADS, (C <= 2 ? 2 : 1))
 rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
-                      unsigned int *ticket, double *out, unsigned nu_mask) {
+                      unsigned int *ticket, double *out, unsigned nu_mask, const CgInit ci, const PeerComm pc) {
   constexpr int T = C * (C + 1) / 2;
   extern __shared__ double dsed[];  // [slot][band][2][blockDim] for the components in nu_mask
   const int nthr = blockDim.x, tid = threadIdx.x;
@@ -257,7 +257,7 @@ rhs_blocks_uni_kernel(const ModelView mv, const CgView<C> cg, double *partials,
       }
     }
   }
-  grid_reduce<2>(acc, smem, partials, ticket, out);
+  cg_init_fold(ci, pc, out, grid_reduce<2>(acc, smem, partials, ticket, out));
 }
 
 // K6, uniform-SED form (chi-square reduction only; map output stays in chisq_kernel).
@@ -514,7 +514,8 @@ __device__ __forceinline__ void tma_issue_item(const ModelView &mv, const TmaRin
 // K1, all SEDs tabulated, no subtracted components (the headline configuration).
 template <int C>
 __global__ void __launch_bounds__(DG_TMA_THREADS, 1)
-rhs_blocks_tma_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsigned int *ticket, double *out) {
+rhs_blocks_tma_kernel(const ModelView mv, const CgView<C> cg, double *partials, unsigned int *ticket, double *out,
+                      const CgInit ci, const PeerComm pc) {
   constexpr int T = C * (C + 1) / 2;
   extern __shared__ __align__(128) unsigned char tma_smem[];
   __shared__ double smem[2 * 32];
@@ -677,5 +678,5 @@ rhs_blocks_tma_kernel(const ModelView mv, const CgView<C> cg, double *partials, 
     }
     __syncthreads();  // every consumer is done with this stage before it is refilled
   }
-  grid_reduce<2>(acc, smem, partials, ticket, out);
+  cg_init_fold(ci, pc, out, grid_reduce<2>(acc, smem, partials, ticket, out));
 }

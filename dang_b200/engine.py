@@ -33,6 +33,7 @@ OPT_L2_PERSIST_MB = 11
 OPT_PERPIXEL_FAST = 12
 OPT_PERPIXEL_BP_SERIES = 13
 OPT_BP_QUADRATURE = 14
+OPT_CG_PERSISTENT = 15
 KERNEL_COUNT = 12
 
 

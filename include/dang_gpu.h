@@ -115,7 +115,13 @@ enum {
    * evaluate_powerlaw / evaluate_mbb / ... to < 1e-15 relative while costing n instead of n_bp
    * transcendentals per band.  Bands with n_bp <= 2n, negative weights or a half-width above 0.25 in
    * ln(nu) keep their table. */
-  DANG_OPT_BP_QUADRATURE = 14
+  DANG_OPT_BP_QUADRATURE = 14,
+  /* 1 (default): the whole loop of cg_search (src/dang_cg_mod.f90:293-314) runs as ONE persistent, cooperatively
+   * launched kernel -- one sweep of the checkpointed-recompute form per CG iteration, a grid barrier and (on
+   * several GPUs) the NVLink mailbox exchange between sweeps, unpack_amplitudes folded into the predicted last
+   * sweep -- instead of one launch per iteration.  Same operations in the same order (bit-identical results).
+   * Needs the recompute form (DANG_OPT_CG_CHECKPOINT > 0) and one rank or mailboxes; 0: one launch per pass. */
+  DANG_OPT_CG_PERSISTENT = 15
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
