@@ -11,12 +11,12 @@ FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompil
 units=(dang_gpu host_cg host_tmpl host_data host_mh_pp host_mh_ppf host_mh_fs)
 declare -A deps=(
   [dang_gpu]="kernels_data.cuh"
-  [host_cg]="kernels_cg.cuh kernels_uni.cuh"
+  [host_cg]="kernels_cg.cuh kernels_cg_solve.cuh kernels_uni.cuh kernels_stream.cuh"
   [host_tmpl]="kernels_tmpl.cuh"
   [host_data]="kernels_data.cuh kernels_uni.cuh"
   [host_mh_pp]="kernels_mh.cuh"
   [host_mh_ppf]="kernels_mh.cuh kernels_mh_fast.cuh"
-  [host_mh_fs]="kernels_mh.cuh kernels_uni.cuh"
+  [host_mh_fs]="kernels_mh.cuh kernels_uni.cuh kernels_stream.cuh kernels_cg.cuh"
 )
 pids=()
 for u in "${units[@]}"; do

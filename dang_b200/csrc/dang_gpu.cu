@@ -361,6 +361,7 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_idx_dl, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
       CK(cudaEventCreateWithFlags(&h->ev_eta[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_eta_used[i], cudaEventDisableTiming));
@@ -421,7 +422,7 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
   if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
   dfree(h->eta_stage[0]); dfree(h->eta_stage[1]);
-  for (cudaEvent_t e : {h->ev_compute, h->ev_idx_dl, h->ev_eta[0], h->ev_eta[1], h->ev_eta_used[0], h->ev_eta_used[1]}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev_compute, h->ev_idx_dl, h->ev_sync, h->ev_eta[0], h->ev_eta[1], h->ev_eta_used[0], h->ev_eta_used[1]}) if (e) cudaEventDestroy(e);
   for (cudaStream_t st : {h->d2h_stream, h->h2d_stream, h->stream}) if (st) cudaStreamDestroy(st);
   delete h;
   return DANG_GPU_OK;
@@ -452,6 +453,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     }
     case DANG_OPT_PERPIXEL_BP_SERIES: h->pp_bp_series = value != 0; break;
     case DANG_OPT_CG_PERSISTENT: h->cg_persistent = value != 0; break;
+    case DANG_OPT_STREAM_RING: h->stream_ring = value != 0; break;
     case DANG_OPT_BP_QUADRATURE:
       h->bp_quad = value < 0 ? 0 : (value > 32 ? 32 : (int)value);
       h->bp_dirty = true;

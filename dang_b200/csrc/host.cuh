@@ -130,6 +130,7 @@ struct dang_gpu {
   int64_t npix = 0, lo = 0, hi = 0, P = 0, Ppad = 0;
   cudaStream_t stream = nullptr, d2h_stream = nullptr, h2d_stream = nullptr;
   cudaEvent_t ev_compute = nullptr, ev_idx_dl = nullptr;
+  cudaEvent_t ev_sync = nullptr;  // host waits for a point of the compute stream (results read back) while later kernels run
   bool idx_dl_pending = false;
   // staged deviates of the next solves: a two-slot FIFO, so the upload for solve k+1 runs while solve k
   // (which consumes the other slot) is still computing
@@ -142,6 +143,7 @@ struct dang_gpu {
   // options
   int fix_q1 = 0, cg_two_pass = 0, fullsky_stream = 0, profile = 0, cg_chunk = 8, record = 0, perpixel_serial = 0;
   int cg_ckpt = 8;  // checkpoint interval of the recompute CG form (0: streaming form)
+  int stream_ring = 1;    // K1 / statistics pass fed by per-thread cp.async rings (DANG_OPT_STREAM_RING)
   int cg_persistent = 1;  // whole solve in one persistent cooperative kernel (DANG_OPT_CG_PERSISTENT)
   int bp_quad = 8;        // nodes of the Gauss-quadrature compression of tabulated bandpasses (0: off)
   int pp_bp_series = 1;   // tabulated bandpasses: moment series in the per-pixel chains (DANG_OPT_PERPIXEL_BP_SERIES)
@@ -386,6 +388,7 @@ inline void touch(dang_gpu *h, int what = 0) {  // the model state changed
 }
 // host_mh_fs.cu: serve compute_chisq from the sufficient statistics of the upcoming full-sky draw
 bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]);
+void prefetch_statistics(dang_gpu *h);  // host_mh_fs.cu: statistics pass of the upcoming full-sky draw, enqueued ahead of time
 void cg_solve_template(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const double *eta, uint64_t seed,
                        const int *comps, int C, int tcomp, const int *og, int nog, int *n_iter,
                        double *delta_final);                                       // host_tmpl.cu

@@ -6,6 +6,7 @@
 #include "kernels_cg.cuh"
 #include "kernels_cg_solve.cuh"
 #include "kernels_uni.cuh"
+#include "kernels_stream.cuh"
 
 namespace {
 // ---------------------------------------------------------------- amplitude draw
@@ -103,7 +104,13 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     }
     const size_t dsm = (size_t)__builtin_popcount(nu_mask) * h->nbands * 2 * DG_THREADS * sizeof(double);
     const size_t tma_smem = (size_t)DG_TMA_STAGES * DG_TMA_BANDS * 2 * 2 * DG_TMA_TILE * sizeof(double);
-    if (h->use_tma && nu_mask == 0 && nog == 0) {
+    const size_t ring_smem = (size_t)DG_RING_STAGES * DG_RING_SLOTS * DG_THREADS * sizeof(double2);
+    if (h->stream_ring && !h->use_tma && nu_mask == 0 && nog == 0) {
+      // asynchronous stream: per-thread cp.async ring in shared memory (kernels_stream.cuh)
+      CK(cudaFuncSetAttribute(rhs_blocks_ring_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+      const int g4 = occ_grid(h, rhs_blocks_ring_kernel<C>, h->Ppad / 2, DG_THREADS, ring_smem);
+      rhs_blocks_ring_kernel<C><<<g4, DG_THREADS, ring_smem, h->stream>>>(mv, cv, h->partials, h->tickets, h->sums_local, ci, h->peer);
+    } else if (h->use_tma && nu_mask == 0 && nog == 0) {
       // TMA-staged stream: one block per SM, 3-stage shared-memory ring filled by cp.async.bulk
       CK(cudaFuncSetAttribute(rhs_blocks_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
       const int64_t ntiles = (h->Ppad + DG_TMA_TILE - 1) / DG_TMA_TILE;
@@ -168,13 +175,15 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     }
   }
   // ---- default form: the whole loop of cg_search in one persistent cooperative kernel (kernels_cg_solve.cuh)
-  const bool persistent = h->cg_persistent && ckpt_m > 0 && fold_all;
+  const bool persistent = h->cg_persistent && ckpt_m > 0 && fold_all && C <= 2;  // (C > 2: the prefetch ring of two resident blocks does not fit in shared memory)
   if (persistent) {
     CgAmpOut<C> ao{};
     for (int c = 0; c < C; c++) ao.p[c] = h->comp[comps[c]].amp + (size_t)cv.plane[0] * h->Ppad;  // S contiguous planes
     int k_pred = g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : 0x7fffffff;  // pass the previous solve ended on
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_solve_kernel<C>, DG_THREADS, 0));
+    const size_t cg_smem = cg_ring_bytes<C>();
+    CK(cudaFuncSetAttribute(cg_solve_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_solve_kernel<C>, DG_THREADS, cg_smem));
     if (per_sm < DG_CG_BLOCKS_PER_SM) fail(DANG_GPU_ECUDA, "cg_solve_kernel: %d resident blocks per SM, %d needed", per_sm, DG_CG_BLOCKS_PER_SM);
     const int64_t cgrid = grid_for(h, n2, DG_THREADS, DG_CG_BLOCKS_PER_SM);  // every block resident: the kernel has a grid barrier
     CgScalars *st = h->cg_scalars;
@@ -185,11 +194,22 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     PeerComm pcv = h->peer;
     void *args[] = {&st, &Mp, &xp, &rp, &dp, &n2v, &part, &tick, &outp, &pcv, &gath, &ao, &k_pred};
     KTimer kt(h, DANG_K_CG_PASS, 0, true);
-    CK(cudaLaunchCooperativeKernel((void *)cg_solve_kernel<C>, dim3((unsigned)cgrid), dim3(DG_THREADS), args, 0, h->stream));
+    CK(cudaLaunchCooperativeKernel((void *)cg_solve_kernel<C>, dim3((unsigned)cgrid), dim3(DG_THREADS), args, cg_smem, h->stream));
     kt.done();
+    // The scalars come back right behind the solve and the host waits for that point of the stream only.  When this
+    // is the run's only solve per Gibbs iteration and a full-sky draw follows, the draw's statistics pass (which
+    // also serves the chi-square printed after the amplitude draw) is enqueued first, so the device keeps
+    // streaming while the host turns the solve around.
     CgScalars *hs = (CgScalars *)h->pinned;
     readback(h, hs, h->cg_scalars, offsetof(CgScalars, ah));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(h->ev_sync, h->stream));
+    {
+      int nsolve = 0;
+      for (auto &gg : h->cg)
+        if (gg.set) nsolve += gg.nflag;
+      if (nsolve == 1) prefetch_statistics(h);
+    }
+    CK(cudaEventSynchronize(h->ev_sync));
     // compulsory traffic of the sweeps that ran: M, r (and d after the first checkpoint) in; checkpoint passes
     // write r, d; sweeps that carry x read it and write x + the amplitude planes
     const int n_pass = hs->iter - 1;

@@ -3,6 +3,7 @@
 #include "host.cuh"
 #include "kernels_mh.cuh"
 #include "kernels_uni.cuh"
+#include "kernels_stream.cuh"
 
 void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode, MhView &mh) {
   if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set) fail(DANG_GPU_EINVAL, "bad component %d", ic);
@@ -88,7 +89,18 @@ int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
     int g2 = occ_grid(h, mh_suffstat_uni_kernel<4>, h->Ppad / 2 * ncombo, DG_THREADS);
     g2 = g2 / ncombo * ncombo;
     if (g2 < ncombo) g2 = ncombo;
-    if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+    if (h->stream_ring) {  // asynchronous stream: per-thread cp.async ring in shared memory (kernels_stream.cuh)
+      const size_t ring_smem = (size_t)DG_RING_STAGES * DG_RING_SLOTS * DG_THREADS * sizeof(double2);
+      auto launch = [&](auto kernel) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        int g3 = occ_grid(h, kernel, h->Ppad / 2 * ncombo, DG_THREADS, ring_smem);
+        g3 = g3 / ncombo * ncombo;
+        if (g3 < ncombo) g3 = ncombo;
+        kernel<<<g3, DG_THREADS, ring_smem, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
+      };
+      if (h->ncomp <= 2) launch(mh_suffstat_ring_kernel<2>);
+      else launch(mh_suffstat_ring_kernel<4>);
+    } else if (h->ncomp <= 2) mh_suffstat_uni_kernel<2><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
     else mh_suffstat_uni_kernel<4><<<g2, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->partials, h->tickets, h->sums_local);
   } else {
     const int grid = occ_grid(h, mh_suffstat_kernel, h->P, DG_THREADS);
@@ -202,15 +214,19 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
     mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->stat_buf, h->nranks, cnt);
     ks.done();
   }
+  // The chain's results go back first and the host waits for THAT point of the stream only; the kernel that
+  // writes the final sample into the index planes (:329, :483) runs while the host is already enqueuing the
+  // next call.
+  MhScalars *hs = (MhScalars *)h->pinned;
+  readback(h, hs, h->mh_scalars, sizeof(MhScalars));
+  CK(cudaEventRecord(h->ev_sync, h->stream));
   {
     const int grid = grid_for(h, h->P, DG_THREADS, 4);
     KTimer kt(h, DANG_K_SCALAR, 0);
     mh_fullsky_store_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars);
     kt.done();
   }
-  MhScalars *hs = (MhScalars *)h->pinned;
-  readback(h, hs, h->mh_scalars, sizeof(MhScalars));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventSynchronize(h->ev_sync));
   if (accept) *accept = hs->accept;
   h->comp[mh.ic].index[mh.nind].last_value = hs->sample[mh.nind];
   touch(h, 2);
@@ -230,6 +246,43 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
 // the chisq likelihood over the same planes: gather that draw's per-plane statistics now.  X_j is
 // the chi-square term of band j about the current state, so chisq_planes = sum_j X_j / nbands, and
 // the draw that follows (and the chi-square after it) need no further pass over the maps.
+// The full-sky chisq draw that follows an amplitude draw in sample_spectral_parameters' order, if there is one
+// whose statistics can be gathered ahead of time.
+static bool upcoming_fullsky_draw(dang_gpu *h, MhView &mh) {
+  if (!h->stat_cache || h->fullsky_stream || h->last_mutation != 1) return false;
+  int ic = -1, nind = -1;
+  for (int c = 0; c < h->ncomp && ic < 0; c++)
+    for (int l = 0; l < h->comp[c].nind && ic < 0; l++)
+      if (h->comp[c].set && h->comp[c].index[l].sample_index && h->comp[c].index[l].nflag > 0) {
+        ic = c;
+        nind = l;
+      }
+  if (ic < 0) return false;
+  const IndexHost &ix = h->comp[ic].index[nind];
+  if (ix.index_mode != DANG_INDEX_FULLSKY || ix.sample_nside != h->nside) return false;
+  const int flag = ix.pol_flag[0];
+  const int map_n = (flag & 8) ? -1 : (flag & 1) ? 1 : (flag & 2) ? 2 : (flag & 4) ? 3 : 0;
+  if (map_n == 0) return false;
+  try {
+    mh_view(h, ic, nind, map_n, 0, DANG_ML_SAMPLE, mh);
+  } catch (const DgError &) {
+    return false;  // the draw itself will report what is wrong with it
+  }
+  return !fullsky_needs_stream(mh);
+}
+
+// Called by the amplitude draw right after its last kernel is enqueued and BEFORE the host waits for the solve's
+// scalars: when the configuration has a full-sky chisq draw coming, its statistics pass (which also serves the
+// chi-square the reference prints after the draw, write_stats_to_term) goes onto the stream now, so the device
+// never idles while the host turns the solve around.
+void prefetch_statistics(dang_gpu *h) {
+  MhView mh;
+  if (!upcoming_fullsky_draw(h, mh)) return;
+  if (h->maps_set && h->n_unmasked < 0) return;  // first call: let compute_chisq count the mask first
+  ModelView mv = model_view(h);
+  if (!stat_cache_hit(h, mh)) fullsky_statistics(h, mv, mh);
+}
+
 bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]) {
   if (!h->stat_cache || h->fullsky_stream || h->last_mutation != 1) return false;
   int ic = -1, nind = -1;

@@ -12,7 +12,7 @@
 // Every CG pass form runs on the same grid (DG_CG_BLOCKS_PER_SM resident blocks per SM x SM count, or fewer when the
 // sky slice is small): the deterministic grid reduction depends on the grid size, and the forms must agree to
 // the last bit; the persistent solve kernel additionally needs every block resident.
-#define DG_CG_BLOCKS_PER_SM 3
+#define DG_CG_BLOCKS_PER_SM 2
 
 template <int C>
 struct CgView {

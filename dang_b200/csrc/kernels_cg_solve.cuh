@@ -6,13 +6,21 @@
 // barrier.  No launch, no host round trip and no scalar kernel between iterations; on a rank whose CG state
 // fits the 126 MB L2 (nside 512 on >= 4 GPUs) the sweeps never touch HBM.
 //
+// The sweeps are asynchronous streams: every thread copies the block matrices and the stored (r, d) of its next
+// two element pairs into a private three-stage ring in shared memory with cp.async while it replays the
+// recurrences of the current pair, so the FP64 work of the replay (up to m block steps per element) overlaps the
+// memory stream instead of alternating with it.
+//
 // unpack_amplitudes (:1284-1396) rides along speculatively: from the pass the previous solve of this
 // (group, flag) ended on (`k_pred`) onwards a sweep also brings x up to date and writes the amplitude
 // planes, so a solve that converges where the previous one did needs no extra sweep at the end.  x carries
 // its own marker (CgScalars::x_at): the additions x += alpha_i d_i happen once each, in iteration order,
 // exactly as :298 performs them -- the result is bit-identical to the pass-per-launch forms.
 #pragma once
+#include "cp_async.cuh"
 #include "kernels_cg.cuh"
+
+#define DG_CGR_STAGES 3
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
   unsigned int v;
@@ -21,6 +29,12 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned int *p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// dynamic shared memory of cg_solve_kernel<C>: [stage][slot][thread] 16-byte slots, slots = T (M) + C (r) + C (d)
+template <int C>
+constexpr size_t cg_ring_bytes() {
+  return (size_t)DG_CGR_STAGES * (C * (C + 1) / 2 + 2 * C) * DG_THREADS * sizeof(double2);
 }
 
 // One sweep over this rank's elements: replay steps c0+1 .. c0+nstep of the block-local recurrences from the
@@ -32,21 +46,51 @@ __device__ __forceinline__ void cg_replay_sweep(const double *__restrict__ M, do
                                                 double *__restrict__ r, double *__restrict__ d, int64_t n2,
                                                 int c0, int nstep, int x_at, bool store_rd, bool with_x,
                                                 const double *sa, const double *sb, const CgAmpOut<C> &ao,
-                                                double (&acc)[4]) {
+                                                double2 *ring, double (&acc)[4]) {
   constexpr int T = C * (C + 1) / 2;
+  constexpr int SLOTS = T + 2 * C;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const size_t vs = (size_t)n2 * 2;
   const int xskip = x_at - c0;  // replay steps i < xskip are already in x
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
-    double2 m[T], xv[C], rv[C], dv[C], q[C];
+  const bool read_d = c0 != 0;  // before the first checkpoint the stored direction is d_0 = r_1 itself (beta_1 = 0)
+  auto issue = [&](int64_t e, int stage) {
+    if (e < n2) {
+      double2 *dst = ring + (size_t)stage * SLOTS * blockDim.x + threadIdx.x;
 #pragma unroll
-    for (int t = 0; t < T; t++) m[t] = ldg_stream2(M + t * vs + 2 * e);
+      for (int t = 0; t < T; t++) cp_async16(dst + (size_t)t * blockDim.x, M + t * vs + 2 * e);
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        cp_async16(dst + (size_t)(T + c) * blockDim.x, r + c * vs + 2 * e);
+        if (read_d) cp_async16(dst + (size_t)(T + C + c) * blockDim.x, d + c * vs + 2 * e);
+      }
+    }
+    cp_async_commit();
+  };
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, epre = e;
+#pragma unroll
+  for (int st = 0; st < DG_CGR_STAGES - 1; st++) {
+    issue(epre, st);
+    epre += stride;
+  }
+  int stage = 0, pstage = DG_CGR_STAGES - 1;
+  for (; e < n2; e += stride) {
+    issue(epre, pstage);
+    epre += stride;
+    pstage = pstage + 1 == DG_CGR_STAGES ? 0 : pstage + 1;
+    double2 m[T], xv[C], rv[C], dv[C], q[C];
+    if (with_x) {
+#pragma unroll
+      for (int c = 0; c < C; c++) xv[c] = __ldcg(reinterpret_cast<const double2 *>(x + c * vs + 2 * e));
+    }
+    cp_async_wait<DG_CGR_STAGES - 1>();
+    const double2 *src = ring + (size_t)stage * SLOTS * blockDim.x + threadIdx.x;
+    stage = stage + 1 == DG_CGR_STAGES ? 0 : stage + 1;
+#pragma unroll
+    for (int t = 0; t < T; t++) m[t] = src[(size_t)t * blockDim.x];
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      rv[c] = __ldcg(reinterpret_cast<const double2 *>(r + c * vs + 2 * e));
-      // before the first checkpoint the stored direction is d_0 = r_1 itself (beta_1 = 0)
-      dv[c] = c0 == 0 ? rv[c] : __ldcg(reinterpret_cast<const double2 *>(d + c * vs + 2 * e));
-      if (with_x) xv[c] = __ldcg(reinterpret_cast<const double2 *>(x + c * vs + 2 * e));
+      rv[c] = src[(size_t)(T + c) * blockDim.x];
+      dv[c] = read_d ? src[(size_t)(T + C + c) * blockDim.x] : rv[c];
     }
     for (int i = 0; i < nstep; i++) {
       const double alpha = sa[i], beta = sb[i];
@@ -66,6 +110,7 @@ __device__ __forceinline__ void cg_replay_sweep(const double *__restrict__ M, do
       }
     }
   }
+  cp_async_wait<0>();
 }
 
 template <int C>
@@ -73,6 +118,8 @@ __global__ void __launch_bounds__(DG_THREADS, DG_CG_BLOCKS_PER_SM)
 cg_solve_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict__ x, double *__restrict__ r,
                 double *__restrict__ d, int64_t n2, double *partials, unsigned int *ticket, double *out,
                 PeerComm pc, double *gathered, CgAmpOut<C> ao, int k_pred) {
+  extern __shared__ __align__(16) unsigned char cg_ring_raw[];
+  double2 *ring = reinterpret_cast<double2 *>(cg_ring_raw);
   __shared__ double smem[4 * 32];
   __shared__ double sa[DG_CG_MAXM + 1], sb[DG_CG_MAXM + 1];
   __shared__ int ctl[6];
@@ -97,7 +144,7 @@ cg_solve_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict_
         }
         __syncthreads();
         double acc[4];
-        cg_replay_sweep<C, false>(M, x, r, d, n2, c0, nstep, x_at, false, true, sa, sb, ao, acc);
+        cg_replay_sweep<C, false>(M, x, r, d, n2, c0, nstep, x_at, false, true, sa, sb, ao, ring, acc);
       }
       return;
     }
@@ -110,7 +157,7 @@ cg_solve_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict_
     }
     __syncthreads();
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    cg_replay_sweep<C, true>(M, x, r, d, n2, c0, nstep, x_at, store, with_x, sa, sb, ao, acc);
+    cg_replay_sweep<C, true>(M, x, r, d, n2, c0, nstep, x_at, store, with_x, sa, sb, ao, ring, acc);
     const bool last = grid_reduce<4>(acc, smem, partials, ticket, out);
     if (last) {  // warp 0 of the block that arrived last: exchange over NVLink (if any), advance the scalars
       if (pc.nranks > 1) peer_exchange(pc, out, 4, gathered);

@@ -34,6 +34,7 @@ OPT_PERPIXEL_FAST = 12
 OPT_PERPIXEL_BP_SERIES = 13
 OPT_BP_QUADRATURE = 14
 OPT_CG_PERSISTENT = 15
+OPT_STREAM_RING = 16
 KERNEL_COUNT = 12
 
 

@@ -121,7 +121,12 @@ enum {
    * several GPUs) the NVLink mailbox exchange between sweeps, unpack_amplitudes folded into the predicted last
    * sweep -- instead of one launch per iteration.  Same operations in the same order (bit-identical results).
    * Needs the recompute form (DANG_OPT_CG_CHECKPOINT > 0) and one rank or mailboxes; 0: one launch per pass. */
-  DANG_OPT_CG_PERSISTENT = 15
+  DANG_OPT_CG_PERSISTENT = 15,
+  /* 1 (default): the two passes over sig / rms of a configuration with tabulated SEDs (K1 = rhs + blocks, and the
+   * full-sky sufficient statistics) prefetch through per-thread three-stage cp.async rings in shared memory, two band
+   * batches ahead of the arithmetic (csrc/kernels_stream.cuh); 0: the 16-byte LDG forms (csrc/kernels_uni.cuh).
+   * Same arithmetic; sums agree to rounding (the grid sizes differ). */
+  DANG_OPT_STREAM_RING = 16
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
