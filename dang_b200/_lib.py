@@ -72,6 +72,8 @@ SIGNATURES = {
     "dang_gpu_launch_count": (C.c_int, [vp, c_i64p, C.c_int]),
     "dang_gpu_kernel_stats": (C.c_int, [vp, C.c_int, c_i64p, c_dp, c_dp, C.c_int]),
     "dang_gpu_kernel_name": (C.c_char_p, [C.c_int]),
+    "dang_gpu_timeline": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), c_dp, c_dp]),
+    "dang_gpu_set_t_cmb": (C.c_int, [vp, C.c_double]),
 }
 
 _lib = None

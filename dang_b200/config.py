@@ -15,12 +15,14 @@ import numpy as np
 MISSVAL = -1.6375e30  # src/dang_util_mod.f90:19
 
 # enums shared with include/dang_gpu.h
-COMP_TYPES = {"power-law": 1, "mbb": 2, "freefree": 3, "lognormal": 4, "cmb": 5, "template": 6}
+COMP_TYPES = {"power-law": 1, "mbb": 2, "freefree": 3, "lognormal": 4, "cmb": 5, "template": 6,
+              "T_cmb": 7, "monopole": 8, "hi_fit": 9}
 LNL_TYPES = {"chisq": 0, "marginal": 1, "prior": 2}
 PRIOR_TYPES = {"uniform": 0, "gaussian": 1, "jeffreys": 2}
 ML_MODES = {"optimize": 0, "sample": 1}
 INDEX_MODES = {"fullsky": 1, "per-pixel": 2}
-NINDICES = {"power-law": 1, "mbb": 2, "freefree": 1, "lognormal": 2, "cmb": 0, "template": 0}
+NINDICES = {"power-law": 1, "mbb": 2, "freefree": 1, "lognormal": 2, "cmb": 0, "template": 0,
+            "T_cmb": 1, "monopole": 0, "hi_fit": 1}
 
 
 def return_poltype_flag(string: str) -> List[int]:

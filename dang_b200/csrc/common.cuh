@@ -41,7 +41,8 @@ struct CompView {
   double nu_ref;
   double *amp;             // [nmaps][Ppad]; type 'template': the (normalised) template map
   double *idx[DG_MAXIND];  // each [nmaps][Ppad]
-  const double *tamp;      // type 'template': template_amplitudes [3][DG_MAX_BANDS] (its "SED" table), else null
+  const double *tamp;      // 'template' / 'monopole' / 'hi_fit': template_amplitudes [3][DG_MAX_BANDS], else null
+  int in_sky;              // 0: left out of the sky model ('monopole', src/dang_data_mod.f90:357-361)
 };
 
 // Model description handed to kernels by value (lives in the constant bank: every thread reads
@@ -60,6 +61,7 @@ struct ModelView {
   const double *sig, *rms;   // [nbands][nmaps][Ppad]
   const unsigned char *mask; // [Ppad], 1 = use pixel (mask /= 0 and /= missval)
   double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
+  double T_cmb;              // the module-global T_CMB (src/dang_util_mod.f90:15; a 'T_cmb' component overwrites it)
 };
 
 __device__ __forceinline__ size_t plane_off(const ModelView &mv, int band, int k) {
@@ -214,7 +216,7 @@ __device__ __forceinline__ double sed_lognormal(const ModelView &mv, int ic, int
 // type 'cmb': 1/a2t(bp(band)), src/dang_component_mod.f90:799-800 with a2t from dang_bp_mod.f90:211-243
 __device__ __forceinline__ double sed_cmb(const ModelView &mv, int band) {
   const BandView &b = mv.band[band];
-  const double T_CMB = 2.7255;  // src/dang_util_mod.f90:15
+  const double T_CMB = mv.T_cmb;  // src/dang_util_mod.f90:15 (2.7255 until a 'T_cmb' draw changes it)
   double sum = 0.0;
   if (b.n == 0) {
     const double y = (b.nu_c > 1e7) ? (DG_H * b.nu_c) / (DG_KB * T_CMB) : (DG_H * b.nu_c * 1e9) / (DG_KB * T_CMB);
@@ -230,15 +232,41 @@ __device__ __forceinline__ double sed_cmb(const ModelView &mv, int band) {
   return 1.0 / sum;
 }
 
-// SED of component ic in `band` for explicit parameters (a Metropolis proposal, or a pixel)
+// evaluate_T_cmb :815-848 and evaluate_hi_fit :850-884 (one body): B_nu(nu, T) / compute_bnu_prime_RJ(nu) * 1e6,
+// B_nu src/dang_component_mod.f90:745-752, compute_bnu_prime_RJ src/dang_bp_mod.f90:160-168; operation order kept.
+#define DG_C 2.99792458e8
+__device__ __forceinline__ double planck_rj_at(double nu, double T) {
+  const double B = ((2.0 * DG_H * (nu * nu * nu)) / (DG_C * DG_C)) * (1.0 / (exp((DG_H * nu) / (DG_KB * T)) - 1.0));
+  return B / (2.0 * DG_KB * (nu * nu) / (DG_C * DG_C));
+}
+__device__ __forceinline__ double sed_planck_rj(const ModelView &mv, int band, double T) {
+  const BandView &b = mv.band[band];
+  double spectrum = 0.0;
+  if (b.n == 0) {
+    spectrum = planck_rj_at(b.nu_c, T);
+  } else {
+    for (int i = 0; i < b.n; i++) {
+      const double nu0 = mv.bp_nu0[b.off + i];
+      if (nu0 == 0.0) continue;
+      spectrum = spectrum + mv.bp_tau0[b.off + i] * planck_rj_at(nu0, T);
+    }
+  }
+  return spectrum * 1e6;
+}
+
+// SED of component ic in `band` for explicit parameters (a Metropolis proposal, or a pixel).  `k`: plane, needed
+// by 'hi_fit' only (its SED carries template_amplitudes(band, plane), see sed_table_kernel).
 __device__ __forceinline__ double sed_theta(const ModelView &mv, int ic, int band, double t0,
-                                            double t1) {
+                                            double t1, int k = 0) {
   switch (mv.comp[ic].type) {
     case 1: return sed_powerlaw(mv, ic, band, t0);
     case 2: return sed_mbb(mv, ic, band, t0, t1);
     case 3: return sed_freefree(mv, ic, band, t0);
     case 4: return sed_lognormal(mv, ic, band, t0, t1);
     case 6: return 0.0;  // 'template': always tabulated (sed_table_kernel copies template_amplitudes)
+    case 7: return sed_planck_rj(mv, band, t0);                                           // 'T_cmb'
+    case 8: return 0.0;  // 'monopole': always tabulated
+    case 9: return mv.comp[ic].tamp[k * DG_MAX_BANDS + band] * sed_planck_rj(mv, band, t0);  // 'hi_fit'
     default: return sed_cmb(mv, band);
   }
 }
@@ -253,7 +281,7 @@ __device__ __forceinline__ bool sed_uniform(const ModelView &mv, int ic, int k) 
 __device__ __forceinline__ double sed_eval(const ModelView &mv, int ic, int k, int band, double t0,
                                            double t1) {
   if (sed_uniform(mv, ic, k)) return mv.tab->sed[ic * 3 + k][band];
-  return sed_theta(mv, ic, band, t0, t1);
+  return sed_theta(mv, ic, band, t0, t1, k);
 }
 
 // ---------------------------------------------------------------- Philox4x32-10

@@ -4,6 +4,8 @@
 // handle's stream; cross-rank traffic is an NCCL all-gather of a few doubles followed by a
 // rank-ordered sum on every rank (deterministic, identical bits everywhere).
 // There is deliberately no CPU fallback: every error surfaces as a nonzero return code.
+#include <algorithm>
+
 #include "host.cuh"
 #include "kernels_data.cuh"
 
@@ -202,6 +204,7 @@ ModelView model_view(dang_gpu *h) {
     mv.gain[j] = h->gain[j];
     mv.offset[j] = h->offset[j];
   }
+  mv.T_cmb = h->T_cmb;
   for (int c = 0; c < h->ncomp; c++) {
     if (!h->comp[c].set) fail(DANG_GPU_ESTATE, "component %d has not been set", c);
     mv.comp[c].type = h->comp[c].type;
@@ -209,7 +212,8 @@ ModelView model_view(dang_gpu *h) {
     mv.comp[c].nu_ref = h->comp[c].nu_ref;
     mv.comp[c].amp = h->comp[c].amp;
     for (int l = 0; l < DG_MAXIND; l++) mv.comp[c].idx[l] = h->comp[c].idx[l];
-    mv.comp[c].tamp = h->comp[c].is_template ? h->comp[c].tamp : nullptr;
+    mv.comp[c].tamp = h->comp[c].is_template ? h->comp[c].tamp : nullptr;  // template / monopole / hi_fit
+    mv.comp[c].in_sky = h->comp[c].type == DANG_COMP_MONOPOLE ? 0 : 1;
   }
   mv.bp_nu0 = h->bp_nu0;
   mv.bp_tau0 = h->bp_tau0;
@@ -269,6 +273,14 @@ void gather(dang_gpu *h, int cnt) {
     NCK(g_nccl.AllGather(h->sums_local, h->gathered, cnt, NCCL_DOUBLE, h->comm, h->stream));
   }
 }
+// update_sky_model's side effect for a monopole component (src/dang_data_mod.f90:357-361): ddata%offset takes the
+// band monopoles, template_amplitudes(:, 1).  The reference runs update_sky_model after every draw, so the offsets
+// always equal the current monopole amplitudes; the library keeps that invariant wherever they change.
+void monopole_to_offset(dang_gpu *h, const CompHost &c) {
+  if (c.type != DANG_COMP_MONOPOLE) return;
+  for (int j = 0; j < h->nbands; j++) h->offset[j] = c.tamp_host[0][j];
+}
+
 // template_amplitudes host mirror -> device table; the tabulated "SEDs" must be rebuilt
 void upload_tamp(dang_gpu *h, CompHost &c) {
   if (!c.tamp) CK(cudaMalloc(&c.tamp, sizeof c.tamp_host));
@@ -434,7 +446,15 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_FIX_SAMPLE_VECTOR: h->fix_q1 = value != 0; break;
     case DANG_OPT_CG_TWO_PASS: h->cg_two_pass = value != 0; break;
     case DANG_OPT_FULLSKY_STREAM: h->fullsky_stream = value != 0; break;
-    case DANG_OPT_PROFILE: h->profile = value != 0; break;
+    case DANG_OPT_PROFILE:
+      h->profile = value != 0;
+      if (h->profile) {  // (re)start the event log here
+        resolve_stats(h);
+        h->tl.clear();
+        if (!h->tl_base) CK(cudaEventCreate(&h->tl_base));
+        CK(cudaEventRecord(h->tl_base, h->stream));
+      }
+      break;
     case DANG_OPT_CG_CHUNK: h->cg_chunk = value < 1 ? 1 : (int)value; break;
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
     case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
@@ -648,10 +668,7 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
                            const double *indices) {
   API_BEGIN
   if (ic < 0 || ic >= h->ncomp) fail(DANG_GPU_EINVAL, "component %d of %d", ic, h->ncomp);
-  if (type < DANG_COMP_POWERLAW || type > DANG_COMP_TEMPLATE)
-    fail(DANG_GPU_EUNSUPPORTED,
-         "component type %d: power-law, mbb, freefree, lognormal, cmb and template are built; monopole / hi_fit / T_cmb "
-         "are not (DESIGN.md)", type);
+  if (type < DANG_COMP_POWERLAW || type > DANG_COMP_HI_FIT) fail(DANG_GPU_EINVAL, "unrecognized component type %d", type);
   CompHost &c = h->comp[ic];
   c.set = true;
   c.type = type;
@@ -659,8 +676,10 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   c.nu_ref = nu_ref_hz;
   c.cg_group = cg_group;
   c.sample_amplitude = sample_amplitude != 0;
-  c.nind = (type == DANG_COMP_MBB || type == DANG_COMP_LOGNORMAL) ? 2 : ((type == DANG_COMP_CMB || type == DANG_COMP_TEMPLATE) ? 0 : 1);
-  c.is_template = type == DANG_COMP_TEMPLATE;
+  c.nind = (type == DANG_COMP_MBB || type == DANG_COMP_LOGNORMAL) ? 2
+           : (type == DANG_COMP_CMB || type == DANG_COMP_TEMPLATE || type == DANG_COMP_MONOPOLE) ? 0 : 1;
+  // "border" types: amp holds the template map, eval_signal carries template_amplitudes(band, plane)
+  c.is_template = type == DANG_COMP_TEMPLATE || type == DANG_COMP_MONOPOLE || type == DANG_COMP_HI_FIT;
   if (c.is_template) {  // until dang_gpu_set_template: empty template, zero amplitudes, no fitted band
     memset(c.tamp_host, 0, sizeof c.tamp_host);
     memset(c.corr, 0, sizeof c.corr);
@@ -671,7 +690,15 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label, d
   if (!c.amp) CK(cudaMalloc(&c.amp, n2 * sizeof(double)));
   amp_write_barrier(h, c);
   CK(cudaMemsetAsync(c.amp, 0, n2 * sizeof(double), h->stream));
-  if (amplitude) h2d_planes(h, c.amp, amplitude, h->nmaps);
+  if (amplitude && !c.is_template && type != DANG_COMP_T_CMB) h2d_planes(h, c.amp, amplitude, h->nmaps);
+  if (type == DANG_COMP_T_CMB) {  // eval_signal = eval_sed (:770-771): an amplitude of exactly 1 everywhere
+    fill_kernel<<<h->num_sms * 2, DG_THREADS, 0, h->stream>>>(c.amp, (int64_t)n2, 1.0);
+    CK(cudaGetLastError());
+  }
+  if (type == DANG_COMP_MONOPOLE) {  // :591-594: template = 1 on plane 1, 0 on the polarisation planes
+    fill_kernel<<<h->num_sms * 2, DG_THREADS, 0, h->stream>>>(c.amp, (int64_t)h->P, 1.0);
+    CK(cudaGetLastError());
+  }
   for (int l = 0; l < c.nind; l++) {
     if (!c.idx[l]) CK(cudaMalloc(&c.idx[l], n2 * sizeof(double)));
     // padding lanes get a harmless finite index
@@ -697,8 +724,8 @@ int dang_gpu_set_template(dang_gpu_t *h, int ic, const double *template_map, con
   API_BEGIN
   if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !h->comp[ic].is_template)
     fail(DANG_GPU_EINVAL, "component %d is not a template component", ic);
-  if (!template_map || !corr) fail(DANG_GPU_EINVAL, "null template / corr pointer");
   CompHost &c = h->comp[ic];
+  if (!corr || (!template_map && c.type != DANG_COMP_MONOPOLE)) fail(DANG_GPU_EINVAL, "null template / corr pointer");
   int count = 0;
   for (int j = 0; j < h->nbands; j++) {
     c.corr[j] = corr[j] != 0;
@@ -707,15 +734,26 @@ int dang_gpu_set_template(dang_gpu_t *h, int ic, const double *template_map, con
   if (count != nfit) fail(DANG_GPU_EINVAL, "nfit = %d but corr selects %d bands", nfit, count);
   c.nfit = nfit;
   amp_write_barrier(h, c);
-  h2d_planes(h, c.amp, template_map, h->nmaps);  // c%template, already divided by temp_norm (:574-577)
+  if (c.type != DANG_COMP_MONOPOLE)
+    h2d_planes(h, c.amp, template_map, h->nmaps);  // c%template ('template': already divided by temp_norm, :574-577)
   memset(c.tamp_host, 0, sizeof c.tamp_host);
   if (template_amplitudes)  // Fortran template_amplitudes(nbands, nmaps) == C [plane][band]
     for (int k = 0; k < h->nmaps; k++)
       for (int j = 0; j < h->nbands; j++) c.tamp_host[k][j] = template_amplitudes[(size_t)k * h->nbands + j];
   upload_tamp(h, c);
+  monopole_to_offset(h, c);
   for (auto &g : h->cg)
     for (int f = 0; f < 3; f++) g.xt_set[f] = false;
   CK(cudaStreamSynchronize(h->stream));
+  touch(h);
+  API_END
+}
+
+int dang_gpu_set_t_cmb(dang_gpu_t *h, double t_cmb) {
+  API_BEGIN
+  if (!(t_cmb > 0.0)) fail(DANG_GPU_EINVAL, "T_CMB = %g", t_cmb);
+  h->T_cmb = t_cmb;
+  h->tab_dirty = true;  // the 'cmb' SED (1 / a2t) depends on it
   touch(h);
   API_END
 }
@@ -985,9 +1023,11 @@ int dang_gpu_get_amplitude_async(dang_gpu_t *h, int ic, int k_lo, int k_hi, doub
   CK(cudaEventRecord(h->ev_compute, h->stream));
   CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute, 0));
   const size_t o = (size_t)(k_lo - 1);
+  CopyTimer ct(h, DANG_TL_D2H_AMP, h->d2h_stream);
   CK(cudaMemcpy2DAsync(amplitude + o * h->npix + h->lo, h->npix * sizeof(double), h->comp[ic].amp + o * h->Ppad,
                        h->Ppad * sizeof(double), h->P * sizeof(double), k_hi - k_lo + 1, cudaMemcpyDeviceToHost,
                        h->d2h_stream));
+  ct.done();
   CompHost &cc = h->comp[ic];
   if (!cc.ev_read) {
     CK(cudaEventCreateWithFlags(&cc.ev_read, cudaEventDisableTiming));
@@ -1006,9 +1046,11 @@ int dang_gpu_get_indices_async(dang_gpu_t *h, int ic, int nind, int k_lo, int k_
   CK(cudaEventRecord(h->ev_compute, h->stream));
   CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute, 0));
   const size_t o = (size_t)(k_lo - 1);
+  CopyTimer ct(h, DANG_TL_D2H_IDX, h->d2h_stream);
   CK(cudaMemcpy2DAsync(indices + ((size_t)nind * h->nmaps + o) * h->npix + h->lo, h->npix * sizeof(double),
                        h->comp[ic].idx[nind] + o * h->Ppad, h->Ppad * sizeof(double), h->P * sizeof(double),
                        k_hi - k_lo + 1, cudaMemcpyDeviceToHost, h->d2h_stream));
+  ct.done();
   CK(cudaEventRecord(h->ev_idx_dl, h->d2h_stream));
   h->idx_dl_pending = true;
   API_END
@@ -1030,8 +1072,10 @@ int dang_gpu_stage_eta(dang_gpu_t *h, const double *eta, int nplanes) {
   ensure(h->eta_stage[slot], h->eta_stage_len[slot], (size_t)nplanes * h->Ppad);
   // the slot's previous consumer (K1 of an earlier solve) must have read it
   if (h->eta_used_recorded[slot]) CK(cudaStreamWaitEvent(h->h2d_stream, h->ev_eta_used[slot], 0));
+  CopyTimer ct(h, DANG_TL_H2D_ETA, h->h2d_stream);
   CK(cudaMemcpy2DAsync(h->eta_stage[slot], h->Ppad * sizeof(double), eta + h->lo, h->npix * sizeof(double),
                        h->P * sizeof(double), nplanes, cudaMemcpyHostToDevice, h->h2d_stream));
+  ct.done();
   CK(cudaEventRecord(h->ev_eta[slot], h->h2d_stream));
   h->eta_stage_planes[slot] = nplanes;
   h->eta_count++;
@@ -1129,11 +1173,28 @@ int dang_gpu_kernel_stats(dang_gpu_t *h, int kernel, int64_t *launches, double *
   API_END
 }
 
+int dang_gpu_timeline(dang_gpu_t *h, int max_n, int *n, int *kind, double *t0_us, double *t1_us) {
+  API_BEGIN
+  resolve_stats(h);
+  std::sort(h->tl.begin(), h->tl.end(), [](const TlRec &a, const TlRec &b) { return a.t0_us < b.t0_us; });
+  int m = (int)h->tl.size();
+  if (m > max_n) m = max_n;
+  for (int i = 0; i < m; i++) {
+    if (kind) kind[i] = h->tl[i].kind;
+    if (t0_us) t0_us[i] = h->tl[i].t0_us;
+    if (t1_us) t1_us[i] = h->tl[i].t1_us;
+  }
+  if (n) *n = m;
+  API_END
+}
+
 const char *dang_gpu_kernel_name(int kernel) {
   static const char *names[DANG_K_COUNT] = {
       "rhs_blocks_kernel", "cg_pass_kernel", "cg_dq_pass_kernel", "cg_update_pass_kernel",
       "chisq_kernel", "chisq_kernel(maps)", "mh_data_kernel", "mh_fullsky_lnl_kernel",
       "mh_suffstat_kernel", "mh_perpixel_kernel", "scalar kernels", "cg_final_pass(x,unpack)"};
+  static const char *extra[DANG_TL_EXTRA] = {"h2d:eta (copy stream)", "d2h:amplitude (copy stream)", "d2h:indices (copy stream)"};
+  if (kernel >= DANG_K_COUNT && kernel < DANG_K_COUNT + DANG_TL_EXTRA) return extra[kernel - DANG_K_COUNT];
   return (kernel >= 0 && kernel < DANG_K_COUNT) ? names[kernel] : "?";
 }
 

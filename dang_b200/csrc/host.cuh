@@ -111,7 +111,7 @@ struct CgGroupHost {
   int cg_group = 0, i_max = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
   double converge = 0;
   double *x[3] = {nullptr, nullptr, nullptr};  // Q10: persists across Gibbs iterations
-  double xt[3][16] = {};                       // ... and so do the template amplitudes in the tail of x
+  double xt[3][32] = {};                       // ... and so do the template amplitudes in the tail of x
   bool xt_set[3] = {false, false, false};
   size_t x_len[3] = {0, 0, 0};
   int last_iter[3] = {0, 0, 0};  // iterations of the previous solve (sizes the first batch)
@@ -124,6 +124,14 @@ struct KStat {
 };
 
 const int GATHER_MAX = 256;  // doubles per rank in one scalar exchange
+
+// event-log kinds beyond the kernel families of dang_gpu.h: staged copies on the side streams
+const int DANG_TL_EXTRA = 3;
+enum { DANG_TL_H2D_ETA = DANG_K_COUNT, DANG_TL_D2H_AMP = DANG_K_COUNT + 1, DANG_TL_D2H_IDX = DANG_K_COUNT + 2 };
+struct TlRec {
+  int kind;
+  double t0_us, t1_us;
+};
 
 struct dang_gpu {
   int device = 0, nside = 0, nmaps = 0, nbands = 0, ncomp = 0, num_sms = 0;
@@ -160,6 +168,7 @@ struct dang_gpu {
   double *sig = nullptr, *rms = nullptr;
   unsigned char *mask = nullptr;
   double gain[DG_MAX_BANDS], offset[DG_MAX_BANDS];
+  double T_cmb = 2.7255;  // src/dang_util_mod.f90:15; dang_gpu_set_t_cmb
 
   BandHost band[DG_MAX_BANDS];
   double *bp_nu0 = nullptr, *bp_tau0 = nullptr, *bp_lnr_hi = nullptr, *bp_lnr_lo = nullptr;
@@ -221,7 +230,9 @@ struct dang_gpu {
 
   // instrumentation
   int64_t launches = 0;
-  KStat kstat[DANG_K_COUNT];
+  KStat kstat[DANG_K_COUNT + DANG_TL_EXTRA];
+  cudaEvent_t tl_base = nullptr;  // origin of the event log
+  std::vector<TlRec> tl;
   cudaEvent_t ev[16] = {};
 };
 // ---------------------------------------------------------------- helpers
@@ -299,19 +310,50 @@ struct KTimer {
   }
 };
 
+// Event log (DANG_OPT_PROFILE): while profiling, every timed launch -- and every staged copy on the h2d / d2h
+// streams (kinds DANG_K_COUNT + ...) -- also lands in h->tl with its start / end relative to h->tl_base, so a run
+// can be laid out as a per-stream timeline (dang_gpu_timeline) without nsys.
 inline void resolve_stats(dang_gpu *h) {
   CK(cudaStreamSynchronize(h->stream));
-  for (int k = 0; k < DANG_K_COUNT; k++) {
+  CK(cudaStreamSynchronize(h->d2h_stream));
+  CK(cudaStreamSynchronize(h->h2d_stream));
+  for (int k = 0; k < DANG_K_COUNT + DANG_TL_EXTRA; k++) {
     for (auto &pr : h->kstat[k].pending) {
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
       h->kstat[k].ms += ms;
+      if (h->tl_base && h->tl.size() < 100000) {
+        float t0 = 0;
+        if (cudaEventElapsedTime(&t0, h->tl_base, pr.first) == cudaSuccess) h->tl.push_back(TlRec{k, 1e3 * t0, 1e3 * (t0 + ms)});
+      }
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
     }
     h->kstat[k].pending.clear();
   }
 }
+
+// a staged copy on one of the side streams, logged like a kernel launch while profiling
+struct CopyTimer {
+  dang_gpu *h;
+  int kind;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  CopyTimer(dang_gpu *h_, int kind_, cudaStream_t st_) : h(h_), kind(kind_), st(st_) {
+    if (h->profile) {
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&b));
+      CK(cudaEventRecord(a, st));
+    }
+  }
+  void done() {
+    if (h->profile) {
+      CK(cudaEventRecord(b, st));
+      h->kstat[kind].launches++;
+      h->kstat[kind].pending.emplace_back(a, b);
+    }
+  }
+};
 
 // host (npix-strided, full sky) <-> device (Ppad-strided slice) plane copies
 inline void h2d_planes(dang_gpu *h, double *dst, const double *src, int nplanes) {
@@ -390,8 +432,9 @@ inline void touch(dang_gpu *h, int what = 0) {  // the model state changed
 bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]);
 void prefetch_statistics(dang_gpu *h);  // host_mh_fs.cu: statistics pass of the upcoming full-sky draw, enqueued ahead of time
 void cg_solve_template(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const double *eta, uint64_t seed,
-                       const int *comps, int C, int tcomp, const int *og, int nog, int *n_iter,
+                       const int *comps, int C, const int *borders, int nb, const int *og, int nog, int *n_iter,
                        double *delta_final);                                       // host_tmpl.cu
+void monopole_to_offset(dang_gpu *h, const CompHost &c);                          // dang_gpu.cu
 void upload_tamp(dang_gpu *h, CompHost &c);                                        // dang_gpu.cu
 void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, double *chi_map,
                double out4[4]);                                                    // host_data.cu

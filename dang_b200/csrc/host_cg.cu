@@ -388,31 +388,28 @@ void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *
     if (gg.set && gg.cg_group == cg_group) g = &gg;
   if (!g) fail(DANG_GPU_ESTATE, "CG group %d has not been set", cg_group);
   if (flag_n < 0 || flag_n >= g->nflag) fail(DANG_GPU_EINVAL, "flag_n %d out of range", flag_n);
-  int comps[DG_MAX_COMPS], og[DG_MAX_COMPS], C = 0, nog = 0, tcomp = -1, ntc = 0;
+  int comps[DG_MAX_COMPS], og[DG_MAX_COMPS], borders[DG_MAX_COMPS], C = 0, nog = 0, nb = 0;
   for (int c = 0; c < h->ncomp; c++) {
     const CompHost &cc = h->comp[c];
     if (!cc.set) fail(DANG_GPU_ESTATE, "component %d has not been set", c);
     if (cc.cg_group == cg_group && cc.sample_amplitude) {
-      if (cc.is_template) {
-        tcomp = c;
-        ntc++;
-      } else {
-        comps[C++] = c;
-      }
+      if (cc.type == DANG_COMP_T_CMB)
+        fail(DANG_GPU_EUNSUPPORTED, "a 'T_cmb' component has no amplitude to fit (eval_signal = eval_sed, src/dang_component_mod.f90:770-771)");
+      if (cc.is_template) borders[nb++] = c;  // template / monopole / hi_fit: border rows
+      else comps[C++] = c;
     } else {
       og[nog++] = c;  // :430
-      // :444-460 removes a template a second time from the bands it is not fitted to; with zero amplitudes
+      // :444-460 removes a template / monopole a second time from the bands it is not fitted to; with zero amplitudes
       // there (the constructor's default) that is a no-op, anything else is not reproduced on this path
-      if (cc.is_template)
+      if (cc.type == DANG_COMP_TEMPLATE || cc.type == DANG_COMP_MONOPOLE)
         for (int j = 0; j < h->nbands; j++)
           for (int k = 0; k < h->nmaps; k++)
             if (!cc.corr[j] && cc.tamp_host[k][j] != 0.0)
               fail(DANG_GPU_EUNSUPPORTED, "an out-of-group template with non-zero amplitude in an unfitted band (component %d, band %d)", c, j);
     }
   }
-  if (ntc > 1) fail(DANG_GPU_EUNSUPPORTED, "%d template components in one CG group (SURVEY Q8)", ntc);
-  if (ntc == 1) {
-    cg_solve_template(h, *g, flag_n, ml_mode, eta, seed, comps, C, tcomp, og, nog, n_iter, delta_final);
+  if (nb > 0) {
+    cg_solve_template(h, *g, flag_n, ml_mode, eta, seed, comps, C, borders, nb, og, nog, n_iter, delta_final);
     return;
   }
   if (C == 0) fail(DANG_GPU_EINVAL, "Woah there, number of CG components = 0 for CG group %d", cg_group);

@@ -231,7 +231,9 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
   h->comp[mh.ic].index[mh.nind].last_value = hs->sample[mh.nind];
   touch(h, 2);
   h->stat_valid = false;
-  if (!h->fullsky_stream && h->stat_cache) {  // chi-square of the new state, from the statistics
+  bool has_monopole = false;
+  for (int c = 0; c < h->ncomp; c++) has_monopole = has_monopole || (h->comp[c].set && h->comp[c].type == DANG_COMP_MONOPOLE);
+  if (!h->fullsky_stream && h->stat_cache && !has_monopole) {  // chi-square of the new state, from the statistics
     h->chisq_valid = true;
     h->chisq_version = h->version;
     h->chisq_lo = mh.plane[0] + 1;
@@ -250,6 +252,10 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
 // whose statistics can be gathered ahead of time.
 static bool upcoming_fullsky_draw(dang_gpu *h, MhView &mh) {
   if (!h->stat_cache || h->fullsky_stream || h->last_mutation != 1) return false;
+  // with a monopole the draw's data ((sig - offset) / gain minus EVERY other component, monopole included,
+  // src/dang_sample_mod.f90:173-196) is not the chi-square's residual (monopole left out, dang_data_mod.f90:357-361)
+  for (int c = 0; c < h->ncomp; c++)
+    if (h->comp[c].set && h->comp[c].type == DANG_COMP_MONOPOLE) return false;
   int ic = -1, nind = -1;
   for (int c = 0; c < h->ncomp && ic < 0; c++)
     for (int l = 0; l < h->comp[c].nind && ic < 0; l++)
@@ -284,27 +290,8 @@ void prefetch_statistics(dang_gpu *h) {
 }
 
 bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]) {
-  if (!h->stat_cache || h->fullsky_stream || h->last_mutation != 1) return false;
-  int ic = -1, nind = -1;
-  for (int c = 0; c < h->ncomp && ic < 0; c++)
-    for (int l = 0; l < h->comp[c].nind && ic < 0; l++)
-      if (h->comp[c].set && h->comp[c].index[l].sample_index && h->comp[c].index[l].nflag > 0) {
-        ic = c;
-        nind = l;
-      }
-  if (ic < 0) return false;
-  const IndexHost &ix = h->comp[ic].index[nind];
-  if (ix.index_mode != DANG_INDEX_FULLSKY || ix.sample_nside != h->nside) return false;
-  const int flag = ix.pol_flag[0];
-  const int map_n = (flag & 8) ? -1 : (flag & 1) ? 1 : (flag & 2) ? 2 : (flag & 4) ? 3 : 0;
-  if (map_n == 0) return false;
   MhView mh;
-  try {
-    mh_view(h, ic, nind, map_n, 0, DANG_ML_SAMPLE, mh);
-  } catch (const DgError &) {
-    return false;  // the draw itself will report what is wrong with it
-  }
-  if (fullsky_needs_stream(mh)) return false;
+  if (!upcoming_fullsky_draw(h, mh)) return false;
   if (mh.plane[0] != pol_lo - 1 || mh.plane[mh.S - 1] != pol_hi - 1 || pol_hi - pol_lo + 1 != mh.S) return false;
   ModelView mv = model_view(h);
   const int64_t n_unmasked = unmasked_count(h);

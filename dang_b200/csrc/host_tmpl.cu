@@ -1,42 +1,63 @@
-// host_tmpl.cu -- amplitude draw for a CG group holding a `template` component:
-// compute_rhs + compute_sample_vector + cg_search + unpack_amplitudes with the template's border rows,
+// host_tmpl.cu -- amplitude draw for a CG group holding border components -- `template`, `monopole`, `hi_fit`
+// (SURVEY 8f-1): compute_rhs + compute_sample_vector + cg_search + unpack_amplitudes with their border rows,
 // src/dang_cg_mod.f90:167-169 (kernels in kernels_tmpl.cuh).
 #include "host.cuh"
 #include "kernels_tmpl.cuh"
 
 void cg_solve_template(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const double *eta, uint64_t seed,
-                       const int *comps, int C, int tcomp, const int *og, int nog, int *n_iter,
+                       const int *comps, int C, const int *borders, int nb, const int *og, int nog, int *n_iter,
                        double *delta_final) {
-  if (C > DG_TMPL_CMAX) fail(DANG_GPU_EUNSUPPORTED, "%d diffuse components next to a template in one CG group (max %d)", C, DG_TMPL_CMAX);
-  CompHost &tc = h->comp[tcomp];
-  if (tc.nfit < 1 || tc.nfit > DG_TMPL_MAX) fail(DANG_GPU_EUNSUPPORTED, "template with %d fitted bands (max %d)", tc.nfit, DG_TMPL_MAX);
-  for (int c = 0; c < C; c++)
-    if (comps[c] > tcomp)
-      fail(DANG_GPU_EUNSUPPORTED, "a diffuse component after the template in component_list: compute_sample_vector and "
-                                  "compute_Ax lay x out differently in the reference (src/dang_cg_mod.f90:950-964 vs :745-768)");
+  if (C > DG_TMPL_CMAX) fail(DANG_GPU_EUNSUPPORTED, "%d diffuse components next to a template / monopole / hi_fit in one CG group (max %d)", C, DG_TMPL_CMAX);
+  if (nb > DG_TMPL_BMAX) fail(DANG_GPU_EUNSUPPORTED, "%d template / monopole / hi_fit components in one CG group (max %d)", nb, DG_TMPL_BMAX);
   ModelView mv = model_view(h);
   TmplView tv;
   memset(&tv, 0, sizeof tv);
   tv.C = C;
   for (int c = 0; c < C; c++) tv.comp[c] = comps[c];
-  tv.tcomp = tcomp;
   tv.S = flag_planes(g.pol_flag[flag_n], tv.plane);
-  if (tv.S != 2)  // compute_rhs sizes b for the template rows only in the Q+U branch (:409-414): single planes overrun it
-    fail(DANG_GPU_EUNSUPPORTED, "template fits are defined for CG_POLTYPE = Q+U only (src/dang_cg_mod.f90:409-414)");
+  tv.nb = nb;
+  tv.nt = 0;
+  for (int b = 0; b < nb; b++) {
+    const CompHost &bc = h->comp[borders[b]];
+    tv.bcomp[b] = borders[b];
+    tv.bkind[b] = bc.type == DANG_COMP_TEMPLATE ? DG_BORDER_TEMPLATE : bc.type == DANG_COMP_MONOPOLE ? DG_BORDER_MONOPOLE : DG_BORDER_HI_FIT;
+    if (bc.nfit < 1) fail(DANG_GPU_EINVAL, "component %d is fitted to no band", borders[b]);
+    // compute_sample_vector puts every border entry after ALL diffuse entries (:950-964) while compute_Ax follows
+    // component_list order (:685-768): the two agree only when the diffuse components come first
+    for (int c = 0; c < C; c++)
+      if (comps[c] > borders[b])
+        fail(DANG_GPU_EUNSUPPORTED, "a diffuse component after a template / monopole / hi_fit component in component_list: "
+                                    "compute_sample_vector and compute_Ax lay x out differently in the reference "
+                                    "(src/dang_cg_mod.f90:950-964 vs :745-768)");
+    if (tv.bkind[b] == DG_BORDER_TEMPLATE) {
+      if (tv.S != 2)  // compute_rhs sizes b for the template rows only in the Q+U branch (:409-414): single planes overrun it
+        fail(DANG_GPU_EUNSUPPORTED, "template fits are defined for CG_POLTYPE = Q+U only (src/dang_cg_mod.f90:409-414)");
+    } else if (tv.S != 1 || tv.plane[0] != 0) {
+      // hi_fit / monopole columns and rows always address plane 1 and the FIRST npix entries of the work vectors
+      // (:722, :736, :840, :856), which is the Stokes-I slot only when CG_POLTYPE = T
+      fail(DANG_GPU_EUNSUPPORTED, "monopole / hi_fit fits are Stokes-I only: CG_POLTYPE must be T (src/dang_cg_mod.f90:717-744)");
+    }
+    for (int j = 0; j < DG_MAX_BANDS; j++) tv.slot_ax[b][j] = (j < h->nbands && bc.corr[j]) ? tv.nt++ : -1;
+  }
+  if (tv.nt > DG_TMPL_MAX) fail(DANG_GPU_EUNSUPPORTED, "%d fitted (component, band) pairs in one CG group (max %d)", tv.nt, DG_TMPL_MAX);
+  {  // compute_sample_vector's running counter (:970): bands outer, border components inner, never reset
+    int l = 0;
+    for (int j = 0; j < DG_MAX_BANDS; j++)
+      for (int b = 0; b < nb; b++) tv.slot_sv[b][j] = (j < h->nbands && h->comp[borders[b]].corr[j]) ? l++ : -1;
+  }
   tv.nog = nog;
   for (int o = 0; o < nog; o++) tv.og[o] = og[o];
-  tv.nt = tc.nfit;
-  int l = 0;
-  for (int j = 0; j < DG_MAX_BANDS; j++) tv.band_slot[j] = (j < h->nbands && tc.corr[j]) ? l++ : -1;
   const int S = tv.S;
   for (int s = 0; s < S; s++)
     if (tv.plane[s] >= h->nmaps) fail(DANG_GPU_EINVAL, "pol flag needs plane %d, nmaps = %d", tv.plane[s] + 1, h->nmaps);
   const size_t vs = (size_t)S * h->Ppad;   // doubles per diffuse component
   const size_t nd = (size_t)(C > 0 ? C : 1) * vs;
   const int64_t n_el = (int64_t)C * (int64_t)vs;
+  // plane whose template_amplitudes seed / receive the tail (initialize_x :1226-1279, unpack :1337-1392)
+  auto tail_plane = [&](int b, int s) { return tv.bkind[b] == DG_BORDER_TEMPLATE ? tv.plane[s] : 0; };
 
   // self%x: allocate + seed on first use only (:227-239, Q10): diffuse planes from c%amplitude, the tail from
-  // template_amplitudes(:, plane 2) (initialize_x :1264-1279)
+  // template_amplitudes (initialize_x :1264-1279)
   if (!g.x[flag_n] || g.x_len[flag_n] != nd) {
     if (g.x[flag_n]) CK(cudaFree(g.x[flag_n]));
     CK(cudaMalloc(&g.x[flag_n], nd * sizeof(double)));
@@ -49,9 +70,11 @@ void cg_solve_template(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, con
     g.xt_set[flag_n] = false;
   }
   if (!g.xt_set[flag_n]) {
-    int ll = 0;
-    for (int j = 0; j < h->nbands && ll < tc.nfit; j++)
-      if (tc.corr[j]) g.xt[flag_n][ll++] = tc.tamp_host[tv.plane[0]][j];
+    for (int b = 0; b < nb; b++) {
+      const CompHost &bc = h->comp[borders[b]];
+      for (int j = 0; j < h->nbands; j++)
+        if (tv.slot_ax[b][j] >= 0) g.xt[flag_n][tv.slot_ax[b][j]] = bc.tamp_host[tail_plane(b, 0)][j];
+    }
     g.xt_set[flag_n] = true;
   }
   if (h->v_len < nd) {
@@ -154,7 +177,8 @@ void cg_solve_template(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, con
   }
   if (enq == 0 || (!done && enq >= max_pass)) read_state();
 
-  // unpack_amplitudes: diffuse planes (:1327-1335), template amplitudes to planes 2 and 3 (:1374-1392)
+  // unpack_amplitudes: diffuse planes (:1327-1335); template amplitudes to planes 2 and 3 (:1374-1392), hi_fit and
+  // monopole amplitudes to plane 1 (:1337-1372) -- and, for a monopole, on into the band offsets (update_sky_model)
   for (int c = 0; c < C; c++) {
     CompHost &cc = h->comp[comps[c]];
     amp_write_barrier(h, cc);
@@ -162,15 +186,17 @@ void cg_solve_template(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, con
       CK(cudaMemcpyAsync(cc.amp + (size_t)tv.plane[s] * h->Ppad, g.x[flag_n] + c * vs + (size_t)s * h->Ppad,
                          h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
-  {
-    int ll = 0;
-    for (int j = 0; j < h->nbands && ll < tc.nfit; j++)
-      if (tc.corr[j]) {
-        g.xt[flag_n][ll] = hs->xt[ll];
-        for (int s = 0; s < S; s++) tc.tamp_host[tv.plane[s]][j] = hs->xt[ll];
-        ll++;
-      }
-    upload_tamp(h, tc);
+  for (int b = 0; b < nb; b++) {
+    CompHost &bc = h->comp[borders[b]];
+    const int SB = tv.bkind[b] == DG_BORDER_TEMPLATE ? S : 1;
+    for (int j = 0; j < h->nbands; j++) {
+      const int slot = tv.slot_ax[b][j];
+      if (slot < 0) continue;
+      g.xt[flag_n][slot] = hs->xt[slot];
+      for (int s = 0; s < SB; s++) bc.tamp_host[tail_plane(b, s)][j] = hs->xt[slot];
+    }
+    upload_tamp(h, bc);
+    monopole_to_offset(h, bc);
   }
   const int n = hs->iter < 256 ? hs->iter : 256;
   h->last_trace.assign(hs->trace, hs->trace + n);

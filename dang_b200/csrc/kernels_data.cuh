@@ -68,7 +68,7 @@ chisq_kernel(const ModelView mv, const ChisqView cv, double *partials, unsigned 
         double sky = 0.0;  // :354, :367
 #pragma unroll
         for (int c = 0; c < NC; c++)
-          if (c < mv.ncomp) sky = sky + a[k][c] * sed[k][c];
+          if (c < mv.ncomp && mv.comp[c].in_sky) sky = sky + a[k][c] * sed[k][c];  // (monopoles are offsets, :357-361)
         const double sig = ldg_stream(mv.sig + off);
         const double t = (k == 0) ? (sig - mv.offset[j]) / mv.gain[j] - sky : sig - sky;  // :384-387
         if (cv.sky) cv.sky[off] = sky;
@@ -147,12 +147,12 @@ static __global__ void sed_table_kernel(const ModelView mv, SedTable *tab) {
   const CompView &cv = mv.comp[c];
   bool uni = true;
   for (int l = 0; l < cv.nind; l++) uni = uni && tab->nonuni[ck][l] == 0;
-  if (cv.tamp) {  // 'template': eval_signal = template_amplitudes(band, plane) * template(pix, plane)
+  if (cv.tamp && cv.type != 9) {  // 'template' / 'monopole': eval_signal = template_amplitudes(band, plane) * template(pix, plane)
     for (int j = threadIdx.x; j < mv.nbands; j += blockDim.x) tab->sed[ck][j] = cv.tamp[k * DG_MAX_BANDS + j];
   } else if (uni) {
     const double t0 = cv.nind > 0 ? cv.idx[0][(size_t)k * mv.Ppad] : 0.0;
     const double t1 = cv.nind > 1 ? cv.idx[1][(size_t)k * mv.Ppad] : 0.0;
-    for (int j = threadIdx.x; j < mv.nbands; j += blockDim.x) tab->sed[ck][j] = sed_theta(mv, c, j, t0, t1);
+    for (int j = threadIdx.x; j < mv.nbands; j += blockDim.x) tab->sed[ck][j] = sed_theta(mv, c, j, t0, t1, k);
   }
   if (threadIdx.x == 0) tab->uni[ck] = uni ? 1 : 0;
 }
@@ -171,6 +171,7 @@ band_gain_kernel(const ModelView mv, int k, int band, double *partials, unsigned
     double sky = 0.0;
     for (int c = 0; c < mv.ncomp; c++) {
       const CompView &cc = mv.comp[c];
+      if (!cc.in_sky) continue;
       const double t0 = cc.nind > 0 ? cc.idx[0][kp] : 0.0, t1 = cc.nind > 1 ? cc.idx[1][kp] : 0.0;
       sky = sky + cc.amp[kp] * sed_eval(mv, c, k, band, t0, t1);
     }

@@ -113,7 +113,7 @@ mh_perpixel_serial_kernel(const ModelView mv, const MhView mh, double *partials,
         for (int j = 0; j < B; j++)
           sS[(size_t)j * T + tid] = sed_powerlaw(mv, mh.ic, j, th[0]);
       } else if (!is_mbb) {
-        for (int j = 0; j < B; j++) sS[(size_t)j * T + tid] = sed_theta(mv, mh.ic, j, th[0], th[1]);
+        for (int j = 0; j < B; j++) sS[(size_t)j * T + tid] = sed_theta(mv, mh.ic, j, th[0], th[1], mh.plane[0]);
       } else if (mh.nind == 0) {
 #pragma unroll 4
         for (int j = 0; j < B; j++)
@@ -163,7 +163,7 @@ mh_perpixel_serial_kernel(const ModelView mv, const MhView mh, double *partials,
         if (mh.is_synch) {
           for (int s = 0; s < S; s++)
             for (int j = 0; j < B; j++) {
-              const double ss = amp[s] * sed_theta(mv, mh.ic, j, val, 0.0);
+              const double ss = amp[s] * sed_theta(mv, mh.ic, j, val, 0.0, mh.plane[0]);
               const double ir = 1.0 / sW[((size_t)j * S + s) * T + tid];
               const double t = (ir * ir) * (ss / amp[s]) * log(mv.band[j].nu_c / cv.nu_ref);
               sum = sum + t * t;
@@ -421,12 +421,12 @@ mh_perpixel_kernel(const ModelView mv, const MhView mh, double *partials, unsign
               for (int k = DG_MH_KM - 1; k >= 0; k--) poly = fma(poly, dlt, mk[k * DG_MH_THREADS]);
               sed = exp_scaled(dlt, Lh[i], Ll[i]) * poly;
             } else {
-              sed = sed_theta(mv, mh.ic, j, xe, idx1);  // far from the first point: sum the bandpass directly
+              sed = sed_theta(mv, mh.ic, j, xe, idx1, mh.plane[0]);  // far from the first point: sum the bandpass directly
             }
           } else if (PLAW) sed = exp_scaled(xe, Lh[i], Ll[i]);
           else if (MBBB) sed = F[i] * exp_scaled(xe + 1.0, Lh[i], Ll[i]);
           else if (MODE == MH_SED_MBB_T) sed = eref * mh_fast_rcp(exp(zT * nuc[i]) - 1.0) * F[i];
-          else sed = sed_theta(mv, mh.ic, j, mh.nind == 0 ? xe : idx0, mh.nind == 0 ? idx1 : xe);
+          else sed = sed_theta(mv, mh.ic, j, mh.nind == 0 ? xe : idx0, mh.nind == 0 ? idx1 : xe, mh.plane[0]);
           const double t0 = (D0[i] - amp0 * sed) * W0[i];
           part = part - 0.5 * (t0 * t0);
           if (S > 1) {
@@ -487,7 +487,7 @@ static __global__ void mh_fullsky_init_kernel(const ModelView mv, const MhView m
   ms->phase = 0;
   ms->skip = 0;
   for (int j = 0; j < mv.nbands; j++) {
-    const double s = sed_theta(mv, mh.ic, j, ms->sample[0], ms->sample[1]);
+    const double s = sed_theta(mv, mh.ic, j, ms->sample[0], ms->sample[1], mh.plane[0]);
     ms->sed[j] = s;
     ms->s0[j] = s;
   }
@@ -523,7 +523,7 @@ __device__ __forceinline__ void mh_next_proposal(const ModelView &mv, const MhVi
       ms->l++;
       continue;
     }
-    for (int j = 0; j < mv.nbands; j++) ms->sed[j] = sed_theta(mv, mh.ic, j, ms->theta[0], ms->theta[1]);
+    for (int j = 0; j < mv.nbands; j++) ms->sed[j] = sed_theta(mv, mh.ic, j, ms->theta[0], ms->theta[1], mh.plane[0]);
     return;
   }
   ms->skip = 1;
@@ -770,7 +770,7 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
   }
   auto sed_of = [&](double t0, double t1) -> double {
     if (j >= B) return 0.0;
-    return planck_fixed ? Fj * exp_scaled(t0 + 1.0, lh, ll) : sed_theta(mv, mh.ic, j, t0, t1);
+    return planck_fixed ? Fj * exp_scaled(t0 + 1.0, lh, ll) : sed_theta(mv, mh.ic, j, t0, t1, mh.plane[0]);
   };
   // lnL(theta) = -1/2 sum_j (X_j - 2 delta_j Y_j + delta_j^2 Z_j), delta_j = sed_j(theta) - s0_j
   auto lnl_of = [&](double sed) -> double {
@@ -889,7 +889,7 @@ mh_suff_tune_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, co
       const double zz = mh.z ? mh.z[slot] : philox_normal(mh.seed, DG_STREAM_TUNE_Z, (uint64_t)slot);
       theta[mh.nind] = sample[mh.nind] + (0.0 + step * zz);  // :668
       if (theta[mh.nind] < mh.uni[0] || theta[mh.nind] > mh.uni[1]) continue;
-      const double sed = (j < B) ? sed_theta(mv, mh.ic, j, theta[0], theta[1]) : 0.0;
+      const double sed = (j < B) ? sed_theta(mv, mh.ic, j, theta[0], theta[1], mh.plane[0]) : 0.0;
       const double lnl = lnl_of(sed);
       if (mh.prior_type == 1) lnl_new = lnl + log_normal_prior(theta[mh.nind], mh.gauss[0], mh.gauss[1]);
       else if (mh.prior_type == 0) lnl_new = lnl;

@@ -1,31 +1,44 @@
-// kernels_tmpl.cuh -- amplitude draw for a CG group that holds a `template` component
-// (SURVEY 8f-1): compute_rhs :326-596 (template rows :560-587, the extra subtraction :444-460),
-// compute_Ax :598-911 (template column / row :745-768, :867-893), compute_sample_vector :913-1100
-// (:1077-1096), cg_search :179-324, src/dang_cg_mod.f90.
+// kernels_tmpl.cuh -- amplitude draw for a CG group that holds "border" components: `template`, `monopole` and
+// `hi_fit`.  compute_rhs :326-596 (border rows :522-587, the extra subtraction :444-460),
+// compute_Ax :598-911 (border columns / rows :717-768, :833-893), compute_sample_vector :913-1100
+// (:1044-1096), cg_search :179-324, src/dang_cg_mod.f90.
 //
-// A template component contributes template_amplitudes(band) * template(pix) to the bands it is
-// fitted to (corr(band)), so the solution vector is [diffuse amplitudes per (pixel, Stokes) ...,
-// one scalar per fitted band] and A = sum_nu T^t N^-1 T is block diagonal plus `nfit` dense border
-// rows / columns.  The apply is matrix-free, band by band as the reference writes it (T x, / sigma^2,
-// T^t), one thread per pixel; the border rows are masked, noise-weighted sums over all pixels
-// (deterministic grid reduction + rank-ordered gather), the `nfit` tail entries of every CG vector
-// live in TmplScalars and are updated by one-thread kernels.  Each CG iteration is two map passes
-// (apply with the direction update folded in; x / r update) -- this path is about coverage of the
-// reference's template fits, the block-diagonal kernels of kernels_cg.cuh remain the fast path.
+// A border component contributes  x_b(band) * t_b(pix, band)  to the bands it is fitted to (corr(band)):
+//     template   t = template(pix, plane)                       on the planes of the solve
+//     monopole   t = template(pix, 1) = 1                       Stokes I only
+//     hi_fit     t = template(pix, 1) * B_nu(T_d(pix)) in RJ    Stokes I only
+// so the solution vector is [diffuse amplitudes per (pixel, Stokes) ..., one scalar per (border component,
+// fitted band)] and A = sum_nu T^t N^-1 T is block diagonal plus `nt` dense border rows / columns.  The apply is
+// matrix-free, band by band as the reference writes it (T x, / sigma^2, T^t), one thread per pixel; the border rows
+// are masked, noise-weighted sums over all pixels (deterministic grid reduction + rank-ordered gather), the `nt`
+// tail entries of every CG vector live in TmplScalars and are updated by one-thread kernels.  Each CG iteration is
+// two map passes (apply with the direction update folded in; x / r update) -- this path is about coverage of the
+// reference's template / monopole / HI fits, the block-diagonal kernels of kernels_cg.cuh remain the fast path.
+//
+// Tail layout: compute_Ax / compute_rhs / initialize_x lay the border components out one after the other in
+// component_list order (`slot_ax`); compute_sample_vector uses ONE running counter over (band, component) pairs
+// (:970, never reset: SURVEY Q8), so with several border components its fluctuation terms land in interleaved slots
+// (`slot_sv`).  Both maps are built on the host; with one border component they coincide.
 #pragma once
 #include "common.cuh"
 
-#define DG_TMPL_MAX 16   // fitted bands of the template component (tail length)
-#define DG_TMPL_CMAX 2   // diffuse components next to it in the group
+#define DG_TMPL_MAX 32   // tail length: fitted bands summed over the group's border components
+#define DG_TMPL_CMAX 2   // diffuse components next to them in the group
+#define DG_TMPL_BMAX 3   // border components in one group
+
+enum { DG_BORDER_TEMPLATE = 0, DG_BORDER_MONOPOLE = 1, DG_BORDER_HI_FIT = 2 };
 
 struct TmplView {
   int C;                       // diffuse components in the group with sample_amplitude
   int comp[DG_TMPL_CMAX];
-  int tcomp;                   // the template component (ModelView::comp index); amp = template map
+  int nb;                      // border components
+  int bcomp[DG_TMPL_BMAX];     // ModelView::comp index; amp = template map
+  int bkind[DG_TMPL_BMAX];
   int S, plane[2];
   int nog, og[DG_MAX_COMPS];   // components subtracted from the data (:427-443)
-  int nt;                      // tail length (nfit)
-  int band_slot[DG_MAX_BANDS]; // tail slot of band j, -1 if the template is not fitted there
+  int nt;                      // tail length
+  int slot_ax[DG_TMPL_BMAX][DG_MAX_BANDS];  // tail slot of (border, band) in compute_Ax's layout, -1 if not fitted
+  int slot_sv[DG_TMPL_BMAX][DG_MAX_BANDS];  // ... in compute_sample_vector's layout (Q8)
   int fluct;                   // 0 none, 1 reference indexing (Q1), 2 per component
   const double *eta;           // [S][Ppad] or nullptr -> Philox
   uint64_t seed;
@@ -41,6 +54,15 @@ struct TmplScalars {
 
 #define DG_TMPL_NV (DG_TMPL_MAX + 2)
 
+// t_b(pix, band) on plane k of the solve: eval_sed of the border component (src/dang_component_mod.f90:803-808)
+__device__ __forceinline__ double border_factor(const ModelView &mv, const TmplView &tv, int b, int k, int64_t p, int j) {
+  const CompView &bc = mv.comp[tv.bcomp[b]];
+  if (tv.bkind[b] == DG_BORDER_TEMPLATE) return bc.amp[(size_t)k * mv.Ppad + p];
+  const double t = bc.amp[p];  // template(pix, 1): hi_fit and monopole rows always read plane 1 (:722, :736)
+  if (tv.bkind[b] == DG_BORDER_MONOPOLE) return t;
+  return t * sed_planck_rj(mv, j, bc.idx[0][p]);
+}
+
 // compute_rhs (+ compute_sample_vector): b planes and the tail sums.
 // out[0..nt) = b_t (+ fluctuation), out[DG_TMPL_MAX] unused
 static __global__ void __launch_bounds__(DG_THREADS)
@@ -49,7 +71,6 @@ tmpl_rhs_kernel(const ModelView mv, const TmplView tv, double *partials, unsigne
   double acc[DG_TMPL_NV];
 #pragma unroll
   for (int i = 0; i < DG_TMPL_NV; i++) acc[i] = 0.0;
-  const CompView &tc = mv.comp[tv.tcomp];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
     const bool use = mv.mask[p] != 0;
@@ -62,7 +83,6 @@ tmpl_rhs_kernel(const ModelView mv, const TmplView tv, double *partials, unsigne
         if (tv.fluct)
           eta = tv.eta ? tv.eta[e]
                        : philox_normal(tv.seed, DG_STREAM_ETA, (uint64_t)s * (uint64_t)mv.npix + (uint64_t)(mv.pix_lo + p));
-        const double t = tc.amp[kp];  // template(pix, plane)
         for (int j = 0; j < mv.nbands; j++) {
           const size_t off = plane_off(mv, j, k) + p;
           double data = ldg_stream(mv.sig + off);
@@ -73,8 +93,11 @@ tmpl_rhs_kernel(const ModelView mv, const TmplView tv, double *partials, unsigne
             const double t0 = cc.nind > 0 ? cc.idx[0][kp] : 0.0, t1 = cc.nind > 1 ? cc.idx[1][kp] : 0.0;
             data = data - cc.amp[kp] * sed_eval(mv, tv.og[o], k, j, t0, t1);
           }
-          const int slot = tv.band_slot[j];
-          if (slot < 0) data = data - mv.tab->sed[tv.tcomp * 3 + k][j] * t;  // :444-460: unfitted bands
+          // :444-460: a template / monopole is also removed from the bands it is NOT fitted to (eval_signal =
+          // template_amplitudes(band, plane) * template(pix, plane); hi_fit is not part of that block)
+          for (int bb = 0; bb < tv.nb; bb++)
+            if (tv.slot_ax[bb][j] < 0 && tv.bkind[bb] != DG_BORDER_HI_FIT)
+              data = data - mv.tab->sed[tv.bcomp[bb] * 3 + k][j] * mv.comp[tv.bcomp[bb]].amp[kp];
           const double tn = eta / rms;  // :1005-1017
           for (int c = 0; c < tv.C; c++) {
             const CompView &cc = mv.comp[tv.comp[c]];
@@ -83,9 +106,12 @@ tmpl_rhs_kernel(const ModelView mv, const TmplView tv, double *partials, unsigne
             b[c] = b[c] + (data * sed) / (rms * rms);  // :489-494
             f[c] += tn * sed;                          // :1030-1042
           }
-          if (slot >= 0) {
-            acc[slot] += data / (rms * rms) * t;       // :568-574
-            if (tv.fluct) acc[slot] += tn * t;         // :1083-1094
+          for (int bb = 0; bb < tv.nb; bb++) {
+            const int slot = tv.slot_ax[bb][j];
+            if (slot < 0) continue;
+            const double t = border_factor(mv, tv, bb, k, p, j);
+            acc[slot] += data / (rms * rms) * t;                 // :530, :548, :568-574
+            if (tv.fluct) acc[tv.slot_sv[bb][j]] += tn * t;      // :1049, :1061 (t = 1), :1083-1094
           }
         }
         if (tv.C > 0) {
@@ -113,7 +139,6 @@ tmpl_apply_kernel(const ModelView mv, const TmplView tv, const TmplScalars *sc, 
   double acc[DG_TMPL_NV];
 #pragma unroll
   for (int i = 0; i < DG_TMPL_NV; i++) acc[i] = 0.0;
-  const CompView &tc = mv.comp[tv.tcomp];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (sc->done && mode) return;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < mv.P; p += stride) {
@@ -132,10 +157,9 @@ tmpl_apply_kernel(const ModelView mv, const TmplView tv, const TmplScalars *sc, 
         }
       }
       if (use) {  // masked pixels contribute nothing (:695)
-        const double t = tc.amp[kp];
         for (int j = 0; j < mv.nbands; j++) {
           const double rms = ldg_stream(mv.rms + plane_off(mv, j, k) + p);
-          double sed[DG_TMPL_CMAX] = {0.0, 0.0};
+          double sed[DG_TMPL_CMAX] = {0.0, 0.0}, tb[DG_TMPL_BMAX] = {0.0, 0.0, 0.0};
           double temp1 = 0.0;
           for (int c = 0; c < tv.C; c++) {
             const CompView &cc = mv.comp[tv.comp[c]];
@@ -143,11 +167,18 @@ tmpl_apply_kernel(const ModelView mv, const TmplView tv, const TmplScalars *sc, 
             sed[c] = sed_eval(mv, tv.comp[c], k, j, t0, t1);
             temp1 = temp1 + v[c] * sed[c];             // :697-704
           }
-          const int slot = tv.band_slot[j];
-          if (slot >= 0) temp1 = temp1 + vt[slot] * t;  // :750-751
+          for (int bb = 0; bb < tv.nb; bb++) {
+            const int slot = tv.slot_ax[bb][j];
+            if (slot < 0) continue;
+            tb[bb] = border_factor(mv, tv, bb, k, p, j);
+            temp1 = temp1 + vt[slot] * tb[bb];          // :722, :736, :750-751
+          }
           temp1 = temp1 / (rms * rms);                  // :775-791
           for (int c = 0; c < tv.C; c++) q[c] += temp1 * sed[c];  // :813-820, :904
-          if (slot >= 0) acc[slot] += temp1 * t;        // :872-887
+          for (int bb = 0; bb < tv.nb; bb++) {
+            const int slot = tv.slot_ax[bb][j];
+            if (slot >= 0) acc[slot] += temp1 * tb[bb];  // :840, :856 (t = 1), :872-887
+          }
         }
       }
       for (int c = 0; c < tv.C; c++) {

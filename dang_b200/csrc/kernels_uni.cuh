@@ -47,9 +47,9 @@ __device__ __forceinline__ void sed_pair_to_smem(const ModelView &mv, int ic, in
   const SedTable &tab = *mv.tab;
   if (cv.type > 2) {  // free-free, lognormal, cmb: the generic per-band evaluation
     for (int j = 0; j < mv.nbands; j++) {
-      const double a = sed_theta(mv, ic, j, t0.x, t1.x);
+      const double a = sed_theta(mv, ic, j, t0.x, t1.x, k);
       dst[(size_t)(j * 2 + 0) * nthr + tid] = a;
-      dst[(size_t)(j * 2 + 1) * nthr + tid] = same ? a : sed_theta(mv, ic, j, t0.y, t1.y);
+      dst[(size_t)(j * 2 + 1) * nthr + tid] = same ? a : sed_theta(mv, ic, j, t0.y, t1.y, k);
     }
   } else if (cv.type == 1) {
     for (int j = 0; j < mv.nbands; j++) {
@@ -272,7 +272,7 @@ chisq_uni_kernel(const ModelView mv, const ChisqView cv, double *partials, unsig
   const int B = mv.nbands;
   for (int i = threadIdx.x; i < 3 * NC * B; i += blockDim.x) {
     const int k = i / (NC * B), c = (i / B) % NC, j = i % B;
-    ssed[k][c][j] = (c < mv.ncomp && k < mv.nmaps) ? mv.tab->sed[c * 3 + k][j] : 0.0;
+    ssed[k][c][j] = (c < mv.ncomp && k < mv.nmaps && mv.comp[c].in_sky) ? mv.tab->sed[c * 3 + k][j] : 0.0;  // (monopoles: offsets, not sky)
   }
   __syncthreads();
   double acc[4] = {0.0, 0.0, 0.0, 0.0};

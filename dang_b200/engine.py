@@ -95,32 +95,40 @@ class Engine:
         # initialize_components
         for ic, c in enumerate(cfg.comps):
             nu_ref = c.nu_ref_ghz * 1e9 if c.nu_ref_ghz < 1e7 else c.nu_ref_ghz  # dang_param_mod.f90:571-573
-            if c.type == "template":
-                # c%template (already divided by temp_norm), c%template_amplitudes(nbands,nmaps), c%corr, c%nfit
+            if c.type in ("template", "monopole", "hi_fit"):
+                # c%template ('template': already divided by temp_norm; 'monopole': the constructor's own map),
+                # c%template_amplitudes(nbands,nmaps), c%corr, c%nfit; hi_fit also carries its T_d index map
+                idx = np.ascontiguousarray(sky.indices[c.label], dtype=np.float64) if c.type == "hi_fit" else None
                 self._ck(self.lib.dang_gpu_set_component(self.h, ic, COMP_TYPES[c.type], c.label.encode(), nu_ref,
-                                                         c.cg_group, int(c.amp_sample), None, None))
+                                                         c.cg_group, int(c.amp_sample), None, _dp(idx)))
                 corr = (C.c_int * cfg.nbands)(*[int(bool(v)) for v in c.corr])
-                tmap = np.ascontiguousarray(sky.template[c.label], dtype=np.float64)
+                tmap = None if c.type == "monopole" else np.ascontiguousarray(sky.template[c.label], dtype=np.float64)
                 tamp = np.ascontiguousarray(sky.template_amplitudes[c.label], dtype=np.float64)
                 self._ck(self.lib.dang_gpu_set_template(self.h, ic, _dp(tmap), _dp(tamp), corr, int(sum(map(bool, c.corr)))))
+                if c.type != "hi_fit":
+                    continue
+                self._set_indices_spec(ic, c)
                 continue
             amp = np.ascontiguousarray(sky.amplitude[c.label], dtype=np.float64)
             idx = np.ascontiguousarray(sky.indices[c.label], dtype=np.float64)
             self._ck(self.lib.dang_gpu_set_component(self.h, ic, COMP_TYPES[c.type], c.label.encode(), nu_ref,
                                                      c.cg_group, int(c.amp_sample), _dp(amp), _dp(idx)))
-            for k, s in enumerate(c.indices):
-                flags = return_poltype_flag(s.poltype)
-                fl = (C.c_int * max(len(flags), 1))(*flags)
-                g = np.asarray(s.gauss, dtype=np.float64)
-                u = np.asarray(s.uni, dtype=np.float64)
-                self._ck(self.lib.dang_gpu_set_index(self.h, ic, k, int(s.sample), INDEX_MODES[s.region],
-                                                     LNL_TYPES[s.lnl_type], PRIOR_TYPES[s.prior], _dp(g), _dp(u),
-                                                     s.step, s.samp_nside or cfg.nside, fl, len(flags)))
+            self._set_indices_spec(ic, c)
         # initialize_cg_groups
         for ig, g in enumerate(cfg.cg_groups):
             flags = return_poltype_flag(g.poltype)
             fl = (C.c_int * len(flags))(*flags)
             self._ck(self.lib.dang_gpu_set_cg_group(self.h, ig + 1, g.max_iter, g.converge, fl, len(flags)))
+
+    def _set_indices_spec(self, ic: int, c):
+        for k, s in enumerate(c.indices):
+            flags = return_poltype_flag(s.poltype)
+            fl = (C.c_int * max(len(flags), 1))(*flags)
+            g = np.asarray(s.gauss, dtype=np.float64)
+            u = np.asarray(s.uni, dtype=np.float64)
+            self._ck(self.lib.dang_gpu_set_index(self.h, ic, k, int(s.sample), INDEX_MODES[s.region],
+                                                 LNL_TYPES[s.lnl_type], PRIOR_TYPES[s.prior], _dp(g), _dp(u),
+                                                 s.step, s.samp_nside or self.cfg.nside, fl, len(flags)))
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc: int):
@@ -200,6 +208,14 @@ class Engine:
         v = C.c_double()
         self._ck(self.lib.dang_gpu_get_index_fullsky(self.h, ic, nind, map_n, C.byref(v)))
         return v.value
+
+    def set_t_cmb(self, t_cmb: float):
+        """The module-global T_CMB (src/dang_util_mod.f90:15), which a 'T_cmb' component overwrites after its draw."""
+        self._ck(self.lib.dang_gpu_set_t_cmb(self.h, float(t_cmb)))
+
+    def _bcast_t_cmb(self, ic: int) -> float:
+        # a full-sky draw leaves the same value on every rank; a rank that does not own pixel 0 reads its own first pixel
+        return float(self.indices(ic)[0, 0, self.lo])
 
     def set_amplitude(self, ic: int, amp: np.ndarray):
         self._ck(self.lib.dang_gpu_set_amplitude(self.h, ic, _dp(np.ascontiguousarray(amp, dtype=np.float64))))
@@ -310,6 +326,8 @@ class Engine:
                     acc.append(self.sample_index_mh(ic, j, flag_to_map_n(flag), nsample, ml_mode, zz, uu,
                                                     seed + 7919 * ncall))
                     ncall += 1
+            if c.type == "T_cmb":  # :76-78: T_CMB = c%indices(0,1,1)
+                self.set_t_cmb(float(self.indices(ic)[0, 0, self.lo]) if self.rank == 0 else self._bcast_t_cmb(ic))
         chisq = self.compute_chisq() if (sampled and stats) else None
         return acc, chisq
 

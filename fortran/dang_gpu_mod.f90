@@ -36,7 +36,7 @@ module dang_gpu_mod
 
   ! enums of include/dang_gpu.h
   integer(c_int), parameter :: COMP_POWERLAW = 1, COMP_MBB = 2, COMP_FREEFREE = 3, COMP_LOGNORMAL = 4, COMP_CMB = 5, &
-       COMP_TEMPLATE = 6
+       COMP_TEMPLATE = 6, COMP_T_CMB = 7, COMP_MONOPOLE = 8, COMP_HI_FIT = 9
   integer(c_int), parameter :: LNL_CHISQ = 0, LNL_MARGINAL = 1, LNL_PRIOR = 2
   integer(c_int), parameter :: PRIOR_UNIFORM = 0, PRIOR_GAUSSIAN = 1, PRIOR_JEFFREYS = 2
   integer(c_int), parameter :: ML_OPTIMIZE = 0, ML_SAMPLE = 1
@@ -270,6 +270,12 @@ module dang_gpu_mod
        integer(c_int) :: blocks_run
        real(c_double) :: step_size
      end function dang_gpu_tune_index
+     ! ---- global T_CMB after a 'T_cmb' draw (dang_sample_mod.f90:76-78)
+     integer(c_int) function dang_gpu_set_t_cmb(h, t_cmb) bind(C, name='dang_gpu_set_t_cmb')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr),    value :: h
+       real(c_double), value :: t_cmb
+     end function dang_gpu_set_t_cmb
      integer(c_int) function dang_gpu_get_step_size(h, ic, nind, step_size) bind(C, name='dang_gpu_get_step_size')
        import :: c_int, c_double, c_ptr
        type(c_ptr), value :: h
@@ -310,6 +316,12 @@ contains
        comp_type_enum = COMP_CMB
     else if (trim(ctype) == 'template') then
        comp_type_enum = COMP_TEMPLATE
+    else if (trim(ctype) == 'T_cmb') then
+       comp_type_enum = COMP_T_CMB
+    else if (trim(ctype) == 'monopole') then
+       comp_type_enum = COMP_MONOPOLE
+    else if (trim(ctype) == 'hi_fit') then
+       comp_type_enum = COMP_HI_FIT
     else
        write(*,*) 'dang_gpu: component type '//trim(ctype)//' is not on the GPU path yet'
        stop
@@ -351,9 +363,21 @@ contains
                merge(1_c_int,0_c_int,c%corr), int(c%nfit,c_int)), 'set_template')
           cycle
        end if
+       if (trim(c%type) == 'monopole') then   ! dang_component_mod.f90:579-597: the library builds the (1,0,0) map itself
+          call gpu_check(dang_gpu_set_component(handle, int(i-1,c_int), COMP_MONOPOLE, &
+               trim(c%label)//c_null_char, c%nu_ref, int(c%cg_group,c_int), merge(1_c_int,0_c_int,c%sample_amplitude), &
+               dummy, dummy), 'set_component')
+          call gpu_check(dang_gpu_set_template(handle, int(i-1,c_int), c%template, c%template_amplitudes, &
+               merge(1_c_int,0_c_int,c%corr), int(c%nfit,c_int)), 'set_template')
+          cycle
+       end if
        call gpu_check(dang_gpu_set_component(handle, int(i-1,c_int), comp_type_enum(c%type), &
             trim(c%label)//c_null_char, c%nu_ref, int(c%cg_group,c_int), merge(1_c_int,0_c_int,c%sample_amplitude), &
             c%amplitude, c%indices), 'set_component')
+       if (trim(c%type) == 'hi_fit') then      ! dang_component_mod.f90:599-700: template + per-band amplitudes + T_d map
+          call gpu_check(dang_gpu_set_template(handle, int(i-1,c_int), c%template, c%template_amplitudes, &
+               merge(1_c_int,0_c_int,c%corr), int(c%nfit,c_int)), 'set_template')
+       end if
        do j = 1, c%nindices
           lnl = LNL_CHISQ
           if (trim(c%lnl_type(j)) == 'marginal') lnl = LNL_MARGINAL
@@ -417,8 +441,8 @@ contains
     type(dang_data)   :: ddata
     type(dang_comps), pointer :: c
     integer(i4b)   :: i, j, k, map_n
-    integer(c_int) :: mode
-    real(c_double) :: accept
+    integer(c_int) :: mode, blocks_run
+    real(c_double) :: accept, step
     logical(lgt)   :: sampled
 
     mode = ML_OPTIMIZE; if (trim(ml_mode) == 'sample') mode = ML_SAMPLE
@@ -443,11 +467,28 @@ contains
                 write(*,*) "There is something wrong with the poltype flag"
                 cycle
              end if
+             ! sample_index_mh tunes the step first whenever .not. c%tuned(j) (tuned = .not. fg_spec_tune,
+             ! dang_sample_mod.f90:270-273 full-sky, :341-347 per-pixel with the mean index as the start) and the
+             ! tuner sets ALL of c%tuned (:711); the tuned step comes back into c%step_size(j)
+             if (.not. c%tuned(j) .and. trim(c%lnl_type(j)) /= 'prior') then
+                write(*,*) 'Tuning!'
+                gpu_seed = gpu_seed + 1
+                call gpu_check(dang_gpu_tune_index(handle, int(i-1,c_int), int(j-1,c_int), int(map_n,c_int), &
+                     int(nsample,c_int), mode, c_null_ptr, c_null_ptr, int(gpu_seed,c_int64_t), 1000_c_int, &
+                     blocks_run, step), 'tune_index')
+                c%step_size(j) = step
+                c%tuned        = .true.
+             end if
              gpu_seed = gpu_seed + 1
              call gpu_check(dang_gpu_sample_index(handle, int(i-1,c_int), int(j-1,c_int), int(map_n,c_int), &
                   int(nsample,c_int), mode, c_null_ptr, c_null_ptr, int(gpu_seed,c_int64_t), accept), 'sample_index')
           end do
        end do
+       if (trim(c%type) == 'T_cmb') then       ! dang_sample_mod.f90:76-78: update the global variable T_CMB
+          call dang_gpu_download_fullsky_index(c, i, 1, 1)
+          T_CMB = c%indices(0,1,1)
+          call gpu_check(dang_gpu_set_t_cmb(handle, T_CMB), 'set_t_cmb')
+       end if
     end do
     if (sampled) then
        call compute_chisq_gpu(ddata)

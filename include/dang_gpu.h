@@ -47,7 +47,7 @@ enum {
 
 /* c%type, src/dang_component_mod.f90:791-809 */
 enum { DANG_COMP_POWERLAW = 1, DANG_COMP_MBB = 2, DANG_COMP_FREEFREE = 3, DANG_COMP_LOGNORMAL = 4, DANG_COMP_CMB = 5,
-       DANG_COMP_TEMPLATE = 6 };
+       DANG_COMP_TEMPLATE = 6, DANG_COMP_T_CMB = 7, DANG_COMP_MONOPOLE = 8, DANG_COMP_HI_FIT = 9 };
 /* c%lnl_type, src/dang_sample_mod.f90:249-258 */
 enum { DANG_LNL_CHISQ = 0, DANG_LNL_MARGINAL = 1, DANG_LNL_PRIOR = 2 };
 /* c%prior_type, src/dang_sample_mod.f90:260-266 */
@@ -180,6 +180,20 @@ int dang_gpu_set_component(dang_gpu_t *h, int ic, int type, const char *label,
  * Built for CG_POLTYPE = Q+U with one template per group placed after the group's diffuse components. */
 int dang_gpu_set_template(dang_gpu_t *h, int ic, const double *template_map, const double *template_amplitudes,
                           const int *corr, int nfit);
+/* The same call completes the two Stokes-I "border" types (after dang_gpu_set_component with that type):
+ *   'monopole' (src/dang_component_mod.f90:579-597): template_map = NULL (the constructor's map: 1 on plane 1, 0 on
+ *     the polarisation planes); eval_signal = template_amplitudes(band, 1).  update_sky_model leaves it out of the sky
+ *     model and copies the amplitudes into ddata%offset instead (src/dang_data_mod.f90:357-361): the library does the
+ *     same to its offsets whenever the amplitudes change.
+ *   'hi_fit' (:599-700): template_map = the HI template (NOT normalised), indices (npix,nmaps,1) = T_d given to
+ *     dang_gpu_set_component; eval_signal = template_amplitudes(band, k) * template(pix, k) * B_nu(T_d) in RJ units
+ *     (evaluate_hi_fit :850-884).
+ * In a CG group both add one scalar unknown per fitted band like a template, on plane 1 only: CG_POLTYPE = T
+ * (compute_rhs :522-559, compute_Ax :717-744 / :833-866, compute_sample_vector :1044-1067).
+ * 'T_cmb' (:430 ff., evaluate_T_cmb :815-848) needs no second call: eval_signal = eval_sed = B_nu(T) in RJ units, no
+ * amplitude.  After its index has been drawn the host updates the global T_CMB as sample_spectral_parameters does
+ * (src/dang_sample_mod.f90:76-78) with dang_gpu_set_t_cmb; the 'cmb' SED (1 / a2t) follows it. */
+int dang_gpu_set_t_cmb(dang_gpu_t *h, double t_cmb);
 int dang_gpu_get_template_amplitudes(dang_gpu_t *h, int ic, double *template_amplitudes); /* -> (nbands,nmaps) */
 int dang_gpu_set_index(dang_gpu_t *h, int ic, int nind, int sample_index, int index_mode,
                        int lnl_type, int prior_type, const double gauss_prior[2],
@@ -294,6 +308,11 @@ enum {
 int dang_gpu_kernel_stats(dang_gpu_t *h, int kernel, int64_t *launches, double *total_ms,
                           double *bytes, int reset);
 const char *dang_gpu_kernel_name(int kernel);
+/* Event log of everything launched since DANG_OPT_PROFILE was switched on: kernel launches on the compute stream
+ * (kind = DANG_K_*) and staged copies on the copy streams (kind = DANG_K_COUNT + 0 h2d eta, + 1 d2h amplitude,
+ * + 2 d2h indices), start / end in microseconds from that moment, sorted by start.  The per-stream timeline of
+ * profiles/ (no nsys in this image). */
+int dang_gpu_timeline(dang_gpu_t *h, int max_n, int *n, int *kind, double *t0_us, double *t1_us);
 
 #ifdef __cplusplus
 }

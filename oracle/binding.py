@@ -90,6 +90,9 @@ def load(omp: bool = False) -> C.CDLL:
         "ora_philox_raw": (None, [C.POINTER(C.c_uint), C.c_uint, C.c_uint]),
         "ora_num_threads": (i, []),
         "ora_set_num_threads": (None, [i]),
+        "ora_get_T_CMB": (d, []),
+        "ora_set_T_CMB": (None, [d]),
+        "ora_offset": (c_dp, [vp]),
     }
     for name_, (res, args) in sigs.items():
         fn = getattr(lib, name_)
@@ -120,19 +123,28 @@ class Oracle:
                          _dp(sky.offset))
         lib.ora_set_pol_type(self.st, *cfg.pol_type)
         for ic, c in enumerate(cfg.comps):
-            if c.type == "template":
+            if c.type in ("template", "monopole", "hi_fit"):
+                idx = _dp(sky.indices[c.label]) if c.type == "hi_fit" else None
                 rc = lib.ora_set_component(self.st, ic, COMP_TYPES[c.type], c.label.encode(),
-                                           c.nu_ref_ghz, c.cg_group, int(c.amp_sample), None, None)
+                                           c.nu_ref_ghz, c.cg_group, int(c.amp_sample), None, idx)
                 assert rc == 0
                 corr = (C.c_int * cfg.nbands)(*[int(bool(v)) for v in c.corr])
+                if c.type == "monopole":
+                    rc = lib.ora_set_template(self.st, ic, None,
+                                              _dp(np.ascontiguousarray(sky.template_amplitudes[c.label])), corr,
+                                              int(sum(map(bool, c.corr))))
+                    assert rc == 0, rc
+                    continue
                 # the oracle divides by the per-plane maximum itself (the constructor's :574-577); the
                 # map handed over here is already normalised, so that division is by 1
                 rc = lib.ora_set_template(self.st, ic, _dp(np.ascontiguousarray(sky.template[c.label])),
                                           _dp(np.ascontiguousarray(sky.template_amplitudes[c.label])), corr,
                                           int(sum(map(bool, c.corr))))
                 assert rc == 0, rc
-                continue
-            rc = lib.ora_set_component(self.st, ic, COMP_TYPES[c.type], c.label.encode(),
+                if c.type != "hi_fit":
+                    continue
+            else:
+                rc = lib.ora_set_component(self.st, ic, COMP_TYPES[c.type], c.label.encode(),
                                        c.nu_ref_ghz, c.cg_group, int(c.amp_sample),
                                        _dp(sky.amplitude[c.label]), _dp(sky.indices[c.label]))
             assert rc == 0
@@ -281,3 +293,10 @@ def philox_uniforms(seed: int, stream: int, slot0: int, n: int) -> np.ndarray:
     u = np.zeros(n)
     load().ora_philox_uniforms(seed, stream, slot0, n, _dp(u))
     return u
+
+
+def planck_rj(nu_hz, T):
+    """B_nu(nu, T) / compute_bnu_prime_RJ(nu) * 1e6 (evaluate_hi_fit / evaluate_T_cmb on a delta band), numpy."""
+    h, k_B, c = 1.0545726691251021e-34 * 2.0 * np.pi, 1.3806503e-23, 2.99792458e8
+    B = ((2.0 * h * nu_hz ** 3.0) / c ** 2.0) * (1.0 / (np.exp((h * nu_hz) / (k_B * np.asarray(T))) - 1))
+    return B / (2.0 * k_B * nu_hz ** 2.0 / c ** 2.0) * 1e6

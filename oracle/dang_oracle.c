@@ -27,8 +27,8 @@
 static const double ORA_PI = 3.141592653589793238462643383279502884197;
 static const double ORA_KB = 1.3806503e-23;
 #define ORA_H (1.0545726691251021e-34 * 2.0 * ORA_PI)
-static const double ORA_C = 2.99792458e8; /* unused by the restated SEDs, kept for the record */
-static const double ORA_TCMB = 2.7255;
+static const double ORA_C = 2.99792458e8;
+static double ORA_TCMB = 2.7255; /* module-global T_CMB: a 'T_cmb' component overwrites it (dang_sample_mod.f90:76-78) */
 
 typedef struct {
   int n;        /* 0 <=> bp%id == 'delta' */
@@ -236,6 +236,9 @@ int ora_set_component(ora_state *st, int ic, int type, const char *label, double
     case ORA_LOGNORMAL: c->nindices = 2; break;
     case ORA_CMB: c->nindices = 0; break;
     case ORA_TEMPLATE: c->nindices = 0; break; /* :537 */
+    case ORA_T_CMB: c->nindices = 1; break;    /* :430 ff. */
+    case ORA_MONOPOLE: c->nindices = 0; break; /* :579-597 */
+    case ORA_HI_FIT: c->nindices = 1; break;   /* :599-700 */
     default: return 2;
   }
   size_t n2 = (size_t)st->npix * st->nmaps;
@@ -259,8 +262,9 @@ int ora_set_component(ora_state *st, int ic, int type, const char *label, double
  * plane (:574-577, done here as the constructor does), template_amplitudes(nbands,nmaps), corr, nfit */
 int ora_set_template(ora_state *st, int ic, const double *template_map, const double *template_amplitudes,
                      const int *corr, int nfit) {
-  if (ic < 0 || ic >= st->ncomp || st->comp[ic].type != ORA_TEMPLATE) return 1;
+  if (ic < 0 || ic >= st->ncomp) return 1;
   ora_comp *c = &st->comp[ic];
+  if (c->type != ORA_TEMPLATE && c->type != ORA_MONOPOLE && c->type != ORA_HI_FIT) return 1;
   const size_t n2 = (size_t)st->npix * st->nmaps;
   free(c->template_map);
   free(c->template_amplitudes);
@@ -268,8 +272,12 @@ int ora_set_template(ora_state *st, int ic, const double *template_map, const do
   c->template_map = xcalloc(n2, sizeof(double));
   c->template_amplitudes = xcalloc((size_t)st->nmaps * st->nbands, sizeof(double));
   c->corr = xcalloc(st->nbands, sizeof(int));
-  memcpy(c->template_map, template_map, n2 * sizeof(double));
-  for (int k = 0; k < st->nmaps; k++) { /* :574-577 */
+  if (c->type == ORA_MONOPOLE) { /* :591-594: offset map = 1 in intensity, 0 in polarisation */
+    for (int i = 0; i < st->npix; i++) c->template_map[IDX2(st, i, 0)] = 1.0;
+  } else {
+    memcpy(c->template_map, template_map, n2 * sizeof(double));
+  }
+  for (int k = 0; k < st->nmaps && c->type == ORA_TEMPLATE; k++) { /* :574-577 (type 'template' only) */
     double mx = c->template_map[IDX2(st, 0, k)];
     for (int i = 1; i < st->npix; i++)
       if (c->template_map[IDX2(st, i, k)] > mx) mx = c->template_map[IDX2(st, i, k)];
@@ -286,6 +294,9 @@ int ora_set_template(ora_state *st, int ic, const double *template_map, const do
   return count == nfit ? 0 : 2;
 }
 double *ora_template_map(ora_state *st, int ic) { return st->comp[ic].template_map; }
+double ora_get_T_CMB(void) { return ORA_TCMB; }
+void ora_set_T_CMB(double t) { ORA_TCMB = t; }
+double *ora_offset(ora_state *st) { return st->offset; }
 double *ora_template_amplitudes(ora_state *st, int ic) { return st->comp[ic].template_amplitudes; }
 
 int ora_set_index(ora_state *st, int ic, int nind, int sample_index, int index_mode, int lnl_type,
@@ -438,6 +449,29 @@ static double eval_freefree(const ora_state *st, const ora_comp *c, int band, in
   return spectrum;
 }
 
+/* B_nu, src/dang_component_mod.f90:745-752; compute_bnu_prime_RJ, src/dang_bp_mod.f90:160-168 */
+static double ora_B_nu(double nu, double T) {
+  return ((2.0 * ORA_H * pow(nu, 3.0)) / pow(ORA_C, 2.0)) * (1.0 / (exp((ORA_H * nu) / (ORA_KB * T)) - 1));
+}
+static double ora_bnu_prime_RJ(double nu) { return 2.0 * ORA_KB * pow(nu, 2.0) / pow(ORA_C, 2.0); }
+
+/* evaluate_T_cmb :815-848 and evaluate_hi_fit :850-884 share one body: the Planck function at T in RJ units */
+static double eval_planck_rj(const ora_state *st, const ora_comp *c, int band, int pix, int k,
+                             const double *theta) {
+  const ora_band *bp = &st->bp[band];
+  double spectrum = 0.0;
+  double T = theta ? theta[0] : c->indices[IDX2(st, pix, k)];
+  if (bp->n == 0) {
+    spectrum = ora_B_nu(bp->nu_c, T) / ora_bnu_prime_RJ(bp->nu_c);
+  } else {
+    for (int i = 0; i < bp->n; i++) {
+      if (bp->nu0[i] == 0.0) continue;
+      spectrum = spectrum + bp->tau0[i] * ora_B_nu(bp->nu0[i], T) / ora_bnu_prime_RJ(bp->nu0[i]);
+    }
+  }
+  return spectrum * (double)1e6f; /* "*1e6": a default-real literal */
+}
+
 /* eval_sed, src/dang_component_mod.f90:778-813.  map_n is 1-based. */
 static double eval_sed_c(const ora_state *st, const ora_comp *c, int band, int pix, int map_n,
                          const double *theta) {
@@ -449,6 +483,10 @@ static double eval_sed_c(const ora_state *st, const ora_comp *c, int band, int p
     case ORA_LOGNORMAL: return eval_lognormal(st, c, band, pix, k, theta);
     case ORA_CMB: return (double)(1.0f) / ora_a2t(&st->bp[band]);
     case ORA_TEMPLATE: return c->template_map[IDX2(st, pix, map_n - 1)]; /* :803-804 */
+    case ORA_T_CMB: return eval_planck_rj(st, c, band, pix, k, theta);     /* :801-802 */
+    case ORA_MONOPOLE: return c->template_map[IDX2(st, pix, map_n - 1)];   /* :805-806 */
+    case ORA_HI_FIT:                                                        /* :807-808 */
+      return c->template_map[IDX2(st, pix, map_n - 1)] * eval_planck_rj(st, c, band, pix, k, theta);
     default: return 0.0;
   }
 }
@@ -456,9 +494,12 @@ static double eval_sed_c(const ora_state *st, const ora_comp *c, int band, int p
 /* eval_signal, src/dang_component_mod.f90:754-776 (template :766-767, diffuse branch :773) */
 static double eval_signal_c(const ora_state *st, const ora_comp *c, int band, int pix, int map_n,
                             const double *theta) {
-  if (c->type == ORA_TEMPLATE)
+  if (c->type == ORA_TEMPLATE || c->type == ORA_MONOPOLE) /* :766-769 */
     return c->template_amplitudes[(size_t)(map_n - 1) * st->nbands + band] *
            c->template_map[IDX2(st, pix, map_n - 1)];
+  if (c->type == ORA_HI_FIT) /* :764-765 */
+    return c->template_amplitudes[(size_t)(map_n - 1) * st->nbands + band] * eval_sed_c(st, c, band, pix, map_n, theta);
+  if (c->type == ORA_T_CMB) return eval_sed_c(st, c, band, pix, map_n, theta); /* :770-771 */
   return c->amplitude[IDX2(st, pix, map_n - 1)] * eval_sed_c(st, c, band, pix, map_n, theta);
 }
 
@@ -523,7 +564,8 @@ long ora_cg_n(const ora_cg *g, int flag_n) {
   for (int ic = 0; ic < g->st->ncomp; ic++) {
     const ora_comp *c = &g->st->comp[ic];
     if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-    if (c->type == ORA_TEMPLATE) n += c->nfit; /* :409-414 (only the Q+U branch sizes b correctly) */
+    if (c->type == ORA_TEMPLATE || c->type == ORA_MONOPOLE || c->type == ORA_HI_FIT)
+      n += c->nfit; /* :399-414 (templates: only the Q+U branch sizes b correctly) */
     else n += m;
   }
   return n;
@@ -533,6 +575,20 @@ double *ora_cg_x(ora_cg *g, int flag_n) { return g->x[flag_n]; }
 
 /* 0-based slot of band j among the fitted bands of a template component (the counter l(l_ind) of
  * compute_Ax, :655,886-887), or -1 when the band is not fitted */
+static int is_border(const ora_comp *c) {
+  return c->type == ORA_TEMPLATE || c->type == ORA_MONOPOLE || c->type == ORA_HI_FIT;
+}
+/* planes a border component's column / row runs over: a template follows the solve's planes, hi_fit and
+ * monopole always use plane 1 and the FIRST npix entries of temp1 (:717-744, :833-866) */
+static int border_planes(const ora_comp *c, int S, const int planes[2], int bp[2]) {
+  if (c->type == ORA_TEMPLATE) {
+    bp[0] = planes[0];
+    bp[1] = planes[1];
+    return S;
+  }
+  bp[0] = bp[1] = 1;
+  return 1;
+}
 static int template_slot(const ora_state *st, const ora_comp *c, int j) {
   if (!c->corr[j]) return -1;
   int l = 0;
@@ -571,7 +627,7 @@ void ora_compute_rhs(ora_cg *g, int flag_n, double *b) {
                 data[IDX3(st, i, k - 1, j)] - eval_signal_c(st, c, j, i, k, NULL);
       }
     }
-    if (c->type == ORA_TEMPLATE) { /* :444-460: templates are also removed from the bands they are not fitted to */
+    if (c->type == ORA_TEMPLATE || c->type == ORA_MONOPOLE) { /* :444-460: also removed from the bands they are not fitted to */
       for (int j = 0; j < nbands; j++) {
         if (c->corr[j]) continue;
         for (int i = 0; i < npix; i++) {
@@ -589,18 +645,20 @@ void ora_compute_rhs(ora_cg *g, int flag_n, double *b) {
     const ora_comp *c = &st->comp[ic];
     if (c->cg_group != g->cg_group) continue;
     if (!c->sample_amplitude) continue;
-    if (c->type == ORA_TEMPLATE) { /* :560-587: one masked, noise-weighted sum per fitted band */
+    if (is_border(c)) { /* :522-587: one masked, noise-weighted sum per fitted band (hi_fit / monopole: plane 1) */
       int l = 0;
+      int bpl[2];
+      const int SB = border_planes(c, S, planes, bpl);
       double *val_array = xcalloc((size_t)S * npix, sizeof(double));
       for (int j = 0; j < nbands; j++) {
         if (!c->corr[j]) continue;
         for (long i = 0; i < (long)S * npix; i++) val_array[i] = 0.0;
         for (int i = 0; i < npix; i++) {
           if (masked(st, i)) continue;
-          for (int s = 0; s < S; s++) { /* :568-569: both planes accumulate into val_array(i) */
-            const double rms = st->rms_map[IDX3(st, i, planes[s] - 1, j)];
-            val_array[i] = val_array[i] + data[IDX3(st, i, planes[s] - 1, j)] / (rms * rms) *
-                                              eval_sed_c(st, c, j, i, planes[s], NULL);
+          for (int s = 0; s < SB; s++) { /* :568-569: both planes accumulate into val_array(i) */
+            const double rms = st->rms_map[IDX3(st, i, bpl[s] - 1, j)];
+            val_array[i] = val_array[i] + data[IDX3(st, i, bpl[s] - 1, j)] / (rms * rms) *
+                                              eval_sed_c(st, c, j, i, bpl[s], NULL);
           }
         }
         double sum = 0.0;
@@ -651,14 +709,16 @@ void ora_compute_Ax(ora_cg *g, const double *x, int flag_n, double *res) {
     for (int ic = 0; ic < st->ncomp; ic++) { /* temp1 = T_nu x, :685-769 */
       const ora_comp *c = &st->comp[ic];
       if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-      if (c->type == ORA_TEMPLATE) { /* :745-768 */
+      if (is_border(c)) { /* :717-768 */
         const int l = template_slot(st, c, j);
+        int bpl[2];
+        const int SB = border_planes(c, S, planes, bpl);
         if (l >= 0)
           for (int i = 0; i < npix; i++) {
             if (masked(st, i)) continue;
-            for (int s = 0; s < S; s++)
+            for (int s = 0; s < SB; s++)
               temp1[(long)s * npix + i] =
-                  temp1[(long)s * npix + i] + x[offset + l] * eval_sed_c(st, c, j, i, planes[s], NULL);
+                  temp1[(long)s * npix + i] + x[offset + l] * eval_sed_c(st, c, j, i, bpl[s], NULL);
           }
         offset += c->nfit;
         continue;
@@ -685,14 +745,17 @@ void ora_compute_Ax(ora_cg *g, const double *x, int flag_n, double *res) {
     for (int ic = 0; ic < st->ncomp; ic++) { /* temp3 = T_nu^t temp1, :801-894 */
       const ora_comp *c = &st->comp[ic];
       if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-      if (c->type == ORA_TEMPLATE) { /* :867-893: val_array over both planes, then sum() */
+      if (is_border(c)) { /* :833-893: val_array over the planes, then sum(); the monopole row adds temp1(i) itself (:856) */
         const int l = template_slot(st, c, j);
+        int bpl[2];
+        const int SB = border_planes(c, S, planes, bpl);
         if (l >= 0) {
           double sum = 0.0;
-          for (int s = 0; s < S; s++)
+          for (int s = 0; s < SB; s++)
             for (int i = 0; i < npix; i++) {
               if (masked(st, i)) continue;
-              sum += temp1[(long)s * npix + i] * eval_sed_c(st, c, j, i, planes[s], NULL);
+              sum += (c->type == ORA_MONOPOLE) ? temp1[(long)s * npix + i]
+                                               : temp1[(long)s * npix + i] * eval_sed_c(st, c, j, i, bpl[s], NULL);
             }
           temp3[offset + l] = temp3[offset + l] + sum;
         }
@@ -712,6 +775,24 @@ void ora_compute_Ax(ora_cg *g, const double *x, int flag_n, double *res) {
   }
   free(temp1);
   free(temp3);
+}
+
+/* Slot (0-based, relative to the end of the diffuse block) that compute_sample_vector writes the fluctuation of
+ * border component `ic` in band `j` to.  The source's counter l (:970) starts at 1 before the band loop and is
+ * incremented after every fitted (component, band) pair in loop order bands-outer / components-inner, never reset:
+ * with ONE border component this is the band's rank among its fitted bands (the same slot compute_Ax uses); with
+ * several the slots interleave across components and run past the component's own block (Q8). */
+static long ora_sv_slot(const ora_cg *g, int ic, int j) {
+  const ora_state *st = g->st;
+  long l = 0;
+  for (int jj = 0; jj <= j; jj++)
+    for (int c2 = 0; c2 < st->ncomp; c2++) {
+      const ora_comp *c = &st->comp[c2];
+      if (c->cg_group != g->cg_group || !c->sample_amplitude || !is_border(c)) continue;
+      if (jj == j && c2 == ic) return l;
+      if (c->corr[jj]) l++;
+    }
+  return l;
 }
 
 /* compute_sample_vector, src/dang_cg_mod.f90:913-1100.
@@ -743,21 +824,30 @@ void ora_compute_sample_vector(ora_cg *g, const double *eta, int flag_n, double 
     for (int ic = 0; ic < st->ncomp; ic++) {
       const ora_comp *c = &st->comp[ic];
       if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-      if (c->type != ORA_TEMPLATE) diffuse_len += n;
+      if (!is_border(c)) diffuse_len += n;
     }
+    int l_run = 0; /* the counter `l` of :970: set once, never reset per component (Q8), restarted here per band
+                    * because every band revisits the same slots in the same order */
     for (int ic = 0; ic < st->ncomp; ic++) { /* temp2 = T^t temp1, :1021-1097 */
       const ora_comp *c = &st->comp[ic];
       if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-      if (c->type == ORA_TEMPLATE) { /* :1077-1096 (one template component per group: Q8 not modelled) */
+      if (is_border(c)) { /* :1044-1096 */
         const int l = template_slot(st, c, j);
+        int bpl[2];
+        const int SB = border_planes(c, S, planes, bpl);
+        (void)l_run;
         if (l >= 0) {
           double sum = 0.0;
-          for (int s = 0; s < S; s++)
+          for (int s = 0; s < SB; s++)
             for (int i = 0; i < npix; i++) {
               if (masked(st, i)) continue;
-              sum += temp1[(long)s * npix + i] * eval_sed_c(st, c, j, i, planes[s], NULL);
+              sum += (c->type == ORA_MONOPOLE) ? temp1[(long)s * npix + i]
+                                               : temp1[(long)s * npix + i] * eval_sed_c(st, c, j, i, bpl[s], NULL);
             }
-          temp2[diffuse_len + l] = temp2[diffuse_len + l] + sum;
+          /* Q8: the slot is diffuse_len + (running count of fitted (component, band) pairs met so far in the
+           * whole band loop), NOT this component's own block; ora_sv_slot reproduces the running counter */
+          const long slot = diffuse_len + ora_sv_slot(g, ic, j);
+          temp2[slot] = temp2[slot] + sum;
         }
         continue;
       }
@@ -786,11 +876,12 @@ static void initialize_x(ora_cg *g, int flag_n) {
   for (int ic = 0; ic < st->ncomp; ic++) {
     const ora_comp *c = &st->comp[ic];
     if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-    if (c->type == ORA_TEMPLATE) { /* :1264-1279: Q+U takes plane 2's amplitudes */
+    if (is_border(c)) { /* :1226-1279: Q+U takes plane 2's amplitudes; hi_fit / monopole plane 1 */
       int l = 0;
+      const int kp = (c->type == ORA_TEMPLATE) ? planes[0] : 1;
       for (int j = 0; j < st->nbands; j++) {
         if (c->corr[j]) {
-          g->x[flag_n][offset + l] = c->template_amplitudes[(size_t)(planes[0] - 1) * st->nbands + j];
+          g->x[flag_n][offset + l] = c->template_amplitudes[(size_t)(kp - 1) * st->nbands + j];
           l++;
         }
         if (l >= c->nfit) break;
@@ -815,12 +906,14 @@ void ora_unpack_amplitudes(ora_cg *g, int flag_n) {
   for (int ic = 0; ic < st->ncomp; ic++) {
     ora_comp *c = &st->comp[ic];
     if (c->cg_group != g->cg_group || !c->sample_amplitude) continue;
-    if (c->type == ORA_TEMPLATE) { /* :1374-1392: Q+U writes the fitted value to planes 2 and 3 */
+    if (is_border(c)) { /* :1337-1392: Q+U writes the fitted value to planes 2 and 3; hi_fit / monopole to plane 1 */
       int l = 0;
+      int bpl[2];
+      const int SB = border_planes(c, S, planes, bpl);
       for (int j = 0; j < st->nbands; j++) {
         if (c->corr[j]) {
-          for (int s = 0; s < S; s++)
-            c->template_amplitudes[(size_t)(planes[s] - 1) * st->nbands + j] = g->x[flag_n][offset + l];
+          for (int s = 0; s < SB; s++)
+            c->template_amplitudes[(size_t)(bpl[s] - 1) * st->nbands + j] = g->x[flag_n][offset + l];
           l++;
         }
         if (l >= c->nfit) break;
@@ -920,6 +1013,10 @@ void ora_update_sky_model(ora_state *st) {
   for (size_t i = 0; i < n3; i++) st->sky_model[i] = 0.0;
   for (int l = 0; l < st->ncomp; l++) {
     const ora_comp *c = &st->comp[l];
+    if (c->type == ORA_MONOPOLE) { /* :357-361: the band monopoles become the offsets, not part of the sky model */
+      for (int j = 0; j < nbands; j++) st->offset[j] = c->template_amplitudes[j];
+      continue;
+    }
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < npix; i++)
       for (int k = 1; k <= nmaps; k++)
@@ -1309,6 +1406,7 @@ int ora_sample_spectral_parameters(ora_state *st, int nsample, int ml_mode, cons
         ncall++;
       }
     }
+    if (c->type == ORA_T_CMB) ORA_TCMB = c->indices[IDX2(st, 0, 0)]; /* :76-78: T_CMB = c%indices(0,1,1) */
   }
   if (sampled) ora_update_sky_model(st);
   return ncall;

@@ -34,7 +34,8 @@ extern "C" {
 #define ORA_MAXIND 2
 
 /* component types, src/dang_component_mod.f90:791-809 */
-enum { ORA_POWERLAW = 1, ORA_MBB = 2, ORA_FREEFREE = 3, ORA_LOGNORMAL = 4, ORA_CMB = 5, ORA_TEMPLATE = 6 };
+enum { ORA_POWERLAW = 1, ORA_MBB = 2, ORA_FREEFREE = 3, ORA_LOGNORMAL = 4, ORA_CMB = 5, ORA_TEMPLATE = 6,
+       ORA_T_CMB = 7, ORA_MONOPOLE = 8, ORA_HI_FIT = 9 };
 /* *_LNL_TYPE, src/dang_sample_mod.f90:249-258 */
 enum { ORA_LNL_CHISQ = 0, ORA_LNL_MARGINAL = 1, ORA_LNL_PRIOR = 2 };
 /* *_PRIOR, src/dang_sample_mod.f90:260-266 */
@@ -160,6 +161,9 @@ void ora_philox_uniforms(unsigned long long seed, unsigned int stream, unsigned 
                          long n, double *u);
 
 int ora_num_threads(void);
+double ora_get_T_CMB(void);
+void ora_set_T_CMB(double t);
+double *ora_offset(ora_state *st);
 void ora_set_num_threads(int n);
 
 #ifdef __cplusplus

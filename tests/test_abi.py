@@ -117,7 +117,7 @@ def test_fortran_shim_binds_the_declared_abi():
     instrumentation = {"dang_gpu_cg_trace", "dang_gpu_get_cg_x", "dang_gpu_get_decisions", "dang_gpu_event_record",
                        "dang_gpu_event_elapsed_ms", "dang_gpu_launch_count", "dang_gpu_kernel_stats",
                        "dang_gpu_kernel_name", "dang_gpu_perpixel_stats", "dang_gpu_share_maps",
-                       "dang_gpu_bandpass_quadrature"}
+                       "dang_gpu_bandpass_quadrature", "dang_gpu_timeline"}
     assert declared - bound <= instrumentation, (declared - bound) - instrumentation
 
 
@@ -138,7 +138,9 @@ def test_python_constants_match_the_header_enums():
     assert engine.KERNEL_COUNT == enums["DANG_K_COUNT"]
     assert config.COMP_TYPES == {"power-law": enums["DANG_COMP_POWERLAW"], "mbb": enums["DANG_COMP_MBB"],
                                  "freefree": enums["DANG_COMP_FREEFREE"], "lognormal": enums["DANG_COMP_LOGNORMAL"],
-                                 "cmb": enums["DANG_COMP_CMB"], "template": enums["DANG_COMP_TEMPLATE"]}
+                                 "cmb": enums["DANG_COMP_CMB"], "template": enums["DANG_COMP_TEMPLATE"],
+                                 "T_cmb": enums["DANG_COMP_T_CMB"], "monopole": enums["DANG_COMP_MONOPOLE"],
+                                 "hi_fit": enums["DANG_COMP_HI_FIT"]}
     assert config.LNL_TYPES == {"chisq": enums["DANG_LNL_CHISQ"], "marginal": enums["DANG_LNL_MARGINAL"],
                                 "prior": enums["DANG_LNL_PRIOR"]}
     assert config.PRIOR_TYPES == {"uniform": enums["DANG_PRIOR_UNIFORM"], "gaussian": enums["DANG_PRIOR_GAUSSIAN"],

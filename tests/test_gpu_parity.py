@@ -858,9 +858,9 @@ def test_errors_are_loud_and_specific():
     with pytest.raises(DangGpuError, match="CG group"):
         eng.cg_solve(ig=5)
     lib = _lib.load()
-    # unsupported component type (monopole / hi_fit / T_cmb have no enum value in the ABI)
-    rc = lib.dang_gpu_set_component(eng.h, 0, 7, b"mono", 30e9, 1, 1, None, None)
-    assert rc == 3 and b"power-law" in lib.dang_gpu_last_error(eng.h)
+    # unknown component type
+    rc = lib.dang_gpu_set_component(eng.h, 0, 12, b"what", 30e9, 1, 1, None, None)
+    assert rc == 1 and b"unrecognized" in lib.dang_gpu_last_error(eng.h)
     # bad geometry at creation
     h = _lib.vp()
     assert lib.dang_gpu_create(0, 4, 191, 3, 5, 2, 0, 191, C.byref(h)) == 1

@@ -230,3 +230,73 @@ def test_template_fit_recovers_a_noiseless_sky():
     m = sky.mask != 0
     assert np.max(np.abs(ora.amplitude(0)[1:3][:, m] - sky.truth["synch"][1:3][:, m])) < 1e-5
     assert ora.compute_chisq()[0] < 1e-12
+
+
+# ------------------------------------------------------------------ Stokes-I component types
+def test_planck_rj_sed_of_t_cmb_and_hi_fit():
+    """evaluate_T_cmb / evaluate_hi_fit (src/dang_component_mod.f90:815-884) against the closed form
+    B_nu(T) / (2 k nu^2 / c^2) * 1e6 = (h nu / k) / (exp(h nu / k T) - 1) * 1e6 [uK_RJ]."""
+    import sys
+    sys.path.insert(0, "tests")
+    from helpers import intensity_case
+    from oracle.binding import Oracle, load
+    load().ora_set_T_CMB(2.7255)
+    cfg, sky, _, hi_true = intensity_case(4, with_hi=True)
+    sky.template_amplitudes["hi"][0] = hi_true
+    ora = Oracle(cfg, sky)
+    h, k_B = 1.0545726691251021e-34 * 2.0 * np.pi, 1.3806503e-23
+    for j, b in enumerate(cfg.bands):
+        nu, T = b.nu_ghz * 1e9, sky.indices["hi"][0][0, 5]
+        closed = (h * nu / k_B) / np.expm1(h * nu / (k_B * T)) * 1e6
+        sed = ora.eval_sed(1, j, 5, 1)                      # hi_fit: template(pix) * planck
+        assert abs(sed - sky.template["hi"][0, 5] * closed) <= 1e-12 * abs(sed)
+        sig = ora.lib.ora_eval_signal(ora.st, 1, j, 5, 1, None)
+        assert abs(sig - hi_true[j] * sed) <= 1e-15 * abs(sig)
+        assert ora.eval_sed(2, j, 5, 1) == 1.0              # monopole: template(:,1) = 1
+        assert ora.eval_sed(2, j, 5, 2) == 0.0              # ... and 0 in polarisation
+
+
+def test_monopole_and_hi_fit_recover_a_noiseless_sky():
+    """Known answer for the border rows of compute_rhs / compute_Ax (src/dang_cg_mod.f90:522-559, 717-744, 833-866):
+    on a noiseless sky the CG recovers the HI band amplitudes and the band monopoles, update_sky_model turns the
+    monopoles into the offsets (src/dang_data_mod.f90:357-361), and chi-square -> 0."""
+    import sys
+    sys.path.insert(0, "tests")
+    from helpers import intensity_case
+    from oracle.binding import Oracle, load
+    load().ora_set_T_CMB(2.7255)
+    cfg, sky, mono, hi = intensity_case(8, noise=False, with_hi=True)
+    ora = Oracle(cfg, sky)
+    its, delta = ora.sample_cg_group(0, 0, None)
+    assert 1 < its[0] < cfg.cg_groups[0].max_iter
+    assert np.allclose(ora.template_amplitudes(1)[0], hi, rtol=1e-6)
+    assert np.allclose(ora.template_amplitudes(2)[0], mono, rtol=1e-6)
+    off = np.ctypeslib.as_array(ora.lib.ora_offset(ora.st), shape=(cfg.nbands,))
+    assert np.array_equal(off, ora.template_amplitudes(2)[0])
+    assert ora.compute_chisq()[0] < 1e-12
+    # dust (diffuse) + monopole, one band left unfitted: chi-square -> 0 as well
+    cfg, sky, mono, _ = intensity_case(8, noise=False, with_hi=False, unfitted_band=3)
+    ora = Oracle(cfg, sky)
+    ora.sample_cg_group(0, 0, None)
+    assert ora.compute_chisq()[0] < 1e-12
+    assert np.allclose(ora.template_amplitudes(1)[0], mono, atol=1e-5)
+
+
+def test_sample_vector_slots_interleave_with_two_border_components():
+    """compute_sample_vector's template counter `l` (src/dang_cg_mod.f90:970) is never reset per
+    component, so with two border components its slots interleave (band-major) while compute_Ax lays the
+    components out one after the other.  With a single border component both layouts coincide."""
+    import sys
+    sys.path.insert(0, "tests")
+    from helpers import intensity_case
+    from oracle.binding import Oracle
+    cfg, sky, _, _ = intensity_case(4, with_hi=True)
+    ora = Oracle(cfg, sky)
+    npix, nb = cfg.npix, cfg.nbands
+    eta = np.random.default_rng(2).standard_normal(npix)
+    sv = ora.compute_sample_vector(eta)           # no diffuse component in this group: the vector is the tail
+    assert sv.shape == (2 * nb,)
+    m = sky.mask != 0
+    hi_rows = np.array([np.sum((eta / sky.rms[j, 0])[m] * np.array([ora.eval_sed(1, j, i, 1) for i in range(npix)])[m]) for j in range(nb)])
+    mono_rows = np.array([np.sum((eta / sky.rms[j, 0])[m]) for j in range(nb)])
+    assert np.allclose(sv[0::2], hi_rows, rtol=1e-12) and np.allclose(sv[1::2], mono_rows, rtol=1e-12)
