@@ -84,7 +84,7 @@ class ClockSampler:
                         self.power.append(pynvml.nvmlDeviceGetPowerUsage(hdl) / 1e3)
                     except Exception:
                         break
-                    time.sleep(0.0005)
+                    time.sleep(0.003)
             self._t = threading.Thread(target=loop, daemon=True)
             self._t.start()
         except Exception:
@@ -190,15 +190,20 @@ def run_gpu(args):
     # --- device-resident timing: `value`
     for w in range(args.warmup):
         step(2 + w)
+    # the NVML sampler is set up BEFORE the barrier: its start-up (tens of ms on rank 0 only) inside the timed region
+    # would leave the other ranks' kernels spinning in their first scalar exchange, and max-over-ranks would report it
+    sampler = ClockSampler(local) if (rank == 0 and os.environ.get("DANG_BENCH_NO_CLOCKS") != "1") else None
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     eng.launch_count(reset=True)
     eng.event_record(0)
+    t_value0 = time.perf_counter()
     n_cg = []
     for k in range(args.steps):
         step(2 + args.warmup + k)
         n_cg.append(info["n_cg"])
     eng.event_record(1)
+    eng.sync()
+    wall_value_ms = (time.perf_counter() - t_value0) * 1e3
     barrier()
     ms = max_over_ranks(eng.event_elapsed_ms(0, 1))
     launches = eng.launch_count()
@@ -215,7 +220,10 @@ def run_gpu(args):
 
     # --- end to end through the C ABI with host buffers: deviates in, maps out, every step
     npix = cfg.npix
-    eta_h = pinned_array(eng.lib, (2 * npix,))
+    # three different sets of deviates, cycled: with ONE set every other solve would start from the previous
+    # solution of the same right-hand side and converge at once
+    eta_hs = [pinned_array(eng.lib, (2 * npix,)) for _ in range(3)]
+    eta_h = eta_hs[0]
     # one (z, u) pair per sample_index_mh call: nsample slots for a full-sky index,
     # nsample*npix for a per-pixel one
     calls = [s for c in cfg.comps for s in c.indices if s.sample for _ in s.poltype.split(",")]
@@ -230,7 +238,8 @@ def run_gpu(args):
     amp_h = [pinned_array(eng.lib, (cfg.nmaps, npix)) for _ in cfg.comps]
     idx_h = [pinned_array(eng.lib, (len(c.indices), cfg.nmaps, npix)) for c in cfg.comps]
     rng = np.random.default_rng(20260103 + rank * 0)
-    eta_h[:] = rng.standard_normal(2 * npix)
+    for e in eta_hs:
+        e[:] = rng.standard_normal(2 * npix)
     for zz, uu in zip(z_h or [], u_h or []):
         zz[:] = rng.standard_normal(zz.size)
         uu[:] = rng.random(uu.size)
@@ -246,12 +255,15 @@ def run_gpu(args):
     single_solve = len(cfg.cg_groups) == 1 and "," not in cfg.cg_groups[0].poltype
     fs_val = {}
 
+    e2e_ncg = []
+
     def e2e_step(it):
         if single_solve:
-            eng.stage_eta(eta_h)                    # next step's deviates: upload overlaps this step's solve
-            eng.sample_cg_groups(eta=None)          # consumes the deviates staged one step earlier
+            eng.stage_eta(eta_hs[(it + 1) % 3])     # next step's deviates: upload overlaps this step's solve
+            r1 = eng.sample_cg_groups(eta=None)     # consumes the deviates staged one step earlier
         else:
-            eng.sample_cg_groups(eta=eta_h)
+            r1 = eng.sample_cg_groups(eta=eta_hs[it % 3])
+        e2e_ncg.append(r1[0][0])
         for ic in range(len(cfg.comps)):
             eng.amplitude_async(ic, amp_h[ic])
         eng.sample_spectral_parameters(z=z_h, u=u_h, seed=7 + 2 * it)
@@ -264,15 +276,17 @@ def run_gpu(args):
                 eng.indices_async(ic, j, idx_h[ic])
 
     if single_solve:
-        eng.stage_eta(eta_h)
-    e2e_step(0)
+        eng.stage_eta(eta_hs[0])
+    for w in range(3):
+        e2e_step(w)
     eng.download_wait()
+    e2e_ncg.clear()
     barrier()
     eng.event_record(2)
     t0 = time.perf_counter()
     ke = max(1, min(args.steps, 50))
     for k in range(ke):
-        e2e_step(k)
+        e2e_step(3 + k)
     eng.download_wait()
     eng.event_record(3)
     barrier()
@@ -305,6 +319,7 @@ def run_gpu(args):
             "metric": METRIC if (cfg.name == "c2" and cfg.nside == 512) else f"Gibbs iterations/sec (nside={cfg.nside}, Q+U, synch+dust)",
             "value": round(1e3 / ms_per_step, 3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "ms_per_step_wall_rank0": round(wall_value_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(cfg),
@@ -320,6 +335,7 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": round(1e3 * ke / e2e_ms, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": ke,
+                    "n_cg_iterations": {"min": int(min(e2e_ncg)), "max": int(max(e2e_ncg)), "mean": round(float(np.mean(e2e_ncg)), 2)},
                     "ms_per_step_device_rank0": round(e2e_dev_ms / ke, 4), "ms_per_step_wall_rank0": round(wall_ms / ke, 4),
                     "what": "per step: injected deviates (eta, z, u) pinned host -> device; changed Q/U planes of every amplitude map and of the per-pixel-sampled index maps, the value of every full-sky-sampled index (one double per plane) + chi-square device -> pinned host; copies overlap compute on dedicated streams"
                             + ("" if host_zu else "; per-pixel Metropolis deviates drawn on the device (16 GB per step otherwise)")},

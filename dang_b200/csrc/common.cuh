@@ -422,6 +422,13 @@ __device__ __forceinline__ void peer_exchange(const PeerComm &pc, const double *
 static __global__ void peer_exchange_kernel(PeerComm pc, const double *local, int cnt, double *gathered) {
   peer_exchange(pc, local, cnt, gathered);
 }
+// `reps` back-to-back exchanges of `cnt` doubles by one warp: the latency floor of a scalar exchange (dang_gpu_comm_probe)
+static __global__ void peer_exchange_probe_kernel(PeerComm pc, double *local, int cnt, double *gathered, int reps) {
+  for (int i = 0; i < reps; i++) {
+    if (threadIdx.x < cnt) local[threadIdx.x] = (double)(i + pc.rank);
+    peer_exchange(pc, local, cnt, gathered);
+  }
+}
 
 // Small results go back to the host through stores into mapped pinned memory, not through the
 // copy engine: a cudaMemcpyAsync of a few bytes queues behind whatever bulk download (amplitude

@@ -225,6 +225,7 @@ ModelView model_view(dang_gpu *h) {
   mv.rms = h->rms;
   mv.mask = h->mask;
   if (h->tab_dirty) {  // an index map changed since the SED tables were built
+    idx_changed(h);    // (whatever left the device for the next full-sky chain is stale now)
     const bool scanned = h->check_mask != 0;
     if (h->check_mask) {
       // maps uploaded by the host are scanned once; maps written by the samplers are not (their
@@ -313,6 +314,10 @@ int64_t unmasked_count(dang_gpu *h) {
   if (!h) return DANG_GPU_EINVAL;                   \
   try {                                             \
     set_device(h);
+#define API_END_OK                                  \
+    if (h->peer_error_host && *h->peer_error_host)  \
+      fail(DANG_GPU_ENCCL, "a peer rank did not answer a scalar exchange within the timeout; results of this handle are poisoned"); \
+    return DANG_GPU_OK;
 #define API_END                                     \
     if (h->peer_error_host && *h->peer_error_host)  \
       fail(DANG_GPU_ENCCL, "a peer rank did not answer a scalar exchange within the timeout; results of this handle are poisoned"); \
@@ -474,6 +479,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_PERPIXEL_BP_SERIES: h->pp_bp_series = value != 0; break;
     case DANG_OPT_CG_PERSISTENT: h->cg_persistent = value != 0; break;
     case DANG_OPT_STREAM_RING: h->stream_ring = value != 0; break;
+    case DANG_OPT_DEFER_D2H: h->defer_d2h = value != 0; break;
     case DANG_OPT_BP_QUADRATURE:
       h->bp_quad = value < 0 ? 0 : (value > 32 ? 32 : (int)value);
       h->bp_dirty = true;
@@ -581,6 +587,26 @@ int dang_gpu_comm_open_peers(dang_gpu_t *h, const char *handles) {
 int dang_gpu_comm_check(dang_gpu_t *h) {
   API_BEGIN
   if (h->use_mail) CK(cudaStreamSynchronize(h->stream));  // API_END reads the (host-mapped) timeout flag
+  API_END
+}
+
+int dang_gpu_comm_probe(dang_gpu_t *h, int reps, int cnt, double *us_per_exchange) {
+  API_BEGIN
+  if (!h->use_mail) fail(DANG_GPU_ESTATE, "dang_gpu_comm_open_peers comes first");
+  if (reps < 1 || cnt < 1 || cnt > 32) fail(DANG_GPU_EINVAL, "comm_probe: reps %d, cnt %d", reps, cnt);
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  peer_exchange_probe_kernel<<<1, 32, 0, h->stream>>>(h->peer, h->sums_local, cnt, h->gathered, 8);  // warm-up, aligns the ranks
+  CK(cudaEventRecord(a, h->stream));
+  peer_exchange_probe_kernel<<<1, 32, 0, h->stream>>>(h->peer, h->sums_local, cnt, h->gathered, reps);
+  CK(cudaEventRecord(b, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  if (us_per_exchange) *us_per_exchange = 1e3 * ms / reps;
   API_END
 }
 
@@ -837,6 +863,13 @@ int dang_gpu_get_index_fullsky(dang_gpu_t *h, int ic, int nind, int map_n, doubl
   if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || nind < 0 || nind >= h->comp[ic].nind || map_n < 1 ||
       map_n > h->nmaps || !value)
     fail(DANG_GPU_EINVAL, "bad component/index/map %d/%d/%d", ic, nind, map_n);
+  {  // the host already knows the value when the plane's last writer was a full-sky draw
+    const IndexHost &ixh = h->comp[ic].index[nind];
+    if (!h->tab_dirty && ixh.last_value_epoch == h->idx_epoch && (ixh.last_value_planes >> (map_n - 1)) & 1) {
+      *value = ixh.last_value;
+      API_END_OK
+    }
+  }
   model_view(h);  // refreshes the uniformity flags
   if (h->nonuni_host[ic * 3 + (map_n - 1)][nind] != 0)
     fail(DANG_GPU_ESTATE, "plane %d of index %d of component %d is not constant", map_n, nind, ic);
@@ -914,11 +947,24 @@ int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsampl
     CK(cudaStreamWaitEvent(h->stream, h->ev_idx_dl, 0));
     h->idx_dl_pending = false;
   }
+  h->fs_tab_written = false;
   if (perpix) {
     touch(h, 2);
+    idx_changed(h);
     sample_perpixel(h, mh, z, u, seed, accept);
   } else {
     sample_fullsky(h, mh, z, u, seed, accept);  // bumps the version itself (after using the cache)
+    // planes that were tabulated before the draw stay tabulated, and the chain kernel has already put the new SED
+    // into the table: nothing to flag, nothing to rebuild
+    IndexHost &ixh = h->comp[ic].index[nind];
+    ixh.last_value_planes = 0;
+    for (int s = 0; s < mh.S; s++) ixh.last_value_planes |= 1 << mh.plane[s];
+    if (h->fs_tab_written) {
+      ixh.last_value_epoch = h->idx_epoch;
+      API_END_OK
+    }
+    idx_changed(h);
+    ixh.last_value_epoch = h->idx_epoch + 1;  // (the table rebuild this draw triggers bumps the epoch once more)
   }
   // the written planes are varying after a per-pixel draw (masked pixels are zeroed, so even a
   // chain that never moved leaves a non-constant plane unless nothing is masked -- treating it as
@@ -1016,25 +1062,49 @@ int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean
   API_END
 }
 
+}  // extern "C"
+
+// issue every recorded amplitude download on the d2h stream, ordered after `after` (an event of the compute stream)
+void issue_deferred_d2h(dang_gpu *h, cudaEvent_t after) {
+  if (h->deferred.empty()) return;
+  CK(cudaStreamWaitEvent(h->d2h_stream, after, 0));
+  for (const DeferredD2H &r : h->deferred) {
+    CompHost &cc = h->comp[r.ic];
+    const size_t o = (size_t)(r.k_lo - 1);
+    CopyTimer ct(h, DANG_TL_D2H_AMP, h->d2h_stream);
+    CK(cudaMemcpy2DAsync(r.dst + o * h->npix + h->lo, h->npix * sizeof(double), r.src + o * h->Ppad,
+                         h->Ppad * sizeof(double), h->P * sizeof(double), r.k_hi - r.k_lo + 1, cudaMemcpyDeviceToHost,
+                         h->d2h_stream));
+    ct.done();
+    // the buffer may have changed roles (amp <-> amp_alt) since the request: flag whichever it is now
+    if (r.src == cc.amp) {
+      CK(cudaEventRecord(cc.ev_read, h->d2h_stream));
+      cc.read_pending = true;
+    } else {
+      CK(cudaEventRecord(cc.ev_read_alt, h->d2h_stream));
+      cc.read_pending_alt = true;
+    }
+  }
+  h->deferred.clear();
+}
+
+extern "C" {
+
 int dang_gpu_get_amplitude_async(dang_gpu_t *h, int ic, int k_lo, int k_hi, double *amplitude) {
   API_BEGIN
   if (ic < 0 || ic >= h->ncomp || !h->comp[ic].set || !amplitude || k_lo < 1 || k_hi > h->nmaps || k_lo > k_hi)
     fail(DANG_GPU_EINVAL, "bad component / plane range %d %d..%d", ic, k_lo, k_hi);
-  CK(cudaEventRecord(h->ev_compute, h->stream));
-  CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute, 0));
-  const size_t o = (size_t)(k_lo - 1);
-  CopyTimer ct(h, DANG_TL_D2H_AMP, h->d2h_stream);
-  CK(cudaMemcpy2DAsync(amplitude + o * h->npix + h->lo, h->npix * sizeof(double), h->comp[ic].amp + o * h->Ppad,
-                       h->Ppad * sizeof(double), h->P * sizeof(double), k_hi - k_lo + 1, cudaMemcpyDeviceToHost,
-                       h->d2h_stream));
-  ct.done();
   CompHost &cc = h->comp[ic];
   if (!cc.ev_read) {
     CK(cudaEventCreateWithFlags(&cc.ev_read, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&cc.ev_read_alt, cudaEventDisableTiming));
   }
-  CK(cudaEventRecord(cc.ev_read, h->d2h_stream));
-  cc.read_pending = true;
+  h->deferred.push_back(DeferredD2H{ic, cc.amp, amplitude, k_lo, k_hi});
+  cc.read_pending = true;  // (requested: the next draw must not unpack into this buffer)
+  if (!h->defer_d2h) {
+    CK(cudaEventRecord(h->ev_compute, h->stream));
+    issue_deferred_d2h(h, h->ev_compute);
+  }
   API_END
 }
 
@@ -1058,6 +1128,10 @@ int dang_gpu_get_indices_async(dang_gpu_t *h, int ic, int nind, int k_lo, int k_
 
 int dang_gpu_download_wait(dang_gpu_t *h) {
   API_BEGIN
+  if (!h->deferred.empty()) {
+    CK(cudaEventRecord(h->ev_compute, h->stream));
+    issue_deferred_d2h(h, h->ev_compute);
+  }
   CK(cudaStreamSynchronize(h->d2h_stream));
   for (auto &c : h->comp) c.read_pending = c.read_pending_alt = false;
   h->idx_dl_pending = false;

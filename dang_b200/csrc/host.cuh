@@ -83,6 +83,8 @@ struct IndexHost {
   double gauss[2] = {0, 1}, uni[2] = {-1e300, 1e300}, step = 0;
   int sample_nside = 0, nflag = 0, pol_flag[3] = {0, 0, 0};
   double last_value = 0;  // value left by the last full-sky draw (the whole plane holds it)
+  uint64_t last_value_epoch = 0;  // dang_gpu::idx_epoch right after that draw: the value is current while they agree
+  int last_value_planes = 0;      // bit k: plane k holds it
 };
 
 struct CompHost {
@@ -138,6 +140,8 @@ struct dang_gpu {
   int64_t npix = 0, lo = 0, hi = 0, P = 0, Ppad = 0;
   cudaStream_t stream = nullptr, d2h_stream = nullptr, h2d_stream = nullptr;
   cudaEvent_t ev_compute = nullptr, ev_idx_dl = nullptr;
+  std::vector<struct DeferredD2H> deferred;  // amplitude downloads requested but not issued yet
+  int defer_d2h = 1;                         // DANG_OPT_DEFER_D2H
   cudaEvent_t ev_sync = nullptr;  // host waits for a point of the compute stream (results read back) while later kernels run
   bool idx_dl_pending = false;
   // staged deviates of the next solves: a two-slot FIFO, so the upload for solve k+1 runs while solve k
@@ -217,6 +221,15 @@ struct dang_gpu {
   int chisq_lo = 0, chisq_hi = 0;
   double chisq_vals[4] = {0, 0, 0, 0};
   int64_t n_unmasked = -1;       // all ranks; -1: not counted yet
+  // chain continuity of full-sky draws: after a statistics-form draw of (ic, nind) over planes that were already
+  // tabulated, the device holds the next chain's start (MhScalars::sample, s0) and the refreshed SED table, so the
+  // next draw of the same index skips the chain-start kernels and the table kernel.  idx_epoch counts every other
+  // change to index maps / bands / component constants.
+  uint64_t idx_epoch = 1;
+  bool fs_cont_valid = false;
+  int fs_cont_ic = -1, fs_cont_nind = -1, fs_cont_S = 0, fs_cont_plane0 = -1;
+  uint64_t fs_cont_epoch = 0;
+  bool fs_tab_written = false;   // set by sample_fullsky for dang_gpu_sample_index: table already refreshed on the device
 
   // comm
   int nranks = 1, rank = 0;
@@ -379,8 +392,26 @@ inline void readback(dang_gpu *h, void *dst_pinned, const void *src_dev, size_t 
   h->launches++;  // (dang_gpu_launch_count: every kernel of this library counts)
 }
 
+// Deferred amplitude downloads (DANG_OPT_DEFER_D2H).  A bulk device->host copy saturates the host link, and while
+// it does the GPU's command fetches queue behind it: every small launch of the spectral-parameter block then costs
+// 50-70 us instead of 5-10 (profiles/r02_timeline_*.md).  So dang_gpu_get_amplitude_async only RECORDS the request;
+// the copy is issued by the next amplitude draw right behind its solve kernel -- one long launch that needs nothing
+// from the host for hundreds of microseconds -- reading the buffer the draw just swapped out (CompHost::amp_alt).
+// Anything else that needs the data or the buffer (dang_gpu_download_wait, in-place writers) issues them at once.
+struct DeferredD2H {
+  int ic;
+  const double *src;  // device planes (the component's amplitude buffer at request time)
+  double *dst;        // host array (full-sky addressing)
+  int k_lo, k_hi;
+};
+void issue_deferred_d2h(dang_gpu *h, cudaEvent_t after);  // dang_gpu.cu
+
 // anything that overwrites c.amp in place waits for a download that may still be reading it
 inline void amp_write_barrier(dang_gpu *h, CompHost &c) {
+  if (!h->deferred.empty()) {
+    CK(cudaEventRecord(h->ev_compute, h->stream));
+    issue_deferred_d2h(h, h->ev_compute);
+  }
   if (c.read_pending) {
     CK(cudaStreamWaitEvent(h->stream, c.ev_read, 0));
     c.read_pending = false;
@@ -419,6 +450,7 @@ inline void set_nonuni(dang_gpu *h, int c, int k, int l, int val) {
 }
 
 inline bool comp_uniform(const dang_gpu *h, int c, int k) { return h->uni_host[c * 3 + k] != 0; }
+inline void idx_changed(dang_gpu *h) { h->idx_epoch++; }  // an index map / band / component constant changed outside a full-sky draw
 
 // ---------------------------------------------------------------- entry points of the other translation units
 void cg_solve(dang_gpu *h, int cg_group, int flag_n, int ml_mode, const double *eta, uint64_t seed,

@@ -193,9 +193,13 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     int64_t n2v = n2;
     PeerComm pcv = h->peer;
     void *args[] = {&st, &Mp, &xp, &rp, &dp, &n2v, &part, &tick, &outp, &pcv, &gath, &ao, &k_pred};
+    // deferred amplitude downloads (host.cuh): they start when this solve starts -- the event fires once K1 is done --
+    // and read the buffers swapped out above while the solve writes the fresh ones
+    if (!h->deferred.empty()) CK(cudaEventRecord(h->ev_compute, h->stream));
     KTimer kt(h, DANG_K_CG_PASS, 0, true);
     CK(cudaLaunchCooperativeKernel((void *)cg_solve_kernel<C>, dim3((unsigned)cgrid), dim3(DG_THREADS), args, cg_smem, h->stream));
     kt.done();
+    if (!h->deferred.empty()) issue_deferred_d2h(h, h->ev_compute);
     // The scalars come back right behind the solve and the host waits for that point of the stream only.  When this
     // is the run's only solve per Gibbs iteration and a full-sky draw follows, the draw's statistics pass (which
     // also serves the chi-square printed after the amplitude draw) is enqueued first, so the device keeps
@@ -231,6 +235,10 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     return;
   }
 
+  if (!h->deferred.empty()) {  // pass-per-launch forms: no long launch to hide a bulk copy behind, start it now
+    CK(cudaEventRecord(h->ev_compute, h->stream));
+    issue_deferred_d2h(h, h->ev_compute);
+  }
   const int fold = (h->nranks == 1 || h->use_mail) ? 1 : 0;
   const int grid = grid_for(h, n2, DG_THREADS, DG_CG_BLOCKS_PER_SM);  // the same grid for every form (bit-equal sums)
   const double el = (double)vs;

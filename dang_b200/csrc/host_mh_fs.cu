@@ -62,17 +62,24 @@ namespace {
 // chain start (sample <- indices at global pixel 0) + sufficient statistics, gathered over ranks
 int fullsky_statistics(dang_gpu *h, const ModelView &mv, MhView &mh) {
   CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
-  {
-    KTimer kt(h, DANG_K_SCALAR, 0);
-    mh_first_pixel_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->sums_local);
-    kt.done();
+  // chain start: sample <- indices at global pixel 0, broadcast, SED at the start -- unless the previous draw of
+  // this very index left all of that on the device (chain continuity, host.cuh)
+  const bool cont = !h->fullsky_stream && h->fs_cont_valid && h->fs_cont_ic == mh.ic && h->fs_cont_nind == mh.nind &&
+                    h->fs_cont_S == mh.S && h->fs_cont_plane0 == mh.plane[0] && h->fs_cont_epoch == h->idx_epoch;
+  if (!cont) {
+    {
+      KTimer kt(h, DANG_K_SCALAR, 0);
+      mh_first_pixel_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->sums_local);
+      kt.done();
+    }
+    gather(h, 2);
+    {
+      KTimer kt(h, DANG_K_SCALAR, 0);
+      mh_fullsky_init_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, 2);
+      kt.done();
+    }
   }
-  gather(h, 2);
-  {
-    KTimer kt(h, DANG_K_SCALAR, 0);
-    mh_fullsky_init_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, 2);
-    kt.done();
-  }
+  h->fs_cont_valid = false;  // (re-armed by the draw that consumes these statistics)
   if (h->fullsky_stream) return 0;
   const double n_el = (double)mh.S * h->P;
   const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
@@ -159,7 +166,18 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
   ModelView mv = model_view(h);
   mh.seed = seed;
   const size_t n = (size_t)mh.nsample;
-  upload_fullsky_deviates(h, mh, z, u, n);
+  // short chains on the statistics form take their injected deviates as a kernel argument (no copy-engine work)
+  static thread_local FsDeviates dev;
+  dev.n = 0;
+  if (z && !h->fullsky_stream && n > 0 && n <= DG_FS_DEV_MAX && (u || mh.ml_mode != DANG_ML_SAMPLE)) {
+    dev.n = (int)n;
+    for (size_t i = 0; i < n; i++) {
+      dev.z[i] = z[i];
+      dev.u[i] = u ? u[i] : 0.0;
+    }
+  } else {
+    upload_fullsky_deviates(h, mh, z, u, n);
+  }
   ensure_decisions(h, n > 0 ? n : 1);
   CK(cudaMemsetAsync(h->decisions, 3, n, h->stream));
   CK(cudaMemsetAsync(h->lnl_trace, 0xff, n * sizeof(double), h->stream));
@@ -170,6 +188,7 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
 
   // statistics gathered by the chi-square call that preceded this draw are still valid when the
   // model state has not changed since (same chain start, same data)
+  h->fs_tab_written = false;
   const bool reuse = !h->fullsky_stream && stat_cache_hit(h, mh);
   const int cnt = reuse ? h->stat_cnt : fullsky_statistics(h, mv, mh);
   const double n_el = (double)mh.S * h->P;
@@ -210,9 +229,22 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
       ks.done();
     }
   } else {
+    // planes already tabulated (constant index maps) and no per-plane factor in the SED: the chain kernel refreshes
+    // the table entry itself and leaves the next chain's start behind
+    bool keep = h->comp[mh.ic].type != DANG_COMP_HI_FIT && !h->record;
+    for (int s = 0; s < mh.S; s++) keep = keep && comp_uniform(h, mh.ic, mh.plane[s]) && !h->tab_dirty;
     KTimer ks(h, DANG_K_SCALAR, 0);
-    mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->stat_buf, h->nranks, cnt);
+    mh_suff_chain_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->stat_buf, h->nranks, cnt, keep ? h->tab : nullptr, dev);
     ks.done();
+    h->fs_tab_written = keep;
+    if (keep) {
+      h->fs_cont_valid = true;
+      h->fs_cont_ic = mh.ic;
+      h->fs_cont_nind = mh.nind;
+      h->fs_cont_S = mh.S;
+      h->fs_cont_plane0 = mh.plane[0];
+      h->fs_cont_epoch = h->idx_epoch;
+    }
   }
   // The chain's results go back first and the host waits for THAT point of the stream only; the kernel that
   // writes the final sample into the index planes (:329, :483) runs while the host is already enqueuing the

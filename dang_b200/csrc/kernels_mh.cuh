@@ -733,9 +733,32 @@ mh_suffstat_kernel(const ModelView mv, const MhView mh, const MhScalars *ms, dou
 // The whole full-sky chain from the statistics (:282-324), no map traffic.  One warp: lane j owns
 // band j (its statistics, s0 and the proposal's SED), lnL is a fixed-order butterfly over lanes;
 // every lane carries the same chain state, lane 0 publishes it.
+// tab_out != nullptr: the component's planes were tabulated already (constant index maps) and stay so, and the
+// next full-sky draw of this index starts where this one ends: the kernel leaves the SED of the final sample in the
+// table (the very value sed_table_kernel would compute) and in ms->s0, so that neither the table kernel nor the
+// chain-start kernels (first pixel, gather, init) have to run before the next statistics pass.
+// Injected deviates of a short chain travel as a kernel ARGUMENT (FsDeviates), not through a host-to-device copy:
+// a cudaMemcpyAsync of 160 bytes on the compute stream queues on a copy engine behind whatever bulk download is
+// running and stalls the whole spectral-parameter block for hundreds of microseconds (profiles/r02_timeline_*).
+#define DG_FS_DEV_MAX 128
+struct FsDeviates {
+  int n;  // 0: not used (device RNG, or the deviates sit in device buffers mh.z / mh.u)
+  double z[DG_FS_DEV_MAX], u[DG_FS_DEV_MAX];
+};
 static __global__ void __launch_bounds__(32)
-mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const double *gathered,
-                     int nranks, int cnt) {
+mh_suff_chain_kernel(const ModelView mv, const MhView mh_in, MhScalars *ms, const double *gathered,
+                     int nranks, int cnt, SedTable *tab_out, const FsDeviates dev) {
+  __shared__ double sz[DG_FS_DEV_MAX], su[DG_FS_DEV_MAX];
+  MhView mh = mh_in;
+  if (dev.n > 0) {
+    for (int i = threadIdx.x; i < dev.n; i += 32) {
+      sz[i] = dev.z[i];
+      su[i] = dev.u[i];
+    }
+    __syncwarp();
+    mh.z = sz;
+    mh.u = su;
+  }
   const int B = mv.nbands, j = threadIdx.x;
   double X = 0.0, Y = 0.0, Z = 0.0, s0 = 0.0;
   double Xk[2] = {0.0, 0.0}, Yk[2] = {0.0, 0.0}, Zk[2] = {0.0, 0.0};  // per plane, summed over ranks in rank order
@@ -817,6 +840,11 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
   double chi[2] = {0.0, 0.0};
   {
     const double sed = sed_of(sample[0], sample[1]);
+    if (tab_out && j < B) {
+      for (int s = 0; s < mh.S; s++) tab_out->sed[mh.ic * 3 + mh.plane[s]][j] = sed;
+      ms->s0[j] = sed;
+      ms->sed[j] = sed;
+    }
     const double dl = sed - s0;
 #pragma unroll
     for (int s = 0; s < 2; s++) {
@@ -829,6 +857,8 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh, MhScalars *ms, const d
   if (j == 0) {
     ms->sample[0] = sample[0];
     ms->sample[1] = sample[1];
+    ms->theta[0] = sample[0];
+    ms->theta[1] = sample[1];
     ms->lnl_old = lnl_old;
     ms->accept = accept;
     ms->l = mh.nsample;

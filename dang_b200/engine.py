@@ -35,6 +35,7 @@ OPT_PERPIXEL_BP_SERIES = 13
 OPT_BP_QUADRATURE = 14
 OPT_CG_PERSISTENT = 15
 OPT_STREAM_RING = 16
+OPT_DEFER_D2H = 17
 KERNEL_COUNT = 12
 
 

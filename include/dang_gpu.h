@@ -126,7 +126,13 @@ enum {
    * full-sky sufficient statistics) prefetch through per-thread three-stage cp.async rings in shared memory, two band
    * batches ahead of the arithmetic (csrc/kernels_stream.cuh); 0: the 16-byte LDG forms (csrc/kernels_uni.cuh).
    * Same arithmetic; sums agree to rounding (the grid sizes differ). */
-  DANG_OPT_STREAM_RING = 16
+  DANG_OPT_STREAM_RING = 16,
+  /* 1 (default): dang_gpu_get_amplitude_async records the request and the NEXT amplitude draw issues the copy right
+   * behind its solve kernel (from the buffer it swapped out), so the bulk transfer overlaps one long launch instead of
+   * the launch-heavy spectral-parameter block: a saturated host link delays the GPU's command fetches, which makes
+   * every small kernel behind it cost 50-70 us (profiles/).  dang_gpu_download_wait and in-place writers issue pending
+   * requests at once.  0: the copy starts as soon as the compute stream reaches the request. */
+  DANG_OPT_DEFER_D2H = 17
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
@@ -150,6 +156,9 @@ int dang_gpu_comm_init(dang_gpu_t *h, int nranks, int rank, const char id[128]);
 int dang_gpu_comm_ipc_handle(dang_gpu_t *h, char handle[64]);
 int dang_gpu_comm_open_peers(dang_gpu_t *h, const char *handles);
 int dang_gpu_comm_check(dang_gpu_t *h);
+/* instrumentation: latency of one in-kernel scalar exchange of `cnt` doubles (1..32) between all ranks over the NVLink
+ * mailboxes, averaged over `reps` back-to-back exchanges by one warp (every rank must call it) */
+int dang_gpu_comm_probe(dang_gpu_t *h, int reps, int cnt, double *us_per_exchange);
 
 /* ---- bp(j): type bandinfo, src/dang_bp_mod.f90:7-15 (as left by init_bp_mod :19-60) ----
  * nu_c [Hz]; n_bp == 0 <=> bp%id == 'delta'; nu0 [Hz]; tau0 already normalised (:62-81). */

@@ -117,7 +117,7 @@ def test_fortran_shim_binds_the_declared_abi():
     instrumentation = {"dang_gpu_cg_trace", "dang_gpu_get_cg_x", "dang_gpu_get_decisions", "dang_gpu_event_record",
                        "dang_gpu_event_elapsed_ms", "dang_gpu_launch_count", "dang_gpu_kernel_stats",
                        "dang_gpu_kernel_name", "dang_gpu_perpixel_stats", "dang_gpu_share_maps",
-                       "dang_gpu_bandpass_quadrature", "dang_gpu_timeline"}
+                       "dang_gpu_bandpass_quadrature", "dang_gpu_timeline", "dang_gpu_comm_probe"}
     assert declared - bound <= instrumentation, (declared - bound) - instrumentation
 
 
