@@ -114,6 +114,10 @@ struct MhView {
   uint64_t seed;
   unsigned char *decisions;   // optional instrumentation
   double *lnl_trace;
+  // device RNG of the full-sky chain kernels: Philox stream ids (0: the draw's own, DG_STREAM_MH_Z / _U) and the
+  // slot of proposal 0 -- the step-size tuner numbers its proposals blk * nsample + l on its own streams
+  int rng_z_stream, rng_u_stream;
+  long long rng_slot0;
 };
 
 struct MhScalars {

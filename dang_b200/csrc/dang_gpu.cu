@@ -1005,7 +1005,35 @@ int dang_gpu_tune_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsample,
   if (nsample < 0) fail(DANG_GPU_EINVAL, "nsample = %d", nsample);
   MhView mh;
   mh_view(h, ic, nind, map_n, nsample, ml_mode, mh);
-  tune_fullsky(h, ic, nind, mh, z, u, seed, max_blocks, blocks_run, step_size);
+  double start[DG_MAXIND] = {0.0, 0.0};
+  const bool perpix = h->comp[ic].index[nind].index_mode == DANG_INDEX_PERPIXEL;
+  if (perpix) {
+    // the per-pixel call site (src/dang_sample_mod.f90:341-347) starts the tuner at
+    // sample(l) = sum(c%indices(:, map_inds(1), l)) / sum(mask(:,1)) -- the sum runs over EVERY pixel -- and calls it
+    // inside the loop over l, i.e. with the later indices still 0: only single-index components survive that
+    if (h->comp[ic].nind != 1)
+      fail(DANG_GPU_EUNSUPPORTED, "per-pixel step-size tuning of a component with %d indices: the reference calls the tuner "
+                                  "with the other index still 0 (src/dang_sample_mod.f90:343-346), which never terminates",
+           h->comp[ic].nind);
+    model_view(h);
+    const int64_t n_unmasked = unmasked_count(h);
+    CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    {
+      KTimer kt(h, DANG_K_SCALAR, 0);
+      masked_sum_kernel<<<grid, DG_THREADS, 0, h->stream>>>(h->comp[ic].idx[nind] + (size_t)mh.plane[0] * h->Ppad, nullptr, h->P,
+                                                            h->partials, h->tickets, h->sums_local);
+      kt.done();
+    }
+    gather(h, 4);
+    double *hp = (double *)h->pinned;
+    readback(h, hp, h->gathered, (size_t)h->nranks * 4 * sizeof(double));
+    CK(cudaStreamSynchronize(h->stream));
+    double sum = 0.0;
+    for (int g = 0; g < h->nranks; g++) sum += hp[g * 4];
+    start[0] = sum / (double)n_unmasked;
+  }
+  tune_fullsky(h, ic, nind, mh, z, u, seed, max_blocks, blocks_run, step_size, perpix ? start : nullptr);
   API_END
 }
 

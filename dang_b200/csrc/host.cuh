@@ -479,4 +479,4 @@ void launch_perpixel_fast(dang_gpu *h, const ModelView &mv, const MhView &mh, in
 void launch_perpixel_split(dang_gpu *h, const ModelView &mv, MhView &mh, int bpl, int mode, int64_t work);  // host_mh_ppf.cu
 void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);   // host_mh_fs.cu
 void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
-                  int max_blocks, int *blocks_run, double *step_size);             // host_mh_fs.cu
+                  int max_blocks, int *blocks_run, double *step_size, const double *start);  // host_mh_fs.cu

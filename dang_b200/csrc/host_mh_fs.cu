@@ -348,34 +348,109 @@ bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]) 
   return true;
 }
 
+// tune_spectral_parameter_length, src/dang_sample_mod.f90:623-717.  `start`: the chain start when the call site gives
+// one (per-pixel indices: the map's mean, :341-347), else indices(0, map_inds(1), :) (:240-243).  The chisq likelihood
+// runs on the sufficient statistics (one pass over the maps, all blocks in one kernel); the marginal likelihood
+// (:650-651, :676-677) streams the maps once per proposal like the draw itself, one host round trip per block.
 void tune_fullsky(dang_gpu *h, int ic, int nind, MhView &mh, const double *z, const double *u, uint64_t seed,
-                  int max_blocks, int *blocks_run, double *step_size) {
-  if (fullsky_needs_stream(mh))
-    fail(DANG_GPU_EUNSUPPORTED, "the step-size tuner is built for the chisq likelihood with uniform / Gaussian prior");
+                  int max_blocks, int *blocks_run, double *step_size, const double *start) {
+  if (mh.prior_type == DANG_PRIOR_JEFFREYS || mh.lnl_type == DANG_LNL_PRIOR)
+    fail(DANG_GPU_EUNSUPPORTED, "the step-size tuner covers the chisq / marginal likelihoods with uniform / Gaussian prior "
+                                "(the reference's tuner has no other branch, src/dang_sample_mod.f90:650-662)");
   if (max_blocks < 0) fail(DANG_GPU_EINVAL, "max_blocks = %d", max_blocks);
   ModelView mv = model_view(h);
   mh.seed = seed;
+  mh.rng_z_stream = DG_STREAM_TUNE_Z;
+  mh.rng_u_stream = DG_STREAM_TUNE_U;
   upload_fullsky_deviates(h, mh, z, u, (size_t)mh.nsample * max_blocks);
+  const bool stream = mh.lnl_type == DANG_LNL_MARGINAL;
   const int saved_stream = h->fullsky_stream;
-  h->fullsky_stream = 0;  // the tuner always runs on the sufficient statistics
-  int cnt = 0;
-  try {
-    cnt = fullsky_statistics(h, mv, mh);
-  } catch (...) {
-    h->fullsky_stream = saved_stream;
-    throw;
+  struct Restore {
+    dang_gpu *h; int v;
+    ~Restore() { h->fullsky_stream = v; }
+  } restore{h, saved_stream};
+  h->fs_cont_valid = false;
+  if (start) {  // the start is not what the maps hold at pixel 0: set it, then gather the statistics about it
+    h->fullsky_stream = 1;  // (chain-start kernels only)
+    fullsky_statistics(h, mv, mh);
+    mh_fullsky_override_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, start[0], start[1]);
+    CK(cudaGetLastError());
+    h->launches++;
   }
-  h->fullsky_stream = saved_stream;
-  double *d_out = h->sums_local + GATHER_MAX - 4;  // scratch beyond the statistics rows
+  if (!stream) {
+    h->fullsky_stream = 0;  // the tuner runs on the sufficient statistics
+    if (start) h->fs_cont_valid = true, h->fs_cont_ic = mh.ic, h->fs_cont_nind = mh.nind, h->fs_cont_S = mh.S,
+               h->fs_cont_plane0 = mh.plane[0], h->fs_cont_epoch = h->idx_epoch;  // keep the overridden start
+    const int cnt = fullsky_statistics(h, mv, mh);
+    h->fs_cont_valid = false;
+    h->stat_valid = false;  // (statistics about a start that is not the maps' state must not serve a chi-square)
+    double *d_out = h->sums_local + GATHER_MAX - 4;  // scratch beyond the statistics rows
+    {
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      mh_suff_tune_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->stat_buf, h->nranks, cnt, max_blocks, d_out);
+      ks.done();
+    }
+    double *hp = (double *)h->pinned;
+    readback(h, hp, d_out, 3 * sizeof(double));
+    CK(cudaStreamSynchronize(h->stream));
+    h->comp[ic].index[nind].step = hp[0];  // c%step_size(nind), :708-710
+    if (blocks_run) *blocks_run = (int)hp[1];
+    if (step_size) *step_size = hp[0];
+    return;
+  }
+  // ---- streaming form (marginal likelihood)
+  h->fullsky_stream = 1;
+  if (!start) fullsky_statistics(h, mv, mh);  // chain start from the maps
+  const double n_el = (double)mh.S * h->P;
+  const size_t dl = (size_t)h->nbands * mh.S * h->Ppad;
+  ensure(h->D, h->D_len, dl);
+  const int grid = grid_for(h, h->P, DG_THREADS, 4);
   {
-    KTimer ks(h, DANG_K_SCALAR, 0);
-    mh_suff_tune_kernel<<<1, 32, 0, h->stream>>>(mv, mh, h->mh_scalars, h->stat_buf, h->nranks, cnt, max_blocks, d_out);
-    ks.done();
+    KTimer kt(h, DANG_K_MH_DATA, bytes_w(n_el * (2.0 * h->nbands + h->ncomp * 2.0)));
+    mh_data_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->D);
+    kt.done();
   }
-  double *hp = (double *)h->pinned;
-  readback(h, hp, d_out, 3 * sizeof(double));
-  CK(cudaStreamSynchronize(h->stream));
-  h->comp[ic].index[nind].step = hp[0];  // c%step_size(nind), :708-710
-  if (blocks_run) *blocks_run = (int)hp[1];
-  if (step_size) *step_size = hp[0];
+  const int nchunk = (h->nbands + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
+  const int cnt = 2 + 4 * DG_SUFF_CHUNK * nchunk;
+  if (cnt > GATHER_MAX) fail(DANG_GPU_EUNSUPPORTED, "full-sky marginal lnL with %d bands", h->nbands);
+  mh.decisions = nullptr;
+  mh.lnl_trace = nullptr;
+  const double *z0 = mh.z, *u0 = mh.u;
+  auto lnl_pass = [&]() {  // lnL of ms->sed (the start, or the pending proposal), then accept / reject + next proposal
+    CK(cudaMemsetAsync(h->sums_local, 0, GATHER_MAX * sizeof(double), h->stream));
+    KTimer kt(h, DANG_K_MH_FULLSKY_LNL, bytes_w(n_el * (2.0 * h->nbands + 1)));
+    mh_fullsky_marginal_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars, h->D, h->partials, h->tickets, h->sums_local);
+    kt.done();
+    gather(h, cnt);
+    KTimer ks(h, DANG_K_SCALAR, 0);
+    mh_fullsky_step_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars, h->gathered, h->nranks, cnt);
+    ks.done();
+  };
+  double step = mh.step;
+  int blk = 0, tuned = 0;
+  MhScalars *hs = (MhScalars *)h->pinned;
+  while (!tuned && blk < max_blocks) {
+    mh.step = step;
+    mh.rng_slot0 = (long long)blk * mh.nsample;
+    mh.z = z0 ? z0 + (size_t)blk * mh.nsample : nullptr;
+    mh.u = u0 ? u0 + (size_t)blk * mh.nsample : nullptr;
+    if (blk == 0) {
+      lnl_pass();  // phase 0: lnL of the start (:647-662); proposes the first candidate of block 0
+    } else {
+      KTimer ks(h, DANG_K_SCALAR, 0);
+      mh_tune_block_start_kernel<<<1, 1, 0, h->stream>>>(mv, mh, h->mh_scalars);
+      ks.done();
+    }
+    for (int l = 0; l < mh.nsample; l++) lnl_pass();  // passes behind the block's last proposal return at once (ms->skip)
+    readback(h, hs, h->mh_scalars, sizeof(MhScalars));
+    CK(cudaStreamSynchronize(h->stream));
+    const double rate = hs->accept / (double)(mh.nsample + 1);  // Fortran loop counter after the loop (:707)
+    if (rate < (double)0.4f) step = step - (double)0.5f * step;
+    else if (rate > (double)0.6f) step = step + (double)0.5f * step;
+    else tuned = 1;
+    blk++;
+  }
+  h->comp[ic].index[nind].step = step;
+  if (blocks_run) *blocks_run = blk;
+  if (step_size) *step_size = step;
 }

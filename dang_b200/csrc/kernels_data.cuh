@@ -98,7 +98,7 @@ masked_sum_kernel(const double *map, const unsigned char *mask, int64_t P, doubl
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride)
-    if (mask[p]) {
+    if (!mask || mask[p]) {  // (mask == nullptr: the plain sum over every pixel)
       acc[0] += map[p];
       acc[1] += 1.0;
     }

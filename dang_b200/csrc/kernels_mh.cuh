@@ -503,12 +503,15 @@ static __global__ void mh_first_pixel_kernel(const ModelView mv, const MhView mh
 }
 
 __device__ __forceinline__ double mh_draw_z(const MhView &mh, int l) {
-  return mh.z ? mh.z[l] : philox_normal(mh.seed, DG_STREAM_MH_Z, (uint64_t)l);
+  return mh.z ? mh.z[l]
+              : philox_normal(mh.seed, mh.rng_z_stream ? (uint32_t)mh.rng_z_stream : (uint32_t)DG_STREAM_MH_Z,
+                              (uint64_t)(mh.rng_slot0 + l));
 }
 __device__ __forceinline__ double mh_draw_u(const MhView &mh, int l) {
   if (mh.u) return mh.u[l];
   double u1, u2;
-  philox_uniform2(mh.seed, DG_STREAM_MH_U, (uint64_t)l, u1, u2);
+  philox_uniform2(mh.seed, mh.rng_u_stream ? (uint32_t)mh.rng_u_stream : (uint32_t)DG_STREAM_MH_U,
+                  (uint64_t)(mh.rng_slot0 + l), u1, u2);
   return u1;
 }
 
@@ -580,6 +583,26 @@ static __global__ void mh_fullsky_step_kernel(const ModelView mv, const MhView m
   } else {
     mh_accept_step(mh, ms, lnl, prior);
   }
+  mh_next_proposal(mv, mh, ms);
+}
+
+// step-size tuner, streaming form: the chain start given explicitly (the per-pixel call site starts the tuner at
+// the map's mean, src/dang_sample_mod.f90:341-347) ...
+static __global__ void mh_fullsky_override_kernel(const ModelView mv, const MhView mh, MhScalars *ms, double t0, double t1) {
+  ms->sample[0] = ms->theta[0] = t0;
+  ms->sample[1] = ms->theta[1] = t1;
+  for (int j = 0; j < mv.nbands; j++) {
+    const double s = sed_theta(mv, mh.ic, j, t0, t1, mh.plane[0]);
+    ms->sed[j] = s;
+    ms->s0[j] = s;
+  }
+}
+// ... and the start of the next block of nsample proposals: the chain goes on (sample, lnl_old stay), the
+// acceptance count restarts (:664-665)
+static __global__ void mh_tune_block_start_kernel(const ModelView mv, const MhView mh, MhScalars *ms) {
+  ms->accept = 0.0;
+  ms->l = 0;
+  ms->skip = 0;
   mh_next_proposal(mv, mh, ms);
 }
 

@@ -82,6 +82,9 @@ class Engine:
             self.h = None
             raise DangGpuError(f"dang_gpu_create failed (rc={rc}): {msg}")
         self.nranks, self.rank = 1, 0
+        # c%tuned(j) = .not. fg_spec_tune (src/dang_component_mod.f90:177): untuned indices are tuned by the first
+        # sample_index_mh that meets them, and the tuner then marks ALL of the component's indices tuned (:711)
+        self._tuned = [[not s.tune for s in c.indices] for c in cfg.comps]
         # init_bp_mod
         for j, b in enumerate(cfg.bands):
             nu_c, nu0, tau0 = init_bandpass(b)
@@ -324,6 +327,12 @@ class Engine:
                     else:
                         zz = None if z is None else z[stride * ncall: stride * (ncall + 1)]
                         uu = None if u is None else u[stride * ncall: stride * (ncall + 1)]
+                    if not self._tuned[ic][j] and s.lnl_type != "prior":
+                        # sample_index_mh: `if (.not. c%tuned(nind))` -> tune_spectral_parameter_length first
+                        # (src/dang_sample_mod.f90:270-273 full sky, :341-347 per pixel); device deviates
+                        self.tune_index(ic, j, flag_to_map_n(flag), nsample, ml_mode, seed=seed + 104729 * (ncall + 1),
+                                        max_blocks=1000)
+                        self._tuned[ic] = [True] * len(c.indices)
                     acc.append(self.sample_index_mh(ic, j, flag_to_map_n(flag), nsample, ml_mode, zz, uu,
                                                     seed + 7919 * ncall))
                     ncall += 1

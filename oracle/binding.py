@@ -83,6 +83,8 @@ def load(omp: bool = False) -> C.CDLL:
         "ora_sample_index_mh": (i, [vp, i, i, i, i, i, c_dp, c_dp, c_dp, C.POINTER(C.c_ubyte), c_dp]),
         "ora_sample_spectral_parameters": (i, [vp, i, i, c_dp, c_dp]),
         "ora_tune_step": (i, [vp, i, i, i, i, i, c_dp, c_dp, i]),
+        "ora_tune_step_from": (i, [vp, i, i, i, i, i, c_dp, c_dp, i, c_dp]),
+        "ora_perpixel_tune_start": (None, [vp, i, i, i, c_dp]),
         "ora_fit_band_gain": (d, [vp, i, i, i, d]),
         "ora_philox_uniform2": (None, [C.c_ulonglong, C.c_uint, C.c_ulonglong, c_dp, c_dp]),
         "ora_philox_normals": (None, [C.c_ulonglong, C.c_uint, C.c_ulonglong, ll, c_dp]),
@@ -275,11 +277,16 @@ class Oracle:
     def fit_band_gain(self, map_n, band, ml_mode, z):
         return self.lib.ora_fit_band_gain(self.st, map_n, band, ml_mode, z)
 
-    def tune_step(self, ic, nind, map_n, nsample, ml_mode, z, u, max_blocks):
+    def tune_step(self, ic, nind, map_n, nsample, ml_mode, z, u, max_blocks, perpixel_start=False):
+        """tune_spectral_parameter_length; perpixel_start: start at the map's mean as the per-pixel call site does."""
         z = np.ascontiguousarray(z, dtype=np.float64)
         u = np.ascontiguousarray(u, dtype=np.float64)
-        nb = self.lib.ora_tune_step(self.st, ic, nind, map_n, nsample, ml_mode, _dp(z), _dp(u),
-                                    max_blocks)
+        th = None
+        if perpixel_start:
+            th = np.zeros(2)
+            self.lib.ora_perpixel_tune_start(self.st, ic, nind, map_n, _dp(th))
+        nb = self.lib.ora_tune_step_from(self.st, ic, nind, map_n, nsample, ml_mode, _dp(z), _dp(u),
+                                         max_blocks, _dp(th))
         return nb, self.lib.ora_step_size(self.st, ic, nind)
 
 

@@ -1414,8 +1414,31 @@ int ora_sample_spectral_parameters(ora_state *st, int nsample, int ml_mode, cons
 
 /* tune_spectral_parameter_length, src/dang_sample_mod.f90:623-717 (full-sky chain started at
  * indices(0, map_inds(1), :), the full-sky call site :272-275) */
+int ora_tune_step_from(ora_state *st, int ic, int nind, int map_n, int nsample, int ml_mode, const double *z,
+                       const double *u, int max_blocks, const double *theta_init);
 int ora_tune_step(ora_state *st, int ic, int nind, int map_n, int nsample, int ml_mode,
                   const double *z, const double *u, int max_blocks) {
+  return ora_tune_step_from(st, ic, nind, map_n, nsample, ml_mode, z, u, max_blocks, NULL);
+}
+/* the per-pixel call site's start, src/dang_sample_mod.f90:341-347: sample(l) = sum(c%indices(:,map_inds(1),l)) /
+ * sum(mask(:,1)) -- the numerator runs over EVERY pixel; the tuner is called inside the loop over l, so for
+ * l = 1 the later entries of sample are still 0 (returned here for l = nind only, the others 0) */
+void ora_perpixel_tune_start(const ora_state *st, int ic, int nind, int map_n, double *theta_init) {
+  const ora_comp *c = &st->comp[ic];
+  const size_t n2 = (size_t)st->npix * st->nmaps;
+  int map_inds[2];
+  set_map_inds(map_n, map_inds);
+  double num = 0.0, den = 0.0;
+  for (int i = 0; i < st->npix; i++) {
+    num += c->indices[n2 * nind + IDX2(st, i, map_inds[0] - 1)];
+    den += st->masks[i];
+  }
+  for (int l = 0; l < ORA_MAXIND; l++) theta_init[l] = 0.0;
+  theta_init[nind] = num / den;
+}
+/* theta_init: the tuner's start (theta_init argument of :623); NULL = indices(0, map_inds(1), :) (:240-243) */
+int ora_tune_step_from(ora_state *st, int ic, int nind, int map_n, int nsample, int ml_mode, const double *z,
+                       const double *u, int max_blocks, const double *theta_init) {
   ora_comp *c = &st->comp[ic];
   const size_t n2 = (size_t)st->npix * st->nmaps;
   int map_inds[2];
@@ -1425,7 +1448,7 @@ int ora_tune_step(ora_state *st, int ic, int nind, int map_n, int nsample, int m
   double sample[ORA_MAXIND] = {0, 0}, theta[ORA_MAXIND] = {0, 0};
   double lnl = 0.0, lnl_new = 0.0, lnl_old = 0.0;
   for (int l = 0; l < c->nindices; l++)
-    sample[l] = theta[l] = c->indices[n2 * l + IDX2(st, 0, map_inds[0] - 1)];
+    sample[l] = theta[l] = theta_init ? theta_init[l] : c->indices[n2 * l + IDX2(st, 0, map_inds[0] - 1)];
   update_sample_model(st, model, c, map_inds, sample, -1);
   lnl = lnl_dispatch(st, c->lnl_type[nind], data, model, map_inds, -1, lnl);
   if (c->prior_type[nind] == ORA_PRIOR_GAUSSIAN)

@@ -161,6 +161,9 @@ void ora_philox_uniforms(unsigned long long seed, unsigned int stream, unsigned 
                          long n, double *u);
 
 int ora_num_threads(void);
+int ora_tune_step_from(ora_state *st, int ic, int nind, int map_n, int nsample, int ml_mode, const double *z,
+                       const double *u, int max_blocks, const double *theta_init);
+void ora_perpixel_tune_start(const ora_state *st, int ic, int nind, int map_n, double *theta_init);
 double ora_get_T_CMB(void);
 void ora_set_T_CMB(double t);
 double *ora_offset(ora_state *st);

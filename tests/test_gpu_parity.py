@@ -873,3 +873,133 @@ def test_errors_are_loud_and_specific():
     assert lib.dang_gpu_chisq(h, 2, 3, planes, C.byref(n)) == 5
     assert b"upload_maps" in lib.dang_gpu_last_error(h)
     lib.dang_gpu_destroy(h)
+
+
+# ------------------------------------------------------------------ round-2 additions (VERDICT r1 "missing" 4, "weak" 12)
+def test_step_size_tuner_marginal_likelihood():
+    """tune_spectral_parameter_length with lnl_type 'marginal' (src/dang_sample_mod.f90:650-651, 676-677): the
+    streaming tuner runs the same blocks and lands on the same step as the oracle."""
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c2", 8, perturb=False)
+    rng = np.random.default_rng(17)
+    for c in cfg.comps:  # non-zero amplitudes: the marginal likelihood divides by sum(TN * model)
+        sky.amplitude[c.label][1:3] = sky.truth[c.label][1:3] * (1.0 + 0.05 * rng.standard_normal((2, cfg.npix)))
+    spec = cfg.comps[1].indices[0]
+    spec.lnl_type, spec.tune = "marginal", True
+    nsample, max_blocks = 10, 6
+    for step0 in (0.3, 0.002):
+        spec.step = step0
+        ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+        z, u = rng.standard_normal(nsample * max_blocks), rng.random(nsample * max_blocks)
+        nb_o, step_o = ora.tune_step(1, 0, -1, nsample, 1, z, u, max_blocks)
+        nb_g, step_g = eng.tune_index(1, 0, -1, nsample, "sample", z, u, max_blocks=max_blocks)
+        assert nb_g == nb_o and nb_o >= 1 and step_g == step_o, (step0, nb_g, nb_o, step_g, step_o)
+
+
+def test_step_size_tuner_starts_a_per_pixel_index_at_the_map_mean():
+    """The per-pixel call site (src/dang_sample_mod.f90:341-347) starts the tuner at sum(indices) / sum(mask)."""
+    from dang_b200.engine import DangGpuError, Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c1", 8)
+    spec = cfg.comps[0].indices[0]
+    spec.tune, spec.step = True, 0.4
+    nsample, max_blocks = 12, 8
+    ora, eng = Oracle(cfg, sky), Engine(cfg, sky)
+    rng = np.random.default_rng(23)
+    z, u = rng.standard_normal(nsample * max_blocks), rng.random(nsample * max_blocks)
+    nb_o, step_o = ora.tune_step(0, 0, -1, nsample, 1, z, u, max_blocks, perpixel_start=True)
+    nb_g, step_g = eng.tune_index(0, 0, -1, nsample, "sample", z, u, max_blocks=max_blocks)
+    assert nb_g == nb_o and step_g == step_o and step_g != 0.4, (nb_g, nb_o, step_g, step_o)
+    # a two-index component cannot be tuned per pixel (the reference calls the tuner with T = 0)
+    cfg2, sky2 = small_case("c4", 4)
+    cfg2.comps[1].indices[0].region = "per-pixel"
+    with pytest.raises(DangGpuError, match="never terminates"):
+        Engine(cfg2, sky2).tune_index(1, 0, -1, 4, "sample", z, u, max_blocks=2)
+
+
+def test_gibbs_loop_tunes_an_untuned_index_once():
+    """Engine.sample_spectral_parameters mirrors sample_index_mh: `.not. c%tuned` -> tune first, then draw; once."""
+    from dang_b200.engine import Engine
+    cfg, sky = small_case("c2", 8, perturb=False)
+    spec = cfg.comps[1].indices[0]
+    spec.tune, spec.step = True, 0.5
+    eng = Engine(cfg, sky)
+    eng.sample_cg_groups(seed=1)
+    eng.sample_spectral_parameters(seed=2)
+    step1 = eng.lib.dang_gpu_get_step_size
+    import ctypes as C
+    v = C.c_double()
+    eng._ck(step1(eng.h, 1, 0, C.byref(v)))
+    assert v.value < 0.5 and eng._tuned[1] == [True, True]
+    s_after = v.value
+    eng.sample_spectral_parameters(seed=3)
+    eng._ck(step1(eng.h, 1, 0, C.byref(v)))
+    assert v.value == s_after
+
+
+def test_perpixel_jeffreys_prior():
+    """eval_jeffreys_prior (src/dang_lnl_mod.f90:242-304, label 'synch' only) in the per-pixel chains."""
+    cfg, sky = small_case("c1", 8)
+    cfg.comps[0].indices[0].prior = "jeffreys"
+    ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(cfg, sky, 0, 0, 10)
+    assert np.array_equal(dec_g, dec_o) and acc_g == acc_o
+    ev = dec_o < 2
+    assert 0 < (dec_o == 1).sum() < ev.sum()
+    assert rel_err(lnl_g[ev], lnl_o[ev]) < TOL
+    assert rel_err(eng.indices(0), ora.indices(0)) < 1e-14
+
+
+def test_reupload_after_cg_swap():
+    """swap_cg_maps (src/dang.f90:92-97, dang_data_mod.f90:179-227) replaces sig / rms between iterations:
+    dang_gpu_upload_maps again, and the next solve behaves exactly like a fresh handle on the new maps that starts
+    from the same amplitudes (self%x survives the swap, Q10); its chi-square matches the oracle on the new maps."""
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c2", 8, perturb=False)
+    sky_b = clone_sky(sky)
+    rng = np.random.default_rng(29)
+    sky_b.sig = sky.sig + 0.5 * sky.rms * rng.standard_normal(sky.sig.shape)
+    sky_b.rms = sky.rms * (1.0 + 0.2 * rng.random(sky.rms.shape))
+    eng = Engine(cfg, sky)
+    eng.sample_cg_groups(eta=rng.standard_normal(2 * cfg.npix))
+    eng.upload_maps(sky_b)                       # the swap
+    eng2 = Engine(cfg, sky_b)                    # a fresh handle on the swapped maps, same start
+    for ic in range(len(cfg.comps)):
+        eng2.set_amplitude(ic, eng.amplitude(ic))
+    eta2 = rng.standard_normal(2 * cfg.npix)
+    it_a, _ = eng.cg_solve(0, 0, "sample", eta=eta2)
+    it_b, _ = eng2.cg_solve(0, 0, "sample", eta=eta2)
+    assert it_a == it_b
+    for ic in range(len(cfg.comps)):
+        assert np.array_equal(eng.amplitude(ic), eng2.amplitude(ic))
+    ora = Oracle(cfg, sky_b)
+    for ic in range(len(cfg.comps)):
+        ora.amplitude(ic)[:] = eng.amplitude(ic)
+    ora.update_sky_model()
+    chisq_o, _ = ora.compute_chisq()
+    assert abs(eng.compute_chisq() - chisq_o) <= TOL * chisq_o
+
+
+def test_bandpass_quadrature_on_a_jagged_table():
+    """The default 8-node Gauss rule against a deliberately jagged bandpass (random tau, unequal spacing): the
+    exactness argument does not care about the shape of tau, only about the smoothness of the SED across the band."""
+    from dang_b200.config import Band
+    from dang_b200.engine import Engine
+    from oracle.binding import Oracle
+    cfg, sky = small_case("c3", 4)
+    rng = np.random.default_rng(31)
+    for j, b in enumerate(cfg.bands):
+        nu = np.sort(b.nu_ghz * (1.0 + 0.12 * (2.0 * rng.random(97) - 1.0)))
+        tau = rng.random(97) ** 3 + 0.01 * (rng.random(97) < 0.3)
+        cfg.bands[j] = Band(nu_ghz=b.nu_ghz, label=b.label, bp_nu_ghz=nu, bp_tau=tau)
+    from dang_b200.synth import make_sky
+    sky2 = make_sky(cfg)
+    sky2.amplitude, sky2.indices = sky.amplitude, sky.indices
+    ora, eng = Oracle(cfg, sky2), Engine(cfg, sky2)
+    ora.update_sky_model()
+    chisq_o, planes_o = ora.compute_chisq()
+    planes_g, _ = eng.chisq_planes()
+    assert rel_err(planes_g, planes_o) < TOL
+    sky_g, _, _ = eng.update_sky_model()
+    assert rel_err(sky_g, ora.sky_model()) < 1e-12
