@@ -74,6 +74,7 @@ SIGNATURES = {
     "dang_gpu_kernel_name": (C.c_char_p, [C.c_int]),
     "dang_gpu_timeline": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), c_dp, c_dp]),
     "dang_gpu_set_t_cmb": (C.c_int, [vp, C.c_double]),
+    "dang_gpu_udgrade": (C.c_int, [vp, C.c_int, c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_double]),
     "dang_gpu_comm_probe": (C.c_int, [vp, C.c_int, C.c_int, c_dp]),
 }
 

@@ -381,6 +381,15 @@ class Engine:
         self._ck(self.lib.dang_gpu_fit_band_gain(self.h, map_n, band, ML_MODES[ml_mode], zz, seed, C.byref(g)))
         return g.value
 
+    def udgrade(self, kind: str, data: np.ndarray, nside_in: int, nside_out: int, threshold: float = 0.5) -> np.ndarray:
+        """udgrade_ring / udgrade_rms / udgrade_mask (HEALPix udgrade_nr; src/dang_util_mod.f90:341-376) on full-sky
+        RING maps [nmaps][npix] -- the resolution changes of sample_index_mh's low-resolution branch."""
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        out = np.zeros((data.shape[0], 12 * nside_out * nside_out))
+        self._ck(self.lib.dang_gpu_udgrade(self.h, {"ring": 0, "rms": 1, "mask": 2}[kind], _dp(data), nside_in, _dp(out),
+                                           nside_out, data.shape[0], float(threshold)))
+        return out
+
     def index_mean(self, ic: int, nind: int, map_n: int) -> float:
         m = C.c_double()
         self._ck(self.lib.dang_gpu_index_mean(self.h, ic, nind, map_n, C.byref(m)))

@@ -270,6 +270,16 @@ module dang_gpu_mod
        integer(c_int) :: blocks_run
        real(c_double) :: step_size
      end function dang_gpu_tune_index
+     ! ---- udgrade_ring / udgrade_rms / udgrade_mask (dang_util_mod.f90:341-376, dang_sample_mod.f90:204-217, 480)
+     integer(c_int) function dang_gpu_udgrade(h, kind, data_in, nside_in, data_out, nside_out, nmaps, threshold) &
+          bind(C, name='dang_gpu_udgrade')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr),    value :: h
+       integer(c_int), value :: kind, nside_in, nside_out, nmaps
+       real(c_double), value :: threshold
+       real(c_double), intent(in)  :: data_in(*)
+       real(c_double), intent(out) :: data_out(*)
+     end function dang_gpu_udgrade
      ! ---- global T_CMB after a 'T_cmb' draw (dang_sample_mod.f90:76-78)
      integer(c_int) function dang_gpu_set_t_cmb(h, t_cmb) bind(C, name='dang_gpu_set_t_cmb')
        import :: c_ptr, c_int, c_double

@@ -275,6 +275,16 @@ int dang_gpu_get_sky_model(dang_gpu_t *h, int pol_lo, int pol_hi, double *sky_mo
 int dang_gpu_fit_band_gain(dang_gpu_t *h, int map_n, int band, int ml_mode, const double *z,
                            uint64_t seed, double *gain);
 
+/* ---- resolution changes of the low-resolution sampling branch (src/dang_sample_mod.f90:204-217, 480) as standalone
+ * operators on full-sky RING maps in host memory, (npix, nmaps) each:
+ *   kind 0  udgrade_ring   HEALPix-F90 udgrade_nr as published: RING -> NESTED, average the (nside_in/nside_out)^2
+ *                          children (bad pixels -1.6375e30 skipped, all bad -> bad) or copy the parent, NESTED -> RING
+ *   kind 1  udgrade_rms    src/dang_util_mod.f90:341-356: sqrt(udgrade_ring(rms^2)) * nside_out / nside_in
+ *   kind 2  udgrade_mask   :358-376: udgrade_ring, then (when degrading) 0 below `threshold`, 1 otherwise
+ * dang_gpu_sample_index itself still requires sample_nside == nside. */
+int dang_gpu_udgrade(dang_gpu_t *h, int kind, const double *in, int nside_in, double *out, int nside_out, int nmaps,
+                     double threshold);
+
 /* mask_avg(c%indices(:,map_n,nind), masks(:,1)), src/dang_util_mod.f90:186-206 */
 int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean);
 

@@ -92,6 +92,11 @@ def load(omp: bool = False) -> C.CDLL:
         "ora_philox_raw": (None, [C.POINTER(C.c_uint), C.c_uint, C.c_uint]),
         "ora_num_threads": (i, []),
         "ora_set_num_threads": (None, [i]),
+        "ora_nest2ring": (ll, [ll, ll]),
+        "ora_ring2nest": (ll, [ll, ll]),
+        "ora_udgrade_ring": (None, [c_dp, ll, c_dp, ll, i]),
+        "ora_udgrade_rms": (None, [c_dp, ll, c_dp, ll, i]),
+        "ora_udgrade_mask": (None, [c_dp, ll, c_dp, ll, i, d]),
         "ora_get_T_CMB": (d, []),
         "ora_set_T_CMB": (None, [d]),
         "ora_offset": (c_dp, [vp]),
@@ -307,3 +312,19 @@ def planck_rj(nu_hz, T):
     h, k_B, c = 1.0545726691251021e-34 * 2.0 * np.pi, 1.3806503e-23, 2.99792458e8
     B = ((2.0 * h * nu_hz ** 3.0) / c ** 2.0) * (1.0 / (np.exp((h * nu_hz) / (k_B * np.asarray(T))) - 1))
     return B / (2.0 * k_B * nu_hz ** 2.0 / c ** 2.0) * 1e6
+
+
+def udgrade(kind: str, data: np.ndarray, nside_in: int, nside_out: int, threshold: float = 0.5) -> np.ndarray:
+    """udgrade_ring / udgrade_rms / udgrade_mask on [nmaps][npix] RING maps (HEALPix udgrade_nr as published +
+    src/dang_util_mod.f90:341-376)."""
+    lib = load()
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    nmaps = data.shape[0]
+    out = np.zeros((nmaps, 12 * nside_out * nside_out))
+    if kind == "ring":
+        lib.ora_udgrade_ring(_dp(data), nside_in, _dp(out), nside_out, nmaps)
+    elif kind == "rms":
+        lib.ora_udgrade_rms(_dp(data), nside_in, _dp(out), nside_out, nmaps)
+    else:
+        lib.ora_udgrade_mask(_dp(data), nside_in, _dp(out), nside_out, nmaps, threshold)
+    return out

@@ -1563,3 +1563,134 @@ void ora_philox_uniforms(unsigned long long seed, unsigned int stream, unsigned 
     u[i] = u1;
   }
 }
+
+/* ------------------------------------------------------------------ udgrade
+ * HEALPix-F90 udgrade_ring (module udgrade_nr, Healpix 3.8x: un-vendored, src/Makefile_gnu:28) as published:
+ * RING -> NESTED, sub_udgrade_nest, NESTED -> RING.  Degrading averages the (nside_in/nside_out)^2 NESTED children of
+ * every output pixel, skipping children equal to the bad value -1.6375e30 (all bad -> bad value; pessimistic = off);
+ * upgrading copies the parent into its children.  Index conversions follow healpix_base (ring2xyf / xyf2nest ...).
+ * Call sites: src/dang_sample_mod.f90:204-217, 480; wrappers udgrade_rms / udgrade_mask src/dang_util_mod.f90:341-376. */
+static const int hp_jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+static const int hp_jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+
+static long hp_isqrt(long v) {
+  long r = (long)sqrt((double)v + 0.5);
+  while (r * r > v) r--;
+  while ((r + 1) * (r + 1) <= v) r++;
+  return r;
+}
+static long hp_spread_bits(long v) { /* bit i of v -> bit 2i */
+  long r = 0;
+  for (int i = 0; i < 31; i++) r |= ((v >> i) & 1L) << (2 * i);
+  return r;
+}
+static long hp_compress_bits(long v) { /* bit 2i of v -> bit i */
+  long r = 0;
+  for (int i = 0; i < 31; i++) r |= ((v >> (2 * i)) & 1L) << i;
+  return r;
+}
+long ora_nest2ring(long nside, long pix) {
+  const long npface = nside * nside, npix = 12 * npface, ncap = 2 * nside * (nside - 1), nl4 = 4 * nside;
+  const int face = (int)(pix / npface);
+  const long p = pix & (npface - 1);
+  const long ix = hp_compress_bits(p), iy = hp_compress_bits(p >> 1);
+  const long jr = hp_jrll[face] * nside - ix - iy - 1;
+  long nr, n_before, kshift;
+  if (jr < nside) {
+    nr = jr;
+    n_before = 2 * nr * (nr - 1);
+    kshift = 0;
+  } else if (jr > 3 * nside) {
+    nr = nl4 - jr;
+    n_before = npix - 2 * (nr + 1) * nr;
+    kshift = 0;
+  } else {
+    nr = nside;
+    n_before = ncap + (jr - nside) * nl4;
+    kshift = (jr - nside) & 1;
+  }
+  long jp = (hp_jpll[face] * nr + ix - iy + 1 + kshift) / 2;
+  if (jp > nl4) jp -= nl4;
+  else if (jp < 1) jp += nl4;
+  return n_before + jp - 1;
+}
+long ora_ring2nest(long nside, long pix) {
+  const long npface = nside * nside, npix = 12 * npface, ncap = 2 * nside * (nside - 1), nl2 = 2 * nside;
+  long iring, iphi, kshift, nr;
+  int face;
+  if (pix < ncap) {
+    iring = (1 + hp_isqrt(1 + 2 * pix)) >> 1;
+    iphi = (pix + 1) - 2 * iring * (iring - 1);
+    kshift = 0;
+    nr = iring;
+    face = (int)((iphi - 1) / nr);
+  } else if (pix < npix - ncap) {
+    const long ip = pix - ncap;
+    iring = ip / (4 * nside) + nside;
+    iphi = ip % (4 * nside) + 1;
+    kshift = (iring + nside) & 1;
+    nr = nside;
+    const long ire = iring - nside + 1, irm = nl2 + 2 - ire;
+    const long ifm = (iphi - ire / 2 + nside - 1) / nside, ifp = (iphi - irm / 2 + nside - 1) / nside;
+    if (ifp == ifm) face = (ifp == 4) ? 4 : (int)ifp + 4;
+    else if (ifp < ifm) face = (int)ifp;
+    else face = (int)ifm + 8;
+  } else {
+    const long ip = npix - pix;
+    iring = (1 + hp_isqrt(2 * ip - 1)) >> 1;
+    iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1));
+    kshift = 0;
+    nr = iring;
+    iring = 2 * nl2 - iring;
+    face = 8 + (int)((iphi - 1) / nr);
+  }
+  const long irt = iring - hp_jrll[face] * nside + 1;
+  long ipt = 2 * iphi - hp_jpll[face] * nr - kshift - 1;
+  if (ipt >= nl2) ipt -= 8 * nside;
+  const long ix = (ipt - irt) >> 1, iy = (-(ipt + irt)) >> 1;
+  return (long)face * npface + hp_spread_bits(ix) + (hp_spread_bits(iy) << 1);
+}
+
+/* udgrade_ring on `nmaps` planes, Fortran (npix, nmaps) == C [map][pix] */
+void ora_udgrade_ring(const double *in, long nside_in, double *out, long nside_out, int nmaps) {
+  const long npix_in = 12 * nside_in * nside_in, npix_out = 12 * nside_out * nside_out;
+  const double bad = ORA_MISSVAL; /* HPX_DBADVAL == dang's missval, -1.6375e30 */
+  for (int k = 0; k < nmaps; k++) {
+    const double *mi = in + (size_t)k * npix_in;
+    double *mo = out + (size_t)k * npix_out;
+    if (nside_out < nside_in) {
+      const long npratio = npix_in / npix_out;
+      for (long id = 0; id < npix_out; id++) { /* id: NESTED output pixel */
+        double total = 0.0;
+        long nobs = 0;
+        for (long ip = 0; ip < npratio; ip++) {
+          const double v = mi[ora_nest2ring(nside_in, id * npratio + ip)];
+          if (v != bad) {
+            total = total + v;
+            nobs++;
+          }
+        }
+        mo[ora_nest2ring(nside_out, id)] = nobs ? total / (double)nobs : bad;
+      }
+    } else {
+      const long npratio = npix_out / npix_in;
+      for (long iu = 0; iu < npix_out; iu++) mo[ora_nest2ring(nside_out, iu)] = mi[ora_nest2ring(nside_in, iu / npratio)];
+    }
+  }
+}
+/* udgrade_rms, src/dang_util_mod.f90:341-356 */
+void ora_udgrade_rms(const double *in, long nside_in, double *out, long nside_out, int nmaps) {
+  const long npix_in = 12 * nside_in * nside_in, npix_out = 12 * nside_out * nside_out;
+  double *buf = xcalloc((size_t)npix_in * nmaps, sizeof(double));
+  for (size_t i = 0; i < (size_t)npix_in * nmaps; i++) buf[i] = in[i] * in[i];
+  ora_udgrade_ring(buf, nside_in, out, nside_out, nmaps);
+  for (size_t i = 0; i < (size_t)npix_out * nmaps; i++) out[i] = sqrt(out[i]) * ((double)nside_out * 1.0 / (double)nside_in);
+  free(buf);
+}
+/* udgrade_mask, src/dang_util_mod.f90:358-376 */
+void ora_udgrade_mask(const double *in, long nside_in, double *out, long nside_out, int nmaps, double threshold) {
+  const long npix_out = 12 * nside_out * nside_out;
+  ora_udgrade_ring(in, nside_in, out, nside_out, nmaps);
+  if (nside_in > nside_out)
+    for (size_t i = 0; i < (size_t)npix_out * nmaps; i++) out[i] = (out[i] < threshold) ? 0.0 : 1.0;
+}

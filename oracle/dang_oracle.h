@@ -161,6 +161,11 @@ void ora_philox_uniforms(unsigned long long seed, unsigned int stream, unsigned 
                          long n, double *u);
 
 int ora_num_threads(void);
+long ora_nest2ring(long nside, long pix);
+long ora_ring2nest(long nside, long pix);
+void ora_udgrade_ring(const double *in, long nside_in, double *out, long nside_out, int nmaps);
+void ora_udgrade_rms(const double *in, long nside_in, double *out, long nside_out, int nmaps);
+void ora_udgrade_mask(const double *in, long nside_in, double *out, long nside_out, int nmaps, double threshold);
 int ora_tune_step_from(ora_state *st, int ic, int nind, int map_n, int nsample, int ml_mode, const double *z,
                        const double *u, int max_blocks, const double *theta_init);
 void ora_perpixel_tune_start(const ora_state *st, int ic, int nind, int map_n, double *theta_init);

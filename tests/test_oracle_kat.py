@@ -300,3 +300,34 @@ def test_sample_vector_slots_interleave_with_two_border_components():
     hi_rows = np.array([np.sum((eta / sky.rms[j, 0])[m] * np.array([ora.eval_sed(1, j, i, 1) for i in range(npix)])[m]) for j in range(nb)])
     mono_rows = np.array([np.sum((eta / sky.rms[j, 0])[m]) for j in range(nb)])
     assert np.allclose(sv[0::2], hi_rows, rtol=1e-12) and np.allclose(sv[1::2], mono_rows, rtol=1e-12)
+
+
+# ------------------------------------------------------------------ udgrade
+def test_healpix_index_conversion_and_udgrade_known_answers():
+    """nest2ring at nside 2 against the published HEALPix table (healpy.nest2ring(2, range(48))); round trips; and
+    the algebra of udgrade_ring / udgrade_rms / udgrade_mask (src/dang_util_mod.f90:341-376)."""
+    from oracle.binding import load, udgrade
+    lib = load()
+    table = [13, 5, 4, 0, 15, 7, 6, 1, 17, 9, 8, 2, 19, 11, 10, 3, 28, 20, 27, 12, 30, 22, 21, 14, 32, 24, 23, 16,
+             34, 26, 25, 18, 44, 37, 36, 29, 45, 39, 38, 31, 46, 41, 40, 33, 47, 43, 42, 35]
+    assert [lib.ora_nest2ring(2, i) for i in range(48)] == table
+    assert [lib.ora_nest2ring(1, i) for i in range(12)] == list(range(12))
+    for ns in (4, 32):
+        n = 12 * ns * ns
+        assert [lib.ora_ring2nest(ns, lib.ora_nest2ring(ns, i)) for i in range(n)] == list(range(n))
+    ns = 16
+    n = 12 * ns * ns
+    rng = np.random.default_rng(3)
+    m = rng.standard_normal((2, n))
+    d = udgrade("ring", m, ns, 4)
+    assert np.isclose(d.sum() * 16, m.sum())                                    # averaging conserves the mean
+    assert np.allclose(udgrade("ring", udgrade("ring", d, 4, ns), ns, 4), d, rtol=1e-14)  # upgrade copies parents
+    bad = m.copy()
+    bad[0, :] = -1.6375e30
+    assert np.all(udgrade("ring", bad, ns, 4)[0] == -1.6375e30)                 # all children bad -> bad
+    rms = np.abs(m) + 0.5
+    assert np.allclose(udgrade("rms", np.full((1, n), 3.0), ns, 4), 3.0 * 4 / 16)  # sqrt(mean sigma^2) * nside_out/nside_in
+    assert np.allclose(udgrade("rms", rms, ns, 8) ** 2, udgrade("ring", rms ** 2, ns, 8) / 4.0)
+    mask = (rng.random((1, n)) < 0.7).astype(float)
+    dm = udgrade("mask", mask, ns, 4)
+    assert set(np.unique(dm)) <= {0.0, 1.0} and np.array_equal(dm, (udgrade("ring", mask, ns, 4) >= 0.5).astype(float))
