@@ -127,7 +127,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from dang_b200.engine import OPT_PROFILE, Engine, setup_torch_comm
+    from dang_b200.engine import OPT_DEFER_SCALARS, OPT_PROFILE, Engine, setup_torch_comm
     from dang_b200.healpix import ring_partition
     from dang_b200.synth import make_config, make_sky, make_sky_slice
     from dang_b200.healpix import pix2z_ring
@@ -181,15 +181,42 @@ def run_gpu(args):
         return float(t.item())
 
     info = {}
+    # Deferred scalars (DANG_OPT_DEFER_SCALARS, include/dang_gpu.h): the numbers of the reference's terminal line
+    # (CG iterations, chi-square, acceptance) reach the host one Gibbs iteration late instead of stalling the device
+    # three times per iteration.  Covers the one-solve + full-sky-draw shape of c1 / c2; every number still arrives
+    # (and is counted below), the kernels and their results are bit-identical (tests/test_gpu_deferred.py).
+    fullsky_only = all(s.region == "fullsky" for c in cfg.comps for s in c.indices if s.sample)
+    one_solve = len(cfg.cg_groups) == 1 and "," not in cfg.cg_groups[0].poltype
+    defer = bool(args.defer_scalars) and fullsky_only and one_solve and (world == 1 or mailboxes)
+    pending = []
+    n_cg = []
+
+    def take(q):
+        n_cg.append(q["n_iter"])
+        info["chisq"] = q["chisq_index"]
+        info["index_value"] = q["index_value"]
 
     def step(it, seed=0):
         r1, r2 = eng.gibbs_iteration(it, seed=seed)
-        info["n_cg"] = r1[0][0]
-        info["chisq"] = r2[1] if r2 else r1[-1]
+        if r1[0][0] == -1:  # deferred: mark this iteration, pick up the one before it
+            pending.append(eng.iteration_mark())
+            if len(pending) > 1:
+                take(eng.iteration_scalars(pending.pop(0)))
+        else:
+            n_cg.append(r1[0][0])
+            info["chisq"] = r2[1] if r2 else r1[-1]
+
+    def drain():
+        while pending:
+            take(eng.iteration_scalars(pending.pop(0)))
 
     # --- device-resident timing: `value`
-    for w in range(args.warmup):
+    step(2)  # (the step-size tuner runs here, once)
+    if defer:
+        eng.set_option(OPT_DEFER_SCALARS, 1)
+    for w in range(1, args.warmup):
         step(2 + w)
+    drain()
     # the NVML sampler is set up BEFORE the barrier: its start-up (tens of ms on rank 0 only) inside the timed region
     # would leave the other ranks' kernels spinning in their first scalar exchange, and max-over-ranks would report it
     sampler = ClockSampler(local) if (rank == 0 and os.environ.get("DANG_BENCH_NO_CLOCKS") != "1") else None
@@ -197,10 +224,11 @@ def run_gpu(args):
     eng.launch_count(reset=True)
     eng.event_record(0)
     t_value0 = time.perf_counter()
-    n_cg = []
+    n_cg.clear()
     for k in range(args.steps):
         step(2 + args.warmup + k)
-        n_cg.append(info["n_cg"])
+    drain()
+    assert len(n_cg) == args.steps and np.isfinite(info["chisq"]), (len(n_cg), info)
     eng.event_record(1)
     eng.sync()
     wall_value_ms = (time.perf_counter() - t_value0) * 1e3
@@ -212,8 +240,11 @@ def run_gpu(args):
     # --- per-kernel timing for the roofline: same steps with CUDA events around every launch
     eng.kernel_stats(reset=True)
     eng.set_option(OPT_PROFILE, 1)
+    ncg_value = list(n_cg)
     for k in range(max(1, min(args.steps, 5))):
         step(2 + args.warmup + args.steps + k)
+    drain()
+    n_cg = ncg_value
     stats = eng.kernel_stats(reset=True)
     eng.set_option(OPT_PROFILE, 0)
     k5_fallbacks = eng.perpixel_stats()[0] if per_pixel else None
@@ -263,10 +294,18 @@ def run_gpu(args):
             r1 = eng.sample_cg_groups(eta=None)     # consumes the deviates staged one step earlier
         else:
             r1 = eng.sample_cg_groups(eta=eta_hs[it % 3])
-        e2e_ncg.append(r1[0][0])
+        if r1[0][0] != -1:
+            e2e_ncg.append(r1[0][0])
         for ic in range(len(cfg.comps)):
             eng.amplitude_async(ic, amp_h[ic])
         eng.sample_spectral_parameters(z=z_h, u=u_h, seed=7 + 2 * it)
+        if r1[0][0] == -1:  # deferred scalars: iterations, chi-square and the full-sky index value arrive one step late
+            pending.append(eng.iteration_mark())
+            if len(pending) > 1:
+                q = eng.iteration_scalars(pending.pop(0))
+                e2e_ncg.append(q["n_iter"])
+                fs_val["deferred"] = q["index_value"]
+            return
         for ic, j in sampled:
             if cfg.comps[ic].indices[j].region == "fullsky":
                 # the whole plane holds the chain's final sample (dang_sample_mod.f90:329,483): 8 bytes per
@@ -277,9 +316,16 @@ def run_gpu(args):
 
     if single_solve:
         eng.stage_eta(eta_hs[0])
+    def e2e_drain():
+        while pending:
+            q = eng.iteration_scalars(pending.pop(0))
+            e2e_ncg.append(q["n_iter"])
+            fs_val["deferred"] = q["index_value"]
+
     for w in range(3):
         e2e_step(w)
     eng.download_wait()
+    e2e_drain()
     e2e_ncg.clear()
     barrier()
     eng.event_record(2)
@@ -288,6 +334,8 @@ def run_gpu(args):
     for k in range(ke):
         e2e_step(3 + k)
     eng.download_wait()
+    e2e_drain()
+    assert len(e2e_ncg) == ke, (len(e2e_ncg), ke)
     eng.event_record(3)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -328,6 +376,8 @@ def run_gpu(args):
                        "parallelism": f"ring-range pixel shards x{world}" + ("" if world == 1 else (", scalar exchange over NVLink mailboxes" if mailboxes else ", scalar exchange by NCCL all-gather")),
                        "l2": f"working set per GPU (sig+rms {16e-9 * cfg.nbands * 2 * P:.2f} GB + CG state) >> 126 MB L2, no flush needed",
                        "rng": "device Philox4x32-10",
+                       "scalars": ("deferred: CG iterations / chi-square / acceptance of step k read by the host during step k+1 "
+                                   "(DANG_OPT_DEFER_SCALARS); all read before the clock stops") if defer else "every call returns its own scalars (three host waits per step)",
                        **({"k5_fp64_fallbacks_per_proposal": round(k5_fallbacks / (cfg.nsample * float((mask_slice != 0).sum()) * world), 6)}
                           if k5_fallbacks is not None else {})},
             "pixel_band_updates_per_s": round(2 * cfg.npix * cfg.nbands * 1e3 / ms_per_step, 1),
@@ -443,6 +493,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--nside", type=int, default=None, help="override the map size (tests only)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--defer-scalars", type=int, default=1, help="1: DANG_OPT_DEFER_SCALARS on the one-solve + full-sky configs")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (experiments), e.g. --opt 8=16")
     args = ap.parse_args()
     if args.impl == "reference":

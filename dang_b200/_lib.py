@@ -60,6 +60,8 @@ SIGNATURES = {
     "dang_gpu_get_sky_model": (C.c_int, [vp, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "dang_gpu_fit_band_gain": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp, C.c_uint64, c_dp]),
     "dang_gpu_index_mean": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp]),
+    "dang_gpu_iteration_mark": (C.c_int, [vp, C.POINTER(C.c_int64)]),
+    "dang_gpu_iteration_scalars": (C.c_int, [vp, C.c_int64, C.POINTER(C.c_int), c_dp, c_dp, c_dp, c_dp, c_dp]),
     "dang_gpu_get_amplitude_async": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_dp]),
     "dang_gpu_get_indices_async": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp]),
     "dang_gpu_download_wait": (C.c_int, [vp]),

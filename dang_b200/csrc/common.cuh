@@ -95,6 +95,9 @@ struct CgScalars {
   int ckpt, m;        // recompute form: pass whose state is stored in (r, d); checkpoint interval
   int x_at;           // persistent solve kernel: x (and the amplitude planes) hold the state after pass x_at
   unsigned int gen;   // ... and its grid barrier: passes completed in the running launch
+  int k_pred;         // passes the previous solve ran (set when a solve ends, NOT reset by cg_init_update): lets a
+                      // solve whose host has not read the previous result yet still predict its last pass
+  int pad2;
   double trace[256];
   double ah[DG_CG_HIST], bh[DG_CG_HIST];  // alpha_i, beta_i used IN pass i (1-based)
 };
@@ -439,6 +442,15 @@ static __global__ void peer_exchange_probe_kernel(PeerComm pc, double *local, in
 // maps on the d2h stream) the device-to-host engine is busy with and would stall the compute stream.
 static __global__ void readback_kernel(unsigned int *dst_host, const unsigned int *src, int nwords) {
   for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst_host[i] = src[i];
+  __threadfence_system();
+}
+
+// three small device regions -> one pinned snapshot slot (dang_gpu_iteration_mark)
+static __global__ void snapshot_kernel(unsigned int *d0, const unsigned int *s0, int n0, unsigned int *d1, const unsigned int *s1,
+                                       int n1, unsigned int *d2, const unsigned int *s2, int n2) {
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) d0[i] = s0[i];
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) d1[i] = s1[i];
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) d2[i] = s2[i];
   __threadfence_system();
 }
 

@@ -395,6 +395,13 @@ int dang_gpu_create(int device, int nside, int64_t npix, int nmaps, int nbands, 
     CK(cudaMalloc(&h->tab, sizeof(SedTable)));
     CK(cudaMemset(h->tab, 0, sizeof(SedTable)));
     CK(cudaMallocHost(&h->pinned, 256 * 1024));
+    CK(cudaMallocHost(&h->snap, DG_SNAP_SLOTS * DG_SNAP_BYTES));
+    for (int i = 0; i < DG_SNAP_SLOTS; i++) CK(cudaEventCreateWithFlags(&h->snap_meta[i].ev, cudaEventDisableTiming));
+    {
+      const int never = 0x7fffffff;  // no solve has run: x is carried on checkpoint passes only
+      CK(cudaMemset(h->cg_scalars, 0, sizeof(CgScalars)));
+      CK(cudaMemcpy(&h->cg_scalars->k_pred, &never, sizeof never, cudaMemcpyHostToDevice));
+    }
     h->peer.nranks = 1;
     h->peer.rank = 0;
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&h->ev[i]));
@@ -434,6 +441,9 @@ int dang_gpu_destroy(dang_gpu_t *h) {
   dfree(h->sums_local); dfree(h->gathered_buf); dfree(h->cg_scalars); dfree(h->mh_scalars); dfree(h->tab);
   dfree(h->bp_lnr_hi); dfree(h->bp_lnr_lo); dfree(h->stat_buf); dfree(h->k5_kj); if (h->k5_st4) cudaFree(h->k5_st4); dfree(h->tb); dfree(h->tq); dfree(h->tmpl_scalars);
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->snap) cudaFreeHost(h->snap);
+  for (int i = 0; i < DG_SNAP_SLOTS; i++)
+    if (h->snap_meta[i].ev) cudaEventDestroy(h->snap_meta[i].ev);
   for (auto &k : h->kstat) for (auto &p : k.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
@@ -480,6 +490,11 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_CG_PERSISTENT: h->cg_persistent = value != 0; break;
     case DANG_OPT_STREAM_RING: h->stream_ring = value != 0; break;
     case DANG_OPT_DEFER_D2H: h->defer_d2h = value != 0; break;
+    case DANG_OPT_DEFER_SCALARS:
+      if (h->pend_cg || h->pend_chisq_cg || h->pend_draw)
+        fail(DANG_GPU_ESTATE, "results are pending: call dang_gpu_iteration_mark / dang_gpu_iteration_scalars before changing DANG_OPT_DEFER_SCALARS");
+      h->defer_scalars = value != 0;
+      break;
     case DANG_OPT_BP_QUADRATURE:
       h->bp_quad = value < 0 ? 0 : (value > 32 ? 32 : (int)value);
       h->bp_dirty = true;
@@ -957,8 +972,9 @@ int dang_gpu_sample_index(dang_gpu_t *h, int ic, int nind, int map_n, int nsampl
     // planes that were tabulated before the draw stay tabulated, and the chain kernel has already put the new SED
     // into the table: nothing to flag, nothing to rebuild
     IndexHost &ixh = h->comp[ic].index[nind];
+    const bool value_known = ixh.last_value_planes != -1;  // (deferred scalars: the draw's outcome is still on the device)
     ixh.last_value_planes = 0;
-    for (int s = 0; s < mh.S; s++) ixh.last_value_planes |= 1 << mh.plane[s];
+    for (int s = 0; s < mh.S && value_known; s++) ixh.last_value_planes |= 1 << mh.plane[s];
     if (h->fs_tab_written) {
       ixh.last_value_epoch = h->idx_epoch;
       API_END_OK
@@ -1067,6 +1083,101 @@ int dang_gpu_get_sky_model(dang_gpu_t *h, int pol_lo, int pol_hi, double *sky_mo
     throw;
   }
   cudaFree(d_sky); cudaFree(d_res); cudaFree(d_chi);
+  API_END
+}
+
+int dang_gpu_iteration_mark(dang_gpu_t *h, int64_t *ticket) {
+  API_BEGIN
+  static_assert(offsetof(CgScalars, ah) <= DG_SNAP_CG && sizeof(MhScalars) <= DG_SNAP_MH, "snapshot sections");
+  if (!ticket) fail(DANG_GPU_EINVAL, "ticket is NULL");
+  const int64_t t = h->snap_ticket;
+  dang_gpu::SnapMeta &m = h->snap_meta[t % DG_SNAP_SLOTS];
+  if (m.ticket >= 0 && !m.read)
+    fail(DANG_GPU_ESTATE, "ticket %lld has not been read and its slot is needed (at most %d marks may be outstanding)",
+         (long long)m.ticket, DG_SNAP_SLOTS);
+  unsigned char *slot = h->snap + (size_t)(t % DG_SNAP_SLOTS) * DG_SNAP_BYTES;
+  h->snap_ticket++;
+  m.ticket = t;
+  m.read = false;
+  m.cg = h->pend_cg;
+  m.chisq_cg = h->pend_chisq_cg;
+  m.draw = h->pend_draw;
+  m.chisq_draw = h->pend_chisq_draw;
+  m.g = h->pend_g;
+  m.flag = h->pend_flag;
+  m.ic = h->pend_ic;
+  m.nind = h->pend_nind;
+  m.S = h->pend_S;
+  m.plane[0] = h->pend_plane[0];
+  m.plane[1] = h->pend_plane[1];
+  m.stat_cnt = h->pend_stat_cnt;
+  m.cg_T = h->pend_cg_T;
+  m.cg_C = h->pend_cg_C;
+  m.cg_m = h->pend_cg_m;
+  m.cg_vs = h->pend_cg_vs;
+  const int n_cg = m.cg ? (int)(offsetof(CgScalars, ah) / 4) : 0;
+  const int n_st = m.chisq_cg ? (int)((size_t)h->nranks * m.stat_cnt * 2) : 0;
+  const int n_mh = m.draw ? (int)(sizeof(MhScalars) / 4) : 0;
+  if (n_cg + n_st + n_mh > 0) {  // one launch, straight into pinned memory (no copy-engine work)
+    snapshot_kernel<<<1, 256, 0, h->stream>>>((unsigned int *)slot, (const unsigned int *)h->cg_scalars, n_cg,
+                                             (unsigned int *)(slot + DG_SNAP_CG), (const unsigned int *)h->mh_scalars, n_mh,
+                                             (unsigned int *)(slot + DG_SNAP_CG + DG_SNAP_MH), (const unsigned int *)h->stat_buf, n_st);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
+  CK(cudaEventRecord(m.ev, h->stream));
+  h->pend_cg = h->pend_chisq_cg = h->pend_draw = h->pend_chisq_draw = false;
+  *ticket = t;
+  API_END
+}
+
+int dang_gpu_iteration_scalars(dang_gpu_t *h, int64_t ticket, int *n_iter, double *delta_final,
+                               double *chisq_after_amplitudes, double *accept, double *index_value,
+                               double *chisq_after_index) {
+  API_BEGIN
+  if (ticket < 0 || ticket >= h->snap_ticket) fail(DANG_GPU_EINVAL, "ticket %lld was never issued", (long long)ticket);
+  dang_gpu::SnapMeta &m = h->snap_meta[ticket % DG_SNAP_SLOTS];
+  if (m.ticket != ticket) fail(DANG_GPU_ESTATE, "ticket %lld has been overwritten by a later mark", (long long)ticket);
+  CK(cudaEventSynchronize(m.ev));
+  const unsigned char *slot = h->snap + (size_t)(ticket % DG_SNAP_SLOTS) * DG_SNAP_BYTES;
+  const double qnan = nan("");
+  if (n_iter) *n_iter = -1;
+  if (delta_final) *delta_final = qnan;
+  if (accept) *accept = qnan;
+  if (index_value) *index_value = qnan;
+  for (int k = 0; k < h->nmaps; k++) {
+    if (chisq_after_amplitudes) chisq_after_amplitudes[k] = qnan;
+    if (chisq_after_index) chisq_after_index[k] = qnan;
+  }
+  if (m.cg) {
+    const CgScalars *hs = (const CgScalars *)slot;
+    CgGroupHost &g = h->cg[m.g];
+    if (!m.read) {  // book the solve's traffic now that its pass count is known; the prediction it ran with was the
+                    // count of the solve before it, which an in-order reader has in last_iter
+      const int k_pred = g.last_iter[m.flag] > 1 ? g.last_iter[m.flag] - 1 : 0x7fffffff;
+      h->kstat[DANG_K_CG_PASS].bytes += bytes_w(cg_solve_bytes(hs->iter - 1, k_pred, m.cg_m, m.cg_T, m.cg_C, m.cg_vs));
+      g.last_iter[m.flag] = hs->iter;
+      const int n = hs->iter < 256 ? hs->iter : 256;
+      h->last_trace.assign(hs->trace, hs->trace + n);
+    }
+    if (n_iter) *n_iter = hs->iter;
+    if (delta_final) *delta_final = hs->delta_new;
+  }
+  if (m.chisq_cg && chisq_after_amplitudes) {
+    double out4[4];
+    chisq_of_statistics(h, (const double *)(slot + DG_SNAP_CG + DG_SNAP_MH), m.stat_cnt, m.S, m.plane, out4);
+    for (int k = 0; k < h->nmaps; k++) chisq_after_amplitudes[k] = out4[k];
+  }
+  if (m.draw) {
+    const MhScalars *hs = (const MhScalars *)(slot + DG_SNAP_CG);
+    if (accept) *accept = hs->accept;
+    if (index_value) *index_value = hs->sample[m.nind];
+    if (m.chisq_draw && chisq_after_index) {
+      for (int k = 0; k < h->nmaps; k++) chisq_after_index[k] = 0.0;
+      for (int s = 0; s < m.S; s++) chisq_after_index[m.plane[s]] = hs->chisq[s];
+    }
+  }
+  m.read = true;
   API_END
 }
 

@@ -126,6 +126,9 @@ struct KStat {
 };
 
 const int GATHER_MAX = 256;  // doubles per rank in one scalar exchange
+const int DG_SNAP_SLOTS = 4;
+const size_t DG_SNAP_CG = 4096, DG_SNAP_MH = 1024, DG_SNAP_STAT = (size_t)GATHER_MAX * 32 * 8;  // bytes per slot section
+const size_t DG_SNAP_BYTES = DG_SNAP_CG + DG_SNAP_MH + DG_SNAP_STAT;
 
 // event-log kinds beyond the kernel families of dang_gpu.h: staged copies on the side streams
 const int DANG_TL_EXTRA = 3;
@@ -142,6 +145,30 @@ struct dang_gpu {
   cudaEvent_t ev_compute = nullptr, ev_idx_dl = nullptr;
   std::vector<struct DeferredD2H> deferred;  // amplitude downloads requested but not issued yet
   int defer_d2h = 1;                         // DANG_OPT_DEFER_D2H
+  // deferred scalars (DANG_OPT_DEFER_SCALARS): cg_solve / chisq / full-sky sample_index enqueue their kernels and
+  // return without waiting; dang_gpu_iteration_mark snapshots the device-side results into a ring of pinned slots
+  // and dang_gpu_iteration_scalars decodes a slot later -- one host wait per Gibbs iteration, one iteration behind
+  int defer_scalars = 0;
+  bool pend_cg = false, pend_chisq_cg = false, pend_draw = false;  // what the calls since the last mark left behind
+  int pend_g = -1, pend_flag = -1, pend_ic = -1, pend_nind = -1, pend_S = 0, pend_plane[2] = {0, 0}, pend_stat_cnt = 0;
+  int pend_chisq_lo = 0, pend_chisq_hi = 0;
+  int pend_cg_T = 0, pend_cg_C = 0, pend_cg_m = 0;
+  double pend_cg_vs = 0.0;
+  bool pend_draw_chisq = false;   // the pending draw's MhScalars::chisq is the chi-square of the state it left
+  uint64_t pend_draw_version = 0;
+  bool pend_chisq_draw = false;   // ... and a dang_gpu_chisq call asked for it
+  unsigned char *snap = nullptr;  // pinned: DG_SNAP_SLOTS slots
+  int64_t snap_ticket = 0;
+  struct SnapMeta {
+    int64_t ticket = -1;
+    bool read = false;
+    bool cg = false, chisq_cg = false, draw = false;
+    bool chisq_draw = false;
+    int g = -1, flag = -1, ic = -1, nind = -1, S = 0, plane[2] = {0, 0}, stat_cnt = 0, chisq_lo = 0, chisq_hi = 0;
+    int cg_T = 0, cg_C = 0, cg_m = 0;
+    double cg_vs = 0.0;
+    cudaEvent_t ev = nullptr;
+  } snap_meta[4];
   cudaEvent_t ev_sync = nullptr;  // host waits for a point of the compute stream (results read back) while later kernels run
   bool idx_dl_pending = false;
   // staged deviates of the next solves: a two-slot FIFO, so the upload for solve k+1 runs while solve k
@@ -384,6 +411,20 @@ inline void dd_log_ratio(double a, double b, double &hi, double &lo) {
   hi = (double)L;
   lo = (double)(L - (long double)hi);
 }
+// Compulsory traffic (doubles) of one persistent solve that ran n_pass passes with prediction k_pred: every sweep
+// reads M, r (and d after the first checkpoint); checkpoint passes write r, d; sweeps that carry x read it and write
+// x + the amplitude planes; a closing sweep follows when x is behind the last pass.
+inline double cg_solve_bytes(int n_pass, int k_pred, int ckpt_m, int T, int C, double vs) {
+  double per_el = 0.0;
+  int x_at = 0;
+  for (int pn = 1; pn <= n_pass; pn++) {
+    const bool store = pn % ckpt_m == 0, with_x = store || pn >= k_pred;
+    per_el += T + C + (pn > ckpt_m ? C : 0) + (store ? 2.0 * C : 0.0) + (with_x ? 3.0 * C : 0.0);
+    if (with_x) x_at = pn;
+  }
+  if (n_pass > x_at) per_el += T + C + (n_pass > ckpt_m ? C : 0) + 3.0 * C;
+  return vs * per_el;
+}
 // device -> pinned host (h->pinned) for small results, stream ordered, bypassing the copy engine
 inline void readback(dang_gpu *h, void *dst_pinned, const void *src_dev, size_t bytes) {
   if (bytes % 4 != 0) fail(DANG_GPU_EINVAL, "readback of %zu bytes", bytes);
@@ -405,6 +446,7 @@ struct DeferredD2H {
   int k_lo, k_hi;
 };
 void issue_deferred_d2h(dang_gpu *h, cudaEvent_t after);  // dang_gpu.cu
+void chisq_of_statistics(const dang_gpu *h, const double *hp, int cnt, int S, const int *plane, double out4[4]);  // host_mh_fs.cu
 
 // anything that overwrites c.amp in place waits for a download that may still be reading it
 inline void amp_write_barrier(dang_gpu *h, CompHost &c) {

@@ -179,7 +179,12 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
   if (persistent) {
     CgAmpOut<C> ao{};
     for (int c = 0; c < C; c++) ao.p[c] = h->comp[comps[c]].amp + (size_t)cv.plane[0] * h->Ppad;  // S contiguous planes
-    int k_pred = g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : 0x7fffffff;  // pass the previous solve ended on
+    int nsolve = 0;
+    for (auto &gg : h->cg)
+      if (gg.set) nsolve += gg.nflag;
+    // deferred scalars (host.cuh): with one solve per Gibbs iteration the device carries the previous count itself
+    const bool defer = h->defer_scalars && nsolve == 1;
+    int k_pred = defer ? -1 : g.last_iter[flag_n] > 1 ? g.last_iter[flag_n] - 1 : 0x7fffffff;  // pass the previous solve ended on
     int per_sm = 0;
     const size_t cg_smem = cg_ring_bytes<C>();
     CK(cudaFuncSetAttribute(cg_solve_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
@@ -204,28 +209,28 @@ void cg_solve_impl(dang_gpu *h, CgGroupHost &g, int flag_n, int ml_mode, const d
     // is the run's only solve per Gibbs iteration and a full-sky draw follows, the draw's statistics pass (which
     // also serves the chi-square printed after the amplitude draw) is enqueued first, so the device keeps
     // streaming while the host turns the solve around.
+    if (defer) {  // no host wait here: dang_gpu_iteration_mark / _scalars pick the outcome up later
+      prefetch_statistics(h);
+      kt.bytes = 0.0;  // booked by dang_gpu_iteration_scalars once the pass count is known
+      kt.commit(true);
+      h->pend_cg = true;
+      h->pend_g = (int)(&g - h->cg.data());
+      h->pend_flag = flag_n;
+      h->pend_cg_T = T;
+      h->pend_cg_C = C;
+      h->pend_cg_m = ckpt_m;
+      h->pend_cg_vs = (double)vs;
+      h->last_trace.clear();
+      if (n_iter) *n_iter = -1;
+      if (delta_final) *delta_final = nan("");
+      return;
+    }
     CgScalars *hs = (CgScalars *)h->pinned;
     readback(h, hs, h->cg_scalars, offsetof(CgScalars, ah));
     CK(cudaEventRecord(h->ev_sync, h->stream));
-    {
-      int nsolve = 0;
-      for (auto &gg : h->cg)
-        if (gg.set) nsolve += gg.nflag;
-      if (nsolve == 1) prefetch_statistics(h);
-    }
+    if (nsolve == 1) prefetch_statistics(h);
     CK(cudaEventSynchronize(h->ev_sync));
-    // compulsory traffic of the sweeps that ran: M, r (and d after the first checkpoint) in; checkpoint passes
-    // write r, d; sweeps that carry x read it and write x + the amplitude planes
-    const int n_pass = hs->iter - 1;
-    double per_el = 0.0;
-    int x_at = 0;
-    for (int pn = 1; pn <= n_pass; pn++) {
-      const bool store = pn % ckpt_m == 0, with_x = store || pn >= k_pred;
-      per_el += T + C + (pn > ckpt_m ? C : 0) + (store ? 2.0 * C : 0.0) + (with_x ? 3.0 * C : 0.0);
-      if (with_x) x_at = pn;
-    }
-    if (n_pass > x_at) per_el += T + C + (n_pass > ckpt_m ? C : 0) + 3.0 * C;  // closing sweep
-    kt.bytes = bytes_w((double)vs * per_el);
+    kt.bytes = bytes_w(cg_solve_bytes(hs->iter - 1, k_pred, ckpt_m, T, C, (double)vs));
     kt.commit(true);
     int n = hs->iter < 256 ? hs->iter : 256;
     h->last_trace.assign(hs->trace, hs->trace + n);

@@ -21,6 +21,14 @@ void run_chisq(dang_gpu *h, int pol_lo, int pol_hi, double *sky, double *res, do
       out4[3] = (double)unmasked_count(h);
       return;
     }
+    if (h->defer_scalars && h->pend_draw && h->pend_draw_chisq && h->pend_draw_version == h->version &&
+        h->pend_plane[0] + 1 == pol_lo && h->pend_plane[h->pend_S - 1] + 1 == pol_hi && pol_hi - pol_lo + 1 == h->pend_S) {
+      // deferred scalars: the pending full-sky draw left this chi-square in its MhScalars (dang_gpu_iteration_scalars)
+      for (int k = 0; k < 3; k++) out4[k] = nan("");
+      out4[3] = (double)unmasked_count(h);
+      h->pend_chisq_draw = true;
+      return;
+    }
     if (chisq_from_statistics(h, pol_lo, pol_hi, out4)) return;
   }
   ModelView mv = model_view(h);

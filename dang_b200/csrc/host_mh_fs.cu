@@ -249,6 +249,28 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
   // The chain's results go back first and the host waits for THAT point of the stream only; the kernel that
   // writes the final sample into the index planes (:329, :483) runs while the host is already enqueuing the
   // next call.
+  bool has_monopole = false;
+  for (int c = 0; c < h->ncomp; c++) has_monopole = has_monopole || (h->comp[c].set && h->comp[c].type == DANG_COMP_MONOPOLE);
+  if (h->defer_scalars && !h->fullsky_stream) {  // deferred scalars (host.cuh): nothing comes back here
+    const int grid = grid_for(h, h->P, DG_THREADS, 4);
+    KTimer kt(h, DANG_K_SCALAR, 0);
+    mh_fullsky_store_kernel<<<grid, DG_THREADS, 0, h->stream>>>(mv, mh, h->mh_scalars);
+    kt.done();
+    if (accept) *accept = nan("");
+    touch(h, 2);
+    h->stat_valid = false;
+    h->chisq_valid = false;
+    h->pend_draw = true;
+    h->pend_ic = mh.ic;
+    h->pend_nind = mh.nind;
+    h->pend_S = mh.S;
+    h->pend_plane[0] = mh.plane[0];
+    h->pend_plane[1] = mh.plane[1];
+    h->pend_draw_chisq = h->stat_cache && !has_monopole;
+    h->pend_draw_version = h->version;
+    h->comp[mh.ic].index[mh.nind].last_value_planes = -1;  // the host does not know the new value (sample_index checks)
+    return;
+  }
   MhScalars *hs = (MhScalars *)h->pinned;
   readback(h, hs, h->mh_scalars, sizeof(MhScalars));
   CK(cudaEventRecord(h->ev_sync, h->stream));
@@ -263,8 +285,6 @@ void sample_fullsky(dang_gpu *h, MhView &mh, const double *z, const double *u, u
   h->comp[mh.ic].index[mh.nind].last_value = hs->sample[mh.nind];
   touch(h, 2);
   h->stat_valid = false;
-  bool has_monopole = false;
-  for (int c = 0; c < h->ncomp; c++) has_monopole = has_monopole || (h->comp[c].set && h->comp[c].type == DANG_COMP_MONOPOLE);
   if (!h->fullsky_stream && h->stat_cache && !has_monopole) {  // chi-square of the new state, from the statistics
     h->chisq_valid = true;
     h->chisq_version = h->version;
@@ -329,12 +349,29 @@ bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]) 
   const int64_t n_unmasked = unmasked_count(h);
   int cnt = h->stat_cnt;
   if (!stat_cache_hit(h, mh)) cnt = fullsky_statistics(h, mv, mh);
+  if (h->defer_scalars) {  // deferred scalars: the rows stay in stat_buf until dang_gpu_iteration_mark snapshots them
+    for (int k = 0; k < 3; k++) out4[k] = nan("");
+    out4[3] = (double)n_unmasked;
+    h->pend_chisq_cg = true;
+    h->pend_S = mh.S;
+    h->pend_plane[0] = mh.plane[0];
+    h->pend_plane[1] = mh.plane[1];
+    h->pend_stat_cnt = cnt;
+    return true;
+  }
   double *hp = (double *)h->pinned;
   readback(h, hp, h->stat_buf, (size_t)h->nranks * cnt * sizeof(double));
   CK(cudaStreamSynchronize(h->stream));
+  chisq_of_statistics(h, hp, cnt, mh.S, mh.plane, out4);
+  out4[3] = (double)n_unmasked;
+  return true;
+}
+
+// chisq_planes = sum_j X_j / nbands from gathered statistics rows (host copy)
+void chisq_of_statistics(const dang_gpu *h, const double *hp, int cnt, int S, const int *plane, double out4[4]) {
   const int B = h->nbands, nchunk = (B + DG_SUFF_CHUNK - 1) / DG_SUFF_CHUNK;
   for (int k = 0; k < 4; k++) out4[k] = 0.0;
-  for (int s = 0; s < mh.S; s++) {
+  for (int s = 0; s < S; s++) {
     double tot = 0.0;
     for (int j = 0; j < B; j++) {
       const int o = (s * nchunk + j / DG_SUFF_CHUNK) * 3 * DG_SUFF_CHUNK + 3 * (j % DG_SUFF_CHUNK);
@@ -342,10 +379,8 @@ bool chisq_from_statistics(dang_gpu *h, int pol_lo, int pol_hi, double out4[4]) 
       for (int g = 0; g < h->nranks; g++) X += hp[(size_t)g * cnt + o];  // rank order: same bits on every rank
       tot += X / (double)B;
     }
-    out4[mh.plane[s]] = tot;
+    out4[plane[s]] = tot;
   }
-  out4[3] = (double)n_unmasked;
-  return true;
 }
 
 // tune_spectral_parameter_length, src/dang_sample_mod.f90:623-717.  `start`: the chain start when the call site gives

@@ -149,18 +149,20 @@ cg_solve_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict_
   double2 *ring = reinterpret_cast<double2 *>(cg_ring_raw);
   __shared__ double smem[4 * 32];
   __shared__ double ha[DG_CG_HIST], hb[DG_CG_HIST];  // alpha_i, beta_i used IN pass i (1-based), as they become known
-  __shared__ int s_done0, s_m, s_done, s_gen;  // s_gen: last pass whose outcome warp 0 has copied into this block
+  __shared__ int s_done0, s_m, s_done, s_gen, s_kpred;  // s_gen: last pass whose outcome warp 0 has copied into this block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {  // state left by cg_init_update (K1's last block): pass 1 is fully known
     s_done0 = __ldcg(&st->done);
     s_done = 0;
     s_gen = 0;
     s_m = __ldcg(&st->m);
+    s_kpred = k_pred >= 0 ? k_pred : __ldcg(&st->k_pred);  // (< 0: the host has not seen the previous solve's count)
     ha[1] = __ldcg(&st->ah[1]);
     hb[1] = __ldcg(&st->bh[1]);
   }
   __syncthreads();
   const int m = s_m;
+  k_pred = s_kpred;
   int k = 1, c0 = 0, x_at = 0;  // pass to run, pass of the last checkpoint, pass x is current for: block-uniform
   bool done = s_done0 != 0;
   while (!done) {
@@ -216,6 +218,7 @@ cg_solve_kernel(CgScalars *st, const double *__restrict__ M, double *__restrict_
       if (threadIdx.x == 0) {
         cg_fused_update(st, pc.nranks > 1 ? gathered : out, pc.nranks);  // iter = k + 1, done, ah / bh[k + 1], ckpt
         if (with_x) st->x_at = k;
+        if (st->done) st->k_pred = k;  // the solve ends with this pass: the next solve's prediction
         __threadfence();
         st_release_gpu(&st->gen, (unsigned)k);  // pass k is complete: its scalars are visible before the count
       }

@@ -260,27 +260,35 @@ mh_suffstat_ring_kernel(const ModelView mv, const MhView mh, const MhScalars *ms
     epre += stride;
   }
   int stage = 0, pstage = DG_RING_STAGES - 1;
-  // amplitudes and mask of the NEXT pixel pair travel in registers, one iteration ahead
-  double2 a_nx[NC];
-  uchar2 mk_nx = make_uchar2(0, 0);
-  auto fetch_next = [&](int64_t en) {
+  // amplitudes and mask of the next TWO pixel pairs travel in registers (a two-deep pipeline, like the ring: one
+  // iteration of this loop is shorter than the memory latency under load)
+  double2 a_n1[NC], a_n2[NC];
+  uchar2 mk_n1 = make_uchar2(0, 0), mk_n2 = make_uchar2(0, 0);
+  auto fetch = [&](int64_t en, double2 (&an)[NC], uchar2 &mkn) {
     const int64_t pn = 2 * (en < n2 ? en : e);  // (a valid address when the thread has run out of items)
-    mk_nx = *reinterpret_cast<const uchar2 *>(mv.mask + pn);
+    mkn = *reinterpret_cast<const uchar2 *>(mv.mask + pn);
 #pragma unroll
     for (int c = 0; c < NC; c++)
-      a_nx[c] = c < mv.ncomp ? ld2(mv.comp[c].amp + (size_t)k * mv.Ppad + pn) : make_double2(0.0, 0.0);
+      an[c] = c < mv.ncomp ? ld2(mv.comp[c].amp + (size_t)k * mv.Ppad + pn) : make_double2(0.0, 0.0);
   };
-  if (e < n2) fetch_next(e);
+  if (e < n2) {
+    fetch(e, a_n1, mk_n1);
+    fetch(e + stride, a_n2, mk_n2);
+  }
   for (; e < n2; e += stride) {
     issue(epre, pstage);
     epre += stride;
     pstage = pstage + 1 == DG_RING_STAGES ? 0 : pstage + 1;
-    const uchar2 mk = mk_nx;
+    const uchar2 mk = mk_n1;
     const bool use0 = mk.x != 0, use1 = mk.y != 0;
     double2 a[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) a[c] = a_nx[c];
-    fetch_next(e + stride);
+    for (int c = 0; c < NC; c++) {
+      a[c] = a_n1[c];
+      a_n1[c] = a_n2[c];
+    }
+    mk_n1 = mk_n2;
+    fetch(e + 2 * stride, a_n2, mk_n2);
     double2 am = make_double2(0.0, 0.0);
 #pragma unroll
     for (int c = 0; c < NC; c++)

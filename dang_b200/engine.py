@@ -36,6 +36,7 @@ OPT_BP_QUADRATURE = 14
 OPT_CG_PERSISTENT = 15
 OPT_STREAM_RING = 16
 OPT_DEFER_D2H = 17
+OPT_DEFER_SCALARS = 18
 KERNEL_COUNT = 12
 
 
@@ -85,6 +86,7 @@ class Engine:
         # c%tuned(j) = .not. fg_spec_tune (src/dang_component_mod.f90:177): untuned indices are tuned by the first
         # sample_index_mh that meets them, and the tuner then marks ALL of the component's indices tuned (:711)
         self._tuned = [[not s.tune for s in c.indices] for c in cfg.comps]
+        self._n_unmasked = 0
         # init_bp_mod
         for j, b in enumerate(cfg.bands):
             nu_c, nu0, tau0 = init_bandpass(b)
@@ -353,6 +355,7 @@ class Engine:
         n = C.c_int64()
         lo, hi = self.cfg.pol_type
         self._ck(self.lib.dang_gpu_chisq(self.h, lo, hi, _dp(planes), C.byref(n)))
+        self._n_unmasked = n.value
         return planes, n.value
 
     def compute_chisq(self) -> float:
@@ -403,6 +406,28 @@ class Engine:
         if it > 1:
             r2 = self.sample_spectral_parameters(z=z, u=u, seed=seed + 2 * it + 1)
         return r1, r2
+
+    # ------------------------------------------------------------------ deferred scalars (OPT_DEFER_SCALARS)
+    def iteration_mark(self) -> int:
+        """Snapshot the results the deferred calls since the last mark left on the device; returns a ticket."""
+        t = C.c_int64()
+        self._ck(self.lib.dang_gpu_iteration_mark(self.h, C.byref(t)))
+        return t.value
+
+    def iteration_scalars(self, ticket: int) -> dict:
+        """The terminal line of src/dang.f90:100-104 for the iteration a ticket closed: waits for that snapshot only."""
+        n_iter, delta, acc, val = C.c_int(), C.c_double(), C.c_double(), C.c_double()
+        chi_a, chi_i = np.zeros(self.cfg.nmaps), np.zeros(self.cfg.nmaps)
+        self._ck(self.lib.dang_gpu_iteration_scalars(self.h, ticket, C.byref(n_iter), C.byref(delta), _dp(chi_a), C.byref(acc),
+                                                     C.byref(val), _dp(chi_i)))
+        def total(planes):  # compute_chisq's normalisation
+            t = 0.0
+            for k in range(self.nmaps):
+                t = t + planes[k]
+            return t / float(self.nmaps * self._n_unmasked) if self._n_unmasked else float("nan")
+
+        return dict(n_iter=n_iter.value, delta=delta.value, chisq_after_amplitudes=chi_a, accept=acc.value,
+                    index_value=val.value, chisq_after_index=chi_i, chisq_amplitudes=total(chi_a), chisq_index=total(chi_i))
 
     # ------------------------------------------------------------------ instrumentation
     def sync(self):

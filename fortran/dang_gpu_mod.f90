@@ -292,6 +292,23 @@ module dang_gpu_mod
        integer(c_int), value :: ic, nind
        real(c_double) :: step_size
      end function dang_gpu_get_step_size
+     ! ---- deferred scalars (DANG_OPT_DEFER_SCALARS = 18): the numbers of write_stats_to_term (dang.f90:100-104)
+     !      one iteration late; a host that prints every iteration calls _mark at the end of iteration k and
+     !      _scalars(ticket of k-1) right after it
+     integer(c_int) function dang_gpu_iteration_mark(h, ticket) bind(C, name='dang_gpu_iteration_mark')
+       import :: c_int, c_int64_t, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int64_t) :: ticket
+     end function dang_gpu_iteration_mark
+     integer(c_int) function dang_gpu_iteration_scalars(h, ticket, n_iter, delta_final, chisq_after_amplitudes, accept, &
+          index_value, chisq_after_index) bind(C, name='dang_gpu_iteration_scalars')
+       import :: c_int, c_int64_t, c_double, c_ptr
+       type(c_ptr), value :: h
+       integer(c_int64_t), value :: ticket
+       integer(c_int) :: n_iter
+       real(c_double) :: delta_final, accept, index_value
+       real(c_double), intent(out) :: chisq_after_amplitudes(*), chisq_after_index(*)
+     end function dang_gpu_iteration_scalars
   end interface
 
 contains

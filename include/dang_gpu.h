@@ -132,7 +132,17 @@ enum {
    * the launch-heavy spectral-parameter block: a saturated host link delays the GPU's command fetches, which makes
    * every small kernel behind it cost 50-70 us (profiles/).  dang_gpu_download_wait and in-place writers issue pending
    * requests at once.  0: the copy starts as soon as the compute stream reaches the request. */
-  DANG_OPT_DEFER_D2H = 17
+  DANG_OPT_DEFER_D2H = 17,
+  /* 1: deferred scalars.  The reference's loop prints n_iter / chi-square / accept after each block
+   * (write_stats_to_term, src/dang.f90:100-104), and by default every call here waits for the device to hand those
+   * numbers back: three host round trips per Gibbs iteration, each leaving the GPU idle for 15-25 us (more on several
+   * GPUs).  With this option dang_gpu_cg_solve (persistent form, one solve per iteration), dang_gpu_chisq (when the
+   * draw's statistics serve it) and full-sky dang_gpu_sample_index (statistics form) only ENQUEUE their kernels and
+   * return n_iter = -1 / NaN; dang_gpu_iteration_mark snapshots the device-side results at that point of the stream
+   * and dang_gpu_iteration_scalars returns them later -- typically one iteration behind, so the device never waits
+   * for the host.  The kernels, their order and every result are identical to the default mode's; calls that are
+   * not covered keep returning their values directly.  0 (default): every call returns its own numbers. */
+  DANG_OPT_DEFER_SCALARS = 18
 };
 
 /* ---- lifetime: after initialize_cg_groups, src/dang.f90:71-75; mpi_finalize, :127 ---- */
@@ -284,6 +294,20 @@ int dang_gpu_fit_band_gain(dang_gpu_t *h, int map_n, int band, int ml_mode, cons
  * dang_gpu_sample_index itself still requires sample_nside == nside. */
 int dang_gpu_udgrade(dang_gpu_t *h, int kind, const double *in, int nside_in, double *out, int nside_out, int nmaps,
                      double threshold);
+
+/* ---- deferred scalars (DANG_OPT_DEFER_SCALARS): the terminal line of src/dang.f90:100-104 one iteration late ----
+ * _mark: snapshot what the deferred calls since the previous mark left on the device (solve count / residual,
+ *   statistics rows, chain outcome) into one of four pinned slots, stream ordered, no host wait; returns a ticket.
+ *   At most four tickets may be outstanding (unread).
+ * _scalars: wait for that snapshot only and decode it.  n_iter / delta_final: the amplitude draw's (as
+ *   dang_gpu_cg_solve); chisq_after_amplitudes[nmaps]: the dang_gpu_chisq call that followed it; accept /
+ *   index_value: the full-sky draw's acceptance ratio and final value; chisq_after_index[nmaps]: the dang_gpu_chisq
+ *   call after the draw.  Entries nothing was deferred for come back as -1 / NaN; any pointer may be NULL.
+ *   Tickets should be read in issue order (the traffic accounting of dang_gpu_kernel_stats assumes it). */
+int dang_gpu_iteration_mark(dang_gpu_t *h, int64_t *ticket);
+int dang_gpu_iteration_scalars(dang_gpu_t *h, int64_t ticket, int *n_iter, double *delta_final,
+                               double *chisq_after_amplitudes, double *accept, double *index_value,
+                               double *chisq_after_index);
 
 /* mask_avg(c%indices(:,map_n,nind), masks(:,1)), src/dang_util_mod.f90:186-206 */
 int dang_gpu_index_mean(dang_gpu_t *h, int ic, int nind, int map_n, double *mean);

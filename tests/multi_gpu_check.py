@@ -99,6 +99,42 @@ def main():
     eng.comm_check()
     eng.close()
     dist.barrier()
+    # deferred scalars (DANG_OPT_DEFER_SCALARS) on several ranks: same numbers as the default mode, one iteration late
+    if os.environ.get("DANG_GPU_MAILBOX", "1") != "0":   # (the persistent solve needs the mailboxes)
+        from dang_b200.engine import OPT_DEFER_SCALARS
+        cfg, sky = small_case("c2", ns, perturb=False)
+        bounds = ring_partition(cfg.nside, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        rows = {}
+        for mode in ("default", "deferred"):
+            eng = Engine(cfg, sky, device=local, pix_range=(lo, hi))
+            setup_torch_comm(eng, mailboxes=True)
+            out, prev = [], None
+            for it in range(1, 8):
+                if mode == "deferred" and it == 3:
+                    eng.set_option(OPT_DEFER_SCALARS, 1)
+                r1, r2 = eng.gibbs_iteration(it, seed=5)
+                if mode == "deferred" and it >= 3:
+                    assert r1[0][0] == -1
+                    t = eng.iteration_mark()
+                    if prev is not None:
+                        q = eng.iteration_scalars(prev)
+                        out.append((q["n_iter"], q["delta"], q["chisq_amplitudes"], q["accept"], q["chisq_index"]))
+                    prev = t
+                else:
+                    out.append((r1[0][0], r1[0][1], r1[1], r2[0][0] if r2 else None, r2[1] if r2 else None))
+            if prev is not None:
+                q = eng.iteration_scalars(prev)
+                out.append((q["n_iter"], q["delta"], q["chisq_amplitudes"], q["accept"], q["chisq_index"]))
+                eng.set_option(OPT_DEFER_SCALARS, 0)
+            rows[mode] = (out, [eng.amplitude(ic)[:, lo:hi].copy() for ic in range(len(cfg.comps))],
+                          [eng.indices(ic)[:, :, lo:hi].copy() for ic in range(len(cfg.comps))])
+            eng.comm_check()
+            eng.close()
+            dist.barrier()
+        assert rows["default"][0] == rows["deferred"][0], (rank, rows["default"][0], rows["deferred"][0])
+        for a, b in zip(rows["default"][1] + rows["default"][2], rows["deferred"][1] + rows["deferred"][2]):
+            assert np.array_equal(a, b), (rank, "deferred-scalars maps differ")
     print(f"rank {rank}/{world}: multi-GPU parity ok (pixels [{lo},{hi}), worst amplitude error {worst:.2e})", flush=True)
     dist.destroy_process_group()
 
