@@ -473,7 +473,7 @@ int dang_gpu_set_option(dang_gpu_t *h, int option, double value) {
     case DANG_OPT_CG_CHUNK: h->cg_chunk = value < 1 ? 1 : (int)value; break;
     case DANG_OPT_RECORD_DECISIONS: h->record = value != 0; break;
     case DANG_OPT_PERPIXEL_SERIAL: h->perpixel_serial = value != 0; break;
-    case DANG_OPT_PERPIXEL_FAST: h->pp_fast = value != 0; h->pp_split = value == 2; break;
+    case DANG_OPT_PERPIXEL_FAST: h->pp_fast = value != 0; h->pp_split = value == 2; h->pp_pix = value == 3; break;
     case DANG_OPT_TMA: h->use_tma = value != 0; break;
     case DANG_OPT_L2_PERSIST_MB: {
       // the set-aside shrinks the L2 every other kernel sees, so it exists only while the option is on

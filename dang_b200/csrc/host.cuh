@@ -186,6 +186,7 @@ struct dang_gpu {
   int cg_persistent = 1;  // whole solve in one persistent cooperative kernel (DANG_OPT_CG_PERSISTENT)
   int bp_quad = 8;        // nodes of the Gauss-quadrature compression of tabulated bandpasses (0: off)
   int pp_bp_series = 1;   // tabulated bandpasses: moment series in the per-pixel chains (DANG_OPT_PERPIXEL_BP_SERIES)
+  int pp_pix = 1;         // 1: one-thread-per-pixel form of the screened kernel (kernels_mh_pix.cuh)
   int pp_split = 0;       // 1: split form of the screened kernel (rng / state / chain kernels), measured slower
   void *k5_st4 = nullptr; float *k5_kj = nullptr; size_t k5_len = 0;  // its fp32 state scratch
   int pp_fast = 1;        // certified fp32 screening in the per-pixel Metropolis kernel (DANG_OPT_PERPIXEL_FAST)
@@ -516,6 +517,7 @@ void mh_view(dang_gpu *h, int ic, int nind, int map_n, int nsample, int ml_mode,
 void ensure_zu(dang_gpu *h, size_t n);
 void ensure_decisions(dang_gpu *h, size_t n);
 void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);  // host_mh_pp.cu
+void launch_perpixel_pix(dang_gpu *h, const ModelView &mv, const MhView &mh, int mode);  // host_mh_ppx.cu
 void launch_perpixel_fast(dang_gpu *h, const ModelView &mv, const MhView &mh, int bpl, int mode, int64_t work,
                           size_t smem);                                            // host_mh_ppf.cu
 void launch_perpixel_split(dang_gpu *h, const ModelView &mv, MhView &mh, int bpl, int mode, int64_t work);  // host_mh_ppf.cu

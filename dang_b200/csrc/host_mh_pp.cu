@@ -84,7 +84,9 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
       else if (mode == MH_SED_BP_MBB_BETA) LAUNCH_PP(BPL, MH_SED_BP_MBB_BETA) \
       else LAUNCH_PP(BPL, MH_SED_GENERIC)                       \
     }
-    if (fast && h->pp_split && !h->record) {
+    if (fast && h->pp_pix && h->nbands <= 32) {
+      launch_perpixel_pix(h, mv, mh, mode);
+    } else if (fast && h->pp_split && !h->record) {
       launch_perpixel_split(h, mv, mh, bpl, mode, work);
     } else if (fast) {
       const int bplr = bpl <= 2 ? 2 : bpl <= 3 ? 3 : bpl <= 5 ? 5 : 8;

@@ -66,7 +66,7 @@ __device__ __forceinline__ float k5_em1f(float x) {
 
 // data_raw and 1/sigma of one (band, plane, pixel): out of line, so that the (large) SED dispatch of the
 // other components exists once in the kernel instead of once per call site
-__device__ __noinline__ void k5_fetch(const ModelView &mv, int ic, int j, int k, int64_t pp, double &D, double &sig) {
+static __device__ __noinline__ void k5_fetch(const ModelView &mv, int ic, int j, int k, int64_t pp, double &D, double &sig) {
   D = mh_data_value(mv, ic, j, k, pp);
   sig = ldg_stream(mv.rms + plane_off(mv, j, k) + pp);
 }

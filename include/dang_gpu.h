@@ -95,14 +95,16 @@ enum {
   /* MB of the CG block matrices M marked persisting in L2 (cudaAccessPolicyWindow) for the passes of a
    * solve; the rest of the CG state streams.  0: off. */
   DANG_OPT_L2_PERSIST_MB = 11,
-  /* Per-pixel Metropolis, delta bands, power-law / mbb indices.  1 (default): every proposal is screened
-   * in single precision from the chi-square DIFFERENCE about the chain's starting point (the data term
+  /* Per-pixel Metropolis, delta bands, power-law / mbb indices.  Screened forms: every proposal is evaluated
+   * in single precision from the chi-square DIFFERENCE about the chain's current point (the data term
    * cancels analytically) with a running error bound; a proposal whose |diff - ln u| is inside the bound
    * is re-evaluated in fp64 with the arithmetic of the fp64 kernel, so the decisions are the fp64
-   * kernel's (dang_gpu_perpixel_stats counts the fallbacks).  2: the same in split form (deviates and the fp64
-   * state in their own kernels, then an fp32-only chain kernel) -- a measured experiment, slower (10.1 against
-   * 7.9 ms per index at nside 512 x 20 bands: the chain loop needs > 128 registers either way).
-   * 0: every proposal in fp64. */
+   * kernel's (dang_gpu_perpixel_stats counts the fallbacks).
+   *   3 (default): one thread per pixel, two numbers of state per band in shared memory (csrc/kernels_mh_pix.cuh;
+   *      6.3 ms per index at nside 512 x 20 bands);
+   *   1: four lanes per pixel, residuals per band and Stokes parameter in registers (csrc/kernels_mh_fast.cuh; 7.9 ms);
+   *   2: form 1 split into deviate / state / chain kernels -- a measured experiment, slower (10.1 ms);
+   *   0: every proposal in fp64 (9.4 ms). */
   DANG_OPT_PERPIXEL_FAST = 12,
   /* Per-pixel Metropolis with tabulated bandpasses, power-law beta / mbb beta.  1 (default): the bandpass-
    * integrated SED of a proposal comes from a 9-term moment series about the chain's first point (the n_bp

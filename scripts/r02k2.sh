@@ -1,0 +1,7 @@
+#!/bin/bash
+bash scripts/r02k.sh
+f=3
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'mh_perpixel' -s 2 -c 2 -o /tmp/r02k_f$f -f \
+  python bench.py --config c4 --nside 512 --steps 1 --warmup 3 --no-cpu --opt 12=$f > gpurun_out/r02k_ncu_f$f.log 2>&1
+ncu -i /tmp/r02k_f$f.ncu-rep --page raw --csv > gpurun_out/r02k_f${f}_raw.csv
+ncu -i /tmp/r02k_f$f.ncu-rep --page source --csv > gpurun_out/r02k_f${f}_source.csv 2>/dev/null || true

@@ -157,14 +157,15 @@ def test_one_statistics_pass_serves_both_chisquares(case):
     assert abs(out[1][2] - out[0][2]) <= 1e-12 * out[0][2]
 
 
-def test_screened_perpixel_chains_equal_fp64_chains_at_full_size():
+@pytest.mark.parametrize("form", [1, 3])
+def test_screened_perpixel_chains_equal_fp64_chains_at_full_size(form):
     """Config c4's per-pixel beta_d and T_d draws at nside 512 (3.1 M chains x 20 proposals x 20 bands): the
     fp32-screened kernel leaves bit-identical index maps and acceptance counts, with a tiny fallback rate."""
     from dang_b200.engine import OPT_PERPIXEL_FAST
     from dang_b200.synth import make_config, make_sky
     cfg = make_config("c4", nside=NSIDE)
     sky = make_sky(cfg)
-    a, b = engine(cfg, sky), engine(cfg, sky, {OPT_PERPIXEL_FAST: 0})
+    a, b = engine(cfg, sky, {OPT_PERPIXEL_FAST: form}), engine(cfg, sky, {OPT_PERPIXEL_FAST: 0})
     n_unmasked = int((sky.mask != 0).sum())
     for eng in (a, b):
         eng.cg_solve(0, 0, "sample", seed=3)

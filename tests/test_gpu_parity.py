@@ -213,7 +213,8 @@ def run_perpixel(cfg, sky, ic, nind, nsample, ml_mode="sample", seed=11, serial=
 
 
 # kernels: fp32-screened lane-cooperative (default), fp64 lane-cooperative, strict reference order
-@pytest.mark.parametrize("kernel", ["screened", "fp64", "serial"])
+# and the one-thread-per-pixel screened form (kernels_mh_pix.cuh)
+@pytest.mark.parametrize("kernel", ["screened", "pixel", "fp64", "serial"])
 @pytest.mark.parametrize("name,ic,nind,nside", [("c1", 0, 0, 16), ("c3", 1, 0, 4), ("c3", 0, 0, 4), ("c4", 1, 0, 8),
                                                 ("c4", 1, 1, 8), ("c2", 1, 1, 8), ("c4", 0, 0, 8)])
 def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside, kernel):
@@ -222,10 +223,10 @@ def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside, kernel):
     cfg.comps[ic].indices[nind].region = "per-pixel"
     nsample = 12
     ora, eng, (acc_o, dec_o, lnl_o), (acc_g, dec_g, lnl_g) = run_perpixel(
-        cfg, sky, ic, nind, nsample, serial=int(kernel == "serial"), fast=int(kernel == "screened"))
+        cfg, sky, ic, nind, nsample, serial=int(kernel == "serial"), fast={"screened": 1, "pixel": 3}.get(kernel, 0))
     assert np.array_equal(dec_g, dec_o), f"{(dec_g != dec_o).sum()} decisions differ"
     assert acc_g == acc_o
-    if kernel == "screened":  # record mode checks every screened difference against its error bound
+    if kernel in ("screened", "pixel"):  # record mode checks every screened difference against its error bound
         fallbacks, violations = eng.perpixel_stats()
         assert violations == 0, (fallbacks, violations)
         assert fallbacks <= 0.02 * (dec_o < 2).sum(), (fallbacks, (dec_o < 2).sum())
@@ -239,8 +240,9 @@ def test_perpixel_metropolis_bit_exact_decisions(name, ic, nind, nside, kernel):
     assert np.array_equal(idx_g[nind][0], idx_o[nind][0])  # I plane untouched
 
 
+@pytest.mark.parametrize("form", [1, 3])
 @pytest.mark.parametrize("name,ic,nind", [("c4", 1, 0), ("c4", 1, 1), ("c1", 0, 0)])
-def test_perpixel_screened_kernel_takes_the_fp64_decisions(name, ic, nind):
+def test_perpixel_screened_kernel_takes_the_fp64_decisions(name, ic, nind, form):
     """Production mode (no recording): the fp32-screened kernel and the fp64 kernel leave identical index
     maps and acceptance counts after long chains with big steps, at a size where ~1e6 proposals are
     decided; the fallback rate stays small."""
@@ -252,6 +254,7 @@ def test_perpixel_screened_kernel_takes_the_fp64_decisions(name, ic, nind):
     nsample = 40
     z, u = deviates(cfg, nsample, seed=5)
     a, b = Engine(cfg, sky), Engine(cfg, sky)
+    a.set_option(OPT_PERPIXEL_FAST, form)
     b.set_option(OPT_PERPIXEL_FAST, 0)
     acc_a = a.sample_index_mh(ic, nind, -1, nsample, "sample", z, u)
     acc_b = b.sample_index_mh(ic, nind, -1, nsample, "sample", z, u)
@@ -259,7 +262,9 @@ def test_perpixel_screened_kernel_takes_the_fp64_decisions(name, ic, nind):
     assert acc_a == acc_b and acc_a > 0
     assert np.array_equal(a.indices(ic), b.indices(ic))
     n_unmasked = int((sky.mask != 0).sum())
-    assert fallbacks < 0.005 * nsample * n_unmasked, (fallbacks, nsample * n_unmasked)
+    # (the one-thread-per-pixel form carries one error bound for all bands of a pixel: with steps three times the
+    # configured ones and 40-proposal chains it gives up earlier -- slower there, never wrong)
+    assert fallbacks < (0.005 if form == 1 else 0.1) * nsample * n_unmasked, (fallbacks, nsample * n_unmasked)
     # and with the device RNG
     acc_a = a.sample_index_mh(ic, nind, -1, nsample, "sample", seed=99)
     acc_b = b.sample_index_mh(ic, nind, -1, nsample, "sample", seed=99)
