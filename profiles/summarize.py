@@ -35,11 +35,17 @@ def raw(path):
             "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "launch__grid_size",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
     out = []
+    units = rows[1]
+    scale = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6,   # bytes -> MB
+             "s": 1e6, "ms": 1e3, "us": 1.0, "ns": 1e-3}                 # time -> us
     for r in rows[2:]:
         rec = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")}
         for w in want:
             if w in hdr:
-                rec[w] = r[hdr.index(w)]
+                v, u = r[hdr.index(w)], units[hdr.index(w)]
+                if u in scale and (w.startswith("dram__bytes") or w == "gpu__time_duration.sum"):
+                    v = f"{float(v.replace(',', '')) * scale[u]:.3f}"   # ncu picks a unit per column
+                rec[w] = v
         out.append(rec)
     return out, rows[1], hdr
 
@@ -70,6 +76,7 @@ def main():
     print("wrote", outp)
     # per-launch DRAM traffic (read + write, bytes) keyed by bench.py's kernel names
     alias = {"rhs_blocks": "rhs_blocks_kernel", "cg_recompute_pass": "cg_pass_kernel", "cg_fused_pass": "cg_pass_kernel",
+             "cg_solve_kernel": "cg_pass_kernel",
              "chisq": "chisq_kernel", "mh_suffstat": "mh_suffstat_kernel", "mh_perpixel": "mh_perpixel_kernel"}
     acc = collections.defaultdict(list)
     for r in recs:

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--nside", type=int, default=None)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--defer", type=int, default=0, help="1: DANG_OPT_DEFER_SCALARS (value mode)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -58,9 +59,15 @@ def main():
     z_h[0][:] = np.random.default_rng(2).standard_normal(cfg.nsample)
     u_h[0][:] = np.random.default_rng(3).random(cfg.nsample)
 
+    pending = []
+
     def step(it):
         if args.mode == "value":
-            eng.gibbs_iteration(2 + it, seed=it)
+            r1, _ = eng.gibbs_iteration(2 + it, seed=it)
+            if r1[0][0] == -1:  # deferred scalars: read the previous iteration's numbers
+                pending.append(eng.iteration_mark())
+                if len(pending) > 1:
+                    eng.iteration_scalars(pending.pop(0))
         else:
             eng.stage_eta(eta_hs[(it + 1) % 3])
             eng.sample_cg_groups(eta=None)
@@ -72,7 +79,11 @@ def main():
 
     if args.mode != "value":
         eng.stage_eta(eta_hs[0])
-    for w in range(4):
+    step(0)
+    if args.defer and args.mode == "value":
+        from dang_b200.engine import OPT_DEFER_SCALARS
+        eng.set_option(OPT_DEFER_SCALARS, 1)
+    for w in range(1, 4):
         step(w)
     eng.download_wait()
     eng.sync()
@@ -83,6 +94,8 @@ def main():
     t0 = time.perf_counter()
     for k in range(args.steps):
         step(10 + k)
+    while pending:
+        eng.iteration_scalars(pending.pop(0))
     eng.download_wait()
     eng.sync()
     wall_us = (time.perf_counter() - t0) * 1e6
