@@ -345,6 +345,59 @@ def run_gpu(args):
     nplanes_out = 2 * len(cfg.comps) + 2 * n_pp
     d2h = 8 * P * nplanes_out + 8 * 8 + 16 * (len(sampled) - n_pp)
 
+    # --- the same loop with fewer bytes on the host link (reported beside `e2e`, which stays the worst case:
+    #     injected deviates in AND all changed maps out on every iteration, i.e. OUTPUT_ITER = 1)
+    variants = {}
+    if fullsky_only and one_solve and not args.no_variants:
+        def run_variant(kind):
+            def vstep(it):
+                if kind == "device_rng":      # the shim's production path: deviates drawn on the device, maps out
+                    r1 = eng.sample_cg_groups(eta=None, seed=1000 + it)
+                    for ic in range(len(cfg.comps)):
+                        eng.amplitude_async(ic, amp_h[ic])
+                    eng.sample_spectral_parameters(seed=7 + 2 * it)
+                else:                          # maps stay on the device between output iterations (OUTPUT_ITER > 1)
+                    eng.stage_eta(eta_hs[(it + 1) % 3])
+                    r1 = eng.sample_cg_groups(eta=None)
+                    eng.sample_spectral_parameters(z=z_h, u=u_h, seed=7 + 2 * it)
+                if r1[0][0] == -1:
+                    pending.append(eng.iteration_mark())
+                    if len(pending) > 1:
+                        eng.iteration_scalars(pending.pop(0))
+                else:
+                    for ic, j in sampled:
+                        eng.index_fullsky(ic, j, 2)
+
+            def vdrain():
+                while pending:
+                    eng.iteration_scalars(pending.pop(0))
+                eng.download_wait()
+
+            if kind == "scalars_only":
+                eng.stage_eta(eta_hs[0])
+            for w in range(3):
+                vstep(w)
+            vdrain()
+            barrier()
+            eng.event_record(4)
+            tv = time.perf_counter()
+            for k in range(ke):
+                vstep(3 + k)
+            vdrain()
+            eng.event_record(5)
+            barrier()
+            wall = (time.perf_counter() - tv) * 1e3
+            vms = max_over_ranks(max(eng.event_elapsed_ms(4, 5), wall))
+            if kind == "scalars_only":     # leave no staged deviates behind
+                eng.sample_cg_groups(eta=None)
+                vdrain()
+            return round(1e3 * ke / vms, 3)
+
+        variants["device_rng_maps_out"] = {"value": run_variant("device_rng"), "unit": UNIT, "h2d_bytes_per_step": 0,
+                                           "d2h_bytes_per_step": d2h}
+        variants["deviates_in_scalars_out"] = {"value": run_variant("scalars_only"), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                               "d2h_bytes_per_step": 8 * 8 + 16 * len(sampled)}
+
     eng.comm_check()  # a timed-out scalar exchange would have poisoned the sums: fail instead of printing
     if rank == 0:
         peak, peak_src = peaks()
@@ -388,7 +441,10 @@ def run_gpu(args):
                     "n_cg_iterations": {"min": int(min(e2e_ncg)), "max": int(max(e2e_ncg)), "mean": round(float(np.mean(e2e_ncg)), 2)},
                     "ms_per_step_device_rank0": round(e2e_dev_ms / ke, 4), "ms_per_step_wall_rank0": round(wall_ms / ke, 4),
                     "what": "per step: injected deviates (eta, z, u) pinned host -> device; changed Q/U planes of every amplitude map and of the per-pixel-sampled index maps, the value of every full-sky-sampled index (one double per plane) + chi-square device -> pinned host; copies overlap compute on dedicated streams"
-                            + ("" if host_zu else "; per-pixel Metropolis deviates drawn on the device (16 GB per step otherwise)")},
+                            + ("" if host_zu else "; per-pixel Metropolis deviates drawn on the device (16 GB per step otherwise)"),
+                    **({"variants": variants,
+                        "variants_what": "same loop, fewer bytes on the host link: `device_rng_maps_out` = the Fortran shim's production path (device Philox, all changed maps out every iteration); `deviates_in_scalars_out` = injected deviates in, only the terminal-line scalars out (maps stay on the device between OUTPUT_ITER iterations, src/dang.f90:119-121)"}
+                       if variants else {})},
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu:
@@ -493,6 +549,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--nside", type=int, default=None, help="override the map size (tests only)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the reduced-traffic e2e variants")
     ap.add_argument("--defer-scalars", type=int, default=1, help="1: DANG_OPT_DEFER_SCALARS on the one-solve + full-sky configs")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (experiments), e.g. --opt 8=16")
     args = ap.parse_args()
