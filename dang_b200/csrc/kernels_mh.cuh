@@ -802,7 +802,6 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh_in, MhScalars *ms, cons
     s0 = ms->s0[j];
   }
   double sample[DG_MAXIND] = {ms->sample[0], ms->sample[1]};
-  double theta[DG_MAXIND] = {sample[0], sample[1]};
   // mbb beta chain on a delta band: the Planck factor eref / (exp(z nu_c) - 1) does not move (T is fixed),
   // so it is formed once; sed_mbb multiplies exactly this quotient by the power law: same bits, 1 exp per
   // proposal on the chain's serial path instead of 3
@@ -831,31 +830,85 @@ mh_suff_chain_kernel(const ModelView mv, const MhView mh_in, MhScalars *ms, cons
   };
   double lnl_old = lnl_of(s0) + prior_of(sample[mh.nind]);  // :250, :261, :268
   double accept = 0.0;
-  double zl = 0.0, ul = 0.0;  // deviates of 32 consecutive proposals, one per lane (off the serial path)
-  for (int l = 0; l < mh.nsample; l++) {
-    if ((l & 31) == 0 && l + j < mh.nsample) {
-      zl = mh_draw_z(mh, l + j);
-      ul = mh_draw_u(mh, l + j);
+  // ---- the chain, speculatively parallel over proposals.  Until a proposal is accepted the chain's state does not
+  // move, so lane i evaluates proposal l0 + i against the CURRENT state -- all bands itself, the band sum in the
+  // very order of the lane butterfly above (same bits as the one-proposal-at-a-time loop this replaces) -- and the
+  // first accepted lane ends the round: proposals before it were rejected against the right state, it becomes the
+  // state, everything after it is re-evaluated.  Rounds = accepted moves + 1 instead of nsample serial steps.
+  __shared__ double cX[32], cY[32], cZ[32], cS0[32], cF[32], cLh[32], cLl[32];
+  __shared__ double gz[DG_FS_DEV_MAX], gu[DG_FS_DEV_MAX];
+  __shared__ double sv[32][33];
+  cX[j] = X;
+  cY[j] = Y;
+  cZ[j] = Z;
+  cS0[j] = s0;
+  cF[j] = Fj;
+  cLh[j] = lh;
+  cLl[j] = ll;
+  const bool pf_all = __all_sync(0xffffffffu, planck_fixed || j >= B);  // (the same SED form in every band)
+  const bool pregen = mh.nsample <= DG_FS_DEV_MAX;
+  if (pregen)
+    for (int i = j; i < mh.nsample; i += 32) {  // deviates of the whole chain, off the serial path
+      gz[i] = mh_draw_z(mh, i);
+      gu[i] = mh.ml_mode == 0 ? 1.0 : mh_draw_u(mh, i);
     }
-    const double z_l = __shfl_sync(0xffffffffu, zl, l & 31), u_l = __shfl_sync(0xffffffffu, ul, l & 31);
-    theta[mh.nind] = sample[mh.nind] + (0.0 + mh.step * z_l);  // :286
-    if (theta[mh.nind] < mh.uni[0] || theta[mh.nind] > mh.uni[1]) {          // :287, Q5
-      if (mh.decisions && j == 0) mh.decisions[l] = 2;
-      continue;
+  __syncwarp();
+  for (int l0 = 0; l0 < mh.nsample;) {
+    const int l = l0 + j;
+    const bool live = l < mh.nsample;
+    double th[DG_MAXIND] = {sample[0], sample[1]};
+    double lnl_new = 0.0, u_l = 1.0;
+    bool oob = false, acc = false;
+    if (live) {
+      const double z_l = pregen ? gz[l] : mh_draw_z(mh, l);
+      th[mh.nind] = sample[mh.nind] + (0.0 + mh.step * z_l);  // :286
+      oob = th[mh.nind] < mh.uni[0] || th[mh.nind] > mh.uni[1];  // :287, Q5
+      if (!oob) {
+        u_l = pregen ? gu[l] : (mh.ml_mode == 0 ? 1.0 : mh_draw_u(mh, l));
+        if (pf_all) {  // independent exps: unrolled so that they overlap
+#pragma unroll 4
+          for (int jb = 0; jb < 32; jb++) {
+            double v = 0.0;
+            if (jb < B) {
+              const double sed = cF[jb] * exp_scaled(th[0] + 1.0, cLh[jb], cLl[jb]);
+              const double dl = sed - cS0[jb];
+              v = -0.5 * (cX[jb] - 2.0 * dl * cY[jb] + dl * dl * cZ[jb]);
+            }
+            sv[j][jb] = v;
+          }
+        } else {
+#pragma unroll 1
+          for (int jb = 0; jb < 32; jb++) {
+            double v = 0.0;
+            if (jb < B) {
+              const double sed = sed_theta(mv, mh.ic, jb, th[0], th[1], mh.plane[0]);
+              const double dl = sed - cS0[jb];
+              v = -0.5 * (cX[jb] - 2.0 * dl * cY[jb] + dl * dl * cZ[jb]);
+            }
+            sv[j][jb] = v;
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1)  // the butterfly's pairing: (i, i ^ o) level by level
+          for (int i = 0; i < o; i++) sv[j][i] += sv[j][i + o];
+        lnl_new = sv[j][0] + prior_of(th[mh.nind]);  // :306
+        const double diff = lnl_new - lnl_old;
+        const double ratio = exp(diff);  // :310, Q4
+        acc = (mh.ml_mode == 0) ? (ratio > 1.0) : (ratio > u_l);
+      }
     }
-    const double sed = sed_of(theta[0], theta[1]);
-    const double lnl_new = lnl_of(sed) + prior_of(theta[mh.nind]);  // :306
-    const double diff = lnl_new - lnl_old;
-    const double ratio = exp(diff);  // :310, Q4
-    const bool acc = (mh.ml_mode == 0) ? (ratio > 1.0) : (ratio > u_l);
-    if (acc) {
-      sample[mh.nind] = theta[mh.nind];
-      lnl_old = lnl_new;
+    const unsigned hit = __ballot_sync(0xffffffffu, live && !oob && acc);
+    const int first = hit ? __ffs(hit) - 1 : 32;  // lane of the first accepted proposal of this round
+    if (live && j <= first) {                     // these proposals are final
+      if (mh.decisions) mh.decisions[l] = oob ? 2 : (acc ? 1 : 0);
+      if (mh.lnl_trace && !oob) mh.lnl_trace[l] = lnl_new;
+    }
+    if (hit) {
+      sample[mh.nind] = __shfl_sync(0xffffffffu, th[mh.nind], first);
+      lnl_old = __shfl_sync(0xffffffffu, lnl_new, first);
       accept += 1.0;
-    }
-    if (j == 0) {
-      if (mh.lnl_trace) mh.lnl_trace[l] = lnl_new;
-      if (mh.decisions) mh.decisions[l] = acc ? 1 : 0;
+      l0 += first + 1;
+    } else {
+      l0 += 32;
     }
   }
   // chi-square of the final state per plane, from the same statistics (what compute_chisq would
