@@ -518,6 +518,11 @@ void ensure_zu(dang_gpu *h, size_t n);
 void ensure_decisions(dang_gpu *h, size_t n);
 void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, uint64_t seed, double *accept);  // host_mh_pp.cu
 void launch_perpixel_pix(dang_gpu *h, const ModelView &mv, const MhView &mh, int mode);  // host_mh_ppx.cu
+// fp64 lane-cooperative per-pixel kernel, one translation unit per bands-per-lane value (host_mh_ppd{2,3,5,8}.cu)
+void launch_perpixel_fp64_2(dang_gpu *h, const ModelView &mv, const MhView &mh, int mode, int64_t work, size_t smem);
+void launch_perpixel_fp64_3(dang_gpu *h, const ModelView &mv, const MhView &mh, int mode, int64_t work, size_t smem);
+void launch_perpixel_fp64_5(dang_gpu *h, const ModelView &mv, const MhView &mh, int mode, int64_t work, size_t smem);
+void launch_perpixel_fp64_8(dang_gpu *h, const ModelView &mv, const MhView &mh, int mode, int64_t work, size_t smem);
 void launch_perpixel_fast(dang_gpu *h, const ModelView &mv, const MhView &mh, int bpl, int mode, int64_t work,
                           size_t smem);                                            // host_mh_ppf.cu
 void launch_perpixel_split(dang_gpu *h, const ModelView &mv, MhView &mh, int bpl, int mode, int64_t work);  // host_mh_ppf.cu

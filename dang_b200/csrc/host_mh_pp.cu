@@ -69,21 +69,6 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
     // else (tabulated bandpasses, other SED types) evaluates every proposal in fp64
     const bool fast = h->pp_fast && mode != MH_SED_GENERIC && mode < MH_SED_BP_POWERLAW;
     KTimer kt(h, DANG_K_MH_PERPIXEL, kbytes);
-#define LAUNCH_PP(BPL, MODE)                                                                               \
-    {                                                                                                      \
-      CK(cudaFuncSetAttribute(mh_perpixel_kernel<BPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + bp_smem))); \
-      const int grid = occ_grid(h, mh_perpixel_kernel<BPL, MODE>, work, DG_MH_THREADS, smem + bp_smem);    \
-      mh_perpixel_kernel<BPL, MODE><<<grid, DG_MH_THREADS, smem + bp_smem, h->stream>>>(mv, mh, h->partials, h->tickets, h->sums_local); \
-    }
-#define LAUNCH_PP_MODE(BPL)                                     \
-    {                                                           \
-      if (mode == MH_SED_POWERLAW) LAUNCH_PP(BPL, MH_SED_POWERLAW) \
-      else if (mode == MH_SED_MBB_BETA) LAUNCH_PP(BPL, MH_SED_MBB_BETA) \
-      else if (mode == MH_SED_MBB_T) LAUNCH_PP(BPL, MH_SED_MBB_T)  \
-      else if (mode == MH_SED_BP_POWERLAW) LAUNCH_PP(BPL, MH_SED_BP_POWERLAW) \
-      else if (mode == MH_SED_BP_MBB_BETA) LAUNCH_PP(BPL, MH_SED_BP_MBB_BETA) \
-      else LAUNCH_PP(BPL, MH_SED_GENERIC)                       \
-    }
     if (fast && h->pp_pix && h->nbands <= 32) {
       launch_perpixel_pix(h, mv, mh, mode);
     } else if (fast && h->pp_split && !h->record) {
@@ -92,12 +77,10 @@ void sample_perpixel(dang_gpu *h, MhView &mh, const double *z, const double *u, 
       const int bplr = bpl <= 2 ? 2 : bpl <= 3 ? 3 : bpl <= 5 ? 5 : 8;
       launch_perpixel_fast(h, mv, mh, bpl, mode, work, smem + (size_t)4 * bplr * DG_MH_THREADS * sizeof(double));
     }
-    else if (bpl <= 2) LAUNCH_PP_MODE(2)
-    else if (bpl <= 3) LAUNCH_PP_MODE(3)
-    else if (bpl <= 5) LAUNCH_PP_MODE(5)
-    else LAUNCH_PP_MODE(8)
-#undef LAUNCH_PP_MODE
-#undef LAUNCH_PP
+    else if (bpl <= 2) launch_perpixel_fp64_2(h, mv, mh, mode, work, smem + bp_smem);
+    else if (bpl <= 3) launch_perpixel_fp64_3(h, mv, mh, mode, work, smem + bp_smem);
+    else if (bpl <= 5) launch_perpixel_fp64_5(h, mv, mh, mode, work, smem + bp_smem);
+    else launch_perpixel_fp64_8(h, mv, mh, mode, work, smem + bp_smem);
     kt.done();
     pp_fast_ran = fast;
   }
