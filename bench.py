@@ -46,6 +46,39 @@ def ncu_traffic(kernel: str):
     return json.load(open(p)).get(kernel)
 
 
+def ncu_pipe(kernel: str, config: str):
+    """Pipe utilisation of `kernel` on `config` from the committed ncu capture (profiles/ncu_pipes.json): the bound
+    of the per-pixel Metropolis kernels is an execution pipe, not HBM, and pipe-busy
+    percentages cannot be measured outside a profiler."""
+    p = os.path.join(ROOT, "profiles", "ncu_pipes.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(f"{kernel}@{config}")
+
+
+def roofline_block(top, stats, config, peak, peak_src):
+    """The `roofline` object of the JSON line for the dominant kernel `top` of `stats` (dang_gpu_kernel_stats)."""
+    s = stats[top]
+    ach = s["bytes"] / (s["ms"] * 1e-3) / 1e9
+    tot = sum(v["ms"] for v in stats.values())
+    roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(ach / peak, 4), "traffic": ncu_traffic(top), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": round(s["bytes"] / max(s["launches"], 1)),
+            "avg_launch_us": round(1e3 * s["ms"] / max(s["launches"], 1), 2),
+            "share_of_kernel_time": round(s["ms"] / tot, 3),
+            "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
+                               "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if (v["ms"] > 0 and v["bytes"] > 0) else None}
+                           for k, v in stats.items() if v["launches"]}}
+    pipe = ncu_pipe(top, config)
+    if pipe:  # not an HBM-bound kernel: report the pipe that bounds it, keep the (small) HBM figures beside it
+        roof["hbm"] = {"achieved": roof["achieved"], "peak": peak, "unit": "GB/s", "frac": roof["frac"]}
+        roof.update({"bound": pipe["bound"], "achieved": pipe["busy_pct"], "peak": 100.0,
+                     "unit": f"% of the {pipe['bound']} pipe's issue slots busy", "frac": round(pipe["busy_pct"] / 100.0, 4),
+                     "peak_source": f"ncu capture {pipe['capture']} (a pipe-busy fraction cannot be measured live; launch time above is live)",
+                     "issue_active_pct": pipe.get("issue_active_pct")})
+    return roof
+
+
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region.  The region is short (20 steps x 1.5 ms), so
@@ -403,19 +436,7 @@ def run_gpu(args):
         peak, peak_src = peaks()
         ms_per_step = ms / args.steps
         top = max((k for k in stats if stats[k]["ms"] > 0), key=lambda k: stats[k]["ms"], default=None)
-        roof = None
-        if top:
-            s = stats[top]
-            ach = s["bytes"] / (s["ms"] * 1e-3) / 1e9
-            tot = sum(v["ms"] for v in stats.values())
-            roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": ncu_traffic(top), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": round(s["bytes"] / max(s["launches"], 1)),
-                    "avg_launch_us": round(1e3 * s["ms"] / max(s["launches"], 1), 2),
-                    "share_of_kernel_time": round(s["ms"] / tot, 3),
-                    "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
-                                       "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if (v["ms"] > 0 and v["bytes"] > 0) else None}
-                                   for k, v in stats.items() if v["launches"]}}
+        roof = roofline_block(top, stats, cfg.name, peak, peak_src) if top else None
         line = {
             "metric": METRIC if (cfg.name == "c2" and cfg.nside == 512) else f"Gibbs iterations/sec (nside={cfg.nside}, Q+U, synch+dust)",
             "value": round(1e3 / ms_per_step, 3), "unit": UNIT, "n_gpus": world,

@@ -41,3 +41,25 @@ def test_product_arm_has_no_cpu_fallback():
     r = _run(["--nside", "16", "--steps", "1", "--warmup", "1", "--no-cpu"])
     assert r.returncode != 0
     assert "dang_gpu" in (r.stderr + r.stdout) or "CUDA" in (r.stderr + r.stdout)
+
+
+def test_roofline_block_reports_the_bounding_pipe(monkeypatch):
+    """HBM-bound kernels report bytes / time against the measured copy peak; a kernel listed in
+    profiles/ncu_pipes.json (per-pixel Metropolis: an execution pipe bounds it) reports that pipe, with the
+    HBM figures kept beside it."""
+    sys.path.insert(0, ROOT)
+    import bench
+    stats = {"cg_pass_kernel": {"launches": 2, "ms": 2.0, "bytes": 10.0e9},
+             "mh_perpixel_kernel": {"launches": 2, "ms": 20.0, "bytes": 4.0e9},
+             "scalar kernels": {"launches": 4, "ms": 0.1, "bytes": 0.0}}
+    monkeypatch.setattr(bench, "ncu_pipe", lambda k, c: None)
+    r = bench.roofline_block("cg_pass_kernel", stats, "c2", 6388.0, "measured")
+    assert r["bound"] == "hbm" and r["achieved"] == 5000.0 and abs(r["frac"] - 5000.0 / 6388.0) < 1e-4
+    assert r["per_kernel"]["scalar kernels"]["GBps"] is None and r["avg_launch_us"] == 1000.0
+    monkeypatch.setattr(bench, "ncu_pipe", lambda k, c: {"bound": "fp64", "busy_pct": 41.5, "issue_active_pct": 60.0,
+                                                         "capture": "profiles/x.csv"} if (k, c) == ("mh_perpixel_kernel", "c3") else None)
+    r = bench.roofline_block("mh_perpixel_kernel", stats, "c3", 6388.0, "measured")
+    assert r["bound"] == "fp64" and r["achieved"] == 41.5 and r["peak"] == 100.0 and r["frac"] == 0.415
+    assert r["hbm"]["achieved"] == 200.0 and r["avg_launch_us"] == 10000.0
+    r = bench.roofline_block("mh_perpixel_kernel", stats, "c4", 6388.0, "measured")
+    assert r["bound"] == "hbm"
