@@ -56,13 +56,18 @@ def ncu_pipe(kernel: str, config: str):
     return json.load(open(p)).get(f"{kernel}@{config}")
 
 
-def roofline_block(top, stats, config, peak, peak_src):
-    """The `roofline` object of the JSON line for the dominant kernel `top` of `stats` (dang_gpu_kernel_stats)."""
+def roofline_block(top, stats, config, peak, peak_src, capture_share=None):
+    """The `roofline` object of the JSON line for the dominant kernel `top` of `stats` (dang_gpu_kernel_stats).
+    `capture_share`: this rank's share of the workload the committed ncu capture was taken on (c2 at nside 512 on one
+    GPU): the captured DRAM bytes per launch scale with it; None when the run is another workload (no traffic figure)."""
     s = stats[top]
     ach = s["bytes"] / (s["ms"] * 1e-3) / 1e9
     tot = sum(v["ms"] for v in stats.values())
+    traffic = ncu_traffic(top) if capture_share is not None else None
+    if traffic is not None:
+        traffic = round(traffic * capture_share)
     roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(ach / peak, 4), "traffic": ncu_traffic(top), "peak_source": peak_src,
+            "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": round(s["bytes"] / max(s["launches"], 1)),
             "avg_launch_us": round(1e3 * s["ms"] / max(s["launches"], 1), 2),
             "share_of_kernel_time": round(s["ms"] / tot, 3),
@@ -436,7 +441,9 @@ def run_gpu(args):
         peak, peak_src = peaks()
         ms_per_step = ms / args.steps
         top = max((k for k in stats if stats[k]["ms"] > 0), key=lambda k: stats[k]["ms"], default=None)
-        roof = roofline_block(top, stats, cfg.name, peak, peak_src) if top else None
+        # the ncu capture behind `traffic` is c2 at nside 512 on one GPU; a rank of an N-GPU run moves its share of it
+        share = (P / cfg.npix) if (cfg.name == "c2" and cfg.nside == 512) else None
+        roof = roofline_block(top, stats, cfg.name, peak, peak_src, capture_share=share) if top else None
         line = {
             "metric": METRIC if (cfg.name == "c2" and cfg.nside == 512) else f"Gibbs iterations/sec (nside={cfg.nside}, Q+U, synch+dust)",
             "value": round(1e3 / ms_per_step, 3), "unit": UNIT, "n_gpus": world,

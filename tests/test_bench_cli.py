@@ -53,8 +53,12 @@ def test_roofline_block_reports_the_bounding_pipe(monkeypatch):
              "mh_perpixel_kernel": {"launches": 2, "ms": 20.0, "bytes": 4.0e9},
              "scalar kernels": {"launches": 4, "ms": 0.1, "bytes": 0.0}}
     monkeypatch.setattr(bench, "ncu_pipe", lambda k, c: None)
-    r = bench.roofline_block("cg_pass_kernel", stats, "c2", 6388.0, "measured")
+    monkeypatch.setattr(bench, "ncu_traffic", lambda k: 4_000_000_000 if k == "cg_pass_kernel" else None)
+    r = bench.roofline_block("cg_pass_kernel", stats, "c2", 6388.0, "measured", capture_share=1.0)
     assert r["bound"] == "hbm" and r["achieved"] == 5000.0 and abs(r["frac"] - 5000.0 / 6388.0) < 1e-4
+    assert r["traffic"] == 4_000_000_000
+    assert bench.roofline_block("cg_pass_kernel", stats, "c2", 6388.0, "measured", capture_share=0.125)["traffic"] == 500_000_000
+    assert bench.roofline_block("cg_pass_kernel", stats, "c2", 6388.0, "measured")["traffic"] is None   # another workload
     assert r["per_kernel"]["scalar kernels"]["GBps"] is None and r["avg_launch_us"] == 1000.0
     monkeypatch.setattr(bench, "ncu_pipe", lambda k, c: {"bound": "fp64", "busy_pct": 41.5, "issue_active_pct": 60.0,
                                                          "capture": "profiles/x.csv"} if (k, c) == ("mh_perpixel_kernel", "c3") else None)
