@@ -214,6 +214,19 @@ def test_golden_vectors():
         assert np.array_equal(gold[k], now[k]) or rel_err(now[k], gold[k]) < 1e-13, k
 
 
+def test_golden_vectors_intensity_components_and_udgrade():
+    """The round-2 oracle features frozen the same way: hi_fit + monopole in a Stokes-I CG group (amplitudes,
+    band monopoles, residual, a full-sky T_d chain) and the resolution operators."""
+    import os
+    from golden.make_golden import run_intensity_case
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "intensity_nside4.npz"))
+    now = run_intensity_case()
+    assert set(gold.files) == set(now)
+    for k in gold.files:
+        assert np.array_equal(gold[k], now[k]) or rel_err(now[k], gold[k]) < 1e-12, k
+    load().ora_set_T_CMB(2.7255)
+
+
 def test_template_fit_recovers_a_noiseless_sky():
     """Template branches of compute_rhs / compute_Ax / unpack_amplitudes (src/dang_cg_mod.f90:560-587,
     :745-768, :867-893, :1374-1392): on a noiseless sky = synchrotron + per-band template amplitudes the CG
